@@ -1,0 +1,123 @@
+/*
+ * ssr_b200.h -- C ABI of the B200-native multi-frame ESRGAN engine (libssr_b200.so).
+ *
+ * The reference (allenai/satlas-super-resolution) has no native layer and no FFI: every operator on
+ * its hot path is a torch call that dispatches to cuDNN / ATen.  The entry
+ * points below are the operators that replace those calls; each one names the reference call site
+ * (file:line under /root/reference) whose arithmetic it takes over.  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host";
+ *   - activations are NHWC bf16, "pix_stride" = elements between consecutive pixels (lets a conv
+ *     read / write a channel slice of a wider dense-block buffer, which is how torch.cat disappears);
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), allocation free and
+ *     never synchronise; return 0 on success, a negative SSR_E_* code otherwise (ssr_last_error()
+ *     gives the text).  There is no CPU fallback: without a GPU the calls fail with SSR_E_CUDA.
+ */
+#ifndef SSR_B200_H_
+#define SSR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSR_OK 0
+#define SSR_E_ARG -1   /* invalid argument / unsupported shape */
+#define SSR_E_CUDA -2  /* CUDA runtime / driver error (including "no device") */
+
+/* residual / output element kinds */
+#define SSR_NONE 0
+#define SSR_BF16 1
+#define SSR_F32 2
+
+/* f32 output modes of ssr_conv_tc */
+#define SSR_OUT32_NONE 0
+#define SSR_OUT32_NHWC 1        /* store   out32[pix*stride + c]              */
+#define SSR_OUT32_NHWC_ATOMIC 2 /* red.add out32[pix*stride + c]  (split-K)   */
+#define SSR_OUT32_NCHW 3        /* store   out32[((n*cout + c)*H + y)*W + x]  */
+
+/* weight packing modes */
+#define SSR_PACK_FWD 0   /* B[n=cout][k=cin], taps as stored          */
+#define SSR_PACK_DGRAD 1 /* B[n=cin][k=cout], taps flipped (conv^T)   */
+
+const char* ssr_last_error(void);
+int ssr_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t ssr_launch_count(void);
+
+/*
+ * Implicit-GEMM convolution, R x R (R = 1 or 3), stride 1, zero padding (R-1)/2, on tcgen05 tensor
+ * cores: NHWC bf16 tiles -> shared memory by TMA (128B swizzle) -> tcgen05.mma (bf16 x bf16 -> f32 in
+ * TMEM) -> fused epilogue.  Replaces nn.Conv2d(k=3,s=1,p=1) forward at ssr/archs/rrdbnet_arch.py:37-44,
+ * :122-136 and ssr/archs/discriminator_arch.py:44-69 (conv0, conv4..conv9), its input-gradient
+ * (same kernel, SSR_PACK_DGRAD weights) and, with R = 1, any K-major GEMM (used for the strided
+ * discriminator convs through im2col and for weight gradients).
+ *
+ * Epilogue, per output element (p = pixel, c = channel):
+ *   v = acc + bias[c]; if (act) v = v > 0 ? v : 0.2 v;           // LeakyReLU(0.2), rrdbnet_arch.py:33
+ *   v = s0*v + s1*res1[p,c] + s2*res2[p,c];                      // x5*0.2 + x (:44), out*0.2 + x (:68)
+ *   if (c >= mask_lo) v *= (mask[p,c] > 0 ? 1 : 0.2);            // LeakyReLU backward on a saved output
+ *   if (relu_mask) v *= (relu_mask[p,c] > 0 ? 1 : 0)             // ReLU backward (VGG)
+ *   out_bf16[p,c] = bf16(v); out_f32[...] (=|+=) v
+ */
+typedef struct ssr_conv_tc_args {
+  /* input activation, NHWC bf16: x[((n*h + y)*w + x)*x_pix_stride + c], c in [0, cin) */
+  const void* x;
+  int32_t n_img, h, w;
+  int32_t x_pix_stride;
+  int32_t cin; /* channels read; multiple of 16; x and x_pix_stride*2 must be 16-byte aligned */
+  /* weights packed by ssr_pack_conv_weight: [cin_chunks][R][R][n_pad][64] bf16 */
+  const void* w_packed;
+  int32_t r;     /* 1 or 3 */
+  int32_t cout;  /* valid output channels */
+  int32_t n_pad; /* padded output channels in w_packed (multiple of 16) */
+  /* epilogue */
+  const float* bias; /* [cout] or NULL */
+  int32_t act;       /* 1 = LeakyReLU(0.2) */
+  float s0;
+  const void* res1;
+  int32_t res1_kind; /* SSR_NONE / SSR_BF16 / SSR_F32 */
+  int32_t res1_pix_stride;
+  float s1;
+  const void* res2;
+  int32_t res2_kind;
+  int32_t res2_pix_stride;
+  float s2;
+  const void* mask; /* bf16 NHWC, or NULL */
+  int32_t mask_pix_stride;
+  int32_t mask_lo;   /* first output channel the mask applies to; mask is indexed [p*stride + c] */
+  int32_t mask_relu; /* 0: LeakyReLU(0.2) derivative, 1: ReLU derivative */
+  void* out_bf16;    /* NHWC bf16 or NULL */
+  int32_t out_pix_stride;
+  float* out_f32;
+  int32_t out32_mode; /* SSR_OUT32_* */
+  int32_t out32_pix_stride;
+  /* tiling knobs, 0 = choose automatically */
+  int32_t n_tile; /* output channels per CTA, multiple of 16, <= 256 */
+  int32_t mt;     /* 128-pixel M tiles per CTA: 1 or 2 */
+  int32_t splits; /* split the cin chunks over this many CTAs (needs SSR_OUT32_NHWC_ATOMIC) */
+} ssr_conv_tc_args;
+
+int ssr_conv_tc(const ssr_conv_tc_args* args, void* stream);
+
+/* bytes of a packed weight buffer for (cin, cout, r) -> n_pad is written back */
+int64_t ssr_packed_weight_bytes(int32_t cin, int32_t cout, int32_t r, int32_t* n_pad);
+
+/*
+ * Pack f32 OIHW weights (the layout of nn.Conv2d.weight, what the reference state_dict holds) into the
+ * bf16 K-major tile layout ssr_conv_tc reads.  `inv_scale` (device, 1 float, may be NULL) divides the
+ * weights: it is sigma of spectral_norm (discriminator_arch.py:30-39).  For SSR_PACK_DGRAD the roles
+ * of cin/cout swap in the packed buffer (n = cin, k = cout) and the taps are mirrored.
+ * cin_pad: channels of the activation buffer the packed weights will be used with (>= cin, mult of 16).
+ */
+int ssr_pack_conv_weight(const float* w_oihw, int32_t cout, int32_t cin, int32_t r, int32_t mode,
+                         const float* inv_scale, void* packed, int32_t k_pad, int32_t n_pad,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSR_B200_H_ */
