@@ -117,6 +117,39 @@ int ssr_pack_conv_weight(const float* w_oihw, int32_t cout, int32_t cin, int32_t
                          const float* inv_scale, void* packed, int32_t k_pad, int32_t n_pad,
                          void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Layout / resampling kernels (HBM-bound, NHWC bf16, 16-byte vectorised).
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Planar NCHW (u8: src_kind 0, f32: src_kind SSR_F32) -> NHWC bf16 with channels [c, c_pad) zero-filled.
+ * v = src*scale, then (v - mean[c]) * inv_std[c] when mean != NULL.  Replaces `.float()/255` of
+ * ssr/models/ssr_esrgan_model.py:106-108 and the ImageNet input-norm of basicsr PerceptualLoss. */
+int ssr_ingest_nchw(const void* src, int32_t src_kind, void* dst_bf16, int32_t dst_pix_stride, int32_t b, int32_t c,
+                    int32_t h, int32_t w, int32_t c_pad, float scale, const float* mean, const float* inv_std,
+                    void* stream);
+/* NHWC bf16 channel slice -> planar NCHW f32 (dst = or += src*scale) */
+int ssr_egress_nchw(const void* src_bf16, int32_t src_pix_stride, float* dst, int32_t b, int32_t c, int32_t h, int32_t w,
+                    float scale, int32_t accumulate, void* stream);
+/* F.interpolate(mode='nearest', scale_factor=factor): rrdbnet_arch.py:127-128, ssr_esrgan_model.py:133 */
+int ssr_upsample_nearest(const void* src, int32_t src_pix_stride, void* dst, int32_t dst_pix_stride, int32_t b, int32_t h,
+                         int32_t w, int32_t c, int32_t factor, void* stream);
+int ssr_upsample_nearest_bwd(const void* dy, int32_t dy_pix_stride, void* dx, int32_t dx_pix_stride, int32_t b, int32_t h,
+                             int32_t w, int32_t c, int32_t factor, void* stream);
+/* F.interpolate(scale_factor=2, mode='bilinear', align_corners=False): discriminator_arch.py:50,55,60 */
+int ssr_upsample_bilinear2x(const void* src, int32_t src_pix_stride, void* dst, int32_t dst_pix_stride, int32_t b,
+                            int32_t h, int32_t w, int32_t c, void* stream);
+int ssr_upsample_bilinear2x_bwd(const void* dy, int32_t dy_pix_stride, void* dx, int32_t dx_pix_stride, int32_t b,
+                                int32_t h, int32_t w, int32_t c, void* stream);
+
+/* One launch packs every conv of a network (descs live in DEVICE memory). */
+typedef struct ssr_pack_desc {
+  const float* w;         /* OIHW f32 */
+  void* dst;              /* packed bf16 */
+  const float* inv_scale; /* spectral-norm sigma (device) or NULL */
+  int32_t cout, cin, r, mode, k_pad, n_pad;
+} ssr_pack_desc;
+int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, int32_t n_layers, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

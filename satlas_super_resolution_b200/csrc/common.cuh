@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <cuda_bf16.h>
 
 #include "../../include/ssr_b200.h"
 

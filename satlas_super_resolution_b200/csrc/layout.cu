@@ -1,0 +1,362 @@
+// HBM-bound layout / resampling kernels: NCHW<->NHWC ingest & egress, nearest and bilinear resampling,
+// batched weight packing.  All are coalesced on the NHWC (channel-contiguous) side and vectorised 16 B
+// where the channel count allows; grids are sized in multiples of the SM count (persistent grid-stride).
+#include "common.cuh"
+
+namespace ssr {
+
+static int g_sms = 0;
+static int grid_for(long work_items, int threads) {
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  long blocks = (work_items + threads - 1) / threads;
+  long cap = (long)g_sms * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------- ingest: planar (NCHW) -> NHWC bf16
+// One thread per (pixel, 8-channel group): reads 8 planar values (each coalesced across the warp, which
+// walks consecutive pixels), writes one 16-byte NHWC vector.  Channels >= C up to c_pad are zero-filled.
+template <typename T>
+__global__ void nchw_to_nhwc_bf16_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int C,
+                                         int H, int W, int dst_stride, int c_pad, float scale,
+                                         const float* __restrict__ mean, const float* __restrict__ inv_std) {
+  const long HW = (long)H * W;
+  const int groups = c_pad / 8;
+  const long total = (long)B * HW * groups;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i % ((long)B * HW);
+    const int g = (int)(i / ((long)B * HW));
+    const long n = pix / HW;
+    const long hw = pix - n * HW;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      float f = 0.f;
+      if (c < C) {
+        f = (float)src[(n * C + c) * HW + hw] * scale;
+        if (mean) f = (f - mean[c]) * inv_std[c];
+      }
+      v[j] = f;
+    }
+    uint4 o;
+    __nv_bfloat162 h;
+    h = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+    *reinterpret_cast<uint4*>(dst + pix * dst_stride + g * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------- egress: NHWC bf16 -> planar f32
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, int src_stride,
+                                             float* __restrict__ dst, int B, int C, int H, int W, float scale,
+                                             int accumulate) {
+  const long HW = (long)H * W;
+  const long total = (long)B * C * HW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long hw = i % HW;
+    const long t = i / HW;
+    const int c = (int)(t % C);
+    const long n = t / C;
+    const float v = __bfloat162float(src[(n * HW + hw) * src_stride + c]) * scale;
+    if (accumulate) dst[i] += v; else dst[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------- nearest upsample (NHWC bf16), factor f
+// out[y, x, :] = in[y / f, x / f, :]   (F.interpolate(mode='nearest'), rrdbnet_arch.py:127-128,
+// ssr_esrgan_model.py:133).  One thread per 16-byte channel vector of an output pixel.
+__global__ void upsample_nearest_kernel(const __nv_bfloat16* __restrict__ src, int src_stride,
+                                        __nv_bfloat16* __restrict__ dst, int dst_stride, int B, int H, int W, int C,
+                                        int f) {
+  const int groups = C / 8;
+  const int OH = H * f, OW = W * f;
+  const long total = (long)B * OH * OW * groups;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long p = i / groups;
+    const int ox = (int)(p % OW);
+    p /= OW;
+    const int oy = (int)(p % OH);
+    const long n = p / OH;
+    const long sp = (n * H + oy / f) * W + ox / f;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + sp * src_stride + g * 8);
+    *reinterpret_cast<uint4*>(dst + ((n * OH + oy) * OW + ox) * (long)dst_stride + g * 8) = v;
+  }
+}
+
+// backward of nearest upsample: sum over each f x f block (fp32 accumulate, bf16 out)
+__global__ void upsample_nearest_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
+                                            __nv_bfloat16* __restrict__ dx, int dx_stride, int B, int H, int W,
+                                            int C, int f) {
+  const int groups = C / 8;
+  const int OH = H * f, OW = W * f;
+  const long total = (long)B * H * W * groups;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long p = i / groups;
+    const int x = (int)(p % W);
+    p /= W;
+    const int y = (int)(p % H);
+    const long n = p / H;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int dyy = 0; dyy < f; ++dyy)
+      for (int dxx = 0; dxx < f; ++dxx) {
+        const long sp = (n * OH + y * f + dyy) * OW + x * f + dxx;
+        const uint4 v = *reinterpret_cast<const uint4*>(dy + sp * dy_stride + g * 8);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += __uint_as_float(u[j] << 16);
+          acc[2 * j + 1] += __uint_as_float(u[j] & 0xFFFF0000u);
+        }
+      }
+    uint4 o;
+    __nv_bfloat162 h;
+    h = __floats2bfloat162_rn(acc[0], acc[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(acc[2], acc[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(acc[4], acc[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(acc[6], acc[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+    *reinterpret_cast<uint4*>(dx + ((n * H + y) * W + x) * (long)dx_stride + g * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------- bilinear x2, align_corners=False
+// F.interpolate(scale_factor=2, mode='bilinear', align_corners=False), discriminator_arch.py:50,55,60.
+// Source coordinate (o + 0.5)/2 - 0.5 clamped at 0: taps (0.25, 0.75) in the interior, replicate at edges.
+__device__ __forceinline__ void bilin_src(int o, int n_in, int& i0, int& i1, float& w1) {
+  float s = (o + 0.5f) * 0.5f - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  w1 = s - (float)i0;
+}
+
+__global__ void upsample_bilinear2x_kernel(const __nv_bfloat16* __restrict__ src, int src_stride,
+                                           __nv_bfloat16* __restrict__ dst, int dst_stride, int B, int H, int W, int C) {
+  const int groups = C / 8;
+  const int OH = H * 2, OW = W * 2;
+  const long total = (long)B * OH * OW * groups;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long p = i / groups;
+    const int ox = (int)(p % OW);
+    p /= OW;
+    const int oy = (int)(p % OH);
+    const long n = p / OH;
+    int y0, y1, x0, x1;
+    float wy, wx;
+    bilin_src(oy, H, y0, y1, wy);
+    bilin_src(ox, W, x0, x1, wx);
+    const __nv_bfloat16* base = src + n * H * W * (long)src_stride + g * 8;
+    const uint4 v00 = *reinterpret_cast<const uint4*>(base + ((long)y0 * W + x0) * src_stride);
+    const uint4 v01 = *reinterpret_cast<const uint4*>(base + ((long)y0 * W + x1) * src_stride);
+    const uint4 v10 = *reinterpret_cast<const uint4*>(base + ((long)y1 * W + x0) * src_stride);
+    const uint4 v11 = *reinterpret_cast<const uint4*>(base + ((long)y1 * W + x1) * src_stride);
+    const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, b[4] = {v01.x, v01.y, v01.z, v01.w};
+    const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
+    // same operation order as ATen's upsample_bilinear2d: w0y*(w0x*a + w1x*b) + w1y*(w0x*c + w1x*d)
+    const float w0x = 1.f - wx, w0y = 1.f - wy;
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo = w0y * (w0x * __uint_as_float(a[j] << 16) + wx * __uint_as_float(b[j] << 16)) +
+                 wy * (w0x * __uint_as_float(c[j] << 16) + wx * __uint_as_float(d[j] << 16));
+      float hi = w0y * (w0x * __uint_as_float(a[j] & 0xFFFF0000u) + wx * __uint_as_float(b[j] & 0xFFFF0000u)) +
+                 wy * (w0x * __uint_as_float(c[j] & 0xFFFF0000u) + wx * __uint_as_float(d[j] & 0xFFFF0000u));
+      __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+      o[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(dst + ((n * OH + oy) * OW + ox) * (long)dst_stride + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// backward (gather form): each input pixel (y, x) collects from the <= 3x3 output pixels whose taps touch it.
+__global__ void upsample_bilinear2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
+                                               __nv_bfloat16* __restrict__ dx, int dx_stride, int B, int H, int W,
+                                               int C) {
+  const int groups = C / 8;
+  const int OH = H * 2, OW = W * 2;
+  const long total = (long)B * H * W * groups;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long p = i / groups;
+    const int x = (int)(p % W);
+    p /= W;
+    const int y = (int)(p % H);
+    const long n = p / H;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // output rows whose (y0, y1) can include y: oy in [2y-1, 2y+2]
+    for (int oy = max(0, 2 * y - 1); oy <= min(OH - 1, 2 * y + 2); ++oy) {
+      int y0, y1;
+      float wy;
+      bilin_src(oy, H, y0, y1, wy);
+      float cy = (y0 == y ? 1.f - wy : 0.f) + (y1 == y ? wy : 0.f);
+      if (cy == 0.f) continue;
+      for (int ox = max(0, 2 * x - 1); ox <= min(OW - 1, 2 * x + 2); ++ox) {
+        int x0, x1;
+        float wx;
+        bilin_src(ox, W, x0, x1, wx);
+        float cx = (x0 == x ? 1.f - wx : 0.f) + (x1 == x ? wx : 0.f);
+        if (cx == 0.f) continue;
+        const float cw = cy * cx;
+        const uint4 v = *reinterpret_cast<const uint4*>(dy + ((n * OH + oy) * OW + ox) * (long)dy_stride + g * 8);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += cw * __uint_as_float(u[j] << 16);
+          acc[2 * j + 1] += cw * __uint_as_float(u[j] & 0xFFFF0000u);
+        }
+      }
+    }
+    uint4 o;
+    __nv_bfloat162 h;
+    h = __floats2bfloat162_rn(acc[0], acc[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(acc[2], acc[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(acc[4], acc[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(acc[6], acc[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+    *reinterpret_cast<uint4*>(dx + ((n * H + y) * W + x) * (long)dx_stride + g * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------- batched weight packing
+struct PackDesc {
+  const float* w;          // OIHW f32
+  __nv_bfloat16* dst;      // [chunks][R][R][n_pad][64]
+  const float* inv_scale;  // sigma (device) or null
+  int cout, cin, r, mode, k_pad, n_pad;
+};
+
+__global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
+  const PackDesc d = descs[blockIdx.y];
+  const int chunks = d.k_pad / 64;
+  const long total = (long)chunks * d.r * d.r * d.n_pad * 64;
+  const float sc = d.inv_scale ? 1.f / *d.inv_scale : 1.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int j = t % 64;
+    t /= 64;
+    const int nn = t % d.n_pad;
+    t /= d.n_pad;
+    const int ky = t % d.r;
+    t /= d.r;
+    const int kx = t % d.r;
+    const int c = t / d.r;
+    const int k = c * 64 + j;
+    float v = 0.f;
+    if (d.mode == SSR_PACK_FWD) {
+      if (nn < d.cout && k < d.cin) v = d.w[(((long)nn * d.cin + k) * d.r + ky) * d.r + kx];
+    } else {
+      if (nn < d.cin && k < d.cout) v = d.w[(((long)k * d.cin + nn) * d.r + (d.r - 1 - ky)) * d.r + (d.r - 1 - kx)];
+    }
+    d.dst[i] = __float2bfloat16(v * sc);
+  }
+}
+
+}  // namespace ssr
+
+using namespace ssr;
+
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int ssr_ingest_nchw(const void* src, int32_t src_kind /*0 = u8, 2 = f32*/, void* dst_bf16, int32_t dst_pix_stride,
+                               int32_t b, int32_t c, int32_t h, int32_t w, int32_t c_pad, float scale,
+                               const float* mean, const float* inv_std, void* stream) {
+  SSR_REQUIRE(src && dst_bf16, "ssr_ingest_nchw: null pointer");
+  SSR_REQUIRE(c_pad % 8 == 0 && c_pad >= c && dst_pix_stride % 8 == 0 && dst_pix_stride >= c_pad, "ssr_ingest_nchw: c_pad/stride");
+  SSR_REQUIRE((reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0, "ssr_ingest_nchw: dst alignment");
+  const long total = (long)b * h * w * (c_pad / 8);
+  const int threads = 256;
+  const int blocks = grid_for(total, threads);
+  if (src_kind == 0)
+    nchw_to_nhwc_bf16_kernel<uint8_t><<<blocks, threads, 0, STREAM(stream)>>>(
+        reinterpret_cast<const uint8_t*>(src), reinterpret_cast<__nv_bfloat16*>(dst_bf16), b, c, h, w, dst_pix_stride,
+        c_pad, scale, mean, inv_std);
+  else if (src_kind == SSR_F32)
+    nchw_to_nhwc_bf16_kernel<float><<<blocks, threads, 0, STREAM(stream)>>>(
+        reinterpret_cast<const float*>(src), reinterpret_cast<__nv_bfloat16*>(dst_bf16), b, c, h, w, dst_pix_stride,
+        c_pad, scale, mean, inv_std);
+  else
+    SSR_REQUIRE(false, "ssr_ingest_nchw: src_kind must be 0 (u8) or 2 (f32)");
+  count_launch();
+  return check_last("ingest launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_egress_nchw(const void* src_bf16, int32_t src_pix_stride, float* dst, int32_t b, int32_t c, int32_t h,
+                               int32_t w, float scale, int32_t accumulate, void* stream) {
+  SSR_REQUIRE(src_bf16 && dst, "ssr_egress_nchw: null pointer");
+  const long total = (long)b * c * h * w;
+  nhwc_bf16_to_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src_bf16), src_pix_stride, dst, b, c, h, w, scale, accumulate);
+  count_launch();
+  return check_last("egress launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+static int check_vec(const void* a, int sa, const void* b, int sb, int c, const char* who) {
+  SSR_REQUIRE(a && b, "%s: null pointer", who);
+  SSR_REQUIRE(c % 8 == 0 && sa % 8 == 0 && sb % 8 == 0, "%s: channels and strides must be multiples of 8", who);
+  SSR_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0, "%s: 16-byte alignment", who);
+  return SSR_OK;
+}
+
+extern "C" int ssr_upsample_nearest(const void* src, int32_t src_pix_stride, void* dst, int32_t dst_pix_stride, int32_t b,
+                                    int32_t h, int32_t w, int32_t c, int32_t factor, void* stream) {
+  if (int rc = check_vec(src, src_pix_stride, dst, dst_pix_stride, c, "ssr_upsample_nearest")) return rc;
+  const long total = (long)b * h * factor * w * factor * (c / 8);
+  upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), src_pix_stride, reinterpret_cast<__nv_bfloat16*>(dst), dst_pix_stride, b,
+      h, w, c, factor);
+  count_launch();
+  return check_last("upsample_nearest launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_upsample_nearest_bwd(const void* dy, int32_t dy_pix_stride, void* dx, int32_t dx_pix_stride, int32_t b,
+                                        int32_t h, int32_t w, int32_t c, int32_t factor, void* stream) {
+  if (int rc = check_vec(dy, dy_pix_stride, dx, dx_pix_stride, c, "ssr_upsample_nearest_bwd")) return rc;
+  const long total = (long)b * h * w * (c / 8);
+  upsample_nearest_bwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), dy_pix_stride, reinterpret_cast<__nv_bfloat16*>(dx), dx_pix_stride, b, h,
+      w, c, factor);
+  count_launch();
+  return check_last("upsample_nearest_bwd launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_upsample_bilinear2x(const void* src, int32_t src_pix_stride, void* dst, int32_t dst_pix_stride, int32_t b,
+                                       int32_t h, int32_t w, int32_t c, void* stream) {
+  if (int rc = check_vec(src, src_pix_stride, dst, dst_pix_stride, c, "ssr_upsample_bilinear2x")) return rc;
+  const long total = (long)b * h * 2 * w * 2 * (c / 8);
+  upsample_bilinear2x_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), src_pix_stride, reinterpret_cast<__nv_bfloat16*>(dst), dst_pix_stride, b,
+      h, w, c);
+  count_launch();
+  return check_last("upsample_bilinear2x launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_upsample_bilinear2x_bwd(const void* dy, int32_t dy_pix_stride, void* dx, int32_t dx_pix_stride, int32_t b,
+                                           int32_t h, int32_t w, int32_t c, void* stream) {
+  if (int rc = check_vec(dy, dy_pix_stride, dx, dx_pix_stride, c, "ssr_upsample_bilinear2x_bwd")) return rc;
+  const long total = (long)b * h * w * (c / 8);
+  upsample_bilinear2x_bwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), dy_pix_stride, reinterpret_cast<__nv_bfloat16*>(dx), dx_pix_stride, b, h,
+      w, c);
+  count_launch();
+  return check_last("upsample_bilinear2x_bwd launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, int32_t n_layers, void* stream) {
+  SSR_REQUIRE(descs_device && n_layers > 0, "ssr_pack_conv_weights_batched: bad args");
+  static_assert(sizeof(ssr_pack_desc) == sizeof(PackDesc), "ssr_pack_desc layout");
+  dim3 grid(32, (unsigned)n_layers);
+  pack_batched_kernel<<<grid, 256, 0, STREAM(stream)>>>(reinterpret_cast<const PackDesc*>(descs_device));
+  count_launch();
+  return check_last("pack_batched launch") ? SSR_OK : SSR_E_CUDA;
+}

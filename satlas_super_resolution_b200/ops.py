@@ -1,0 +1,153 @@
+"""Host-side helpers over the C ABI: device buffers, pre-built argument structs and launch plans.
+
+torch is used for device memory and streams only; every arithmetic op below is a kernel of
+libssr_b200.so called through ctypes (include/ssr_b200.h).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._protos import PackDesc
+
+BF16 = torch.bfloat16
+
+
+def lib():
+    return L.load()
+
+
+def cur_stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class Act:
+    """A bf16 NHWC activation buffer [B, H, W, stride]; `ch(lo)` gives the device pointer of a channel slice."""
+
+    def __init__(self, B, H, W, C_, device, zero=False):
+        self.B, self.H, self.W, self.C = B, H, W, C_
+        self.t = (torch.zeros if zero else torch.empty)((B, H, W, C_), dtype=BF16, device=device)
+
+    @property
+    def stride(self):
+        return self.C
+
+    def ptr(self, ch=0):
+        return self.t.data_ptr() + 2 * ch
+
+
+class Plan:
+    """A recorded, allocation-free sequence of C-ABI calls (replayed every step, CUDA-graph capturable)."""
+
+    def __init__(self):
+        self.calls = []
+        self.keep = []
+
+    def add(self, fn, *args):
+        self.calls.append((fn, args))
+
+    def conv(self, args):
+        self.keep.append(args)
+        self.calls.append((lib().ssr_conv_tc, (C.byref(args),)))
+
+    def extend(self, other):
+        self.calls.extend(other.calls)
+        self.keep.extend(other.keep)
+
+    def run(self, stream=None):
+        s = stream if stream is not None else cur_stream()
+        for fn, args in self.calls:
+            rc = fn(*args, s)
+            if rc != 0:
+                L.check(rc)
+
+    def __len__(self):
+        return len(self.calls)
+
+
+class PackedConv:
+    """Packed bf16 tensor-core operand(s) of one convolution (forward and, optionally, input-gradient form)."""
+
+    def __init__(self, weight, bias, cin_buf, want_dgrad, device, inv_scale=None, cout_buf=None):
+        # weight: f32 OIHW tensor view living in the owner's flat parameter buffer
+        self.weight, self.bias = weight, bias
+        self.cout, self.cin, self.r, _ = weight.shape
+        self.cin_buf = cin_buf                      # channels the forward conv reads (multiple of 16)
+        self.inv_scale = inv_scale
+        n_pad = C.c_int32(0)
+        self.k_pad = round_up(cin_buf, 64)
+        nbytes = lib().ssr_packed_weight_bytes(self.k_pad, self.cout, self.r, C.byref(n_pad))
+        self.n_pad = n_pad.value
+        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.packed_dg = None
+        if want_dgrad:
+            # reduce dim = conv output channels as stored in the gradient buffer (multiple of 16)
+            self.cout_buf = cout_buf or round_up(self.cout, 16)
+            self.k_pad_dg = round_up(self.cout_buf, 64)
+            nbytes = lib().ssr_packed_weight_bytes(self.k_pad_dg, self.cin, self.r, C.byref(n_pad))
+            self.n_pad_dg = n_pad.value
+            self.packed_dg = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+    def descs(self):
+        out = []
+        d = PackDesc()
+        d.w = self.weight.data_ptr()
+        d.dst = self.packed.data_ptr()
+        d.inv_scale = self.inv_scale.data_ptr() if self.inv_scale is not None else None
+        d.cout, d.cin, d.r, d.mode, d.k_pad, d.n_pad = self.cout, self.cin, self.r, L.PACK_FWD, self.k_pad, self.n_pad
+        out.append(d)
+        if self.packed_dg is not None:
+            d = PackDesc()
+            d.w = self.weight.data_ptr()
+            d.dst = self.packed_dg.data_ptr()
+            d.inv_scale = self.inv_scale.data_ptr() if self.inv_scale is not None else None
+            d.cout, d.cin, d.r, d.mode, d.k_pad, d.n_pad = (self.cout, self.cin, self.r, L.PACK_DGRAD, self.k_pad_dg,
+                                                            self.n_pad_dg)
+            out.append(d)
+        return out
+
+
+class Packer:
+    """All PackedConv of a network -> one ssr_pack_conv_weights_batched launch."""
+
+    def __init__(self, convs, device):
+        descs = []
+        for cv in convs:
+            descs.extend(cv.descs())
+        arr = (PackDesc * len(descs))(*descs)
+        raw = bytes(arr)
+        self.n = len(descs)
+        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+    def run(self, stream=None):
+        L.check(lib().ssr_pack_conv_weights_batched(self.table.data_ptr(), self.n,
+                                                    stream if stream is not None else cur_stream()))
+
+
+def conv_args(x_ptr, B, H, W, x_stride, cin, w_ptr, r, cout, n_pad, bias=None, act=0, s0=1.0,
+              res1=None, res1_kind=L.SSR_BF16, res1_stride=0, s1=0.0,
+              res2=None, res2_kind=L.SSR_BF16, res2_stride=0, s2=0.0,
+              mask=None, mask_stride=0, mask_lo=0, mask_relu=0,
+              out=None, out_stride=0, out32=None, out32_mode=L.OUT32_NONE, out32_stride=0,
+              n_tile=0, mt=0, splits=0):
+    a = L.ConvTcArgs()
+    a.x, a.n_img, a.h, a.w, a.x_pix_stride, a.cin = x_ptr, B, H, W, x_stride, cin
+    a.w_packed, a.r, a.cout, a.n_pad = w_ptr, r, cout, n_pad
+    a.bias = bias
+    a.act, a.s0 = act, s0
+    if res1 is not None:
+        a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = res1, res1_kind, res1_stride, s1
+    if res2 is not None:
+        a.res2, a.res2_kind, a.res2_pix_stride, a.s2 = res2, res2_kind, res2_stride, s2
+    if mask is not None:
+        a.mask, a.mask_pix_stride, a.mask_lo, a.mask_relu = mask, mask_stride, mask_lo, mask_relu
+    if out is not None:
+        a.out_bf16, a.out_pix_stride = out, out_stride
+    if out32 is not None:
+        a.out_f32, a.out32_mode, a.out32_pix_stride = out32, out32_mode, out32_stride
+    a.n_tile, a.mt, a.splits = n_tile, mt, splits
+    return a
