@@ -150,6 +150,34 @@ typedef struct ssr_pack_desc {
 } ssr_pack_desc;
 int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, int32_t n_layers, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Weight gradient on tensor cores (MN-major operands straight from the NHWC buffers).
+ *   out[(ky*R + kx)][cx][cy] += scale * sum_p x[p + (ky-pad, kx-pad), cx] * dy[p, cy]      (f32, red.add)
+ * `out` is [R*R][out_cx_rows][out_stride] f32 and must be zeroed by the caller before the first
+ * accumulation; ssr_wgrad_unpack scatters it into the OIHW gradient of nn.Conv2d.weight.
+ * Replaces the wgrad half of autograd for every nn.Conv2d of rrdbnet_arch.py / discriminator_arch.py.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct ssr_wgrad_tc_args {
+  const void* x; /* NHWC bf16 conv input (channel slice) */
+  int32_t n_img, h, w;
+  int32_t x_pix_stride;
+  int32_t cx; /* input channels  */
+  const void* dy; /* NHWC bf16 gradient of the conv output */
+  int32_t dy_pix_stride;
+  int32_t cy; /* output channels */
+  int32_t r;  /* 1 or 3 */
+  float* out;
+  int32_t out_cx_rows;
+  int32_t out_stride;
+  float scale;
+  int32_t splits; /* 0 = auto */
+} ssr_wgrad_tc_args;
+int ssr_wgrad_tc(const ssr_wgrad_tc_args* args, void* stream);
+int ssr_wgrad_unpack(const float* acc, int32_t cx_rows, int32_t acc_stride, float* grad_oihw, int32_t cout, int32_t cin,
+                     int32_t r, float scale, int32_t accumulate, void* stream);
+/* out[c] += scale * sum_p dy[p*stride + c]   (bias gradient) */
+int ssr_bias_grad(const void* dy_bf16, int32_t dy_pix_stride, int64_t npix, int32_t c, float* out, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

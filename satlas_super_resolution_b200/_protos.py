@@ -10,7 +10,17 @@ class PackDesc(C.Structure):
                 ("cout", i32), ("cin", i32), ("r", i32), ("mode", i32), ("k_pad", i32), ("n_pad", i32)]
 
 
+class WgradArgs(C.Structure):
+    """Mirror of struct ssr_wgrad_tc_args."""
+    _fields_ = [("x", vp), ("n_img", i32), ("h", i32), ("w", i32), ("x_pix_stride", i32), ("cx", i32),
+                ("dy", vp), ("dy_pix_stride", i32), ("cy", i32), ("r", i32),
+                ("out", vp), ("out_cx_rows", i32), ("out_stride", i32), ("scale", f32), ("splits", i32)]
+
+
 PROTOS = {
+    "ssr_wgrad_tc": (C.c_int, [C.POINTER(WgradArgs), vp]),
+    "ssr_wgrad_unpack": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, f32, i32, vp]),
+    "ssr_bias_grad": (C.c_int, [vp, i32, C.c_int64, i32, vp, f32, vp]),
     "ssr_ingest_nchw": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
     "ssr_egress_nchw": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, f32, i32, vp]),
     "ssr_upsample_nearest": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),

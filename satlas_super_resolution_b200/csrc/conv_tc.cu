@@ -14,6 +14,7 @@
 // ssr/archs/rrdbnet_arch.py:37-44, :63-68, :122-136 and ssr/archs/discriminator_arch.py:44-69.
 #include "common.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace ssr {
 
@@ -39,6 +40,7 @@ struct ConvTcK {
   int out_stride;
   float* out_f32;
   int out32_mode, out32_stride;
+  int dbg_aoff;  // experiment: extra row offset (x128 B) of the A descriptor, see scripts/probe_swizzle.py
 };
 
 static constexpr int kThreads = 192;
@@ -163,7 +165,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
           for (int ky = 0; ky < p.R; ++ky) {
-            const uint32_t a_row = a_base + (uint32_t)((m * p.TH + ky) * p.TW) * 128u;
+            const uint32_t a_row = a_base + (uint32_t)((m * p.TH + ky) * p.TW + p.dbg_aoff) * 128u;
             const uint32_t b_row = b_base + (uint32_t)(ky * p.n_tile) * 128u;
             for (int k = 0; k < ks; ++k) {
               umma_bf16_ss(tmem_base + (uint32_t)(m * p.n_tile), umma_desc_k128(a_row + k * 32),
@@ -436,6 +438,10 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   p.out_f32 = a->out_f32;
   p.out32_mode = a->out_f32 ? a->out32_mode : SSR_OUT32_NONE;
   p.out32_stride = a->out32_pix_stride;
+  {
+    const char* e = getenv("SSR_DBG_AOFF");
+    p.dbg_aoff = e ? atoi(e) : 0;
+  }
   if (a->cout % 16 == 0) {
     // vector epilogue alignment contract
     if (p.out_bf16) SSR_REQUIRE(p.out_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0, "ssr_conv_tc: out_bf16 alignment");

@@ -149,6 +149,27 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   return d;
 }
 
+// General form: leading/stride byte offsets and swizzle layout (0 none, 2 = 128B, 4 = 64B, 6 = 32B).
+// K-major operand:  rows of (swizzle width) bytes along K; SBO = bytes between 8-row groups along M/N.
+// MN-major operand: rows of (swizzle width) bytes along M/N, one row per K index; SBO = bytes between
+//                   8-row groups along K; LBO = bytes between consecutive (swizzle width) blocks along M/N.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout & 7) << 61;
+  return d;
+}
+
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn_major,
+                                                       uint32_t b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) |
+         ((m >> 4) << 24);
+}
+
 // Instruction descriptor, kind::f16: bf16 x bf16 -> f32, both operands K-major, M=128.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_m128(uint32_t n) {
   return (1u << 4)               // D format: f32

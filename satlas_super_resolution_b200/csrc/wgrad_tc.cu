@@ -1,0 +1,294 @@
+// Weight-gradient ("pixel-reduction") GEMM on tcgen05 tensor cores (sm_100a):
+//
+//   dW[ky][kx][cx][cy] += scale * sum_{pixels p} X[p + (ky - pad, kx - pad), cx] * dY[p, cy]
+//
+// Both operands are read straight from the NHWC bf16 activation / gradient buffers: a TMA box of 128
+// pixels x 64 channels lands in shared memory as 128-byte rows (one row per pixel = one row per K index), which
+// is exactly the MN-major 128B-swizzle operand layout of tcgen05.mma, so no transposed copy is ever made.
+//   A (M = 128 input channels = two 64-channel boxes, LBO apart) = X window shifted by the tap,
+//   B (N = cy, 64-byte rows / SWIZZLE_64B when cy <= 32)          = dY tile,
+//   K = the 128 pixels of the tile (8 MMAs of K = 16); a CTA owns one (128-channel block, kx) pair, keeps
+//   the R vertical taps in R TMEM accumulators and walks a range of pixel tiles (split over gridDim.x);
+//   image borders are zero-filled by TMA.  The epilogue reduces the per-CTA partial sums with red.add.f32.
+//
+// Replaces the cuDNN wgrad behind autograd of every nn.Conv2d on the path
+// (/root/reference/ssr/archs/rrdbnet_arch.py:26-30,99-112; discriminator_arch.py:28-40).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace ssr {
+
+struct WgradK {
+  int n_img, H, W, R, pad;
+  int TW, TH, tiles_x, tiles_y, total_tiles, ksteps;
+  int cx, cx_rows, cy, n_tile, y_blocks, y_rowbytes, out_stride;
+  int stages, splits;
+  uint32_t x_chunk_bytes, y_blk_bytes, stage_bytes, tmem_cols;
+  float* out;
+  float scale;
+};
+
+static constexpr int kWThreads = 192;
+
+__global__ void __launch_bounds__(kWThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const WgradK p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* bar_empty = bar_full + p.stages;
+  uint64_t* bar_tmem = bar_empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tmem + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mtile = blockIdx.y / p.R;
+  const int kx = blockIdx.y % p.R;
+  const int n0 = blockIdx.z * p.n_tile;
+  const int per = (p.total_tiles + p.splits - 1) / p.splits;
+  const int t_begin = blockIdx.x * per;
+  const int t_end = min(p.total_tiles, t_begin + per);
+  const int iters = t_end - t_begin;
+  if (iters <= 0) return;
+  const int nchunks = min(2, (p.cx - mtile * 128 + 63) / 64);
+  const uint32_t x_bytes = 2 * p.x_chunk_bytes;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmX);
+      prefetch_tmap(&tmY);
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(&bar_full[s], 1);
+        mbar_init(&bar_empty[s], 1);
+      }
+      mbar_init(bar_tmem, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        int t = t_begin + it;
+        const int tx = t % p.tiles_x;
+        t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int n = t / p.tiles_y;
+        const int x0 = tx * p.TW, y0 = ty * p.TH;
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        uint8_t* xs = smem + (size_t)s * p.stage_bytes;
+        uint8_t* ys = xs + x_bytes;
+        mbar_expect_tx(&bar_full[s], nchunks * p.x_chunk_bytes + p.y_blocks * p.y_blk_bytes);
+        for (int ch = 0; ch < nchunks; ++ch)
+          tma_load_4d(xs + (size_t)ch * p.x_chunk_bytes, &tmX, &bar_full[s], mtile * 128 + ch * 64, x0 + kx - p.pad,
+                      y0 - p.pad, n);
+        for (int yb = 0; yb < p.y_blocks; ++yb)
+          tma_load_4d(ys + (size_t)yb * p.y_blk_bytes, &tmY, &bar_full[s], n0 + yb * 64, x0, y0, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128u, (uint32_t)p.n_tile, 1u, 1u);
+      const uint32_t y_layout = p.y_rowbytes == 128 ? 2u : 4u;
+      uint32_t acc = 0;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&bar_full[s], ph);
+        tc_fence_after_sync();
+        const uint32_t xs = smem_u32(smem + (size_t)s * p.stage_bytes);
+        const uint32_t ys = xs + x_bytes;
+        for (int ky = 0; ky < p.R; ++ky) {
+          for (int ks = 0; ks < p.ksteps; ++ks) {
+            const uint64_t da = umma_desc(xs + (uint32_t)(ky * p.TW + ks * 16) * 128u, p.x_chunk_bytes, 1024u, 2u);
+            const uint64_t db = umma_desc(ys + (uint32_t)(ks * 16 * p.y_rowbytes), p.y_blk_bytes,
+                                          8u * (uint32_t)p.y_rowbytes, y_layout);
+            umma_bf16_ss(tmem_base + (uint32_t)(ky * p.n_tile), da, db, idesc, (acc | (uint32_t)ks) ? 1u : 0u);
+          }
+        }
+        acc = 1;
+        umma_commit(&bar_empty[s]);
+      }
+      umma_commit(bar_tmem);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int cxi = mtile * 128 + row;
+    const bool valid = cxi < p.cx;
+    mbar_wait(bar_tmem, 0);
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int ky = 0; ky < p.R; ++ky) {
+      float* dst = p.out + ((long)(ky * p.R + kx) * p.cx_rows + cxi) * p.out_stride + n0;
+#pragma unroll 1
+      for (int cb = 0; cb < p.n_tile; cb += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ky * p.n_tile + cb), v);
+        tmem_ld_wait();
+        if (!valid) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n0 + cb + j < p.cy) atomicAdd(dst + cb + j, p.scale * __uint_as_float(v[j]));
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// out[taps][cx_rows][stride] (f32) -> grad OIHW [cy][cx][R][R] += scale * out
+__global__ void wgrad_unpack_kernel(const float* __restrict__ acc, int cx_rows, int stride, float* __restrict__ grad,
+                                    int cy, int cx, int r, float scale, int accumulate) {
+  const long total = (long)cy * cx * r * r;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int kxx = t % r;
+    t /= r;
+    const int kyy = t % r;
+    t /= r;
+    const int ci = t % cx;
+    const int co = t / cx;
+    const float v = scale * acc[((long)(kyy * r + kxx) * cx_rows + ci) * stride + co];
+    if (accumulate) grad[i] += v; else grad[i] = v;
+  }
+}
+
+// bias gradient: out[c] += scale * sum_p dy[p*stride + c]
+__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, int stride, long npix, int C, float* __restrict__ out,
+                                 float scale) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < C)
+    for (long pth = blockIdx.y * 8L + threadIdx.y; pth < npix; pth += (long)gridDim.y * 8) acc += __bfloat162float(dy[pth * stride + c]);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    atomicAdd(out + c, scale * s);
+  }
+}
+
+static int g_w_smem_optin = -1;
+
+}  // namespace ssr
+
+using namespace ssr;
+
+extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SSR_REQUIRE(a && a->x && a->dy && a->out, "ssr_wgrad_tc: null pointer");
+  SSR_REQUIRE(a->r == 1 || a->r == 3, "ssr_wgrad_tc: r must be 1 or 3");
+  SSR_REQUIRE(a->w >= 8 && a->h > 0 && a->n_img > 0, "ssr_wgrad_tc: geometry");
+  SSR_REQUIRE(a->cx > 0 && a->cy > 0, "ssr_wgrad_tc: channels");
+  SSR_REQUIRE(a->x_pix_stride % 8 == 0 && a->dy_pix_stride % 8 == 0, "ssr_wgrad_tc: strides must be multiples of 8");
+  SSR_REQUIRE(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->dy)) & 15) == 0, "ssr_wgrad_tc: alignment");
+  if (g_w_smem_optin < 0) {
+    int dev = 0, v = 0;
+    if (!check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return SSR_E_CUDA;
+    if (!check_cuda(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev), "smem attr")) return SSR_E_CUDA;
+    g_w_smem_optin = v;
+    if (!check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v), "cudaFuncSetAttribute(wgrad)"))
+      return SSR_E_CUDA;
+  }
+  WgradK p{};
+  p.n_img = a->n_img; p.H = a->h; p.W = a->w; p.R = a->r; p.pad = (a->r - 1) / 2;
+  p.TW = a->w >= 128 ? 128 : round_up(a->w, 8);
+  p.TH = 128 / p.TW;
+  while (p.TH > 1 && (p.TW * p.TH) % 16) --p.TH;
+  SSR_REQUIRE((p.TW * p.TH) % 16 == 0, "ssr_wgrad_tc: tile %dx%d not a multiple of 16 pixels", p.TW, p.TH);
+  p.ksteps = p.TW * p.TH / 16;
+  p.tiles_x = (a->w + p.TW - 1) / p.TW;
+  p.tiles_y = (a->h + p.TH - 1) / p.TH;
+  p.total_tiles = p.tiles_x * p.tiles_y * a->n_img;
+  p.cx = a->cx; p.cx_rows = a->out_cx_rows; p.cy = a->cy; p.out_stride = a->out_stride;
+  SSR_REQUIRE(p.cx_rows >= p.cx && p.out_stride >= p.cy, "ssr_wgrad_tc: output too small");
+  if (a->cy <= 32) { p.n_tile = 32; p.y_blocks = 1; p.y_rowbytes = 64; }
+  else if (a->cy <= 64) { p.n_tile = 64; p.y_blocks = 1; p.y_rowbytes = 128; }
+  else { p.n_tile = 128; p.y_blocks = 2; p.y_rowbytes = 128; }
+  const int n_tiles = (a->cy + p.n_tile - 1) / p.n_tile;
+  const int mtiles = (a->cx + 127) / 128;
+  p.x_chunk_bytes = (uint32_t)(p.TW * (p.TH + p.R - 1)) * 128u;
+  p.y_blk_bytes = (uint32_t)(p.TW * p.TH * p.y_rowbytes);
+  p.stage_bytes = (uint32_t)round_up((int)(2 * p.x_chunk_bytes + p.y_blocks * p.y_blk_bytes), 1024);
+  int stages = (g_w_smem_optin - 1280) / (int)p.stage_bytes;
+  SSR_REQUIRE(stages >= 1, "ssr_wgrad_tc: stage does not fit shared memory");
+  if (stages > 4) stages = 4;
+  int units = mtiles * p.R * n_tiles;
+  int splits = a->splits > 0 ? a->splits : (2 * 148 + units - 1) / units;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  { int per = (p.total_tiles + splits - 1) / splits; splits = (p.total_tiles + per - 1) / per; }
+  p.splits = splits;
+  { int per = (p.total_tiles + splits - 1) / splits; if (stages > per) stages = per; }
+  p.stages = stages;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p.R * p.n_tile)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.out = a->out;
+  p.scale = a->scale;
+
+  CUtensorMap tmX, tmY;
+  {
+    uint64_t dims[4] = {(uint64_t)a->cx, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
+    uint64_t str[3] = {(uint64_t)a->x_pix_stride * 2, (uint64_t)a->x_pix_stride * 2 * a->w, (uint64_t)a->x_pix_stride * 2 * a->w * a->h};
+    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)(p.TH + p.R - 1), 1};
+    if (!encode_tmap_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return SSR_E_CUDA;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)a->cy, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
+    uint64_t str[3] = {(uint64_t)a->dy_pix_stride * 2, (uint64_t)a->dy_pix_stride * 2 * a->w, (uint64_t)a->dy_pix_stride * 2 * a->w * a->h};
+    uint32_t box[4] = {(uint32_t)(p.y_rowbytes / 2), (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    if (!encode_tmap_tiled(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->dy, dims, str, box,
+                           p.y_rowbytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return SSR_E_CUDA;
+  }
+  const size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024 + 256;
+  dim3 grid((unsigned)splits, (unsigned)(mtiles * p.R), (unsigned)n_tiles);
+  wgrad_tc_kernel<<<grid, kWThreads, smem_bytes, stream>>>(tmX, tmY, p);
+  count_launch();
+  return check_last("wgrad_tc launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_wgrad_unpack(const float* acc, int32_t cx_rows, int32_t acc_stride, float* grad_oihw, int32_t cout, int32_t cin,
+                                int32_t r, float scale, int32_t accumulate, void* stream) {
+  SSR_REQUIRE(acc && grad_oihw, "ssr_wgrad_unpack: null pointer");
+  const long total = (long)cout * cin * r * r;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  wgrad_unpack_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(acc, cx_rows, acc_stride, grad_oihw, cout, cin, r,
+                                                                                   scale, accumulate);
+  count_launch();
+  return check_last("wgrad_unpack launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_bias_grad(const void* dy_bf16, int32_t dy_pix_stride, int64_t npix, int32_t c, float* out, float scale,
+                             void* stream) {
+  SSR_REQUIRE(dy_bf16 && out && c > 0, "ssr_bias_grad: bad args");
+  dim3 block(32, 8);
+  long slabs = (npix + 8 * 64 - 1) / (8 * 64);
+  if (slabs > 296) slabs = 296;
+  if (slabs < 1) slabs = 1;
+  dim3 grid((unsigned)((c + 31) / 32), (unsigned)slabs);
+  bias_grad_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16),
+                                                                               dy_pix_stride, npix, c, out, scale);
+  count_launch();
+  return check_last("bias_grad launch") ? SSR_OK : SSR_E_CUDA;
+}

@@ -93,6 +93,10 @@ class _Workspace:
             self.bufs = [Act(B, h, w, cw, dev) for _ in range(min(n_rdb, 5))]
             rdb_buf = lambda i: self.bufs[0] if i == 0 else self.bufs[1 + (i - 1) % 4]
         self.rdb_buf = rdb_buf
+        # f32 copy of the 64-channel trunk (the x of every x5*0.2 + x): keeps the 69 chained residual adds out of
+        # bf16.  Forward-only, so it always rotates (slot 0 is block 0's, needed again by conv_body's skip add).
+        self.trunk = [torch.empty((B, h, w, nf), dtype=torch.float32, device=dev) for _ in range(min(n_rdb, 5) + 1)]
+        self.trunk_of = lambda i: self.trunk[0] if i == 0 else self.trunk[1 + (i - 1) % 4]
         self.body_out = Act(B, h, w, nf, dev)
         self.feat = Act(B, h, w, nf, dev)
         self.up_in, self.up_out = [], []
@@ -115,12 +119,14 @@ class _Workspace:
         c = eng.cv["conv_first"]
         b0 = self.rdb_buf(0)
         plan.conv(conv_args(self.in0.ptr(), B, h, w, self.in0.stride, eng.cin_pad, c.packed.data_ptr(), 3, c.cout, c.n_pad,
-                            bias=bptr(c), out=b0.ptr(0), out_stride=b0.stride))
+                            bias=bptr(c), out=b0.ptr(0), out_stride=b0.stride,
+                            out32=self.trunk_of(0).data_ptr(), out32_mode=L.OUT32_NHWC, out32_stride=nf))
         n_rdb = 3 * nb
         for i in range(n_rdb):
             blk, j = divmod(i, 3)
             cur = self.rdb_buf(i)
             nxt = self.rdb_buf(i + 1) if i + 1 < n_rdb else self.body_out
+            t_cur, t_nxt = self.trunk_of(i), self.trunk_of(i + 1)
             for k in range(1, 5):
                 c = eng.cv[f"body.{blk}.rdb{j + 1}.conv{k}"]
                 cin = nf + (k - 1) * g
@@ -129,18 +135,21 @@ class _Workspace:
             c = eng.cv[f"body.{blk}.rdb{j + 1}.conv5"]
             if j < 2:
                 plan.conv(conv_args(cur.ptr(0), B, h, w, cur.stride, nf + 4 * g, c.packed.data_ptr(), 3, c.cout, c.n_pad,
-                                    bias=bptr(c), s0=0.2, res1=cur.ptr(0), res1_stride=cur.stride, s1=1.0,
-                                    out=nxt.ptr(0), out_stride=nxt.stride))
+                                    bias=bptr(c), s0=0.2, res1=t_cur.data_ptr(), res1_kind=L.SSR_F32, res1_stride=nf, s1=1.0,
+                                    out=nxt.ptr(0), out_stride=nxt.stride,
+                                    out32=t_nxt.data_ptr(), out32_mode=L.OUT32_NHWC, out32_stride=nf))
             else:
-                blk_in = self.rdb_buf(3 * blk)
+                t_blk = self.trunk_of(3 * blk)
                 # (x5*0.2 + x_rdb3)*0.2 + x_rrdb
                 plan.conv(conv_args(cur.ptr(0), B, h, w, cur.stride, nf + 4 * g, c.packed.data_ptr(), 3, c.cout, c.n_pad,
-                                    bias=bptr(c), s0=0.04, res1=cur.ptr(0), res1_stride=cur.stride, s1=0.2,
-                                    res2=blk_in.ptr(0), res2_stride=blk_in.stride, s2=1.0,
-                                    out=nxt.ptr(0), out_stride=nxt.stride))
+                                    bias=bptr(c), s0=0.04, res1=t_cur.data_ptr(), res1_kind=L.SSR_F32, res1_stride=nf, s1=0.2,
+                                    res2=t_blk.data_ptr(), res2_kind=L.SSR_F32, res2_stride=nf, s2=1.0,
+                                    out=nxt.ptr(0), out_stride=nxt.stride,
+                                    out32=t_nxt.data_ptr(), out32_mode=L.OUT32_NHWC, out32_stride=nf))
         c = eng.cv["conv_body"]
         plan.conv(conv_args(self.body_out.ptr(), B, h, w, nf, nf, c.packed.data_ptr(), 3, c.cout, c.n_pad, bias=bptr(c),
-                            res1=b0.ptr(0), res1_stride=b0.stride, s1=1.0, out=self.feat.ptr(), out_stride=nf))
+                            res1=self.trunk_of(0).data_ptr(), res1_kind=L.SSR_F32, res1_stride=nf, s1=1.0,
+                            out=self.feat.ptr(), out_stride=nf))
         src = self.feat
         hh, ww = h, w
         for u in range(eng.n_up):
