@@ -76,7 +76,7 @@ typedef struct ssr_conv_tc_args {
   int32_t n_pad; /* padded output channels in w_packed (multiple of 16) */
   /* epilogue */
   const float* bias; /* [cout] or NULL */
-  int32_t act;       /* 1 = LeakyReLU(0.2) */
+  int32_t act;       /* 1 = LeakyReLU(0.2), 2 = ReLU */
   float s0;
   const void* res1;
   int32_t res1_kind; /* SSR_NONE / SSR_BF16 / SSR_F32 */
@@ -129,12 +129,13 @@ int ssr_ingest_nchw(const void* src, int32_t src_kind, void* dst_bf16, int32_t d
                     void* stream);
 /* NHWC bf16 channel slice -> planar NCHW f32 (dst = or += src*scale) */
 int ssr_egress_nchw(const void* src_bf16, int32_t src_pix_stride, float* dst, int32_t b, int32_t c, int32_t h, int32_t w,
-                    float scale, int32_t accumulate, void* stream);
+                    float scale, int32_t accumulate, const float* ch_scale /* [c] or NULL */, void* stream);
 /* F.interpolate(mode='nearest', scale_factor=factor): rrdbnet_arch.py:127-128, ssr_esrgan_model.py:133 */
 int ssr_upsample_nearest(const void* src, int32_t src_pix_stride, void* dst, int32_t dst_pix_stride, int32_t b, int32_t h,
                          int32_t w, int32_t c, int32_t factor, void* stream);
 int ssr_upsample_nearest_bwd(const void* dy, int32_t dy_pix_stride, void* dx, int32_t dx_pix_stride, int32_t b, int32_t h,
-                             int32_t w, int32_t c, int32_t factor, void* stream);
+                             int32_t w, int32_t c, int32_t factor, const void* lrelu_mask /* or NULL */,
+                             int32_t mask_pix_stride, void* stream);
 /* F.interpolate(scale_factor=2, mode='bilinear', align_corners=False): discriminator_arch.py:50,55,60 */
 int ssr_upsample_bilinear2x(const void* src, int32_t src_pix_stride, void* dst, int32_t dst_pix_stride, int32_t b,
                             int32_t h, int32_t w, int32_t c, void* stream);
@@ -177,6 +178,53 @@ int ssr_wgrad_unpack(const float* acc, int32_t cx_rows, int32_t acc_stride, floa
                      int32_t r, float scale, int32_t accumulate, void* stream);
 /* out[c] += scale * sum_p dy[p*stride + c]   (bias gradient) */
 int ssr_bias_grad(const void* dy_bf16, int32_t dy_pix_stride, int64_t npix, int32_t c, float* out, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Training-step kernels (HBM-bound).  Losses accumulate into device scalars the caller zeroes.
+ * ------------------------------------------------------------------------------------------------- */
+/* im2col / col2im for the 4x4 stride-2 discriminator convs (discriminator_arch.py:30-32): col is
+ * [b*oh*ow][k*k*c] bf16 with (ky, kx, c) order; col2im is the gather-form adjoint and can fuse the LeakyReLU
+ * derivative taken from the saved activation `lrelu_mask` (may be NULL). */
+int ssr_im2col(const void* x, int32_t x_pix_stride, void* col, int32_t b, int32_t h, int32_t w, int32_t c, int32_t k, int32_t s,
+               int32_t p, void* stream);
+int ssr_col2im(const void* dcol, void* dx, int32_t dx_pix_stride, int32_t b, int32_t h, int32_t w, int32_t c, int32_t k, int32_t s,
+               int32_t p, const void* lrelu_mask, int32_t mask_pix_stride, void* stream);
+/* y = a*x1 + b*x2 (x2 may be NULL), times the LeakyReLU(0.2) (mask_relu=0) or ReLU (1) derivative from `mask` (may be NULL) */
+int ssr_axpby(const void* x1, int32_t s1, float a, const void* x2, int32_t s2, float b, const void* mask, int32_t sm,
+              int32_t mask_relu, void* y, int32_t sy, int64_t npix, int32_t c, void* stream);
+/* VGG19 feature extractor pieces of basicsr PerceptualLoss (ssr_esrgan_model.py:154): x holds 2b images (generated | gt) */
+int ssr_maxpool_relu(const void* x, void* y, int32_t b, int32_t h, int32_t w, int32_t c, void* stream);
+int ssr_feat_grad(const void* x, const void* dpool, void* dx, int32_t b, int32_t h, int32_t w, int32_t c, float l1_scale, void* stream);
+int ssr_feat_l1(const void* x, int64_t n_half, float scale, float* loss, void* stream);
+/* basicsr L1Loss(mean)*weight (ssr_esrgan_model.py:148): loss += ..., grad (=|+=) weight*sign(a-b)/n */
+int ssr_l1_loss(const float* a, const float* b, int64_t n, float weight, float* loss, float* grad, int32_t accumulate, void* stream);
+/* basicsr GANLoss('vanilla') = BCEWithLogitsLoss against a constant target (ssr_esrgan_model.py:182,218,224) */
+int ssr_bce_logits(const float* x, int64_t n, float target, float weight, float* loss, float* mean_logit, float* grad, void* stream);
+/* torch.cat((img, F.interpolate(lr, scale_factor=factor)), 1) -> NHWC bf16 (ssr_esrgan_model.py:133,176,208-210) */
+int ssr_disc_input(const float* img, int32_t ci, const void* lr, int32_t lr_pix_stride, int32_t cl, int32_t factor, void* out,
+                   int32_t out_pix_stride, int32_t b, int32_t h, int32_t w, void* stream);
+
+/* torch.nn.utils.spectral_norm, batched over the 8 normalised convs of the discriminator (device-resident table) */
+typedef struct ssr_sn_desc {
+  const float* w; /* weight_orig viewed [rows = cout][cols = cin*k*k] */
+  float* u;
+  float* v;
+  float* sigma;   /* out: u^T W v */
+  float* scratch; /* cols + rows + 4 floats, zero-initialised once */
+  float* geff;    /* gradient w.r.t. weight_orig / sigma (input of ssr_spectral_norm_bwd) */
+  float* grad;    /* gradient of weight_orig (accumulated) */
+  int32_t rows, cols;
+} ssr_sn_desc;
+int ssr_spectral_norm(const ssr_sn_desc* descs_device, int32_t n_layers, int32_t power_iteration, float eps, void* stream);
+int ssr_spectral_norm_bwd(const ssr_sn_desc* descs_device, int32_t n_layers, void* stream);
+
+/* basicsr USMSharp (ssr_esrgan_model.py:31,109): separable Gaussian (host taps), reflect padding; scratch = 3*planes*h*w floats */
+int ssr_usm_sharp(const float* img, float* out, float* scratch, int32_t planes, int32_t h, int32_t w, const float* gauss_host,
+                  int32_t taps, float weight, float threshold, void* stream);
+int ssr_u8_to_f32(const void* src, float* dst, int64_t n, float scale, void* stream);
+/* torch.optim.Adam step (+ basicsr model_ema when ema != NULL) over flat f32 buffers, one launch */
+int ssr_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int32_t step, float ema_decay, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -213,8 +213,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 16; ++j) f[j] += b[j];
           }
           if (p.act) {
+            const float neg = p.act == 2 ? 0.f : 0.2f;  // 1 = LeakyReLU(0.2), 2 = ReLU
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
+            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : neg * f[j];
           }
           if (p.s0 != 1.f) {
 #pragma unroll
@@ -280,7 +281,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (c >= p.cout) break;
             float val = f[j];
             if (add_bias) val += p.bias[c];
-            if (p.act) val = val > 0.f ? val : 0.2f * val;
+            if (p.act) val = val > 0.f ? val : (p.act == 2 ? 0.f : 0.2f * val);
             val *= p.s0;
             if (p.res1_kind == SSR_BF16)
               val += p.s1 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res1)[pix * p.res1_stride + c]);

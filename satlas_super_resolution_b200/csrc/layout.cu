@@ -59,7 +59,7 @@ __global__ void nchw_to_nhwc_bf16_kernel(const T* __restrict__ src, __nv_bfloat1
 // ---------------------------------------------------------------- egress: NHWC bf16 -> planar f32
 __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, int src_stride,
                                              float* __restrict__ dst, int B, int C, int H, int W, float scale,
-                                             int accumulate) {
+                                             int accumulate, const float* __restrict__ ch_scale) {
   const long HW = (long)H * W;
   const long total = (long)B * C * HW;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -67,7 +67,8 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ s
     const long t = i / HW;
     const int c = (int)(t % C);
     const long n = t / C;
-    const float v = __bfloat162float(src[(n * HW + hw) * src_stride + c]) * scale;
+    float v = __bfloat162float(src[(n * HW + hw) * src_stride + c]) * scale;
+    if (ch_scale) v *= ch_scale[c];
     if (accumulate) dst[i] += v; else dst[i] = v;
   }
 }
@@ -97,7 +98,7 @@ __global__ void upsample_nearest_kernel(const __nv_bfloat16* __restrict__ src, i
 // backward of nearest upsample: sum over each f x f block (fp32 accumulate, bf16 out)
 __global__ void upsample_nearest_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
                                             __nv_bfloat16* __restrict__ dx, int dx_stride, int B, int H, int W,
-                                            int C, int f) {
+                                            int C, int f, const __nv_bfloat16* __restrict__ mask, int mask_stride) {
   const int groups = C / 8;
   const int OH = H * f, OW = W * f;
   const long total = (long)B * H * W * groups;
@@ -120,6 +121,15 @@ __global__ void upsample_nearest_bwd_kernel(const __nv_bfloat16* __restrict__ dy
           acc[2 * j + 1] += __uint_as_float(u[j] & 0xFFFF0000u);
         }
       }
+    if (mask) {  // LeakyReLU(0.2) derivative from the saved activation
+      const uint4 mv = *reinterpret_cast<const uint4*>(mask + ((n * H + y) * W + x) * (long)mask_stride + g * 8);
+      const uint32_t mu[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] *= (__uint_as_float(mu[j] << 16) > 0.f ? 1.f : 0.2f);
+        acc[2 * j + 1] *= (__uint_as_float(mu[j] & 0xFFFF0000u) > 0.f ? 1.f : 0.2f);
+      }
+    }
     uint4 o;
     __nv_bfloat162 h;
     h = __floats2bfloat162_rn(acc[0], acc[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
@@ -292,11 +302,11 @@ extern "C" int ssr_ingest_nchw(const void* src, int32_t src_kind /*0 = u8, 2 = f
 }
 
 extern "C" int ssr_egress_nchw(const void* src_bf16, int32_t src_pix_stride, float* dst, int32_t b, int32_t c, int32_t h,
-                               int32_t w, float scale, int32_t accumulate, void* stream) {
+                               int32_t w, float scale, int32_t accumulate, const float* ch_scale, void* stream) {
   SSR_REQUIRE(src_bf16 && dst, "ssr_egress_nchw: null pointer");
   const long total = (long)b * c * h * w;
   nhwc_bf16_to_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src_bf16), src_pix_stride, dst, b, c, h, w, scale, accumulate);
+      reinterpret_cast<const __nv_bfloat16*>(src_bf16), src_pix_stride, dst, b, c, h, w, scale, accumulate, ch_scale);
   count_launch();
   return check_last("egress launch") ? SSR_OK : SSR_E_CUDA;
 }
@@ -320,12 +330,13 @@ extern "C" int ssr_upsample_nearest(const void* src, int32_t src_pix_stride, voi
 }
 
 extern "C" int ssr_upsample_nearest_bwd(const void* dy, int32_t dy_pix_stride, void* dx, int32_t dx_pix_stride, int32_t b,
-                                        int32_t h, int32_t w, int32_t c, int32_t factor, void* stream) {
+                                        int32_t h, int32_t w, int32_t c, int32_t factor, const void* lrelu_mask,
+                                        int32_t mask_pix_stride, void* stream) {
   if (int rc = check_vec(dy, dy_pix_stride, dx, dx_pix_stride, c, "ssr_upsample_nearest_bwd")) return rc;
   const long total = (long)b * h * w * (c / 8);
   upsample_nearest_bwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), dy_pix_stride, reinterpret_cast<__nv_bfloat16*>(dx), dx_pix_stride, b, h,
-      w, c, factor);
+      w, c, factor, reinterpret_cast<const __nv_bfloat16*>(lrelu_mask), mask_pix_stride);
   count_launch();
   return check_last("upsample_nearest_bwd launch") ? SSR_OK : SSR_E_CUDA;
 }
