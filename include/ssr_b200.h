@@ -42,6 +42,8 @@ extern "C" {
 /* weight packing modes */
 #define SSR_PACK_FWD 0   /* B[n=cout][k=cin], taps as stored          */
 #define SSR_PACK_DGRAD 1 /* B[n=cin][k=cout], taps flipped (conv^T)   */
+#define SSR_PACK_FWD_GEMM 2   /* 1x1 form over im2col columns: B[n=cout][k'=(ky*R+kx)*cin+ci]          */
+#define SSR_PACK_DGRAD_GEMM 3 /* 1x1 form producing dcol:      B[n=k'][k=cout]                           */
 
 const char* ssr_last_error(void);
 int ssr_abi_version(void);
@@ -99,6 +101,7 @@ typedef struct ssr_conv_tc_args {
   int32_t n_tile; /* output channels per CTA, multiple of 16, <= 256 */
   int32_t mt;     /* 128-pixel M tiles per CTA: 1 or 2 */
   int32_t splits; /* split the cin chunks over this many CTAs (needs SSR_OUT32_NHWC_ATOMIC) */
+  int32_t res1_cmax; /* res1 is added only to channels < res1_cmax (0 = all); multiple of 16 */
 } ssr_conv_tc_args;
 
 int ssr_conv_tc(const ssr_conv_tc_args* args, void* stream);
@@ -137,8 +140,9 @@ int ssr_upsample_nearest_bwd(const void* dy, int32_t dy_pix_stride, void* dx, in
                              int32_t w, int32_t c, int32_t factor, const void* lrelu_mask /* or NULL */,
                              int32_t mask_pix_stride, void* stream);
 /* F.interpolate(scale_factor=2, mode='bilinear', align_corners=False): discriminator_arch.py:50,55,60 */
-int ssr_upsample_bilinear2x(const void* src, int32_t src_pix_stride, void* dst, int32_t dst_pix_stride, int32_t b,
-                            int32_t h, int32_t w, int32_t c, void* stream);
+int ssr_upsample_bilinear2x(const void* src, int32_t src_pix_stride, const void* src2 /* added to src, or NULL */,
+                            int32_t src2_pix_stride, void* dst, int32_t dst_pix_stride, int32_t b, int32_t h, int32_t w,
+                            int32_t c, void* stream);
 int ssr_upsample_bilinear2x_bwd(const void* dy, int32_t dy_pix_stride, void* dx, int32_t dx_pix_stride, int32_t b,
                                 int32_t h, int32_t w, int32_t c, void* stream);
 
@@ -149,7 +153,7 @@ typedef struct ssr_pack_desc {
   const float* inv_scale; /* spectral-norm sigma (device) or NULL */
   int32_t cout, cin, r, mode, k_pad, n_pad;
 } ssr_pack_desc;
-int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, int32_t n_layers, void* stream);
+int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, int32_t n_layers, int32_t has_gemm_forms, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Weight gradient on tensor cores (MN-major operands straight from the NHWC buffers).
@@ -176,6 +180,15 @@ typedef struct ssr_wgrad_tc_args {
 int ssr_wgrad_tc(const ssr_wgrad_tc_args* args, void* stream);
 int ssr_wgrad_unpack(const float* acc, int32_t cx_rows, int32_t acc_stride, float* grad_oihw, int32_t cout, int32_t cin,
                      int32_t r, float scale, int32_t accumulate, void* stream);
+/* every conv of a network in one launch (device-resident table) */
+typedef struct ssr_unpack_desc {
+  const float* acc;
+  float* grad;
+  int32_t cx_rows, acc_stride, cout, cin, r, accumulate;
+  float scale;
+  int32_t pad_;
+} ssr_unpack_desc;
+int ssr_wgrad_unpack_batched(const ssr_unpack_desc* descs_device, int32_t n_layers, void* stream);
 /* out[c] += scale * sum_p dy[p*stride + c]   (bias gradient) */
 int ssr_bias_grad(const void* dy_bf16, int32_t dy_pix_stride, int64_t npix, int32_t c, float* out, float scale, void* stream);
 
@@ -188,7 +201,8 @@ int ssr_bias_grad(const void* dy_bf16, int32_t dy_pix_stride, int64_t npix, int3
 int ssr_im2col(const void* x, int32_t x_pix_stride, void* col, int32_t b, int32_t h, int32_t w, int32_t c, int32_t k, int32_t s,
                int32_t p, void* stream);
 int ssr_col2im(const void* dcol, void* dx, int32_t dx_pix_stride, int32_t b, int32_t h, int32_t w, int32_t c, int32_t k, int32_t s,
-               int32_t p, const void* lrelu_mask, int32_t mask_pix_stride, void* stream);
+               int32_t p, const void* add /* bf16 NHWC added before the mask, or NULL */, int32_t add_pix_stride,
+               const void* lrelu_mask, int32_t mask_pix_stride, void* stream);
 /* y = a*x1 + b*x2 (x2 may be NULL), times the LeakyReLU(0.2) (mask_relu=0) or ReLU (1) derivative from `mask` (may be NULL) */
 int ssr_axpby(const void* x1, int32_t s1, float a, const void* x2, int32_t s2, float b, const void* mask, int32_t sm,
               int32_t mask_relu, void* y, int32_t sy, int64_t npix, int32_t c, void* stream);
@@ -224,7 +238,9 @@ int ssr_usm_sharp(const float* img, float* out, float* scratch, int32_t planes, 
 int ssr_u8_to_f32(const void* src, float* dst, int64_t n, float scale, void* stream);
 /* torch.optim.Adam step (+ basicsr model_ema when ema != NULL) over flat f32 buffers, one launch */
 int ssr_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr, float beta1, float beta2, float eps,
-                 float weight_decay, int32_t step, float ema_decay, float grad_scale, void* stream);
+                 float weight_decay, int32_t step, float ema_decay, float grad_scale,
+                 const float* dev_hyper /* device [lr, 1-b1^t, sqrt(1-b2^t)] overriding lr/step (graph replay), or NULL */,
+                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libssr_b200.so")
 
 SSR_NONE, SSR_BF16, SSR_F32 = 0, 1, 2
 OUT32_NONE, OUT32_NHWC, OUT32_NHWC_ATOMIC, OUT32_NCHW = 0, 1, 2, 3
-PACK_FWD, PACK_DGRAD = 0, 1
+PACK_FWD, PACK_DGRAD, PACK_FWD_GEMM, PACK_DGRAD_GEMM = 0, 1, 2, 3
 
 
 class ConvTcArgs(C.Structure):
@@ -31,7 +31,7 @@ class ConvTcArgs(C.Structure):
         ("mask", C.c_void_p), ("mask_pix_stride", C.c_int32), ("mask_lo", C.c_int32), ("mask_relu", C.c_int32),
         ("out_bf16", C.c_void_p), ("out_pix_stride", C.c_int32),
         ("out_f32", C.c_void_p), ("out32_mode", C.c_int32), ("out32_pix_stride", C.c_int32),
-        ("n_tile", C.c_int32), ("mt", C.c_int32), ("splits", C.c_int32),
+        ("n_tile", C.c_int32), ("mt", C.c_int32), ("splits", C.c_int32), ("res1_cmax", C.c_int32),
     ]
 
 

@@ -17,6 +17,12 @@ class WgradArgs(C.Structure):
                 ("out", vp), ("out_cx_rows", i32), ("out_stride", i32), ("scale", f32), ("splits", i32)]
 
 
+class UnpackDesc(C.Structure):
+    """Mirror of struct ssr_unpack_desc."""
+    _fields_ = [("acc", vp), ("grad", vp), ("cx_rows", i32), ("acc_stride", i32), ("cout", i32), ("cin", i32), ("r", i32),
+                ("accumulate", i32), ("scale", f32), ("pad_", i32)]
+
+
 class SnDesc(C.Structure):
     """Mirror of struct ssr_sn_desc."""
     _fields_ = [("w", vp), ("u", vp), ("v", vp), ("sigma", vp), ("scratch", vp), ("geff", vp), ("grad", vp),
@@ -26,7 +32,7 @@ class SnDesc(C.Structure):
 i64 = C.c_int64
 PROTOS = {
     "ssr_im2col": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
-    "ssr_col2im": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "ssr_col2im": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
     "ssr_axpby": (C.c_int, [vp, i32, f32, vp, i32, f32, vp, i32, i32, vp, i32, i64, i32, vp]),
     "ssr_maxpool_relu": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "ssr_feat_grad": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, f32, vp]),
@@ -38,7 +44,7 @@ PROTOS = {
     "ssr_spectral_norm_bwd": (C.c_int, [vp, i32, vp]),
     "ssr_usm_sharp": (C.c_int, [vp, vp, vp, i32, i32, i32, vp, i32, f32, f32, vp]),
     "ssr_u8_to_f32": (C.c_int, [vp, vp, i64, f32, vp]),
-    "ssr_adam_ema": (C.c_int, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, f32, vp]),
+    "ssr_adam_ema": (C.c_int, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, f32, vp, vp]),
     "ssr_wgrad_tc": (C.c_int, [C.POINTER(WgradArgs), vp]),
     "ssr_wgrad_unpack": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, f32, i32, vp]),
     "ssr_bias_grad": (C.c_int, [vp, i32, C.c_int64, i32, vp, f32, vp]),
@@ -46,9 +52,10 @@ PROTOS = {
     "ssr_egress_nchw": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, f32, i32, vp, vp]),
     "ssr_upsample_nearest": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
     "ssr_upsample_nearest_bwd": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
-    "ssr_upsample_bilinear2x": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    "ssr_upsample_bilinear2x": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "ssr_upsample_bilinear2x_bwd": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
-    "ssr_pack_conv_weights_batched": (C.c_int, [vp, i32, vp]),
+    "ssr_pack_conv_weights_batched": (C.c_int, [vp, i32, i32, vp]),
+    "ssr_wgrad_unpack_batched": (C.c_int, [vp, i32, vp]),
 }
 
 

@@ -34,6 +34,7 @@ struct ConvTcK {
   const void* res2;
   int res1_kind, res2_kind;
   int res1_stride, res2_stride;
+  int res1_cmax;  // res1 applies to channels < res1_cmax (0 = all)
   const __nv_bfloat16* mask;
   int mask_stride, mask_lo, mask_relu;
   __nv_bfloat16* out_bf16;
@@ -221,7 +222,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] *= p.s0;
           }
-          if (p.res1_kind != SSR_NONE) {
+          if (p.res1_kind != SSR_NONE && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
             float r[16];
             if (p.res1_kind == SSR_BF16)
               load16_bf16(reinterpret_cast<const __nv_bfloat16*>(p.res1) + pix * p.res1_stride + c0, r);
@@ -283,10 +284,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (add_bias) val += p.bias[c];
             if (p.act) val = val > 0.f ? val : (p.act == 2 ? 0.f : 0.2f * val);
             val *= p.s0;
-            if (p.res1_kind == SSR_BF16)
-              val += p.s1 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res1)[pix * p.res1_stride + c]);
-            else if (p.res1_kind == SSR_F32)
-              val += p.s1 * reinterpret_cast<const float*>(p.res1)[pix * p.res1_stride + c];
+            if (p.res1_cmax == 0 || c < p.res1_cmax) {
+              if (p.res1_kind == SSR_BF16)
+                val += p.s1 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res1)[pix * p.res1_stride + c]);
+              else if (p.res1_kind == SSR_F32)
+                val += p.s1 * reinterpret_cast<const float*>(p.res1)[pix * p.res1_stride + c];
+            }
             if (p.res2_kind == SSR_BF16)
               val += p.s2 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res2)[pix * p.res2_stride + c]);
             else if (p.res2_kind == SSR_F32)
@@ -429,6 +432,7 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   p.res1_kind = a->res1 ? a->res1_kind : SSR_NONE;
   p.res2_kind = a->res2 ? a->res2_kind : SSR_NONE;
   p.res1_stride = a->res1_pix_stride;
+  p.res1_cmax = a->res1_cmax;
   p.res2_stride = a->res2_pix_stride;
   p.mask = reinterpret_cast<const __nv_bfloat16*>(a->mask);
   p.mask_stride = a->mask_pix_stride;

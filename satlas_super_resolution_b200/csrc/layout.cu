@@ -151,7 +151,22 @@ __device__ __forceinline__ void bilin_src(int o, int n_in, int& i0, int& i1, flo
   w1 = s - (float)i0;
 }
 
+__device__ __forceinline__ uint4 add_bf16x8(const uint4& a, const uint4& b) {
+  const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(ua[j] << 16) + __uint_as_float(ub[j] << 16),
+                                             __uint_as_float(ua[j] & 0xFFFF0000u) + __uint_as_float(ub[j] & 0xFFFF0000u));
+    o[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// src2 (optional) is added to src before interpolating: the U-Net skip `x4 = x4 + x2` of discriminator_arch.py:53-64
+// (the sum is rounded to bf16 once, like a materialised tensor would be).
 __global__ void upsample_bilinear2x_kernel(const __nv_bfloat16* __restrict__ src, int src_stride,
+                                           const __nv_bfloat16* __restrict__ src2, int src2_stride,
                                            __nv_bfloat16* __restrict__ dst, int dst_stride, int B, int H, int W, int C) {
   const int groups = C / 8;
   const int OH = H * 2, OW = W * 2;
@@ -168,10 +183,17 @@ __global__ void upsample_bilinear2x_kernel(const __nv_bfloat16* __restrict__ src
     bilin_src(oy, H, y0, y1, wy);
     bilin_src(ox, W, x0, x1, wx);
     const __nv_bfloat16* base = src + n * H * W * (long)src_stride + g * 8;
-    const uint4 v00 = *reinterpret_cast<const uint4*>(base + ((long)y0 * W + x0) * src_stride);
-    const uint4 v01 = *reinterpret_cast<const uint4*>(base + ((long)y0 * W + x1) * src_stride);
-    const uint4 v10 = *reinterpret_cast<const uint4*>(base + ((long)y1 * W + x0) * src_stride);
-    const uint4 v11 = *reinterpret_cast<const uint4*>(base + ((long)y1 * W + x1) * src_stride);
+    uint4 v00 = *reinterpret_cast<const uint4*>(base + ((long)y0 * W + x0) * src_stride);
+    uint4 v01 = *reinterpret_cast<const uint4*>(base + ((long)y0 * W + x1) * src_stride);
+    uint4 v10 = *reinterpret_cast<const uint4*>(base + ((long)y1 * W + x0) * src_stride);
+    uint4 v11 = *reinterpret_cast<const uint4*>(base + ((long)y1 * W + x1) * src_stride);
+    if (src2) {
+      const __nv_bfloat16* b2 = src2 + n * H * W * (long)src2_stride + g * 8;
+      v00 = add_bf16x8(v00, *reinterpret_cast<const uint4*>(b2 + ((long)y0 * W + x0) * src2_stride));
+      v01 = add_bf16x8(v01, *reinterpret_cast<const uint4*>(b2 + ((long)y0 * W + x1) * src2_stride));
+      v10 = add_bf16x8(v10, *reinterpret_cast<const uint4*>(b2 + ((long)y1 * W + x0) * src2_stride));
+      v11 = add_bf16x8(v11, *reinterpret_cast<const uint4*>(b2 + ((long)y1 * W + x1) * src2_stride));
+    }
     const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, b[4] = {v01.x, v01.y, v01.z, v01.w};
     const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
     // same operation order as ATen's upsample_bilinear2d: w0y*(w0x*a + w1x*b) + w1y*(w0x*c + w1x*d)
@@ -248,6 +270,7 @@ struct PackDesc {
 
 __global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
   const PackDesc d = descs[blockIdx.y];
+  if (d.mode != SSR_PACK_FWD && d.mode != SSR_PACK_DGRAD) return;
   const int chunks = d.k_pad / 64;
   const long total = (long)chunks * d.r * d.r * d.n_pad * 64;
   const float sc = d.inv_scale ? 1.f / *d.inv_scale : 1.f;
@@ -267,6 +290,35 @@ __global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
       if (nn < d.cout && k < d.cin) v = d.w[(((long)nn * d.cin + k) * d.r + ky) * d.r + kx];
     } else {
       if (nn < d.cin && k < d.cout) v = d.w[(((long)k * d.cin + nn) * d.r + (d.r - 1 - ky)) * d.r + (d.r - 1 - kx)];
+    }
+    d.dst[i] = __float2bfloat16(v * sc);
+  }
+}
+
+// GEMM (1x1) forms for a conv computed through im2col: K' = (ky*R + kx)*cin + ci
+__global__ void pack_gemm_kernel(const PackDesc* __restrict__ descs) {
+  const PackDesc d = descs[blockIdx.y];
+  if (d.mode != SSR_PACK_FWD_GEMM && d.mode != SSR_PACK_DGRAD_GEMM) return;
+  const int chunks = d.k_pad / 64;
+  const long total = (long)chunks * d.n_pad * 64;
+  const float sc = d.inv_scale ? 1.f / *d.inv_scale : 1.f;
+  const int kk = d.r * d.r * d.cin;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % 64);
+    const int nn = (int)((i / 64) % d.n_pad);
+    const int c = (int)(i / (64L * d.n_pad));
+    const int k = c * 64 + j;
+    float v = 0.f;
+    if (d.mode == SSR_PACK_FWD_GEMM) {
+      if (nn < d.cout && k < kk) {
+        const int tap = k / d.cin, ci = k % d.cin;
+        v = d.w[(((long)nn * d.cin + ci) * d.r + tap / d.r) * d.r + tap % d.r];
+      }
+    } else {
+      if (nn < kk && k < d.cout) {
+        const int tap = nn / d.cin, ci = nn % d.cin;
+        v = d.w[(((long)k * d.cin + ci) * d.r + tap / d.r) * d.r + tap % d.r];
+      }
     }
     d.dst[i] = __float2bfloat16(v * sc);
   }
@@ -341,13 +393,14 @@ extern "C" int ssr_upsample_nearest_bwd(const void* dy, int32_t dy_pix_stride, v
   return check_last("upsample_nearest_bwd launch") ? SSR_OK : SSR_E_CUDA;
 }
 
-extern "C" int ssr_upsample_bilinear2x(const void* src, int32_t src_pix_stride, void* dst, int32_t dst_pix_stride, int32_t b,
-                                       int32_t h, int32_t w, int32_t c, void* stream) {
+extern "C" int ssr_upsample_bilinear2x(const void* src, int32_t src_pix_stride, const void* src2, int32_t src2_pix_stride,
+                                       void* dst, int32_t dst_pix_stride, int32_t b, int32_t h, int32_t w, int32_t c,
+                                       void* stream) {
   if (int rc = check_vec(src, src_pix_stride, dst, dst_pix_stride, c, "ssr_upsample_bilinear2x")) return rc;
   const long total = (long)b * h * 2 * w * 2 * (c / 8);
   upsample_bilinear2x_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), src_pix_stride, reinterpret_cast<__nv_bfloat16*>(dst), dst_pix_stride, b,
-      h, w, c);
+      reinterpret_cast<const __nv_bfloat16*>(src), src_pix_stride, reinterpret_cast<const __nv_bfloat16*>(src2),
+      src2_pix_stride, reinterpret_cast<__nv_bfloat16*>(dst), dst_pix_stride, b, h, w, c);
   count_launch();
   return check_last("upsample_bilinear2x launch") ? SSR_OK : SSR_E_CUDA;
 }
@@ -363,11 +416,16 @@ extern "C" int ssr_upsample_bilinear2x_bwd(const void* dy, int32_t dy_pix_stride
   return check_last("upsample_bilinear2x_bwd launch") ? SSR_OK : SSR_E_CUDA;
 }
 
-extern "C" int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, int32_t n_layers, void* stream) {
+extern "C" int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, int32_t n_layers, int32_t has_gemm_forms,
+                                             void* stream) {
   SSR_REQUIRE(descs_device && n_layers > 0, "ssr_pack_conv_weights_batched: bad args");
   static_assert(sizeof(ssr_pack_desc) == sizeof(PackDesc), "ssr_pack_desc layout");
   dim3 grid(32, (unsigned)n_layers);
   pack_batched_kernel<<<grid, 256, 0, STREAM(stream)>>>(reinterpret_cast<const PackDesc*>(descs_device));
   count_launch();
+  if (has_gemm_forms) {
+    pack_gemm_kernel<<<grid, 256, 0, STREAM(stream)>>>(reinterpret_cast<const PackDesc*>(descs_device));
+    count_launch();
+  }
   return check_last("pack_batched launch") ? SSR_OK : SSR_E_CUDA;
 }

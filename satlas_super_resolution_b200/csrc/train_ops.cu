@@ -81,8 +81,8 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ x, int x_stride,
 
 // dx[n, iy, ix, c] = sum over taps with (iy + p - ky) % s == 0 ... of dcol[m(oy, ox)][tap][c]   (gather form)
 __global__ void col2im_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, int dx_stride, int B, int H,
-                              int W, int C, int k, int s, int p, int OH, int OW, const __nv_bfloat16* __restrict__ mask,
-                              int mask_stride) {
+                              int W, int C, int k, int s, int p, int OH, int OW, const __nv_bfloat16* __restrict__ add,
+                              int add_stride, const __nv_bfloat16* __restrict__ mask, int mask_stride) {
   const int groups = C / 8;
   const long K = (long)k * k * C;
   const long total = (long)B * H * W * groups;
@@ -112,6 +112,12 @@ __global__ void col2im_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloa
       }
     }
     const long pix = (n * H + iy) * W + ix;
+    if (add) {
+      float ad[8];
+      unpack8(*reinterpret_cast<const uint4*>(add + pix * add_stride + g * 8), ad);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += ad[j];
+    }
     if (mask) {
       float mk[8];
       unpack8(*reinterpret_cast<const uint4*>(mask + pix * mask_stride + g * 8), mk);
@@ -461,7 +467,12 @@ __global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restr
 // then, when ema != null: ema = decay*ema + (1-decay)*p    (basicsr model_ema, ssr_esrgan_model.py:230-231)
 __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                 float* __restrict__ ema, long n, float lr, float b1, float b2, float eps, float wd, float bc1,
-                                float bc2_sqrt, float ema_decay, float grad_scale) {
+                                float bc2_sqrt, float ema_decay, float grad_scale, const float* __restrict__ dev_hyper) {
+  if (dev_hyper) {  // CUDA-graph replay: the step-dependent scalars live in device memory
+    lr = dev_hyper[0];
+    bc1 = dev_hyper[1];
+    bc2_sqrt = dev_hyper[2];
+  }
   const float step_size = lr / bc1;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     float gi = g[i] * grad_scale;
@@ -495,14 +506,15 @@ extern "C" int ssr_im2col(const void* x, int32_t x_pix_stride, void* col, int32_
 }
 
 extern "C" int ssr_col2im(const void* dcol, void* dx, int32_t dx_pix_stride, int32_t b, int32_t h, int32_t w, int32_t c, int32_t k,
-                          int32_t s, int32_t p, const void* lrelu_mask, int32_t mask_pix_stride, void* stream) {
+                          int32_t s, int32_t p, const void* add, int32_t add_pix_stride, const void* lrelu_mask,
+                          int32_t mask_pix_stride, void* stream) {
   SSR_REQUIRE(dcol && dx && c % 8 == 0 && dx_pix_stride % 8 == 0, "ssr_col2im: bad args");
   const int oh = (h + 2 * p - k) / s + 1, ow = (w + 2 * p - k) / s + 1;
   const long total = (long)b * h * w * (c / 8);
   col2im_kernel<<<grid_for2(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dcol),
                                                                   reinterpret_cast<__nv_bfloat16*>(dx), dx_pix_stride, b, h, w, c, k, s, p,
-                                                                  oh, ow, reinterpret_cast<const __nv_bfloat16*>(lrelu_mask),
-                                                                  mask_pix_stride);
+                                                                  oh, ow, reinterpret_cast<const __nv_bfloat16*>(add), add_pix_stride,
+                                                                  reinterpret_cast<const __nv_bfloat16*>(lrelu_mask), mask_pix_stride);
   return LAUNCH_OK("col2im");
 }
 
@@ -628,11 +640,13 @@ extern "C" int ssr_u8_to_f32(const void* src, float* dst, int64_t n, float scale
 }
 
 extern "C" int ssr_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr, float beta1, float beta2,
-                            float eps, float weight_decay, int32_t step, float ema_decay, float grad_scale, void* stream) {
-  SSR_REQUIRE(p && g && m && v && n > 0 && step >= 1, "ssr_adam_ema: bad args");
+                            float eps, float weight_decay, int32_t step, float ema_decay, float grad_scale, const float* dev_hyper,
+                            void* stream) {
+  SSR_REQUIRE(p && g && m && v && n > 0 && (step >= 1 || dev_hyper), "ssr_adam_ema: bad args");
+  if (step < 1) step = 1;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_ema_kernel<<<grid_for2(n, 256), 256, 0, STREAM(stream)>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
-                                                                 (float)sqrt(bc2), ema_decay, grad_scale);
+                                                                 (float)sqrt(bc2), ema_decay, grad_scale, dev_hyper);
   return LAUNCH_OK("adam_ema");
 }

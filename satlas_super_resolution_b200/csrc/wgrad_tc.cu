@@ -170,6 +170,29 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ acc, int cx_rows, 
   }
 }
 
+struct UnpackDesc {
+  const float* acc;
+  float* grad;
+  int cx_rows, acc_stride, cout, cin, r, accumulate;
+  float scale;
+  int pad_;
+};
+__global__ void wgrad_unpack_batched_kernel(const UnpackDesc* __restrict__ descs) {
+  const UnpackDesc d = descs[blockIdx.y];
+  const long total = (long)d.cout * d.cin * d.r * d.r;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int kxx = t % d.r;
+    t /= d.r;
+    const int kyy = t % d.r;
+    t /= d.r;
+    const int ci = t % d.cin;
+    const int co = t / d.cin;
+    const float v = d.scale * d.acc[((long)(kyy * d.r + kxx) * d.cx_rows + ci) * d.acc_stride + co];
+    if (d.accumulate) d.grad[i] += v; else d.grad[i] = v;
+  }
+}
+
 // bias gradient: out[c] += scale * sum_p dy[p*stride + c]
 __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, int stride, long npix, int C, float* __restrict__ out,
                                  float scale) {
@@ -277,6 +300,15 @@ extern "C" int ssr_wgrad_unpack(const float* acc, int32_t cx_rows, int32_t acc_s
                                                                                    scale, accumulate);
   count_launch();
   return check_last("wgrad_unpack launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_wgrad_unpack_batched(const ssr_unpack_desc* descs_device, int32_t n_layers, void* stream) {
+  static_assert(sizeof(ssr_unpack_desc) == sizeof(UnpackDesc), "ssr_unpack_desc layout");
+  SSR_REQUIRE(descs_device && n_layers > 0, "ssr_wgrad_unpack_batched: bad args");
+  dim3 grid(16, (unsigned)n_layers);
+  wgrad_unpack_batched_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const UnpackDesc*>(descs_device));
+  count_launch();
+  return check_last("wgrad_unpack_batched launch") ? SSR_OK : SSR_E_CUDA;
 }
 
 extern "C" int ssr_bias_grad(const void* dy_bf16, int32_t dy_pix_stride, int64_t npix, int32_t c, float* out, float scale,

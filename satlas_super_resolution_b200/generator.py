@@ -11,12 +11,12 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from .ops import Act, PackedConv, Packer, Plan, conv_args, cur_stream, lib, round_up
+from .ops import Act, PackedConv, Packer, Plan, WgradSet, conv_args, cur_stream, lib, plan_wgrad, round_up
 
 
 class RRDBNetEngine:
     def __init__(self, params, num_in_ch, num_out_ch=3, scale=4, num_feat=64, num_block=23, num_grow_ch=32,
-                 want_grad=True):
+                 want_grad=True, grads=None):
         if scale not in (4, 8, 16):
             raise NotImplementedError("RRDBNetEngine: scale 1/2 (pixel_unshuffle front-end) is not built yet")
         if num_feat % 16 or num_grow_ch % 16:
@@ -47,6 +47,14 @@ class RRDBNetEngine:
         self.cv = cv
         self.packer = Packer(list(cv.values()), self.device)
         self._ws = {}
+        # gradients: `grads` maps parameter name -> f32 tensor of the parameter's shape (views of a flat buffer)
+        self.grads = grads
+        self.wg = None
+        if want_grad and grads is not None:
+            self.wg = WgradSet(self.device)
+            for name, c in cv.items():
+                self.wg.add(name, c, c.cin_buf)
+            self.wg.finalize(lambda name: grads[f"{name}.weight"])
 
     # ------------------------------------------------------------------ weights
     def repack(self, stream=None):
@@ -72,6 +80,19 @@ class RRDBNetEngine:
                                       1.0, None, None, s))
         ws.fwd.run(s)
         return ws.out
+
+    def backward(self, d_out, B, h, w, stream=None):
+        """d_out: f32 NCHW gradient of the forward output; accumulates into self.grads (weights and biases)."""
+        assert self.wg is not None, "engine built without gradient buffers"
+        ws = self.workspace(B, h, w, True)
+        s = stream if stream is not None else cur_stream()
+        if ws.bwd is None:
+            ws.bwd = ws._build_backward(self)
+        self.wg.zero()
+        L.check(lib().ssr_ingest_nchw(d_out.data_ptr(), L.SSR_F32, ws.d_last.ptr(), 16, B, self.cout, ws.H, ws.W, 16, 1.0,
+                                      None, None, s))
+        ws.bwd.run(s)
+        self.wg.unpack(s)
 
 
 class _Workspace:
@@ -109,6 +130,7 @@ class _Workspace:
         self.hr = Act(B, hh, ww, nf, dev)
         self.out = torch.empty((B, eng.cout, hh, ww), dtype=torch.float32, device=dev)
         self.fwd = self._build_forward(eng)
+        self.bwd = None
 
     def _build_forward(self, eng):
         B, h, w = self.B, self.h, self.w
@@ -166,4 +188,120 @@ class _Workspace:
         c = eng.cv["conv_last"]
         plan.conv(conv_args(self.hr.ptr(), B, hh, ww, nf, nf, c.packed.data_ptr(), 3, c.cout, c.n_pad, bias=bptr(c),
                             out32=self.out.data_ptr(), out32_mode=L.OUT32_NCHW))
+        return plan
+
+    # ------------------------------------------------------------------ backward
+    def _build_backward(self, eng):
+        """Input-gradient (dgrad) chain + weight gradients for the whole generator.
+
+        Per ResidualDenseBlock, with cur = the block's saved dense buffer (x | x1..x4):
+          G32 (f32, 192 ch) accumulates the gradient w.r.t. every channel of the dense buffer; D (bf16) holds, per
+          channel group, that gradient times LeakyReLU'(x_k) once the group is final = dY of conv_k.
+          conv5^T first (scaled by the 0.2 of x5*0.2 + x), then conv4^T ... conv1^T, each adding into G32 through the
+          epilogue's f32 residual and masking with the sign of the saved activation (rrdbnet_arch.py:37-44 reversed).
+        """
+        B, h, w, H, W = self.B, self.h, self.w, self.H, self.W
+        nf, g, nb = eng.nf, eng.g, eng.nb
+        cw = nf + 4 * g
+        dev = eng.device
+        wg = eng.wg
+        F32 = L.SSR_F32
+        plan = Plan()
+        grads = eng.grads
+        self.d_last = Act(B, H, W, 16, dev)
+        gA, gB = Act(B, H, W, nf, dev), Act(B, H, W, nf, dev)
+        d_feat = Act(B, h, w, nf, dev)
+        G32 = torch.empty((B, h, w, cw), dtype=torch.float32, device=dev)
+        GO32 = torch.empty((B, h, w, nf), dtype=torch.float32, device=dev)
+        Dg = Act(B, h, w, cw, dev)
+        gR_b, gO_b = Act(B, h, w, nf, dev), Act(B, h, w, nf, dev)
+        d_first = Act(B, h, w, nf, dev)
+        self._bwd_keep = [gA, gB, d_feat, G32, GO32, Dg, gR_b, gO_b, d_first]
+
+        def bias_grad(name, dy_ptr, dy_stride, npix, cy, scale=1.0):
+            plan.add(lib().ssr_bias_grad, dy_ptr, dy_stride, npix, cy, grads[f"{name}.bias"].data_ptr(), scale)
+
+        def wgrad(name, x_ptr, x_stride, cx, dy_ptr, dy_stride, cy, BB, HH, WW, scale=1.0):
+            plan_wgrad(plan, wg.args(name, x_ptr, x_stride, cx, dy_ptr, dy_stride, cy, BB, HH, WW, 3, scale))
+            bias_grad(name, dy_ptr, dy_stride, BB * HH * WW, cy, scale)
+
+        # ---- tail: conv_last <- conv_hr <- conv_up_n ... conv_up1
+        c = eng.cv["conv_last"]
+        plan.conv(conv_args(self.d_last.ptr(), B, H, W, 16, 16, c.packed_dg.data_ptr(), 3, nf, c.n_pad_dg,
+                            mask=self.hr.ptr(), mask_stride=nf, mask_lo=0, out=gA.ptr(), out_stride=nf))
+        wgrad("conv_last", self.hr.ptr(), nf, nf, self.d_last.ptr(), 16, eng.cout, B, H, W)
+        c = eng.cv["conv_hr"]
+        top = self.up_out[-1]
+        plan.conv(conv_args(gA.ptr(), B, H, W, nf, nf, c.packed_dg.data_ptr(), 3, nf, c.n_pad_dg,
+                            mask=top.ptr(), mask_stride=nf, mask_lo=0, out=gB.ptr(), out_stride=nf))
+        wgrad("conv_hr", top.ptr(), nf, nf, gA.ptr(), nf, nf, B, H, W)
+        dy = gB            # dY of conv_up{n}
+        hh, ww = H, W
+        spare = gA
+        for u in range(eng.n_up - 1, -1, -1):
+            c = eng.cv[f"conv_up{u + 1}"]
+            ui = self.up_in[u]
+            d_ui = Act(B, hh, ww, nf, dev) if (spare.H, spare.W) != (hh, ww) else spare
+            self._bwd_keep.append(d_ui)
+            plan.conv(conv_args(dy.ptr(), B, hh, ww, nf, nf, c.packed_dg.data_ptr(), 3, nf, c.n_pad_dg,
+                                out=d_ui.ptr(), out_stride=nf))
+            wgrad(f"conv_up{u + 1}", ui.ptr(), nf, nf, dy.ptr(), nf, nf, B, hh, ww)
+            hh, ww = hh // 2, ww // 2
+            if u > 0:
+                nxt = Act(B, hh, ww, nf, dev)
+                self._bwd_keep.append(nxt)
+                prev_act = self.up_out[u - 1]
+                plan.add(lib().ssr_upsample_nearest_bwd, d_ui.ptr(), nf, nxt.ptr(), nf, B, hh, ww, nf, 2,
+                         prev_act.ptr(), nf)
+                dy = nxt
+                spare = Act(B, hh, ww, nf, dev)
+                self._bwd_keep.append(spare)
+            else:
+                plan.add(lib().ssr_upsample_nearest_bwd, d_ui.ptr(), nf, d_feat.ptr(), nf, B, hh, ww, nf, 2, None, 0)
+        # ---- conv_body
+        c = eng.cv["conv_body"]
+        plan.conv(conv_args(d_feat.ptr(), B, h, w, nf, nf, c.packed_dg.data_ptr(), 3, nf, c.n_pad_dg,
+                            out=gO_b.ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_NHWC, out32_stride=nf))
+        wgrad("conv_body", self.body_out.ptr(), nf, nf, d_feat.ptr(), nf, nf, B, h, w)
+        # ---- the trunk, last block first
+        for i in range(3 * nb - 1, -1, -1):
+            blk, j = divmod(i, 3)
+            cur = self.bufs[i]
+            pre = f"body.{blk}.rdb{j + 1}"
+            c5 = eng.cv[f"{pre}.conv5"]
+            if j == 2:
+                xin, s0, r1, r1s, s1 = gO_b, 0.04, GO32.data_ptr(), nf, 0.2
+            else:
+                xin, s0, r1, r1s, s1 = gR_b, 0.2, G32.data_ptr(), cw, 1.0
+            plan.conv(conv_args(xin.ptr(), B, h, w, nf, nf, c5.packed_dg.data_ptr(), 3, cw, c5.n_pad_dg, s0=s0,
+                                res1=r1, res1_kind=F32, res1_stride=r1s, s1=s1, res1_cmax=nf,
+                                mask=cur.ptr(), mask_stride=cw, mask_lo=nf,
+                                out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(), out32_mode=L.OUT32_NHWC, out32_stride=cw))
+            wgrad(f"{pre}.conv5", cur.ptr(), cw, cw, xin.ptr(), nf, nf, B, h, w, scale=s0)
+            for k in range(4, 0, -1):
+                ck = eng.cv[f"{pre}.conv{k}"]
+                nk = nf + (k - 1) * g
+                dyk = Dg.ptr(nk)
+                if k > 1:
+                    plan.conv(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
+                                        res1=G32.data_ptr(), res1_kind=F32, res1_stride=cw, s1=1.0,
+                                        mask=cur.ptr(), mask_stride=cw, mask_lo=nf,
+                                        out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(), out32_mode=L.OUT32_NHWC,
+                                        out32_stride=cw))
+                elif j > 0:
+                    plan.conv(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
+                                        res1=G32.data_ptr(), res1_kind=F32, res1_stride=cw, s1=1.0,
+                                        out=gR_b.ptr(), out_stride=nf, out32=G32.data_ptr(), out32_mode=L.OUT32_NHWC,
+                                        out32_stride=cw))
+                else:
+                    # first block of the RRDB: add the RRDB-level skip gradient and hand over to the previous RRDB
+                    plan.conv(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
+                                        res1=G32.data_ptr(), res1_kind=F32, res1_stride=cw, s1=1.0,
+                                        res2=GO32.data_ptr(), res2_kind=F32, res2_stride=nf, s2=1.0,
+                                        out=gO_b.ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_NHWC,
+                                        out32_stride=nf))
+                wgrad(f"{pre}.conv{k}", cur.ptr(), cw, nk, dyk, cw, g, B, h, w)
+        # ---- conv_first: dY = trunk gradient + the long skip (feat = conv_first + conv_body(...))
+        plan.add(lib().ssr_axpby, gO_b.ptr(), nf, 1.0, d_feat.ptr(), nf, 1.0, None, 0, 0, d_first.ptr(), nf, B * h * w, nf)
+        wgrad("conv_first", self.in0.ptr(), self.in0.stride, eng.cin_pad, d_first.ptr(), nf, nf, B, h, w)
         return plan

@@ -121,10 +121,11 @@ class Packer:
         arr = (PackDesc * len(descs))(*descs)
         raw = bytes(arr)
         self.n = len(descs)
+        self.has_gemm = int(any(d.mode in (L.PACK_FWD_GEMM, L.PACK_DGRAD_GEMM) for d in descs))
         self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
 
     def run(self, stream=None):
-        L.check(lib().ssr_pack_conv_weights_batched(self.table.data_ptr(), self.n,
+        L.check(lib().ssr_pack_conv_weights_batched(self.table.data_ptr(), self.n, self.has_gemm,
                                                     stream if stream is not None else cur_stream()))
 
 
@@ -133,7 +134,7 @@ def conv_args(x_ptr, B, H, W, x_stride, cin, w_ptr, r, cout, n_pad, bias=None, a
               res2=None, res2_kind=L.SSR_BF16, res2_stride=0, s2=0.0,
               mask=None, mask_stride=0, mask_lo=0, mask_relu=0,
               out=None, out_stride=0, out32=None, out32_mode=L.OUT32_NONE, out32_stride=0,
-              n_tile=0, mt=0, splits=0):
+              n_tile=0, mt=0, splits=0, res1_cmax=0):
     a = L.ConvTcArgs()
     a.x, a.n_img, a.h, a.w, a.x_pix_stride, a.cin = x_ptr, B, H, W, x_stride, cin
     a.w_packed, a.r, a.cout, a.n_pad = w_ptr, r, cout, n_pad
@@ -149,5 +150,128 @@ def conv_args(x_ptr, B, H, W, x_stride, cin, w_ptr, r, cout, n_pad, bias=None, a
         a.out_bf16, a.out_pix_stride = out, out_stride
     if out32 is not None:
         a.out_f32, a.out32_mode, a.out32_pix_stride = out32, out32_mode, out32_stride
-    a.n_tile, a.mt, a.splits = n_tile, mt, splits
+    a.n_tile, a.mt, a.splits, a.res1_cmax = n_tile, mt, splits, res1_cmax
     return a
+
+
+# --------------------------------------------------------------------------------------------- flat parameter storage
+class FlatBuffer:
+    """One contiguous f32 device buffer holding every tensor of a network (each aligned to 256 bytes), so that the
+    optimiser, the EMA and the gradient all-reduce are single launches over one pointer."""
+
+    ALIGN = 64  # floats
+
+    def __init__(self, shapes, device):
+        self.offsets = {}
+        off = 0
+        for name, shp in shapes.items():
+            n = 1
+            for s in shp:
+                n *= s
+            self.offsets[name] = (off, n, tuple(shp))
+            off += round_up(n, self.ALIGN)
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+
+    def view(self, name):
+        off, n, shp = self.offsets[name]
+        return self.flat[off:off + n].view(shp)
+
+    def views(self):
+        return {k: self.view(k) for k in self.offsets}
+
+    def like(self):
+        other = FlatBuffer.__new__(FlatBuffer)
+        other.offsets, other.numel = self.offsets, self.numel
+        other.flat = torch.zeros_like(self.flat)
+        return other
+
+
+class GemmConv:
+    """A k x k strided conv computed as im2col + 1x1 GEMM (the 4x4 stride-2 discriminator convs)."""
+
+    def __init__(self, weight, want_dgrad, device, inv_scale=None):
+        self.weight, self.bias = weight, None
+        self.cout, self.cin, self.r, _ = weight.shape
+        self.inv_scale = inv_scale
+        self.kk = self.r * self.r * self.cin
+        n_pad = C.c_int32(0)
+        self.k_pad = round_up(self.kk, 64)
+        nbytes = lib().ssr_packed_weight_bytes(self.k_pad, self.cout, 1, C.byref(n_pad))
+        self.n_pad = n_pad.value
+        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.packed_dg = None
+        if want_dgrad:
+            self.k_pad_dg = round_up(self.cout, 64)
+            nbytes = lib().ssr_packed_weight_bytes(self.k_pad_dg, self.kk, 1, C.byref(n_pad))
+            self.n_pad_dg = n_pad.value
+            self.packed_dg = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+    def descs(self):
+        out = []
+        for mode, dst, k_pad, n_pad in ((L.PACK_FWD_GEMM, self.packed, self.k_pad, self.n_pad),
+                                        (L.PACK_DGRAD_GEMM, self.packed_dg, getattr(self, "k_pad_dg", 0),
+                                         getattr(self, "n_pad_dg", 0))):
+            if dst is None:
+                continue
+            d = PackDesc()
+            d.w, d.dst = self.weight.data_ptr(), dst.data_ptr()
+            d.inv_scale = self.inv_scale.data_ptr() if self.inv_scale is not None else None
+            d.cout, d.cin, d.r, d.mode, d.k_pad, d.n_pad = self.cout, self.cin, self.r, mode, k_pad, n_pad
+            out.append(d)
+        return out
+
+
+class WgradSet:
+    """f32 accumulators [taps][cx_rows][cy_stride] for every conv of a network + the batched unpack into OIHW grads."""
+
+    def __init__(self, device):
+        self.device = device
+        self.items = []   # (name, conv, cx_rows, cy_stride, offset)
+        self.total = 0
+        self.acc = None
+        self.table = None
+
+    def add(self, name, conv, cx_rows):
+        cy_stride = round_up(conv.cout, 4)
+        n = conv.r * conv.r * cx_rows * cy_stride
+        self.items.append((name, conv, cx_rows, cy_stride, self.total))
+        self.total += round_up(n, 64)
+
+    def finalize(self, grad_of, accumulate=1):
+        from ._protos import UnpackDesc
+        self.acc = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.slot = {}
+        descs = []
+        for name, conv, cx_rows, cy_stride, off in self.items:
+            self.slot[name] = (self.acc.data_ptr() + 4 * off, cx_rows, cy_stride)
+            d = UnpackDesc()
+            d.acc = self.acc.data_ptr() + 4 * off
+            d.grad = grad_of(name).data_ptr()
+            d.cx_rows, d.acc_stride, d.cout, d.cin, d.r = cx_rows, cy_stride, conv.cout, conv.cin, conv.r
+            d.accumulate, d.scale = accumulate, 1.0
+            descs.append(d)
+        arr = (UnpackDesc * len(descs))(*descs)
+        self.n = len(descs)
+        self.table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+
+    def args(self, name, x_ptr, x_stride, cx, dy_ptr, dy_stride, cy, B, H, W, r, scale=1.0):
+        from ._protos import WgradArgs
+        ptr, cx_rows, cy_stride = self.slot[name]
+        a = WgradArgs()
+        a.x, a.n_img, a.h, a.w, a.x_pix_stride, a.cx = x_ptr, B, H, W, x_stride, cx
+        a.dy, a.dy_pix_stride, a.cy, a.r = dy_ptr, dy_stride, cy, r
+        # r == 1 on a k x k conv = the im2col GEMM form: rows are (tap, ci) flattened, i.e. the same memory
+        a.out, a.out_cx_rows, a.out_stride, a.scale, a.splits = ptr, max(cx_rows, cx), cy_stride, scale, 0
+        return a
+
+    def zero(self):
+        self.acc.zero_()
+
+    def unpack(self, stream=None):
+        L.check(lib().ssr_wgrad_unpack_batched(self.table.data_ptr(), self.n, stream if stream is not None else cur_stream()))
+
+
+def plan_wgrad(plan, args):
+    plan.keep.append(args)
+    plan.calls.append((lib().ssr_wgrad_tc, (C.byref(args),)))

@@ -1,0 +1,279 @@
+"""The ESRGAN training step (feed_data + optimize_parameters) driven entirely through libssr_b200.
+
+Statement order, loss weights, detach points and the three discriminator forwards follow
+/root/reference/ssr/models/ssr_esrgan_model.py:104-233; what differs is HOW each statement executes:
+every tensor op is a kernel of the C ABI, parameters / gradients / Adam moments / EMA live in flat f32 buffers
+(one fused Adam(+EMA) launch and one all-reduce per network), and the whole step is replayable as one CUDA graph.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import _lib as L
+from .discriminator import UNetDiscEngine
+from .generator import RRDBNetEngine
+from .ops import FlatBuffer, cur_stream, lib
+from .vgg import PerceptualEngine
+
+LOSS_KEYS = ["l_g_pix", "l_g_percep", "l_g_gan", "l_d_real", "out_d_real", "l_d_fake", "out_d_fake"]
+
+
+def gaussian_taps(ksize=51, sigma=0.0):
+    """cv2.getGaussianKernel(ksize, sigma) (basicsr USMSharp): sigma <= 0 -> 0.3*((ksize-1)*0.5 - 1) + 0.8."""
+    if sigma <= 0:
+        sigma = 0.3 * ((ksize - 1) * 0.5 - 1) + 0.8
+    c = (ksize - 1) / 2
+    k = [math.exp(-((i - c) ** 2) / (2 * sigma * sigma)) for i in range(ksize)]
+    s = sum(k)
+    return [v / s for v in k]
+
+
+class FusedAdamState:
+    """Adam moments (and the EMA copy) for one flat parameter buffer; one ssr_adam_ema launch per step."""
+
+    def __init__(self, params: FlatBuffer, grads: FlatBuffer, lr=1e-4, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0,
+                 ema: FlatBuffer = None, ema_decay=0.0):
+        self.p, self.g = params, grads
+        self.m, self.v = params.like(), params.like()
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.ema, self.ema_decay = ema, ema_decay
+        self.step_count = 0
+        self.hyper_host = torch.zeros(3, dtype=torch.float32).pin_memory() if torch.cuda.is_available() else None
+        self.hyper_dev = torch.zeros(3, dtype=torch.float32, device=params.flat.device)
+
+    def push_hyper(self):
+        """advance the step counter and stage [lr, 1-b1^t, sqrt(1-b2^t)] for a graph replay"""
+        self.step_count += 1
+        t = self.step_count
+        self.hyper_host[0] = self.lr
+        self.hyper_host[1] = 1.0 - self.betas[0] ** t
+        self.hyper_host[2] = math.sqrt(1.0 - self.betas[1] ** t)
+        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
+
+    def step(self, grad_scale=1.0, stream=None, from_device=False):
+        if not from_device:
+            self.step_count += 1
+        L.check(lib().ssr_adam_ema(self.p.flat.data_ptr(), self.g.flat.data_ptr(), self.m.flat.data_ptr(),
+                                   self.v.flat.data_ptr(), self.ema.flat.data_ptr() if self.ema is not None else None,
+                                   self.p.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                                   self.step_count, self.ema_decay, grad_scale,
+                                   self.hyper_dev.data_ptr() if from_device else None,
+                                   stream if stream is not None else cur_stream()))
+
+
+class ESRGANTrainer:
+    D_BUFFERS = ("weight_u", "weight_v")
+
+    def __init__(self, g_state, d_state, vgg_state, cfg=None, device="cuda", process_group=None):
+        cfg = dict(cfg or {})
+        self.cfg = cfg
+        self.device = torch.device(device)
+        dev = self.device
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        net_g = cfg.get("network_g", {})
+        self.num_in_ch = net_g.get("num_in_ch", g_state["conv_first.weight"].shape[1])
+        self.num_block = net_g.get("num_block", 23)
+        self.scale = net_g.get("scale", 4)
+        # ---- generator: flat params / grads / EMA
+        self.gbuf = FlatBuffer(OrderedDict((k, tuple(v.shape)) for k, v in g_state.items()), dev)
+        for k, v in g_state.items():
+            self.gbuf.view(k).copy_(v)
+        self.ggrad = self.gbuf.like()
+        self.ema_decay = cfg.get("ema_decay", 0.999)
+        self.gema = self.gbuf.like() if self.ema_decay > 0 else None
+        if self.gema is not None:
+            self.gema.flat.copy_(self.gbuf.flat)          # model_ema(0): ssr_esrgan_model.py:49
+        self.G = RRDBNetEngine(self.gbuf.views(), self.num_in_ch, g_state["conv_last.weight"].shape[0], scale=self.scale,
+                               num_feat=g_state["conv_first.weight"].shape[0], num_block=self.num_block,
+                               num_grow_ch=g_state["body.0.rdb1.conv1.weight"].shape[0], want_grad=True,
+                               grads=self.ggrad.views())
+        self.G_ema = None
+        # ---- discriminator
+        learn = OrderedDict((k, tuple(v.shape)) for k, v in d_state.items() if not k.endswith(self.D_BUFFERS))
+        self.dbuf = FlatBuffer(learn, dev)
+        for k in learn:
+            self.dbuf.view(k).copy_(d_state[k])
+        self.dgrad = self.dbuf.like()
+        self.d_uv = {k: v.detach().clone().to(dev, torch.float32) for k, v in d_state.items() if k.endswith(self.D_BUFFERS)}
+        self.d_in_ch = d_state["conv0.weight"].shape[1]
+        d_params = dict(self.dbuf.views())
+        d_params.update(self.d_uv)
+        self.D = UNetDiscEngine(d_params, self.d_in_ch, num_feat=d_state["conv0.weight"].shape[0], grads=self.dgrad.views())
+        # ---- losses
+        self.pixel_weight = cfg.get("pixel_weight", 1.0)
+        self.gan_weight = cfg.get("gan_weight", 0.1)
+        self.P = None
+        if vgg_state is not None and cfg.get("perceptual", True):
+            vp = {k: v.to(dev, torch.float32).contiguous() for k, v in vgg_state.items()}
+            self.P = PerceptualEngine(vp, cfg.get("layer_weights", {"conv1_2": 0.1, "conv2_2": 0.1, "conv3_4": 1.0,
+                                                                     "conv4_4": 1.0, "conv5_4": 1.0}),
+                                      cfg.get("perceptual_weight", 1.0), cfg.get("use_input_norm", True),
+                                      cfg.get("range_norm", False))
+        self.feed_disc_lr = cfg.get("feed_disc_lr", True)
+        self.l1_gt_usm = cfg.get("l1_gt_usm", True)
+        self.percep_gt_usm = cfg.get("percep_gt_usm", True)
+        self.gan_gt_usm = cfg.get("gan_gt_usm", False)
+        self.net_d_iters = cfg.get("net_d_iters", 1)
+        self.net_d_init_iters = cfg.get("net_d_init_iters", 0)
+        lr = cfg.get("lr", 1e-4)
+        betas = tuple(cfg.get("betas", (0.9, 0.99)))
+        self.opt_g = FusedAdamState(self.gbuf, self.ggrad, lr, betas, ema=self.gema, ema_decay=self.ema_decay)
+        self.opt_d = FusedAdamState(self.dbuf, self.dgrad, lr, betas)
+        self.loss_dev = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.usm_taps = (C_float_array(gaussian_taps(51, 0)), 51)
+        self._io = {}
+        self._graph = None
+        self.log_dict = OrderedDict()
+
+    # ------------------------------------------------------------------ data
+    def _io_for(self, B, C_lr, h, w, H, W):
+        key = (B, C_lr, h, w, H, W)
+        io = self._io.get(key)
+        if io is None:
+            dev = self.device
+            io = dict(lr_u8=torch.empty((B, C_lr, h, w), dtype=torch.uint8, device=dev),
+                      hr_u8=torch.empty((B, 3, H, W), dtype=torch.uint8, device=dev),
+                      lr=torch.empty((B, C_lr, h, w), dtype=torch.float32, device=dev),
+                      gt=torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
+                      gt_usm=torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
+                      usm_scratch=torch.empty((3, B, 3, H, W), dtype=torch.float32, device=dev),
+                      d_out=torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
+                      d_logits=torch.empty((B, 1, H, W), dtype=torch.float32, device=dev))
+            self._io[key] = io
+        return io
+
+    @torch.no_grad()
+    def feed_data(self, lr_u8, hr_u8, stream=None):
+        """ssr_esrgan_model.py:104-117: uint8 -> float / 255 (+ USM-sharpened ground truth).  lr_u8 / hr_u8 may be host
+        (pinned) or device uint8 tensors; the H2D copy is part of this call."""
+        s = stream if stream is not None else cur_stream()
+        B, C_lr, h, w = lr_u8.shape
+        H, W = hr_u8.shape[-2:]
+        io = self._io_for(B, C_lr, h, w, H, W)
+        io["lr_u8"].copy_(lr_u8, non_blocking=True)
+        io["hr_u8"].copy_(hr_u8, non_blocking=True)
+        self._feed_kernels(io, s)
+        self.io = io
+        self.lr, self.gt, self.gt_usm = io["lr"], io["gt"], io["gt_usm"]
+
+    def _feed_kernels(self, io, s):
+        lb = lib()
+        L.check(lb.ssr_u8_to_f32(io["lr_u8"].data_ptr(), io["lr"].data_ptr(), io["lr"].numel(), 1.0 / 255.0, s))
+        L.check(lb.ssr_u8_to_f32(io["hr_u8"].data_ptr(), io["gt"].data_ptr(), io["gt"].numel(), 1.0 / 255.0, s))
+        B, _, H, W = io["gt"].shape
+        taps, n = self.usm_taps
+        L.check(lb.ssr_usm_sharp(io["gt"].data_ptr(), io["gt_usm"].data_ptr(), io["usm_scratch"].data_ptr(), B * 3, H, W, taps, n,
+                                 0.5, 10.0, s))
+
+    # ------------------------------------------------------------------ the step
+    def _step_kernels(self, io, do_g, s, graph_mode=False):
+        lb = lib()
+        lr, gt, gt_usm = io["lr"], io["gt"], io["gt_usm"]
+        B, C_lr, h, w = lr.shape
+        H, W = gt.shape[-2:]
+        n_img = gt.numel()
+        l1_gt = gt_usm if self.l1_gt_usm else gt
+        percep_gt = gt_usm if self.percep_gt_usm else gt
+        gan_gt = gt_usm if self.gan_gt_usm else gt
+        loss = self.loss_dev
+        lp = lambda i: loss.data_ptr() + 4 * i
+        d_out, d_logits = io["d_out"], io["d_logits"]
+        loss.zero_()
+        gws = self.G.workspace(B, h, w, True)
+        dws = self.D.workspace(B, H, W)
+        n_logit = B * H * W
+        cl = C_lr if self.feed_disc_lr else 0
+        f = H // h
+
+        def disc_in(img):
+            L.check(lb.ssr_disc_input(img.data_ptr(), 3, gws.in0.ptr() if cl else None, gws.in0.stride, cl, f, dws.x_in.ptr(),
+                                      dws.x_in.stride, B, H, W, s))
+
+        # ---------------- generator (ssr_esrgan_model.py:136-193)
+        self.G.repack(s)
+        out = self.G.forward(lr, train=True, stream=s)
+        self.output = out
+        if do_g:
+            self.ggrad.flat.zero_()
+            L.check(lb.ssr_l1_loss(out.data_ptr(), l1_gt.data_ptr(), n_img, self.pixel_weight, lp(0), d_out.data_ptr(), 0, s))
+            if self.P is not None:
+                self.P.loss_and_grad(out, percep_gt, loss[1:2], d_out, s)
+            disc_in(out)
+            logits = self.D.forward(dws, training=True, stream=s)
+            L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 1.0, self.gan_weight, lp(2), None, d_logits.data_ptr(), s))
+            self.D.backward(dws, d_logits, need_wgrad=False, need_dinput=True, stream=s)
+            L.check(lb.ssr_egress_nchw(dws.d_in.ptr(), dws.d_in.stride, d_out.data_ptr(), B, 3, H, W, 1.0, 1, None, s))
+            self.G.backward(d_out, B, h, w, s)
+            if self.world > 1:
+                torch.distributed.all_reduce(self.ggrad.flat, group=self.pg)
+            self.opt_g.step(1.0 / self.world, s, from_device=graph_mode)
+        # ---------------- discriminator (:196-228)
+        self.dgrad.flat.zero_()
+        disc_in(gan_gt)
+        logits = self.D.forward(dws, training=True, stream=s)
+        L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 1.0, 1.0, lp(3), lp(4), d_logits.data_ptr(), s))
+        self.D.backward(dws, d_logits, need_wgrad=True, stream=s)
+        disc_in(out)
+        logits = self.D.forward(dws, training=True, stream=s)
+        L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 0.0, 1.0, lp(5), lp(6), d_logits.data_ptr(), s))
+        self.D.backward(dws, d_logits, need_wgrad=True, stream=s)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.dgrad.flat, group=self.pg)
+        self.opt_d.step(1.0 / self.world, s, from_device=graph_mode)
+
+    def optimize_parameters(self, current_iter=1):
+        s = cur_stream()
+        do_g = (current_iter % self.net_d_iters == 0) and (current_iter > self.net_d_init_iters)
+        self._step_kernels(self.io, do_g, s)
+        self._log_ready = False
+
+    def get_current_log(self):
+        """loss scalars (one D2H read, only when asked -- the reference syncs every iteration at :233)"""
+        vals = self.loss_dev.tolist()
+        log = OrderedDict()
+        for i, k in enumerate(LOSS_KEYS):
+            if k == "l_g_percep" and self.P is None:
+                continue
+            log[k] = vals[i]
+        if self.world > 1:
+            t = torch.tensor(list(log.values()), device=self.device)
+            torch.distributed.reduce(t, dst=0, group=self.pg)
+            t = t / self.world
+            log = OrderedDict(zip(log.keys(), t.tolist()))
+        self.log_dict = log
+        return log
+
+    # ------------------------------------------------------------------ state access (reference key schema)
+    def g_state_dict(self, ema=False):
+        buf = self.gema if ema else self.gbuf
+        return OrderedDict((k, buf.view(k).detach().clone()) for k in buf.offsets)
+
+    def d_state_dict(self):
+        sd = OrderedDict((k, self.dbuf.view(k).detach().clone()) for k in self.dbuf.offsets)
+        sd.update({k: v.detach().clone() for k, v in self.d_uv.items()})
+        return sd
+
+    def g_grads(self):
+        return OrderedDict((k, self.ggrad.view(k)) for k in self.ggrad.offsets)
+
+    def d_grads(self):
+        return OrderedDict((k, self.dgrad.view(k)) for k in self.dgrad.offsets)
+
+    @torch.no_grad()
+    def test(self, lr=None):
+        """ssr_esrgan_model.py:235-244: EMA generator in eval mode."""
+        if self.G_ema is None:
+            src = self.gema if self.gema is not None else self.gbuf
+            self.G_ema = RRDBNetEngine(src.views(), self.num_in_ch, 3, scale=self.scale, num_block=self.num_block,
+                                       want_grad=False)
+        self.G_ema.repack()
+        x = lr if lr is not None else self.lr
+        self.output = self.G_ema.forward(x.contiguous(), train=False).clone()
+        return self.output
+
+
+def C_float_array(vals):
+    import ctypes
+    return (ctypes.c_float * len(vals))(*vals)
