@@ -61,9 +61,9 @@ int64_t ssr_launch_count(void);
  * Epilogue, per output element (p = pixel, c = channel):
  *   v = acc + bias[c]; if (act) v = v > 0 ? v : 0.2 v;           // LeakyReLU(0.2), rrdbnet_arch.py:33
  *   v = s0*v + s1*res1[p,c] + s2*res2[p,c];                      // x5*0.2 + x (:44), out*0.2 + x (:68)
- *   if (c >= mask_lo) v *= (mask[p,c] > 0 ? 1 : 0.2);            // LeakyReLU backward on a saved output
- *   if (relu_mask) v *= (relu_mask[p,c] > 0 ? 1 : 0)             // ReLU backward (VGG)
- *   out_bf16[p,c] = bf16(v); out_f32[...] (=|+=) v
+ *   out_f32[...] (=|+=) v                                        // unmasked (a running f32 gradient sum)
+ *   if (c >= mask_lo) v *= (mask[p,c] > 0 ? 1 : 0.2 | 0);        // LeakyReLU / ReLU backward on a saved output
+ *   out_bf16[p,c] = bf16(v)
  */
 typedef struct ssr_conv_tc_args {
   /* input activation, NHWC bf16: x[((n*h + y)*w + x)*x_pix_stride + c], c in [0, cin) */

@@ -46,8 +46,23 @@ def vgg19_init(seed=0):
     return p
 
 
-def vgg19_features(p, x, layer_names, use_input_norm=True, range_norm=False):
+def masked_relu_pool(relu_masks, pool_index):
+    """(relu_fn, pool_fn) whose active sets / arg-max choices are DICTATED by the engine's saved activations (see
+    oracle.nets.masked_lrelu): relu_masks[name] bool [N,C,H,W]; pool_index[name] int64 [N,C,H/2,W/2] in 0..3."""
+    def relu_fn(name, t):
+        return t * relu_masks[name].to(t.dtype)
+
+    def pool_fn(name, t):
+        n, c, h, w = t.shape
+        win = t.view(n, c, h // 2, 2, w // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(n, c, h // 2, w // 2, 4)
+        return torch.gather(win, 4, pool_index[name].unsqueeze(-1)).squeeze(-1)
+    return relu_fn, pool_fn
+
+
+def vgg19_features(p, x, layer_names, use_input_norm=True, range_norm=False, relu_fn=None, pool_fn=None):
     """basicsr VGGFeatureExtractor(vgg19): pre-ReLU conv outputs by name; MaxPool2d(2,2) kept."""
+    relu_fn = relu_fn or (lambda name, t: F.relu(t))
+    pool_fn = pool_fn or (lambda name, t: F.max_pool2d(t, 2, 2))
     if range_norm:
         x = (x + 1) / 2
     if use_input_norm:
@@ -58,7 +73,7 @@ def vgg19_features(p, x, layer_names, use_input_norm=True, range_norm=False):
     remaining = set(layer_names)
     for c in VGG19_LAYERS:
         if isinstance(c, str):
-            x = F.max_pool2d(x, 2, 2)
+            x = pool_fn(c, x)
             continue
         name = c[0]
         x = F.conv2d(x, p[f"{name}.weight"], p[f"{name}.bias"], padding=1)
@@ -67,14 +82,15 @@ def vgg19_features(p, x, layer_names, use_input_norm=True, range_norm=False):
             remaining.discard(name)
             if not remaining:
                 break
-        x = F.relu(x)
+        x = relu_fn(name, x)
     return out
 
 
-def perceptual_loss(p, x, gt, layer_weights=None, perceptual_weight=1.0, use_input_norm=True, range_norm=False):
+def perceptual_loss(p, x, gt, layer_weights=None, perceptual_weight=1.0, use_input_norm=True, range_norm=False,
+                    relu_fn=None, pool_fn=None):
     """basicsr PerceptualLoss(criterion='l1', style_weight=0): sum_k w_k * L1(vgg_k(x), vgg_k(gt.detach()))."""
     lw = layer_weights or DEFAULT_LAYER_WEIGHTS
-    fx = vgg19_features(p, x, lw.keys(), use_input_norm, range_norm)
+    fx = vgg19_features(p, x, lw.keys(), use_input_norm, range_norm, relu_fn, pool_fn)
     with torch.no_grad():
         fg = vgg19_features(p, gt.detach(), lw.keys(), use_input_norm, range_norm)
     loss = 0

@@ -11,21 +11,36 @@ import torch.nn.functional as F
 
 
 # --------------------------------------------------------------------------- generator
-def rdb_forward(p, pre, x):
+def _lrelu(name, t):
+    return F.leaky_relu(t, 0.2)
+
+
+def masked_lrelu(masks):
+    """LeakyReLU(0.2) whose active set is DICTATED by `masks[name]` (bool, same shape) instead of sign(t): the network
+    becomes the piecewise-linear map with the engine's activation pattern, so its autograd gradients are exactly what
+    the engine's backward kernels must produce (used by tests/test_train_gpu.py; values differ from the true
+    LeakyReLU only where |t| is within rounding noise of zero)."""
+    def act(name, t):
+        m = masks[name].to(t.dtype)
+        return t * (m + (1 - m) * 0.2)
+    return act
+
+
+def rdb_forward(p, pre, x, act=_lrelu):
     """ResidualDenseBlock.forward -- /root/reference/ssr/archs/rrdbnet_arch.py:37-44."""
     feats = [x]
     for k in range(1, 5):
         y = F.conv2d(torch.cat(feats, 1), p[f"{pre}.conv{k}.weight"], p[f"{pre}.conv{k}.bias"], padding=1)
-        feats.append(F.leaky_relu(y, 0.2))
+        feats.append(act(f"{pre}.conv{k}", y))
     x5 = F.conv2d(torch.cat(feats, 1), p[f"{pre}.conv5.weight"], p[f"{pre}.conv5.bias"], padding=1)
     return x5 * 0.2 + x
 
 
-def rrdb_forward(p, pre, x):
+def rrdb_forward(p, pre, x, act=_lrelu):
     """RRDB.forward -- rrdbnet_arch.py:63-68."""
     out = x
     for j in (1, 2, 3):
-        out = rdb_forward(p, f"{pre}.rdb{j}", out)
+        out = rdb_forward(p, f"{pre}.rdb{j}", out, act)
     return out * 0.2 + x
 
 
@@ -36,7 +51,7 @@ def pixel_unshuffle(x, scale):
     return x.view(b, c, h, scale, w, scale).permute(0, 1, 3, 5, 2, 4).reshape(b, c * scale * scale, h, w)
 
 
-def rrdbnet_forward(p, x, scale=4, num_block=23):
+def rrdbnet_forward(p, x, scale=4, num_block=23, act=_lrelu):
     """SSR_RRDBNet.forward -- rrdbnet_arch.py:116-137."""
     if scale == 2:
         feat = pixel_unshuffle(x, 2)
@@ -48,15 +63,15 @@ def rrdbnet_forward(p, x, scale=4, num_block=23):
     feat = conv("conv_first", feat)
     body = feat
     for i in range(num_block):
-        body = rrdb_forward(p, f"body.{i}", body)
+        body = rrdb_forward(p, f"body.{i}", body, act)
     feat = feat + conv("conv_body", body)
-    feat = F.leaky_relu(conv("conv_up1", F.interpolate(feat, scale_factor=2, mode="nearest")), 0.2)
-    feat = F.leaky_relu(conv("conv_up2", F.interpolate(feat, scale_factor=2, mode="nearest")), 0.2)
+    feat = act("conv_up1", conv("conv_up1", F.interpolate(feat, scale_factor=2, mode="nearest")))
+    feat = act("conv_up2", conv("conv_up2", F.interpolate(feat, scale_factor=2, mode="nearest")))
     if scale in (8, 16):
-        feat = F.leaky_relu(conv("conv_up3", F.interpolate(feat, scale_factor=2, mode="nearest")), 0.2)
+        feat = act("conv_up3", conv("conv_up3", F.interpolate(feat, scale_factor=2, mode="nearest")))
         if scale == 16:
-            feat = F.leaky_relu(conv("conv_up4", F.interpolate(feat, scale_factor=2, mode="nearest")), 0.2)
-    return conv("conv_last", F.leaky_relu(conv("conv_hr", feat), 0.2))
+            feat = act("conv_up4", conv("conv_up4", F.interpolate(feat, scale_factor=2, mode="nearest")))
+    return conv("conv_last", act("conv_hr", conv("conv_hr", feat)))
 
 
 def rrdbnet_init(num_in_ch, num_out_ch=3, num_feat=64, num_block=23, num_grow_ch=32, scale=4, seed=0):
@@ -125,29 +140,28 @@ def spectral_norm_weight(p, name, training, update_state=True):
     return w / sigma
 
 
-def unet_disc_forward(p, x, training=True, skip_connection=True, update_state=True):
+def unet_disc_forward(p, x, training=True, skip_connection=True, update_state=True, act=_lrelu):
     """SSR_UNetDiscriminatorSN.forward -- discriminator_arch.py:42-71."""
     sn = lambda name: spectral_norm_weight(p, name, training, update_state)
-    lrelu = lambda t: F.leaky_relu(t, 0.2)
     up = lambda t: F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=False)
-    x0 = lrelu(F.conv2d(x, p["conv0.weight"], p["conv0.bias"], padding=1))
-    x1 = lrelu(F.conv2d(x0, sn("conv1"), None, stride=2, padding=1))
-    x2 = lrelu(F.conv2d(x1, sn("conv2"), None, stride=2, padding=1))
-    x3 = lrelu(F.conv2d(x2, sn("conv3"), None, stride=2, padding=1))
+    x0 = act("conv0", F.conv2d(x, p["conv0.weight"], p["conv0.bias"], padding=1))
+    x1 = act("conv1", F.conv2d(x0, sn("conv1"), None, stride=2, padding=1))
+    x2 = act("conv2", F.conv2d(x1, sn("conv2"), None, stride=2, padding=1))
+    x3 = act("conv3", F.conv2d(x2, sn("conv3"), None, stride=2, padding=1))
     x3 = up(x3)
-    x4 = lrelu(F.conv2d(x3, sn("conv4"), None, padding=1))
+    x4 = act("conv4", F.conv2d(x3, sn("conv4"), None, padding=1))
     if skip_connection:
         x4 = x4 + x2
     x4 = up(x4)
-    x5 = lrelu(F.conv2d(x4, sn("conv5"), None, padding=1))
+    x5 = act("conv5", F.conv2d(x4, sn("conv5"), None, padding=1))
     if skip_connection:
         x5 = x5 + x1
     x5 = up(x5)
-    x6 = lrelu(F.conv2d(x5, sn("conv6"), None, padding=1))
+    x6 = act("conv6", F.conv2d(x5, sn("conv6"), None, padding=1))
     if skip_connection:
         x6 = x6 + x0
-    out = lrelu(F.conv2d(x6, sn("conv7"), None, padding=1))
-    out = lrelu(F.conv2d(out, sn("conv8"), None, padding=1))
+    out = act("conv7", F.conv2d(x6, sn("conv7"), None, padding=1))
+    out = act("conv8", F.conv2d(out, sn("conv8"), None, padding=1))
     return F.conv2d(out, p["conv9.weight"], p["conv9.bias"], padding=1)
 
 

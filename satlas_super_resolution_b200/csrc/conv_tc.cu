@@ -240,6 +240,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s2, r[j], f[j]);
           }
+          // the f32 output is the UNMASKED value (a running gradient sum); the derivative mask only shapes the bf16 copy
+          if (p.out32_mode == SSR_OUT32_NHWC) {
+            float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.out32_stride + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC) {
+            float* dst = p.out_f32 + pix * p.out32_stride + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(dst + j, f[j]);
+          } else if (p.out32_mode == SSR_OUT32_NCHW) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              p.out_f32[(((long)n * p.cout + c0 + j) * p.H + y) * p.W + x] = f[j];
+          }
           if (p.mask != nullptr && c0 >= p.mask_lo) {
             float r[16];
             load16_bf16(p.mask + pix * p.mask_stride + c0, r);
@@ -261,20 +276,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             dst[0] = o0;
             dst[1] = o1;
           }
-          if (p.out32_mode == SSR_OUT32_NHWC) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.out32_stride + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC) {
-            float* dst = p.out_f32 + pix * p.out32_stride + c0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(dst + j, f[j]);
-          } else if (p.out32_mode == SSR_OUT32_NCHW) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              p.out_f32[(((long)n * p.cout + c0 + j) * p.H + y) * p.W + x] = f[j];
-          }
         } else {
           // ragged tail of the channel dimension (cout not a multiple of 16): scalar path
           for (int j = 0; j < 16; ++j) {
@@ -294,17 +295,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               val += p.s2 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res2)[pix * p.res2_stride + c]);
             else if (p.res2_kind == SSR_F32)
               val += p.s2 * reinterpret_cast<const float*>(p.res2)[pix * p.res2_stride + c];
-            if (p.mask != nullptr && c >= p.mask_lo) {
-              const float mv = __bfloat162float(p.mask[pix * p.mask_stride + c]);
-              val *= (mv > 0.f ? 1.f : (p.mask_relu ? 0.f : 0.2f));
-            }
-            if (p.out_bf16 != nullptr) p.out_bf16[pix * p.out_stride + c] = __float2bfloat16(val);
             if (p.out32_mode == SSR_OUT32_NHWC)
               p.out_f32[pix * p.out32_stride + c] = val;
             else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC)
               atomicAdd(p.out_f32 + pix * p.out32_stride + c, val);
             else if (p.out32_mode == SSR_OUT32_NCHW)
               p.out_f32[(((long)n * p.cout + c) * p.H + y) * p.W + x] = val;
+            if (p.mask != nullptr && c >= p.mask_lo) {
+              const float mv = __bfloat162float(p.mask[pix * p.mask_stride + c]);
+              val *= (mv > 0.f ? 1.f : (p.mask_relu ? 0.f : 0.2f));
+            }
+            if (p.out_bf16 != nullptr) p.out_bf16[pix * p.out_stride + c] = __float2bfloat16(val);
           }
         }
       }

@@ -130,6 +130,7 @@ class _PWorkspace:
                 self.loss_calls.append((lb.ssr_feat_l1, (out.ptr(), n_half, eng.layer_weights[name] * eng.pw / n_half)))
             cur, cur_c = out, cout
         self.fwd = fwd
+        self.order = order
         # ---------------- backward over the generated half (first B images of every buffer)
         self.d_inp = Act(B, H, W, 16, dev)
         self._keep = []
