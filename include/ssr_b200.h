@@ -49,6 +49,10 @@ const char* ssr_last_error(void);
 int ssr_abi_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t ssr_launch_count(void);
+/* per-launch CUDA-event timing of the two tensor-core kernels (class 0 = ssr_conv_tc, 1 = ssr_wgrad_tc) for the
+ * roofline figure: start, run the step eagerly, stop -> total ms and launch count per class (synchronises). */
+int ssr_profile_start(void);
+int ssr_profile_stop(double* ms, int64_t* count, int32_t n_classes);
 
 /*
  * Implicit-GEMM convolution, R x R (R = 1 or 3), stride 1, zero padding (R-1)/2, on tcgen05 tensor

@@ -31,6 +31,8 @@ class SnDesc(C.Structure):
 
 i64 = C.c_int64
 PROTOS = {
+    "ssr_profile_start": (C.c_int, []),
+    "ssr_profile_stop": (C.c_int, [vp, vp, i32]),
     "ssr_im2col": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "ssr_col2im": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
     "ssr_axpby": (C.c_int, [vp, i32, f32, vp, i32, f32, vp, i32, i32, vp, i32, i64, i32, vp]),

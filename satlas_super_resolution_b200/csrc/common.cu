@@ -1,6 +1,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <vector>
 #include <stdarg.h>
 #include <string.h>
 
@@ -80,10 +81,63 @@ bool encode_tmap_tiled(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t ran
 const char* last_error();
 int64_t launch_count();
 
+// ------------------------------------------------------------------ per-kernel-class device timing (bench.py roofline)
+static bool g_prof_on = false;
+struct ProfRec { cudaEvent_t a, b; int cls; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t pool_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+bool prof_enabled() { return g_prof_on; }
+void prof_before(int cls, cudaStream_t s) {
+  if (!g_prof_on) return;
+  ProfRec r{pool_event(), pool_event(), cls};
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+}
+void prof_after(cudaStream_t s) {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().b, s);
+}
+
 }  // namespace ssr
 
 extern "C" {
 const char* ssr_last_error(void) { return ssr::last_error(); }
 int ssr_abi_version(void) { return 1; }
 int64_t ssr_launch_count(void) { return ssr::launch_count(); }
+
+int ssr_profile_start(void) {
+  ssr::g_prof.clear();
+  ssr::g_prof_on = true;
+  return SSR_OK;
+}
+// ms[c] / count[c] for c = 0 (ssr_conv_tc), 1 (ssr_wgrad_tc); synchronises the device
+int ssr_profile_stop(double* ms, int64_t* count, int32_t n_classes) {
+  ssr::g_prof_on = false;
+  if (!ssr::check_cuda(cudaDeviceSynchronize(), "profile sync")) return SSR_E_CUDA;
+  for (int i = 0; i < n_classes; ++i) { ms[i] = 0.0; count[i] = 0; }
+  for (auto& r : ssr::g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.cls < n_classes) {
+      ms[r.cls] += t;
+      count[r.cls] += 1;
+    }
+    ssr::g_event_pool.push_back(r.a);
+    ssr::g_event_pool.push_back(r.b);
+  }
+  ssr::g_prof.clear();
+  cudaGetLastError();
+  return SSR_OK;
+}
 }

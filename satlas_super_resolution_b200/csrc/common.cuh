@@ -12,6 +12,9 @@ namespace ssr {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// optional per-launch CUDA-event timing by kernel class (0 = conv_tc, 1 = wgrad_tc), see ssr_profile_start/stop
+void prof_before(int cls, cudaStream_t s);
+void prof_after(cudaStream_t s);
 
 // returns false (and sets the error text) when the launch / previous call failed
 bool check_cuda(cudaError_t e, const char* what);

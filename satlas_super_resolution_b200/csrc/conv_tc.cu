@@ -490,7 +490,9 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
       return SSR_E_CUDA;
     configured[mt] = (size_t)g_smem_optin;
   }
+  prof_before(0, stream);
   kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  prof_after(stream);
   count_launch();
   if (!check_last("conv_tc launch")) return SSR_E_CUDA;
   return SSR_OK;

@@ -285,7 +285,9 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
   }
   const size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024 + 256;
   dim3 grid((unsigned)splits, (unsigned)(mtiles * p.R), (unsigned)n_tiles);
+  prof_before(1, stream);
   wgrad_tc_kernel<<<grid, kWThreads, smem_bytes, stream>>>(tmX, tmY, p);
+  prof_after(stream);
   count_launch();
   return check_last("wgrad_tc launch") ? SSR_OK : SSR_E_CUDA;
 }

@@ -124,7 +124,9 @@ class ESRGANTrainer:
         self.loss_dev = torch.zeros(8, dtype=torch.float32, device=dev)
         self.usm_taps = (C_float_array(gaussian_taps(51, 0)), 51)
         self._io = {}
-        self._graph = None
+        self._graphs = {}
+        self._warm = set()
+        self.use_graph = bool(cfg.get("cuda_graph", False))
         self.log_dict = OrderedDict()
 
     # ------------------------------------------------------------------ data
@@ -224,10 +226,25 @@ class ESRGANTrainer:
         self.opt_d.step(1.0 / self.world, s, from_device=graph_mode)
 
     def optimize_parameters(self, current_iter=1):
-        s = cur_stream()
         do_g = (current_iter % self.net_d_iters == 0) and (current_iter > self.net_d_init_iters)
-        self._step_kernels(self.io, do_g, s)
-        self._log_ready = False
+        key = (id(self.io), do_g)
+        if not self.use_graph or key not in self._warm:
+            # eager: also the mandatory first pass per shape (allocates workspaces, sets kernel attributes)
+            self._step_kernels(self.io, do_g, cur_stream())
+            self._warm.add(key)
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            # capture the whole step (~2.5k launches) once; replays cost one cudaGraphLaunch
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_kernels(self.io, do_g, cur_stream(), graph_mode=True)
+            self._graphs[key] = g
+        if do_g:
+            self.opt_g.push_hyper()
+        self.opt_d.push_hyper()
+        g.replay()
 
     def get_current_log(self):
         """loss scalars (one D2H read, only when asked -- the reference syncs every iteration at :233)"""
