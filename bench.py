@@ -41,6 +41,31 @@ def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
+def log(msg):
+    if os.environ.get("SSR_BENCH_VERBOSE"):
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def usable_cores():
+    """host threads this process may actually use: affinity mask capped by the cgroup CPU quota (os.cpu_count() reports
+    the whole host, and oversubscribing a quota-limited container makes OpenMP spin for minutes)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as fq, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as fp:
+                q, per = int(fq.read()), int(fp.read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -119,7 +144,7 @@ def cpu_step_time(batch, iters, warm, threads):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     batch = 2
     steps = max(1, min(args.steps, 3))
     t = cpu_step_time(batch, steps, 1 if args.warmup > 0 else 0, threads)
@@ -194,9 +219,12 @@ def main():
         return tr.get_current_log()
 
     # ---- warm-up (eager first pass allocates workspaces; the next ones capture + replay the CUDA graph)
+    log("trainer built")
     tr.feed_data(lr_h, hr_h)
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         step_resident()
+        torch.cuda.synchronize()
+        log(f"warm-up step {i} done")
     barrier()
 
     def timed(fn, k):
@@ -217,9 +245,11 @@ def main():
         sampler.start()
     launches0 = lib.ssr_launch_count()
     ms_total = timed(step_resident, args.steps)
+    log(f"resident timing done: {ms_total / args.steps:.2f} ms/step")
     # launches per step: graph replays do not pass through the host entry points, so count one eager step below
     ms_e2e = timed(step_e2e, args.steps)
     sampler.stop_flag = True
+    log(f"e2e timing done: {ms_e2e / args.steps:.2f} ms/step")
 
     # ---- one eager, instrumented step: per-launch CUDA events around the two tensor-core kernels
     tr.use_graph = False
@@ -232,6 +262,7 @@ def main():
     ms_cls = (ctypes.c_double * 2)()
     cnt_cls = (ctypes.c_int64 * 2)()
     L.check(lib.ssr_profile_stop(ms_cls, cnt_cls, 2))
+    log(f"instrumented step: conv_tc {ms_cls[0]:.2f} ms / {cnt_cls[0]} launches, wgrad_tc {ms_cls[1]:.2f} ms / {cnt_cls[1]} launches")
 
     if rank != 0:
         if world > 1:
@@ -268,7 +299,8 @@ def main():
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = usable_cores()
+        log(f"cpu baseline on {threads} threads")
         t = cpu_step_time(2, 2, 1, threads)
         line["cpu_baseline"] = {"value": 2 / t, "unit": "img-pairs/s", "cores": threads, "kind": "port",
                                 "sample": "2 timed optimize_parameters steps of 2 pairs (oracle/step.py, torch fp32 CPU, all host "
