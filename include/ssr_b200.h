@@ -195,6 +195,10 @@ typedef struct ssr_unpack_desc {
 int ssr_wgrad_unpack_batched(const ssr_unpack_desc* descs_device, int32_t n_layers, void* stream);
 /* out[c] += scale * sum_p dy[p*stride + c]   (bias gradient) */
 int ssr_bias_grad(const void* dy_bf16, int32_t dy_pix_stride, int64_t npix, int32_t c, float* out, float scale, void* stream);
+/* grouped: channel c accumulates into outs_device[c / group_ch][c % group_ch] (one launch for the four 32-channel dY slots
+ * of a ResidualDenseBlock) */
+int ssr_bias_grad_groups(const void* dy_bf16, int32_t dy_pix_stride, int64_t npix, int32_t c, int32_t group_ch,
+                         float* const* outs_device, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Training-step kernels (HBM-bound).  Losses accumulate into device scalars the caller zeroes.

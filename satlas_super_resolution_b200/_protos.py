@@ -50,6 +50,7 @@ PROTOS = {
     "ssr_wgrad_tc": (C.c_int, [C.POINTER(WgradArgs), vp]),
     "ssr_wgrad_unpack": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, f32, i32, vp]),
     "ssr_bias_grad": (C.c_int, [vp, i32, C.c_int64, i32, vp, f32, vp]),
+    "ssr_bias_grad_groups": (C.c_int, [vp, i32, C.c_int64, i32, i32, vp, f32, vp]),
     "ssr_ingest_nchw": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
     "ssr_egress_nchw": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, f32, i32, vp, vp]),
     "ssr_upsample_nearest": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),

@@ -378,7 +378,20 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   p.TW = a->w >= 128 ? 128 : round_up(a->w, 8);
   p.TH = 128 / p.TW;
   int mt = a->mt;
-  if (mt == 0) mt = 1;
+  if (mt == 0) {
+    // two stacked M tiles per CTA when one-tile CTAs would spill past a single co-resident wave: the weight tiles
+    // and the halo rows are then shared by 256 pixels (less L2 traffic per MMA) and the grid fits the 148 SMs
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("SSR_CONV_MT");
+      forced = e ? atoi(e) : 0;
+    }
+    const int nt_guess = a->n_tile ? a->n_tile : (a->n_pad <= 128 ? a->n_pad : 128);
+    const long tiles1 = (long)((a->w + p.TW - 1) / p.TW) * ((a->h + p.TH - 1) / p.TH) * a->n_img;
+    mt = 1;
+    if (forced == 1 || forced == 2) mt = forced;
+    else if (a->h >= 2 * p.TH && tiles1 >= 200 && 2 * nt_guess <= 512) mt = 2;
+  }
   SSR_REQUIRE(mt == 1 || mt == 2, "ssr_conv_tc: mt must be 1 or 2");
   p.tiles_x = (a->w + p.TW - 1) / p.TW;
   p.tiles_y = (a->h + mt * p.TH - 1) / (mt * p.TH);

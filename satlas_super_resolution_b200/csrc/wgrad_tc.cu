@@ -15,6 +15,7 @@
 // (/root/reference/ssr/archs/rrdbnet_arch.py:26-30,99-112; discriminator_arch.py:28-40).
 #include "common.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace ssr {
 
@@ -211,6 +212,24 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, int strid
   }
 }
 
+// grouped form: channel c of dy belongs to output tensor outs[c / group_ch], element c % group_ch
+__global__ void bias_grad_groups_kernel(const __nv_bfloat16* __restrict__ dy, int stride, long npix, int C, int group_ch,
+                                        float* const* __restrict__ outs, float scale) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < C)
+    for (long pth = blockIdx.y * 8L + threadIdx.y; pth < npix; pth += (long)gridDim.y * 8) acc += __bfloat162float(dy[pth * stride + c]);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    atomicAdd(outs[c / group_ch] + (c % group_ch), scale * s);
+  }
+}
+
 static int g_w_smem_optin = -1;
 
 }  // namespace ssr
@@ -257,7 +276,12 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
   SSR_REQUIRE(stages >= 1, "ssr_wgrad_tc: stage does not fit shared memory");
   if (stages > 4) stages = 4;
   int units = mtiles * p.R * n_tiles;
-  int splits = a->splits > 0 ? a->splits : (2 * 148 + units - 1) / units;
+  static int target_ctas = -1;
+  if (target_ctas < 0) {
+    const char* e = getenv("SSR_WGRAD_CTAS");
+    target_ctas = e ? atoi(e) : 2 * 148;
+  }
+  int splits = a->splits > 0 ? a->splits : (target_ctas + units - 1) / units;
   if (splits > p.total_tiles) splits = p.total_tiles;
   { int per = (p.total_tiles + splits - 1) / splits; splits = (p.total_tiles + per - 1) / per; }
   p.splits = splits;
@@ -325,4 +349,18 @@ extern "C" int ssr_bias_grad(const void* dy_bf16, int32_t dy_pix_stride, int64_t
                                                                                dy_pix_stride, npix, c, out, scale);
   count_launch();
   return check_last("bias_grad launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_bias_grad_groups(const void* dy_bf16, int32_t dy_pix_stride, int64_t npix, int32_t c, int32_t group_ch,
+                                    float* const* outs_device, float scale, void* stream) {
+  SSR_REQUIRE(dy_bf16 && outs_device && c > 0 && group_ch > 0, "ssr_bias_grad_groups: bad args");
+  dim3 block(32, 8);
+  long slabs = (npix + 8 * 64 - 1) / (8 * 64);
+  if (slabs > 148) slabs = 148;
+  if (slabs < 1) slabs = 1;
+  dim3 grid((unsigned)((c + 31) / 32), (unsigned)slabs);
+  bias_grad_groups_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dy_pix_stride, npix, c, group_ch, outs_device, scale);
+  count_launch();
+  return check_last("bias_grad_groups launch") ? SSR_OK : SSR_E_CUDA;
 }

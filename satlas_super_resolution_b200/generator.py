@@ -221,9 +221,17 @@ class _Workspace:
         def bias_grad(name, dy_ptr, dy_stride, npix, cy, scale=1.0):
             plan.add(lib().ssr_bias_grad, dy_ptr, dy_stride, npix, cy, grads[f"{name}.bias"].data_ptr(), scale)
 
-        def wgrad(name, x_ptr, x_stride, cx, dy_ptr, dy_stride, cy, BB, HH, WW, scale=1.0):
+        def wgrad(name, x_ptr, x_stride, cx, dy_ptr, dy_stride, cy, BB, HH, WW, scale=1.0, bias=True):
             plan_wgrad(plan, wg.args(name, x_ptr, x_stride, cx, dy_ptr, dy_stride, cy, BB, HH, WW, 3, scale))
-            bias_grad(name, dy_ptr, dy_stride, BB * HH * WW, cy, scale)
+            if bias:
+                bias_grad(name, dy_ptr, dy_stride, BB * HH * WW, cy, scale)
+
+        # one table of bias-gradient pointers per dense block: the four 32-channel dY slots of Dg in ONE launch
+        ptr_rows = []
+        for i in range(3 * nb):
+            blk, j = divmod(i, 3)
+            ptr_rows.append([grads[f"body.{blk}.rdb{j + 1}.conv{k}.bias"].data_ptr() for k in range(1, 5)])
+        self._bias_ptrs = torch.tensor(ptr_rows, dtype=torch.int64, device=dev)
 
         # ---- tail: conv_last <- conv_hr <- conv_up_n ... conv_up1
         c = eng.cv["conv_last"]
@@ -300,7 +308,8 @@ class _Workspace:
                                         res2=GO32.data_ptr(), res2_kind=F32, res2_stride=nf, s2=1.0,
                                         out=gO_b.ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_NHWC,
                                         out32_stride=nf))
-                wgrad(f"{pre}.conv{k}", cur.ptr(), cw, nk, dyk, cw, g, B, h, w)
+                wgrad(f"{pre}.conv{k}", cur.ptr(), cw, nk, dyk, cw, g, B, h, w, bias=False)
+            plan.add(lib().ssr_bias_grad_groups, Dg.ptr(nf), cw, B * h * w, 4 * g, g, self._bias_ptrs.data_ptr() + 32 * i, 1.0)
         # ---- conv_first: dY = trunk gradient + the long skip (feat = conv_first + conv_body(...))
         plan.add(lib().ssr_axpby, gO_b.ptr(), nf, 1.0, d_feat.ptr(), nf, 1.0, None, 0, 0, d_first.ptr(), nf, B * h * w, nf)
         wgrad("conv_first", self.in0.ptr(), self.in0.stride, eng.cin_pad, d_first.ptr(), nf, nf, B, h, w)
