@@ -279,7 +279,7 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
   static int target_ctas = -1;
   if (target_ctas < 0) {
     const char* e = getenv("SSR_WGRAD_CTAS");
-    target_ctas = e ? atoi(e) : 2 * 148;
+    target_ctas = e ? atoi(e) : 148;
   }
   int splits = a->splits > 0 ? a->splits : (target_ctas + units - 1) / units;
   if (splits > p.total_tiles) splits = p.total_tiles;
