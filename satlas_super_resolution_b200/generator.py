@@ -69,22 +69,24 @@ class RRDBNetEngine:
             self._ws[key] = ws
         return ws
 
-    def forward(self, x, train=False, stream=None):
+    def forward(self, x, train=False, stream=None, ws=None):
         """x: f32 NCHW cuda tensor [B, num_in_ch, h, w] -> f32 NCHW [B, num_out_ch, scale*h, scale*w] (engine-owned)."""
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
         B, Cc, h, w = x.shape
         assert Cc == self.cin
-        ws = self.workspace(B, h, w, train)
+        if ws is None:
+            ws = self.workspace(B, h, w, train)
         s = stream if stream is not None else cur_stream()
         L.check(lib().ssr_ingest_nchw(x.data_ptr(), L.SSR_F32, ws.in0.ptr(), ws.in0.stride, B, Cc, h, w, self.cin_pad,
                                       1.0, None, None, s))
         ws.fwd.run(s)
         return ws.out
 
-    def backward(self, d_out, B, h, w, stream=None):
+    def backward(self, d_out, B, h, w, stream=None, ws=None):
         """d_out: f32 NCHW gradient of the forward output; accumulates into self.grads (weights and biases)."""
         assert self.wg is not None, "engine built without gradient buffers"
-        ws = self.workspace(B, h, w, True)
+        if ws is None:
+            ws = self.workspace(B, h, w, True)
         s = stream if stream is not None else cur_stream()
         if ws.bwd is None:
             ws.bwd = ws._build_backward(self)

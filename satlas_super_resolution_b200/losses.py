@@ -1,0 +1,127 @@
+"""Registry-facing loss modules with the call shapes the reference step uses
+(/root/reference/ssr/models/ssr_esrgan_model.py:148,154,182,218,224; basicsr L1Loss / GANLoss / PerceptualLoss):
+
+    cri_pix(pred, target) -> scalar
+    cri_perceptual(x, gt) -> (percep | None, style | None)
+    cri_gan(pred, target_is_real: bool, is_disc: bool = False) -> scalar
+
+Each is an autograd Function over kernels of libssr_b200 (loss value + gradient in one pass); CUDA tensors only.
+"""
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import weights
+from .ops import cur_stream, lib
+from .registry import LOSS_REGISTRY, _register
+
+
+class _L1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, weight):
+        pred, target = pred.contiguous().float(), target.contiguous().float()
+        loss = torch.zeros(1, dtype=torch.float32, device=pred.device)
+        grad = torch.empty_like(pred) if pred.requires_grad or torch.is_grad_enabled() else None
+        L.check(lib().ssr_l1_loss(pred.data_ptr(), target.data_ptr(), pred.numel(), weight, loss.data_ptr(),
+                                  grad.data_ptr() if grad is not None else None, 0, cur_stream()))
+        ctx.grad = grad
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return (ctx.grad * g if ctx.grad is not None else None), None, None
+
+
+class L1Loss(nn.Module):
+    """basicsr L1Loss(loss_weight=1.0, reduction='mean')"""
+
+    def __init__(self, loss_weight=1.0, reduction="mean"):
+        super().__init__()
+        if reduction != "mean":
+            raise NotImplementedError("L1Loss: only reduction='mean' (what every shipped config uses) is built")
+        self.loss_weight = loss_weight
+
+    def forward(self, pred, target, weight=None, **kwargs):
+        if weight is not None:
+            raise NotImplementedError("L1Loss: element-wise weights are not built")
+        return _L1Fn.apply(pred, target.detach(), float(self.loss_weight))
+
+
+class _BceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target, weight):
+        x = x.contiguous().float()
+        loss = torch.zeros(1, dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x)
+        L.check(lib().ssr_bce_logits(x.data_ptr(), x.numel(), target, weight, loss.data_ptr(), None, grad.data_ptr(), cur_stream()))
+        ctx.grad = grad
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.grad * g, None, None
+
+
+class GANLoss(nn.Module):
+    """basicsr GANLoss: 'vanilla' = BCEWithLogitsLoss against a constant label map; loss_weight applies when is_disc=False."""
+
+    def __init__(self, gan_type, real_label_val=1.0, fake_label_val=0.0, loss_weight=1.0):
+        super().__init__()
+        if gan_type != "vanilla":
+            raise NotImplementedError(f"GANLoss: gan_type '{gan_type}' is not built (every shipped config uses 'vanilla')")
+        self.gan_type, self.loss_weight = gan_type, loss_weight
+        self.real_label_val, self.fake_label_val = real_label_val, fake_label_val
+
+    def forward(self, input, target_is_real, is_disc=False):
+        label = self.real_label_val if target_is_real else self.fake_label_val
+        return _BceFn.apply(input, float(label), 1.0 if is_disc else float(self.loss_weight))
+
+
+class _PercepFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gt, mod):
+        x, gt = x.contiguous().float(), gt.contiguous().float()
+        loss = torch.zeros(1, dtype=torch.float32, device=x.device)
+        dx = torch.zeros_like(x) if x.requires_grad else None
+        mod.engine(x.device).loss_and_grad(x, gt, loss, dx, cur_stream())
+        ctx.dx = dx
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return (ctx.dx * g if ctx.dx is not None else None), None, None
+
+
+class PerceptualLoss(nn.Module):
+    """basicsr PerceptualLoss(layer_weights, vgg_type='vgg19', use_input_norm, range_norm, perceptual_weight, style_weight=0,
+    criterion='l1').  VGG19 weights: `experiments/pretrained_models/vgg19-dcbb9e9d.pth` when present (the file basicsr looks
+    for), else seeded random weights (offline)."""
+
+    VGG_PATH = "experiments/pretrained_models/vgg19-dcbb9e9d.pth"
+
+    def __init__(self, layer_weights, vgg_type="vgg19", use_input_norm=True, range_norm=False, perceptual_weight=1.0,
+                 style_weight=0.0, criterion="l1", vgg_seed=0):
+        super().__init__()
+        if vgg_type != "vgg19" or criterion != "l1" or style_weight:
+            raise NotImplementedError("PerceptualLoss: only vgg19 / l1 / style_weight=0 (the shipped config) is built")
+        self.layer_weights, self.perceptual_weight = dict(layer_weights), perceptual_weight
+        self.use_input_norm, self.range_norm, self.vgg_seed = use_input_norm, range_norm, vgg_seed
+        self._engine = None
+
+    def engine(self, device):
+        if self._engine is None:
+            import os
+            from .vgg import PerceptualEngine
+            sd = weights.vgg19_state(self.vgg_seed, self.VGG_PATH if os.path.exists(self.VGG_PATH) else None)
+            self._engine = PerceptualEngine({k: v.to(device) for k, v in sd.items()}, self.layer_weights, self.perceptual_weight,
+                                            self.use_input_norm, self.range_norm)
+        return self._engine
+
+    def forward(self, x, gt):
+        if self.perceptual_weight <= 0:
+            return None, None
+        return _PercepFn.apply(x, gt.detach(), self), None
+
+
+for _c in (L1Loss, GANLoss, PerceptualLoss):
+    _register(LOSS_REGISTRY, _c)
