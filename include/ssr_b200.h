@@ -247,8 +247,10 @@ int ssr_u8_to_f32(const void* src, float* dst, int64_t n, float scale, void* str
 /* torch.optim.Adam step (+ basicsr model_ema when ema != NULL) over flat f32 buffers, one launch */
 int ssr_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int32_t step, float ema_decay, float grad_scale,
-                 const float* dev_hyper /* device [lr, 1-b1^t, sqrt(1-b2^t)] overriding lr/step (graph replay), or NULL */,
+                 const float* dev_hyper /* device [lr, 1-b1^t, sqrt(1-b2^t), t, b1, b2] overriding lr/step (graph replay), or NULL */,
                  void* stream);
+/* t += 1 and refresh the two bias corrections in a device-resident hyper block (recorded inside the step's CUDA graph) */
+int ssr_adam_tick(float* hyper_dev, void* stream);
 
 #ifdef __cplusplus
 }

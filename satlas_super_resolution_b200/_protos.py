@@ -46,6 +46,7 @@ PROTOS = {
     "ssr_spectral_norm_bwd": (C.c_int, [vp, i32, vp]),
     "ssr_usm_sharp": (C.c_int, [vp, vp, vp, i32, i32, i32, vp, i32, f32, f32, vp]),
     "ssr_u8_to_f32": (C.c_int, [vp, vp, i64, f32, vp]),
+    "ssr_adam_tick": (C.c_int, [vp, vp]),
     "ssr_adam_ema": (C.c_int, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, f32, vp, vp]),
     "ssr_wgrad_tc": (C.c_int, [C.POINTER(WgradArgs), vp]),
     "ssr_wgrad_unpack": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, f32, i32, vp]),

@@ -98,10 +98,10 @@ class _RRDB(nn.Module):
 
 class _GeneratorFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, anchor, mod):
+    def forward(ctx, x, anchor, mod, grad_mode):
         eng = mod._get_engine()
         B, _, h, w = x.shape
-        need_grad = torch.is_grad_enabled() and anchor.requires_grad
+        need_grad = grad_mode and anchor.requires_grad      # (grad mode is always off inside Function.forward)
         ctx.mod, ctx.shape, ctx.need_grad = mod, (B, h, w), need_grad
         if mod._weights_dirty():
             eng.repack()
@@ -121,7 +121,7 @@ class _GeneratorFn(torch.autograd.Function):
             B, h, w = ctx.shape
             mod._get_engine().backward(d_out.contiguous(), B, h, w, ws=ctx.ws)
             ctx.token.done = True
-        return None, None, None
+        return None, None, None, None
 
 
 class SSR_RRDBNet(_FlatModule):
@@ -200,7 +200,7 @@ class SSR_RRDBNet(_FlatModule):
         if x.requires_grad and torch.is_grad_enabled():
             raise NotImplementedError("SSR_RRDBNet: the gradient w.r.t. the low-res input is never needed on the path and is not built")
         anchor = self._anchor if any(p.requires_grad for p in self.parameters()) else self._anchor.detach()
-        return _GeneratorFn.apply(x.float(), anchor, self)
+        return _GeneratorFn.apply(x.float(), anchor, self, torch.is_grad_enabled())
 
 
 # ======================================================================================= discriminator
@@ -216,10 +216,10 @@ class _SNConv(nn.Module):
 
 class _DiscFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, anchor, mod):
+    def forward(ctx, x, anchor, mod, grad_mode):
         eng = mod._get_engine()
         B, Cc, H, W = x.shape
-        need = torch.is_grad_enabled() and (anchor.requires_grad or x.requires_grad)
+        need = grad_mode and (anchor.requires_grad or x.requires_grad)
         ws, token = mod._acquire(B, H, W) if need else (eng.workspace(B, H, W), None)
         s = cur_stream()
         L.check(lib().ssr_ingest_nchw(x.contiguous().data_ptr(), L.SSR_F32, ws.x_in.ptr(), ws.x_in.stride, B, Cc, H, W,
@@ -243,7 +243,7 @@ class _DiscFn(torch.autograd.Function):
             L.check(lib().ssr_egress_nchw(ws.d_in.ptr(), ws.d_in.stride, dx.data_ptr(), B, Cc, H, W, 1.0, 0, None, cur_stream()))
         if ctx.token is not None:
             ctx.token.done = True
-        return dx, None, None
+        return dx, None, None, None
 
 
 class SSR_UNetDiscriminatorSN(_FlatModule):
@@ -302,7 +302,7 @@ class SSR_UNetDiscriminatorSN(_FlatModule):
         if not x.is_cuda:
             raise RuntimeError("SSR_UNetDiscriminatorSN: the B200 engine has no CPU path (input must be a CUDA tensor)")
         anchor = self._anchor if any(p.requires_grad for p in self.parameters()) else self._anchor.detach()
-        return _DiscFn.apply(x.float(), anchor, self)
+        return _DiscFn.apply(x.float(), anchor, self, torch.is_grad_enabled())
 
 
 _register(ARCH_REGISTRY, SSR_RRDBNet)

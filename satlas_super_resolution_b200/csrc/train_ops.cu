@@ -489,6 +489,17 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
   }
 }
 
+// hyper = [lr, 1 - b1^t, sqrt(1 - b2^t), t, b1, b2]: advance t on the device (CUDA-graph replays cannot take new kernel
+// arguments, and a host-staged copy could be overwritten by a CPU that runs several steps ahead)
+__global__ void adam_tick_kernel(float* __restrict__ hyper) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float t = hyper[3] + 1.f;
+    hyper[3] = t;
+    hyper[1] = 1.f - powf(hyper[4], t);
+    hyper[2] = sqrtf(1.f - powf(hyper[5], t));
+  }
+}
+
 }  // namespace ssr
 
 using namespace ssr;
@@ -649,4 +660,10 @@ extern "C" int ssr_adam_ema(float* p, const float* g, float* m, float* v, float*
   adam_ema_kernel<<<grid_for2(n, 256), 256, 0, STREAM(stream)>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
                                                                  (float)sqrt(bc2), ema_decay, grad_scale, dev_hyper);
   return LAUNCH_OK("adam_ema");
+}
+
+extern "C" int ssr_adam_tick(float* hyper_dev, void* stream) {
+  SSR_REQUIRE(hyper_dev, "ssr_adam_tick: null pointer");
+  adam_tick_kernel<<<1, 32, 0, STREAM(stream)>>>(hyper_dev);
+  return LAUNCH_OK("adam_tick");
 }

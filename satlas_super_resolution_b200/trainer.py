@@ -39,20 +39,26 @@ class FusedAdamState:
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.ema, self.ema_decay = ema, ema_decay
         self.step_count = 0
-        self.hyper_host = torch.zeros(3, dtype=torch.float32).pin_memory() if torch.cuda.is_available() else None
-        self.hyper_dev = torch.zeros(3, dtype=torch.float32, device=params.flat.device)
+        # device-resident [lr, 1-b1^t, sqrt(1-b2^t), t, b1, b2] for CUDA-graph replays (advanced by ssr_adam_tick in-graph)
+        self.hyper_dev = torch.zeros(6, dtype=torch.float32, device=params.flat.device)
+        self._dev_lr = None
 
-    def push_hyper(self):
-        """advance the step counter and stage [lr, 1-b1^t, sqrt(1-b2^t)] for a graph replay"""
+    def sync_device_hyper(self):
+        """make the device block agree with the host state (called before capturing / when lr or the step changed eagerly)"""
+        self.hyper_dev.copy_(torch.tensor([self.lr, 0.0, 0.0, float(self.step_count), self.betas[0], self.betas[1]]))
+        self._dev_lr = self.lr
+
+    def before_replay(self):
         self.step_count += 1
-        t = self.step_count
-        self.hyper_host[0] = self.lr
-        self.hyper_host[1] = 1.0 - self.betas[0] ** t
-        self.hyper_host[2] = math.sqrt(1.0 - self.betas[1] ** t)
-        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
+        if self._dev_lr != self.lr:
+            self.hyper_dev[0:1].fill_(self.lr)
+            self._dev_lr = self.lr
 
     def step(self, grad_scale=1.0, stream=None, from_device=False):
-        if not from_device:
+        s_ = stream if stream is not None else cur_stream()
+        if from_device:
+            L.check(lib().ssr_adam_tick(self.hyper_dev.data_ptr(), s_))
+        else:
             self.step_count += 1
         L.check(lib().ssr_adam_ema(self.p.flat.data_ptr(), self.g.flat.data_ptr(), self.m.flat.data_ptr(),
                                    self.v.flat.data_ptr(), self.ema.flat.data_ptr() if self.ema is not None else None,
@@ -126,6 +132,7 @@ class ESRGANTrainer:
         self._io = {}
         self._graphs = {}
         self._warm = set()
+        self._last_mode = "eager"
         self.use_graph = bool(cfg.get("cuda_graph", False))
         self.log_dict = OrderedDict()
 
@@ -232,6 +239,7 @@ class ESRGANTrainer:
             # eager: also the mandatory first pass per shape (allocates workspaces, sets kernel attributes)
             self._step_kernels(self.io, do_g, cur_stream())
             self._warm.add(key)
+            self._last_mode = "eager"
             return
         g = self._graphs.get(key)
         if g is None:
@@ -241,9 +249,15 @@ class ESRGANTrainer:
             with torch.cuda.graph(g):
                 self._step_kernels(self.io, do_g, cur_stream(), graph_mode=True)
             self._graphs[key] = g
+            self.opt_g.sync_device_hyper()
+            self.opt_d.sync_device_hyper()
+        elif self._last_mode != "graph":
+            self.opt_g.sync_device_hyper()
+            self.opt_d.sync_device_hyper()
+        self._last_mode = "graph"
         if do_g:
-            self.opt_g.push_hyper()
-        self.opt_d.push_hyper()
+            self.opt_g.before_replay()
+        self.opt_d.before_replay()
         g.replay()
 
     def get_current_log(self):
