@@ -137,6 +137,10 @@ int ssr_ingest_nchw(const void* src, int32_t src_kind, void* dst_bf16, int32_t d
 /* NHWC bf16 channel slice -> planar NCHW f32 (dst = or += src*scale) */
 int ssr_egress_nchw(const void* src_bf16, int32_t src_pix_stride, float* dst, int32_t b, int32_t c, int32_t h, int32_t w,
                     float scale, int32_t accumulate, const float* ch_scale /* [c] or NULL */, void* stream);
+/* Inference egress: uint8(clamp(v,0,1)*255) of an f32 NCHW batch, image i pasted at tile (i/grid_cols, i%grid_cols) of an
+ * HWC uint8 canvas -- clamp / transpose / astype(uint8) of ssr/infer.py:61-64 and `stitch` of ssr/utils/infer_utils.py:41-60. */
+int ssr_f32_nchw_to_u8_canvas(const float* src, void* dst_u8, int32_t b, int32_t c, int32_t h, int32_t w, int32_t canvas_w,
+                              int32_t grid_cols, int32_t first_index, void* stream);
 /* F.interpolate(mode='nearest', scale_factor=factor): rrdbnet_arch.py:127-128, ssr_esrgan_model.py:133 */
 int ssr_upsample_nearest(const void* src, int32_t src_pix_stride, void* dst, int32_t dst_pix_stride, int32_t b, int32_t h,
                          int32_t w, int32_t c, int32_t factor, void* stream);

@@ -53,6 +53,7 @@ PROTOS = {
     "ssr_bias_grad": (C.c_int, [vp, i32, C.c_int64, i32, vp, f32, vp]),
     "ssr_bias_grad_groups": (C.c_int, [vp, i32, C.c_int64, i32, i32, vp, f32, vp]),
     "ssr_ingest_nchw": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
+    "ssr_f32_nchw_to_u8_canvas": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "ssr_egress_nchw": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, f32, i32, vp, vp]),
     "ssr_upsample_nearest": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
     "ssr_upsample_nearest_bwd": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]),

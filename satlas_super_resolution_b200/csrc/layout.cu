@@ -73,6 +73,28 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ s
   }
 }
 
+// ---------------------------------------------------------------- inference egress: f32 NCHW -> uint8 HWC canvas
+// out = uint8(clamp(v, 0, 1) * 255) with truncation (np.astype(np.uint8) of ssr/infer.py:61-64), image i of the batch
+// pasted at tile (i / grid_cols, i % grid_cols) of a canvas with `canvas_w` pixels per row (ssr/utils/infer_utils.py:41-60).
+__global__ void f32_nchw_to_u8_canvas_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int B, int C, int H, int W,
+                                             int canvas_w, int grid_cols, int first_index) {
+  const long HW = (long)H * W;
+  const long total = (long)B * HW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / HW;
+    const long hw = i - n * HW;
+    const int y = (int)(hw / W), x = (int)(hw % W);
+    const long idx = n + first_index;
+    const long ty = idx / grid_cols, tx = idx % grid_cols;
+    uint8_t* o = dst + ((ty * H + y) * (long)canvas_w + tx * W + x) * C;
+    for (int c = 0; c < C; ++c) {
+      float v = src[(n * C + c) * HW + hw];
+      v = fminf(fmaxf(v, 0.f), 1.f) * 255.f;
+      o[c] = (uint8_t)v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- nearest upsample (NHWC bf16), factor f
 // out[y, x, :] = in[y / f, x / f, :]   (F.interpolate(mode='nearest'), rrdbnet_arch.py:127-128,
 // ssr_esrgan_model.py:133).  One thread per 16-byte channel vector of an output pixel.
@@ -361,6 +383,16 @@ extern "C" int ssr_egress_nchw(const void* src_bf16, int32_t src_pix_stride, flo
       reinterpret_cast<const __nv_bfloat16*>(src_bf16), src_pix_stride, dst, b, c, h, w, scale, accumulate, ch_scale);
   count_launch();
   return check_last("egress launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_f32_nchw_to_u8_canvas(const float* src, void* dst_u8, int32_t b, int32_t c, int32_t h, int32_t w, int32_t canvas_w,
+                                         int32_t grid_cols, int32_t first_index, void* stream) {
+  SSR_REQUIRE(src && dst_u8 && grid_cols > 0 && canvas_w >= grid_cols * w, "ssr_f32_nchw_to_u8_canvas: bad args");
+  const long total = (long)b * h * w;
+  f32_nchw_to_u8_canvas_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(src, reinterpret_cast<uint8_t*>(dst_u8), b, c, h, w,
+                                                                                canvas_w, grid_cols, first_index);
+  count_launch();
+  return check_last("f32_nchw_to_u8_canvas launch") ? SSR_OK : SSR_E_CUDA;
 }
 
 static int check_vec(const void* a, int sa, const void* b, int sb, int c, const char* who) {

@@ -275,3 +275,18 @@ class WgradSet:
 def plan_wgrad(plan, args):
     plan.keep.append(args)
     plan.calls.append((lib().ssr_wgrad_tc, (C.byref(args),)))
+
+
+def allreduce_sum_(flat, process_group=None):
+    """sum all-reduce of one flat gradient buffer (the averaging 1/world is folded into the fused Adam kernel)"""
+    import torch.distributed as dist
+    if process_group is None and not (dist.is_available() and dist.is_initialized()):
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=process_group)
+    return flat
+
+
+def rank_slice(n_items, rank, world):
+    """contiguous shard of `n_items` independent work items (tiles / chunks) for `rank`: no collective needed"""
+    per = (n_items + world - 1) // world
+    return range(min(n_items, rank * per), min(n_items, (rank + 1) * per))

@@ -13,7 +13,7 @@ import torch
 from . import _lib as L
 from .discriminator import UNetDiscEngine
 from .generator import RRDBNetEngine
-from .ops import FlatBuffer, cur_stream, lib
+from .ops import FlatBuffer, allreduce_sum_, cur_stream, lib
 from .vgg import PerceptualEngine
 
 LOSS_KEYS = ["l_g_pix", "l_g_percep", "l_g_gan", "l_d_real", "out_d_real", "l_d_fake", "out_d_fake"]
@@ -216,7 +216,7 @@ class ESRGANTrainer:
             L.check(lb.ssr_egress_nchw(dws.d_in.ptr(), dws.d_in.stride, d_out.data_ptr(), B, 3, H, W, 1.0, 1, None, s))
             self.G.backward(d_out, B, h, w, s)
             if self.world > 1:
-                torch.distributed.all_reduce(self.ggrad.flat, group=self.pg)
+                allreduce_sum_(self.ggrad.flat, self.pg)
             self.opt_g.step(1.0 / self.world, s, from_device=graph_mode)
         # ---------------- discriminator (:196-228)
         self.dgrad.flat.zero_()
@@ -229,7 +229,7 @@ class ESRGANTrainer:
         L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 0.0, 1.0, lp(5), lp(6), d_logits.data_ptr(), s))
         self.D.backward(dws, d_logits, need_wgrad=True, stream=s)
         if self.world > 1:
-            torch.distributed.all_reduce(self.dgrad.flat, group=self.pg)
+            allreduce_sum_(self.dgrad.flat, self.pg)
         self.opt_d.step(1.0 / self.world, s, from_device=graph_mode)
 
     def optimize_parameters(self, current_iter=1):

@@ -246,7 +246,7 @@ def test_cuda_graph_replay_equals_eager():
     gp, dp, vp = nets.rrdbnet_init(24, 3, num_block=1, seed=1), nets.unet_disc_init(27, seed=2), losses.vgg19_init(seed=3)
     data = _batch(seed=2)
     outs = []
-    for graph in (False, True):
+    for graph in (False, True, False):
         tr = ESRGANTrainer(gp, dp, vp, dict(ema_decay=0.999, lr=1e-4, network_g=dict(num_in_ch=24, num_block=1), cuda_graph=graph))
         grads2 = None
         for it in range(1, 5):
@@ -262,11 +262,17 @@ def test_cuda_graph_replay_equals_eager():
     # the device-side step counter advanced with the host one: t = 4, 1 - 0.9^4, sqrt(1 - 0.99^4)
     h = outs[1][5]
     assert h[3].item() == 4 and abs(h[1].item() - (1 - 0.9 ** 4)) < 1e-6 and abs(h[2].item() - (1 - 0.99 ** 4) ** 0.5) < 1e-6
-    # gradients of the first replayed step equal the eager ones up to atomic-add ordering
+    # Two EAGER runs already differ from each other after a step (f32 atomic-add ordering -> Adam's sign-like first
+    # update at eps-level gradients -> ReLU / L1 kink flips in the next step); the graph run must sit inside that same
+    # run-to-run spread: outs[0], outs[2] = eager twice, outs[1] = graph.
     for k in ("conv_first.weight", "body.0.rdb3.conv5.weight", "conv_last.bias"):
-        assert rel_l2(outs[1][4][k], outs[0][4][k]) < 2e-3, k
+        spread = rel_l2(outs[2][4][k], outs[0][4][k])
+        dev = rel_l2(outs[1][4][k], outs[0][4][k])
+        print(f"  step-2 grad {k}: eager-vs-eager {spread:.3e}  graph-vs-eager {dev:.3e}")
+        assert dev < 3 * spread + 2e-3, k
     for k in ("conv_first.weight", "body.0.rdb3.conv5.weight"):
-        assert rel_l2(outs[1][0][k], outs[0][0][k]) < 1e-3, k
+        spread = rel_l2(outs[2][0][k], outs[0][0][k])
+        assert rel_l2(outs[1][0][k], outs[0][0][k]) < 3 * spread + 1e-4, k
     assert rel_l2(outs[1][1]["conv4.weight_orig"], outs[0][1]["conv4.weight_orig"]) < 1e-3
     for k, v in outs[0][2].items():
         assert abs(outs[1][2][k] - v) < 2e-3 * abs(v) + 2e-4
