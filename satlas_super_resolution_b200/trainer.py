@@ -177,7 +177,12 @@ class ESRGANTrainer:
                                  0.5, 10.0, s))
 
     # ------------------------------------------------------------------ the step
-    def _step_kernels(self, io, do_g, s, graph_mode=False):
+    def _step_phase(self, phase, io, do_g, s, graph_mode=False):
+        """The step in three collective-free phases (so each can be a CUDA graph even when NCCL runs between them):
+        1 = G forward, generator losses, frozen-D pass, G backward          (ssr_esrgan_model.py:136-192)
+        2 = Adam(G)+EMA, D real pass, D fake pass                            (:193-227)
+        3 = Adam(D)                                                          (:228)
+        The G / D gradient all-reduces sit between 1|2 and 2|3."""
         lb = lib()
         lr, gt, gt_usm = io["lr"], io["gt"], io["gt_usm"]
         B, C_lr, h, w = lr.shape
@@ -189,7 +194,6 @@ class ESRGANTrainer:
         loss = self.loss_dev
         lp = lambda i: loss.data_ptr() + 4 * i
         d_out, d_logits = io["d_out"], io["d_logits"]
-        loss.zero_()
         gws = self.G.workspace(B, h, w, True)
         dws = self.D.workspace(B, H, W)
         n_logit = B * H * W
@@ -200,37 +204,46 @@ class ESRGANTrainer:
             L.check(lb.ssr_disc_input(img.data_ptr(), 3, gws.in0.ptr() if cl else None, gws.in0.stride, cl, f, dws.x_in.ptr(),
                                       dws.x_in.stride, B, H, W, s))
 
-        # ---------------- generator (ssr_esrgan_model.py:136-193)
-        self.G.repack(s)
-        out = self.G.forward(lr, train=True, stream=s)
-        self.output = out
-        if do_g:
-            self.ggrad.flat.zero_()
-            L.check(lb.ssr_l1_loss(out.data_ptr(), l1_gt.data_ptr(), n_img, self.pixel_weight, lp(0), d_out.data_ptr(), 0, s))
-            if self.P is not None:
-                self.P.loss_and_grad(out, percep_gt, loss[1:2], d_out, s)
+        if phase == 1:
+            loss.zero_()
+            self.G.repack(s)
+            out = self.G.forward(lr, train=True, stream=s)
+            self.output = out
+            if do_g:
+                self.ggrad.flat.zero_()
+                L.check(lb.ssr_l1_loss(out.data_ptr(), l1_gt.data_ptr(), n_img, self.pixel_weight, lp(0), d_out.data_ptr(), 0, s))
+                if self.P is not None:
+                    self.P.loss_and_grad(out, percep_gt, loss[1:2], d_out, s)
+                disc_in(out)
+                logits = self.D.forward(dws, training=True, stream=s)
+                L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 1.0, self.gan_weight, lp(2), None, d_logits.data_ptr(), s))
+                self.D.backward(dws, d_logits, need_wgrad=False, need_dinput=True, stream=s)
+                L.check(lb.ssr_egress_nchw(dws.d_in.ptr(), dws.d_in.stride, d_out.data_ptr(), B, 3, H, W, 1.0, 1, None, s))
+                self.G.backward(d_out, B, h, w, s)
+        elif phase == 2:
+            out = self.output
+            if do_g:
+                self.opt_g.step(1.0 / self.world, s, from_device=graph_mode)
+            self.dgrad.flat.zero_()
+            disc_in(gan_gt)
+            logits = self.D.forward(dws, training=True, stream=s)
+            L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 1.0, 1.0, lp(3), lp(4), d_logits.data_ptr(), s))
+            self.D.backward(dws, d_logits, need_wgrad=True, stream=s)
             disc_in(out)
             logits = self.D.forward(dws, training=True, stream=s)
-            L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 1.0, self.gan_weight, lp(2), None, d_logits.data_ptr(), s))
-            self.D.backward(dws, d_logits, need_wgrad=False, need_dinput=True, stream=s)
-            L.check(lb.ssr_egress_nchw(dws.d_in.ptr(), dws.d_in.stride, d_out.data_ptr(), B, 3, H, W, 1.0, 1, None, s))
-            self.G.backward(d_out, B, h, w, s)
-            if self.world > 1:
-                allreduce_sum_(self.ggrad.flat, self.pg)
-            self.opt_g.step(1.0 / self.world, s, from_device=graph_mode)
-        # ---------------- discriminator (:196-228)
-        self.dgrad.flat.zero_()
-        disc_in(gan_gt)
-        logits = self.D.forward(dws, training=True, stream=s)
-        L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 1.0, 1.0, lp(3), lp(4), d_logits.data_ptr(), s))
-        self.D.backward(dws, d_logits, need_wgrad=True, stream=s)
-        disc_in(out)
-        logits = self.D.forward(dws, training=True, stream=s)
-        L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 0.0, 1.0, lp(5), lp(6), d_logits.data_ptr(), s))
-        self.D.backward(dws, d_logits, need_wgrad=True, stream=s)
+            L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 0.0, 1.0, lp(5), lp(6), d_logits.data_ptr(), s))
+            self.D.backward(dws, d_logits, need_wgrad=True, stream=s)
+        else:
+            self.opt_d.step(1.0 / self.world, s, from_device=graph_mode)
+
+    def _step_kernels(self, io, do_g, s, graph_mode=False):
+        self._step_phase(1, io, do_g, s, graph_mode)
+        if self.world > 1 and do_g:
+            allreduce_sum_(self.ggrad.flat, self.pg)
+        self._step_phase(2, io, do_g, s, graph_mode)
         if self.world > 1:
             allreduce_sum_(self.dgrad.flat, self.pg)
-        self.opt_d.step(1.0 / self.world, s, from_device=graph_mode)
+        self._step_phase(3, io, do_g, s, graph_mode)
 
     def optimize_parameters(self, current_iter=1):
         do_g = (current_iter % self.net_d_iters == 0) and (current_iter > self.net_d_init_iters)
@@ -241,14 +254,25 @@ class ESRGANTrainer:
             self._warm.add(key)
             self._last_mode = "eager"
             return
-        g = self._graphs.get(key)
-        if g is None:
-            # capture the whole step (~2.5k launches) once; replays cost one cudaGraphLaunch
+        graphs = self._graphs.get(key)
+        if graphs is None:
+            # capture once: the whole step as ONE graph on a single GPU, three graphs around the two NCCL calls otherwise
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._step_kernels(self.io, do_g, cur_stream(), graph_mode=True)
-            self._graphs[key] = g
+            graphs = []
+            if self.world == 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_kernels(self.io, do_g, cur_stream(), graph_mode=True)
+                graphs.append(g)
+            else:
+                pool = None
+                for phase in (1, 2, 3):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool):
+                        self._step_phase(phase, self.io, do_g, cur_stream(), graph_mode=True)
+                    pool = g.pool()
+                    graphs.append(g)
+            self._graphs[key] = graphs
             self.opt_g.sync_device_hyper()
             self.opt_d.sync_device_hyper()
         elif self._last_mode != "graph":
@@ -258,7 +282,15 @@ class ESRGANTrainer:
         if do_g:
             self.opt_g.before_replay()
         self.opt_d.before_replay()
-        g.replay()
+        if self.world == 1:
+            graphs[0].replay()
+        else:
+            graphs[0].replay()
+            if do_g:
+                allreduce_sum_(self.ggrad.flat, self.pg)
+            graphs[1].replay()
+            allreduce_sum_(self.dgrad.flat, self.pg)
+            graphs[2].replay()
 
     def get_current_log(self):
         """loss scalars (one D2H read, only when asked -- the reference syncs every iteration at :233)"""
