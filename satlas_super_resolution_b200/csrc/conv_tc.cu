@@ -181,132 +181,195 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // Work items = (M tile, 16-channel chunk).  Everything that does NOT depend on the accumulator -- bias (staged once in
+    // shared memory), residuals, the derivative mask -- is fetched one item AHEAD, the first one while the MMAs are still
+    // running, so the global-load latency is off the critical path between "accumulator ready" and "tile stored".
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
-    mbar_wait(bar_tmem, 0);
-    tc_fence_after_sync();
+    const int et = (int)threadIdx.x - 64;
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+    const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
+    for (int i = et; i < p.n_tile; i += 128) s_bias[i] = (add_bias && n0 + i < p.cout) ? p.bias[n0 + i] : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int tyy = m / p.TW;
     const int txx = m - tyy * p.TW;
-    const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
-#pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
-      const int y = y0 + mt * p.TH + tyy;
-      const int x = x0 + txx;
-      const bool valid = (tyy < p.TH) && (y < p.H) && (x < p.W);
-      const long pix = ((long)n * p.H + y) * p.W + x;
-#pragma unroll 1
-      for (int cb = 0; cb < p.n_tile; cb += 16) {
-        uint32_t v[16];
-        __syncwarp();
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.n_tile + cb), v);
-        tmem_ld_wait();
-        const int c0 = n0 + cb;
-        if (!valid || c0 >= p.cout) continue;
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        const bool full16 = (c0 + 16 <= p.cout);
-        if (full16) {
-          if (add_bias) {
-            float b[16];
-            load16_f32(p.bias + c0, b);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += b[j];
-          }
-          if (p.act) {
-            const float neg = p.act == 2 ? 0.f : 0.2f;  // 1 = LeakyReLU(0.2), 2 = ReLU
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : neg * f[j];
-          }
-          if (p.s0 != 1.f) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] *= p.s0;
-          }
-          if (p.res1_kind != SSR_NONE && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
-            float r[16];
-            if (p.res1_kind == SSR_BF16)
-              load16_bf16(reinterpret_cast<const __nv_bfloat16*>(p.res1) + pix * p.res1_stride + c0, r);
-            else
-              load16_f32(reinterpret_cast<const float*>(p.res1) + pix * p.res1_stride + c0, r);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s1, r[j], f[j]);
-          }
-          if (p.res2_kind != SSR_NONE) {
-            float r[16];
-            if (p.res2_kind == SSR_BF16)
-              load16_bf16(reinterpret_cast<const __nv_bfloat16*>(p.res2) + pix * p.res2_stride + c0, r);
-            else
-              load16_f32(reinterpret_cast<const float*>(p.res2) + pix * p.res2_stride + c0, r);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s2, r[j], f[j]);
-          }
-          // the f32 output is the UNMASKED value (a running gradient sum); the derivative mask only shapes the bf16 copy
-          if (p.out32_mode == SSR_OUT32_NHWC) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.out32_stride + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC) {
-            float* dst = p.out_f32 + pix * p.out32_stride + c0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(dst + j, f[j]);
-          } else if (p.out32_mode == SSR_OUT32_NCHW) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              p.out_f32[(((long)n * p.cout + c0 + j) * p.H + y) * p.W + x] = f[j];
-          }
-          if (p.mask != nullptr && c0 >= p.mask_lo) {
-            float r[16];
-            load16_bf16(p.mask + pix * p.mask_stride + c0, r);
-            const float neg = p.mask_relu ? 0.f : 0.2f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] *= (r[j] > 0.f ? 1.f : neg);
-          }
-          if (p.out_bf16 != nullptr) {
-            uint4 o0, o1;
-            o0.x = pack_bf16(f[0], f[1]);
-            o0.y = pack_bf16(f[2], f[3]);
-            o0.z = pack_bf16(f[4], f[5]);
-            o0.w = pack_bf16(f[6], f[7]);
-            o1.x = pack_bf16(f[8], f[9]);
-            o1.y = pack_bf16(f[10], f[11]);
-            o1.z = pack_bf16(f[12], f[13]);
-            o1.w = pack_bf16(f[14], f[15]);
-            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.out_stride + c0);
-            dst[0] = o0;
-            dst[1] = o1;
-          }
+    const int x = x0 + txx;
+    const int nchunks = p.n_tile >> 4;
+    const int total = MT * nchunks;
+
+    struct Ops {
+      uint4 r1[4], r2[4], mk[2];
+    };
+    auto item = [&](int i, int& mt, int& c0, int& y, long& pix, bool& live) {
+      mt = i / nchunks;
+      c0 = n0 + (i - mt * nchunks) * 16;
+      y = y0 + mt * p.TH + tyy;
+      pix = ((long)n * p.H + y) * p.W + x;
+      live = (tyy < p.TH) && (y < p.H) && (x < p.W) && (c0 + 16 <= p.cout);
+    };
+    auto prefetch = [&](int i, Ops& o) {
+      int mt, c0, y;
+      long pix;
+      bool live;
+      item(i, mt, c0, y, pix, live);
+      if (!live) return;
+      if (p.res1_kind != SSR_NONE && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
+        if (p.res1_kind == SSR_BF16) {
+          const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res1) + pix * p.res1_stride + c0);
+          o.r1[0] = s4[0];
+          o.r1[1] = s4[1];
         } else {
-          // ragged tail of the channel dimension (cout not a multiple of 16): scalar path
-          for (int j = 0; j < 16; ++j) {
-            const int c = c0 + j;
-            if (c >= p.cout) break;
-            float val = f[j];
-            if (add_bias) val += p.bias[c];
-            if (p.act) val = val > 0.f ? val : (p.act == 2 ? 0.f : 0.2f * val);
-            val *= p.s0;
-            if (p.res1_cmax == 0 || c < p.res1_cmax) {
-              if (p.res1_kind == SSR_BF16)
-                val += p.s1 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res1)[pix * p.res1_stride + c]);
-              else if (p.res1_kind == SSR_F32)
-                val += p.s1 * reinterpret_cast<const float*>(p.res1)[pix * p.res1_stride + c];
-            }
-            if (p.res2_kind == SSR_BF16)
-              val += p.s2 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res2)[pix * p.res2_stride + c]);
-            else if (p.res2_kind == SSR_F32)
-              val += p.s2 * reinterpret_cast<const float*>(p.res2)[pix * p.res2_stride + c];
-            if (p.out32_mode == SSR_OUT32_NHWC)
-              p.out_f32[pix * p.out32_stride + c] = val;
-            else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC)
-              atomicAdd(p.out_f32 + pix * p.out32_stride + c, val);
-            else if (p.out32_mode == SSR_OUT32_NCHW)
-              p.out_f32[(((long)n * p.cout + c) * p.H + y) * p.W + x] = val;
-            if (p.mask != nullptr && c >= p.mask_lo) {
-              const float mv = __bfloat162float(p.mask[pix * p.mask_stride + c]);
-              val *= (mv > 0.f ? 1.f : (p.mask_relu ? 0.f : 0.2f));
-            }
-            if (p.out_bf16 != nullptr) p.out_bf16[pix * p.out_stride + c] = __float2bfloat16(val);
+          const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.res1) + pix * p.res1_stride + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o.r1[j] = s4[j];
+        }
+      }
+      if (p.res2_kind != SSR_NONE) {
+        if (p.res2_kind == SSR_BF16) {
+          const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res2) + pix * p.res2_stride + c0);
+          o.r2[0] = s4[0];
+          o.r2[1] = s4[1];
+        } else {
+          const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.res2) + pix * p.res2_stride + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o.r2[j] = s4[j];
+        }
+      }
+      if (p.mask != nullptr && c0 >= p.mask_lo) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_stride + c0);
+        o.mk[0] = s4[0];
+        o.mk[1] = s4[1];
+      }
+    };
+    auto expand = [&](const uint4* src, int kind, float (&r)[16]) {
+      if (kind == SSR_BF16) {
+        const uint32_t u[8] = {src[0].x, src[0].y, src[0].z, src[0].w, src[1].x, src[1].y, src[1].z, src[1].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          r[2 * j] = bf16_lo(u[j]);
+          r[2 * j + 1] = bf16_hi(u[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          r[4 * j] = __uint_as_float(src[j].x);
+          r[4 * j + 1] = __uint_as_float(src[j].y);
+          r[4 * j + 2] = __uint_as_float(src[j].z);
+          r[4 * j + 3] = __uint_as_float(src[j].w);
+        }
+      }
+    };
+
+    Ops cur, nxt;
+    prefetch(0, nxt);
+    mbar_wait(bar_tmem, 0);
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int i = 0; i < total; ++i) {
+      cur = nxt;
+      if (i + 1 < total) prefetch(i + 1, nxt);
+      int mt, c0, y;
+      long pix;
+      bool live;
+      item(i, mt, c0, y, pix, live);
+      uint32_t v[16];
+      __syncwarp();
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.n_tile + (c0 - n0)), v);
+      tmem_ld_wait();
+      const bool in_img = (tyy < p.TH) && (y < p.H) && (x < p.W);
+      if (!in_img || c0 >= p.cout) continue;
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+      if (live) {
+        if (add_bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] += s_bias[c0 - n0 + j];
+        }
+        if (p.act) {
+          const float neg = p.act == 2 ? 0.f : 0.2f;  // 1 = LeakyReLU(0.2), 2 = ReLU
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : neg * f[j];
+        }
+        if (p.s0 != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] *= p.s0;
+        }
+        if (p.res1_kind != SSR_NONE && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
+          float r[16];
+          expand(cur.r1, p.res1_kind, r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s1, r[j], f[j]);
+        }
+        if (p.res2_kind != SSR_NONE) {
+          float r[16];
+          expand(cur.r2, p.res2_kind, r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s2, r[j], f[j]);
+        }
+        // the f32 output is the UNMASKED value (a running gradient sum); the derivative mask only shapes the bf16 copy
+        if (p.out32_mode == SSR_OUT32_NHWC) {
+          float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.out32_stride + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC) {
+          float* dst = p.out_f32 + pix * p.out32_stride + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + j, f[j]);
+        } else if (p.out32_mode == SSR_OUT32_NCHW) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) p.out_f32[(((long)n * p.cout + c0 + j) * p.H + y) * p.W + x] = f[j];
+        }
+        if (p.mask != nullptr && c0 >= p.mask_lo) {
+          float r[16];
+          expand(cur.mk, SSR_BF16, r);
+          const float neg = p.mask_relu ? 0.f : 0.2f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] *= (r[j] > 0.f ? 1.f : neg);
+        }
+        if (p.out_bf16 != nullptr) {
+          uint4 o0, o1;
+          o0.x = pack_bf16(f[0], f[1]);
+          o0.y = pack_bf16(f[2], f[3]);
+          o0.z = pack_bf16(f[4], f[5]);
+          o0.w = pack_bf16(f[6], f[7]);
+          o1.x = pack_bf16(f[8], f[9]);
+          o1.y = pack_bf16(f[10], f[11]);
+          o1.z = pack_bf16(f[12], f[13]);
+          o1.w = pack_bf16(f[14], f[15]);
+          uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.out_stride + c0);
+          dst[0] = o0;
+          dst[1] = o1;
+        }
+      } else {
+        // ragged tail of the channel dimension (cout not a multiple of 16): scalar path
+        for (int j = 0; j < 16; ++j) {
+          const int c = c0 + j;
+          if (c >= p.cout) break;
+          float val = f[j] + s_bias[c - n0];
+          if (p.act) val = val > 0.f ? val : (p.act == 2 ? 0.f : 0.2f * val);
+          val *= p.s0;
+          if (p.res1_cmax == 0 || c < p.res1_cmax) {
+            if (p.res1_kind == SSR_BF16)
+              val += p.s1 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res1)[pix * p.res1_stride + c]);
+            else if (p.res1_kind == SSR_F32)
+              val += p.s1 * reinterpret_cast<const float*>(p.res1)[pix * p.res1_stride + c];
           }
+          if (p.res2_kind == SSR_BF16)
+            val += p.s2 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res2)[pix * p.res2_stride + c]);
+          else if (p.res2_kind == SSR_F32)
+            val += p.s2 * reinterpret_cast<const float*>(p.res2)[pix * p.res2_stride + c];
+          if (p.out32_mode == SSR_OUT32_NHWC)
+            p.out_f32[pix * p.out32_stride + c] = val;
+          else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC)
+            atomicAdd(p.out_f32 + pix * p.out32_stride + c, val);
+          else if (p.out32_mode == SSR_OUT32_NCHW)
+            p.out_f32[(((long)n * p.cout + c) * p.H + y) * p.W + x] = val;
+          if (p.mask != nullptr && c >= p.mask_lo) {
+            const float mv = __bfloat162float(p.mask[pix * p.mask_stride + c]);
+            val *= (mv > 0.f ? 1.f : (p.mask_relu ? 0.f : 0.2f));
+          }
+          if (p.out_bf16 != nullptr) p.out_bf16[pix * p.out_stride + c] = __float2bfloat16(val);
         }
       }
     }
@@ -423,7 +486,7 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   p.b_bytes = (uint32_t)(p.R * p.n_tile * 128);
   const uint32_t stage_bytes = p.a_alloc + p.b_bytes;
   const int iters_max = ((p.chunks + p.splits - 1) / p.splits) * p.R;
-  const int budget = g_smem_optin - 1024 - 256;
+  const int budget = g_smem_optin - 1024 - 256 - 1024;
   int stages = budget / (int)stage_bytes;
   SSR_REQUIRE(stages >= 1, "ssr_conv_tc: stage of %u bytes does not fit shared memory", stage_bytes);
   // prefer two co-resident CTAs per SM when that still leaves a >= 3 deep pipeline
@@ -493,7 +556,7 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
       return SSR_E_CUDA;
   }
 
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.n_img), (unsigned)(p.n_pad / p.n_tile), (unsigned)p.splits);
   auto kern = mt == 1 ? conv_tc_kernel<1> : conv_tc_kernel<2>;
   static size_t configured[3] = {0, 0, 0};
