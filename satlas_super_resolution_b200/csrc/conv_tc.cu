@@ -75,7 +75,7 @@ __device__ __forceinline__ void load16_f32(const float* p, float (&f)[16]) {
   }
 }
 
-template <int MT>
+template <int MT, int R>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcK p) {
@@ -106,7 +106,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int per = (p.chunks + p.splits - 1) / p.splits;
   const int c_begin = blockIdx.z * per;
   const int c_end = min(p.chunks, c_begin + per);
-  const int iters = (c_end - c_begin) * p.R;
+  const int iters = (c_end - c_begin) * R;
   if (iters <= 0) return;
 
   if (warp == 0) {
@@ -130,54 +130,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int c = c_begin + it / p.R;
-        const int kx = it % p.R;
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&bar_empty[s], ph ^ 1);
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+    for (int it = 0; it < iters; ++it) {
+      const int c = c_begin + it / R;
+      const int kx = it - (it / R) * R;
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(&bar_empty[s], ph ^ 1);
+      if (elect_one()) {
         uint8_t* a_dst = smem + (size_t)s * stage_bytes;
         uint8_t* b_dst = a_dst + p.a_alloc;
         mbar_expect_tx(&bar_full[s], p.a_box_bytes + p.b_bytes);
         tma_load_4d(a_dst, &tmA, &bar_full[s], c * 64, x0 + kx - p.pad, y0 - p.pad, n);
-        for (int ky = 0; ky < p.R; ++ky)
-          tma_load_2d(b_dst + (size_t)ky * p.n_tile * 128, &tmB, &bar_full[s], 0,
-                      ((c * p.R + kx) * p.R + ky) * p.n_pad + n0);
+#pragma unroll
+        for (int ky = 0; ky < R; ++ky)
+          tma_load_2d(b_dst + (size_t)ky * p.n_tile * 128, &tmB, &bar_full[s], 0, ((c * R + kx) * R + ky) * p.n_pad + n0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.n_tile);
-      uint32_t acc[MT];
-#pragma unroll
-      for (int m = 0; m < MT; ++m) acc[m] = 0;
-      for (int it = 0; it < iters; ++it) {
-        const int c = c_begin + it / p.R;
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&bar_full[s], ph);
-        tc_fence_after_sync();
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    // Descriptors differ only in their 14-bit start-address field: build one per stage, then add constant offsets.
+    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.n_tile);
+    const uint32_t a_tap = (uint32_t)(p.TW * 128) >> 4;        // one tile row down  (descriptor address units of 16 B)
+    const uint32_t a_mt = (uint32_t)(p.TH * p.TW * 128) >> 4;  // next stacked M tile
+    const uint32_t b_tap = (uint32_t)(p.n_tile * 128) >> 4;    // next vertical tap's weight tile
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+      const int c = c_begin + it / R;
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(&bar_full[s], ph);
+      tc_fence_after_sync();
+      if (elect_one()) {
         const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_base = a_base + p.a_alloc;
+        const uint64_t da0 = umma_desc_k128(a_base);
+        const uint64_t db0 = umma_desc_k128(a_base + p.a_alloc);
         const int ks = min(4, (p.cin - c * 64) >> 4);
+        if (ks == 4) {
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          for (int ky = 0; ky < p.R; ++ky) {
-            const uint32_t a_row = a_base + (uint32_t)((m * p.TH + ky) * p.TW + p.dbg_aoff) * 128u;
-            const uint32_t b_row = b_base + (uint32_t)(ky * p.n_tile) * 128u;
-            for (int k = 0; k < ks; ++k) {
-              umma_bf16_ss(tmem_base + (uint32_t)(m * p.n_tile), umma_desc_k128(a_row + k * 32),
-                           umma_desc_k128(b_row + k * 32), idesc, acc[m]);
-              acc[m] = 1;
+          for (int m = 0; m < MT; ++m) {
+#pragma unroll
+            for (int ky = 0; ky < R; ++ky) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_ss(tmem_base + (uint32_t)(m * p.n_tile), da0 + (m * a_mt + ky * a_tap + 2 * k),
+                             db0 + (ky * b_tap + 2 * k), idesc, (ky == 0 && k == 0) ? acc : 1u);
+              }
             }
           }
+        } else {
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            for (int ky = 0; ky < R; ++ky)
+              for (int k = 0; k < ks; ++k)
+                umma_bf16_ss(tmem_base + (uint32_t)(m * p.n_tile), da0 + (m * a_mt + ky * a_tap + 2 * k),
+                             db0 + (ky * b_tap + 2 * k), idesc, (ky == 0 && k == 0) ? acc : 1u);
         }
-        umma_commit(&bar_empty[s]);  // frees this smem stage once the MMAs above have read it
+        umma_commit_raw(&bar_empty[s]);  // frees this smem stage once the MMAs above have read it
+        if (it == iters - 1) umma_commit_raw(bar_tmem);  // accumulators complete
       }
-      umma_commit(bar_tmem);  // accumulators complete
+      __syncwarp();
+      acc = 1;
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -558,13 +572,14 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
 
   const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.n_img), (unsigned)(p.n_pad / p.n_tile), (unsigned)p.splits);
-  auto kern = mt == 1 ? conv_tc_kernel<1> : conv_tc_kernel<2>;
-  static size_t configured[3] = {0, 0, 0};
-  if (configured[mt] < smem_bytes) {
+  auto kern = mt == 1 ? (p.R == 3 ? conv_tc_kernel<1, 3> : conv_tc_kernel<1, 1>) : (p.R == 3 ? conv_tc_kernel<2, 3> : conv_tc_kernel<2, 1>);
+  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+  const int cfg_idx = mt * 2 + (p.R == 3 ? 1 : 0);
+  if (configured[cfg_idx] < smem_bytes) {
     if (!check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin),
                     "cudaFuncSetAttribute(conv_tc)"))
       return SSR_E_CUDA;
-    configured[mt] = (size_t)g_smem_optin;
+    configured[cfg_idx] = (size_t)g_smem_optin;
   }
   prof_before(0, stream);
   kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);

@@ -120,6 +120,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                    smem_u32(bar))
                : "memory");
 }
+// same, for callers that already run on exactly one (elected) thread
+__device__ __forceinline__ void umma_commit_raw(uint64_t* bar) { umma_commit(bar); }
 // 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (thread t <-> lane t).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(

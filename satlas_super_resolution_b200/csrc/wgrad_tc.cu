@@ -31,6 +31,7 @@ struct WgradK {
 
 static constexpr int kWThreads = 192;
 
+template <int R>
 __global__ void __launch_bounds__(kWThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const WgradK p) {
   extern __shared__ uint8_t smem_raw[];
@@ -43,8 +44,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int mtile = blockIdx.y / p.R;
-  const int kx = blockIdx.y % p.R;
+  const int mtile = blockIdx.y / R;
+  const int kx = blockIdx.y % R;
   const int n0 = blockIdx.z * p.n_tile;
   const int per = (p.total_tiles + p.splits - 1) / p.splits;
   const int t_begin = blockIdx.x * per;
@@ -75,51 +76,64 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        int t = t_begin + it;
-        const int tx = t % p.tiles_x;
-        t /= p.tiles_x;
-        const int ty = t % p.tiles_y;
-        const int n = t / p.tiles_y;
-        const int x0 = tx * p.TW, y0 = ty * p.TH;
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&bar_empty[s], ph ^ 1);
+    // TMA producer: whole warp converged, one elected lane issues
+    for (int it = 0; it < iters; ++it) {
+      int t = t_begin + it;
+      const int tx = t % p.tiles_x;
+      t /= p.tiles_x;
+      const int ty = t % p.tiles_y;
+      const int n = t / p.tiles_y;
+      const int x0 = tx * p.TW, y0 = ty * p.TH;
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(&bar_empty[s], ph ^ 1);
+      if (elect_one()) {
         uint8_t* xs = smem + (size_t)s * p.stage_bytes;
         uint8_t* ys = xs + x_bytes;
         mbar_expect_tx(&bar_full[s], nchunks * p.x_chunk_bytes + p.y_blocks * p.y_blk_bytes);
         for (int ch = 0; ch < nchunks; ++ch)
-          tma_load_4d(xs + (size_t)ch * p.x_chunk_bytes, &tmX, &bar_full[s], mtile * 128 + ch * 64, x0 + kx - p.pad,
-                      y0 - p.pad, n);
+          tma_load_4d(xs + (size_t)ch * p.x_chunk_bytes, &tmX, &bar_full[s], mtile * 128 + ch * 64, x0 + kx - p.pad, y0 - p.pad, n);
         for (int yb = 0; yb < p.y_blocks; ++yb)
           tma_load_4d(ys + (size_t)yb * p.y_blk_bytes, &tmY, &bar_full[s], n0 + yb * 64, x0, y0, n);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128u, (uint32_t)p.n_tile, 1u, 1u);
-      const uint32_t y_layout = p.y_rowbytes == 128 ? 2u : 4u;
-      uint32_t acc = 0;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&bar_full[s], ph);
-        tc_fence_after_sync();
+    // MMA issuer: descriptors differ only in the 14-bit start-address field -> one per stage + constant offsets
+    const uint32_t idesc = umma_idesc_bf16(128u, (uint32_t)p.n_tile, 1u, 1u);
+    const uint32_t y_layout = p.y_rowbytes == 128 ? 2u : 4u;
+    const uint32_t a_tap = (uint32_t)(p.TW * 128) >> 4;         // one tile row down
+    const uint32_t a_k = (16u * 128u) >> 4;                      // next 16 pixels of K
+    const uint32_t b_k = (uint32_t)(16 * p.y_rowbytes) >> 4;
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(&bar_full[s], ph);
+      tc_fence_after_sync();
+      if (elect_one()) {
         const uint32_t xs = smem_u32(smem + (size_t)s * p.stage_bytes);
-        const uint32_t ys = xs + x_bytes;
-        for (int ky = 0; ky < p.R; ++ky) {
-          for (int ks = 0; ks < p.ksteps; ++ks) {
-            const uint64_t da = umma_desc(xs + (uint32_t)(ky * p.TW + ks * 16) * 128u, p.x_chunk_bytes, 1024u, 2u);
-            const uint64_t db = umma_desc(ys + (uint32_t)(ks * 16 * p.y_rowbytes), p.y_blk_bytes,
-                                          8u * (uint32_t)p.y_rowbytes, y_layout);
-            umma_bf16_ss(tmem_base + (uint32_t)(ky * p.n_tile), da, db, idesc, (acc | (uint32_t)ks) ? 1u : 0u);
+        const uint64_t da0 = umma_desc(xs, p.x_chunk_bytes, 1024u, 2u);
+        const uint64_t db0 = umma_desc(xs + x_bytes, p.y_blk_bytes, 8u * (uint32_t)p.y_rowbytes, y_layout);
+        if (p.ksteps == 8) {
+#pragma unroll
+          for (int ky = 0; ky < R; ++ky) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16_ss(tmem_base + (uint32_t)(ky * p.n_tile), da0 + (ky * a_tap + ks * a_k), db0 + ks * b_k, idesc,
+                           ks == 0 ? acc : 1u);
           }
+        } else {
+          for (int ky = 0; ky < R; ++ky)
+            for (int ks = 0; ks < p.ksteps; ++ks)
+              umma_bf16_ss(tmem_base + (uint32_t)(ky * p.n_tile), da0 + (ky * a_tap + ks * a_k), db0 + ks * b_k, idesc,
+                           ks == 0 ? acc : 1u);
         }
-        acc = 1;
         umma_commit(&bar_empty[s]);
+        if (it == iters - 1) umma_commit(bar_tmem);
       }
-      umma_commit(bar_tmem);
+      __syncwarp();
+      acc = 1;
     }
   } else {
     const int q = warp & 3;
@@ -129,8 +143,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_wait(bar_tmem, 0);
     tc_fence_after_sync();
 #pragma unroll 1
-    for (int ky = 0; ky < p.R; ++ky) {
-      float* dst = p.out + ((long)(ky * p.R + kx) * p.cx_rows + cxi) * p.out_stride + n0;
+    for (int ky = 0; ky < R; ++ky) {
+      float* dst = p.out + ((long)(ky * R + kx) * p.cx_rows + cxi) * p.out_stride + n0;
 #pragma unroll 1
       for (int cb = 0; cb < p.n_tile; cb += 16) {
         uint32_t v[16];
@@ -249,7 +263,9 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
     if (!check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return SSR_E_CUDA;
     if (!check_cuda(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev), "smem attr")) return SSR_E_CUDA;
     g_w_smem_optin = v;
-    if (!check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v), "cudaFuncSetAttribute(wgrad)"))
+    if (!check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v), "cudaFuncSetAttribute(wgrad)"))
+      return SSR_E_CUDA;
+    if (!check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v), "cudaFuncSetAttribute(wgrad)"))
       return SSR_E_CUDA;
   }
   WgradK p{};
@@ -310,7 +326,10 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
   const size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024 + 256;
   dim3 grid((unsigned)splits, (unsigned)(mtiles * p.R), (unsigned)n_tiles);
   prof_before(1, stream);
-  wgrad_tc_kernel<<<grid, kWThreads, smem_bytes, stream>>>(tmX, tmY, p);
+  if (p.R == 3)
+    wgrad_tc_kernel<3><<<grid, kWThreads, smem_bytes, stream>>>(tmX, tmY, p);
+  else
+    wgrad_tc_kernel<1><<<grid, kWThreads, smem_bytes, stream>>>(tmX, tmY, p);
   prof_after(stream);
   count_launch();
   return check_last("wgrad_tc launch") ? SSR_OK : SSR_E_CUDA;
