@@ -4,6 +4,7 @@
 #include <vector>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace ssr {
 
@@ -99,6 +100,15 @@ static cudaEvent_t pool_event() {
 }
 
 bool prof_enabled() { return g_prof_on; }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSR_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 void prof_before(int cls, cudaStream_t s) {
   if (!g_prof_on) return;
   ProfRec r{pool_event(), pool_event(), cls};

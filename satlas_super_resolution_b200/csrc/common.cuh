@@ -25,6 +25,9 @@ bool encode_tmap_tiled(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t ran
                        const uint64_t* dims, const uint64_t* strides_bytes /* rank-1 */,
                        const uint32_t* box, CUtensorMapSwizzle swizzle);
 
+// true unless SSR_PDL=0: tensor-core kernels are launched with programmatic stream serialization
+bool pdl_enabled();
+
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -108,6 +108,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int c_end = min(p.chunks, c_begin + per);
   const int iters = (c_end - c_begin) * R;
   if (iters <= 0) return;
+  griddep_launch_dependents();  // let the next kernel's prologue overlap this kernel (it still waits for our completion)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -128,6 +129,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // everything above touched only this CTA's smem / TMEM; global memory of earlier kernels is read below
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
@@ -582,7 +584,19 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
     configured[cfg_idx] = (size_t)g_smem_optin;
   }
   prof_before(0, stream);
-  kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    if (!check_cuda(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p), "conv_tc launch")) return SSR_E_CUDA;
+  }
   prof_after(stream);
   count_launch();
   if (!check_last("conv_tc launch")) return SSR_E_CUDA;

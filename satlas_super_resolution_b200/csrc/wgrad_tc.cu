@@ -52,6 +52,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int t_end = min(p.total_tiles, t_begin + per);
   const int iters = t_end - t_begin;
   if (iters <= 0) return;
+  griddep_launch_dependents();
   const int nchunks = min(2, (p.cx - mtile * 128 + 63) / 64);
   const uint32_t x_bytes = 2 * p.x_chunk_bytes;
 
@@ -74,6 +75,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
 
   if (warp == 0) {
     // TMA producer: whole warp converged, one elected lane issues
@@ -326,10 +328,20 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
   const size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024 + 256;
   dim3 grid((unsigned)splits, (unsigned)(mtiles * p.R), (unsigned)n_tiles);
   prof_before(1, stream);
-  if (p.R == 3)
-    wgrad_tc_kernel<3><<<grid, kWThreads, smem_bytes, stream>>>(tmX, tmY, p);
-  else
-    wgrad_tc_kernel<1><<<grid, kWThreads, smem_bytes, stream>>>(tmX, tmY, p);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kWThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t e = p.R == 3 ? cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<3>, tmX, tmY, p) : cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<1>, tmX, tmY, p);
+    if (!check_cuda(e, "wgrad_tc launch")) return SSR_E_CUDA;
+  }
   prof_after(stream);
   count_launch();
   return check_last("wgrad_tc launch") ? SSR_OK : SSR_E_CUDA;
