@@ -41,10 +41,11 @@ struct ConvTcK {
   int out_stride;
   float* out_f32;
   int out32_mode, out32_stride;
+  int dbg_times; // print per-phase globaltimer stamps of CTA 0 (SSR_DBG_TIMES=1)
   int dbg_aoff;  // experiment: extra row offset (x128 B) of the A descriptor, see scripts/probe_swizzle.py
 };
 
-static constexpr int kThreads = 192;
+static constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
@@ -75,10 +76,17 @@ __device__ __forceinline__ void load16_f32(const float* p, float (&f)[16]) {
   }
 }
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <int MT, int R>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcK p) {
+  const unsigned long long t_start = p.dbg_times ? gtime() : 0ull;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -129,7 +137,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const unsigned long long t_prol = p.dbg_times ? gtime() : 0ull;
   griddep_wait();  // everything above touched only this CTA's smem / TMEM; global memory of earlier kernels is read below
+  const unsigned long long t_dep = p.dbg_times ? gtime() : 0ull;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
@@ -196,40 +206,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       acc = 1;
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    // Work items = (M tile, 16-channel chunk).  Everything that does NOT depend on the accumulator -- bias (staged once in
-    // shared memory), residuals, the derivative mask -- is fetched one item AHEAD, the first one while the MMAs are still
-    // running, so the global-load latency is off the critical path between "accumulator ready" and "tile stored".
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9: two warps per TMEM lane quarter) =====================
+    // Work items = (M tile, 16-channel chunk); the two warps of a lane quarter take alternate chunks.  Operands that do NOT
+    // depend on the accumulator -- bias (staged once in shared memory), residuals, the derivative mask -- are fetched for the
+    // first item while the MMAs are still running and for later items before the TMEM load is issued.
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // 0: even chunks, 1: odd chunks
     const int m = q * 32 + lane;
     const int et = (int)threadIdx.x - 64;
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
     const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
-    for (int i = et; i < p.n_tile; i += 128) s_bias[i] = (add_bias && n0 + i < p.cout) ? p.bias[n0 + i] : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int i = et; i < p.n_tile; i += kThreads - 64) s_bias[i] = (add_bias && n0 + i < p.cout) ? p.bias[n0 + i] : 0.f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const int tyy = m / p.TW;
     const int txx = m - tyy * p.TW;
     const int x = x0 + txx;
     const int nchunks = p.n_tile >> 4;
-    const int total = MT * nchunks;
+    int ys[MT];
+    long pixs[MT];
+    bool oks[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      ys[mt] = y0 + mt * p.TH + tyy;
+      pixs[mt] = ((long)n * p.H + ys[mt]) * p.W + x;
+      oks[mt] = (tyy < p.TH) && (ys[mt] < p.H) && (x < p.W);
+    }
+    const bool use_r1 = p.res1_kind != SSR_NONE, use_r2 = p.res2_kind != SSR_NONE, use_mk = p.mask != nullptr;
 
     struct Ops {
       uint4 r1[4], r2[4], mk[2];
     };
-    auto item = [&](int i, int& mt, int& c0, int& y, long& pix, bool& live) {
-      mt = i / nchunks;
-      c0 = n0 + (i - mt * nchunks) * 16;
-      y = y0 + mt * p.TH + tyy;
-      pix = ((long)n * p.H + y) * p.W + x;
-      live = (tyy < p.TH) && (y < p.H) && (x < p.W) && (c0 + 16 <= p.cout);
-    };
-    auto prefetch = [&](int i, Ops& o) {
-      int mt, c0, y;
-      long pix;
-      bool live;
-      item(i, mt, c0, y, pix, live);
-      if (!live) return;
-      if (p.res1_kind != SSR_NONE && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
+    auto fetch = [&](long pix, int c0, Ops& o) {
+      if (use_r1 && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
         if (p.res1_kind == SSR_BF16) {
           const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res1) + pix * p.res1_stride + c0);
           o.r1[0] = s4[0];
@@ -240,7 +248,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 4; ++j) o.r1[j] = s4[j];
         }
       }
-      if (p.res2_kind != SSR_NONE) {
+      if (use_r2) {
         if (p.res2_kind == SSR_BF16) {
           const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res2) + pix * p.res2_stride + c0);
           o.r2[0] = s4[0];
@@ -251,7 +259,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 4; ++j) o.r2[j] = s4[j];
         }
       }
-      if (p.mask != nullptr && c0 >= p.mask_lo) {
+      if (use_mk && c0 >= p.mask_lo) {
         const uint4* s4 = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_stride + c0);
         o.mk[0] = s4[0];
         o.mk[1] = s4[1];
@@ -276,118 +284,134 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     };
 
-    Ops cur, nxt;
-    prefetch(0, nxt);
+    Ops o;
+    bool first = true;
+    if (half < nchunks && oks[0] && n0 + half * 16 + 16 <= p.cout) fetch(pixs[0], n0 + half * 16, o);   // overlaps the MMAs
     mbar_wait(bar_tmem, 0);
     tc_fence_after_sync();
+    const unsigned long long t_acc = p.dbg_times ? gtime() : 0ull;
+    unsigned long long t_s1 = 0, t_s2 = 0, t_s3 = 0;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int y = ys[mt];
+      const long pix = pixs[mt];
+      const bool in_img = oks[mt];
 #pragma unroll 1
-    for (int i = 0; i < total; ++i) {
-      cur = nxt;
-      if (i + 1 < total) prefetch(i + 1, nxt);
-      int mt, c0, y;
-      long pix;
-      bool live;
-      item(i, mt, c0, y, pix, live);
-      uint32_t v[16];
-      __syncwarp();
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.n_tile + (c0 - n0)), v);
-      tmem_ld_wait();
-      const bool in_img = (tyy < p.TH) && (y < p.H) && (x < p.W);
-      if (!in_img || c0 >= p.cout) continue;
-      float f[16];
+      for (int ci = half; ci < nchunks; ci += 2) {
+        const int c0 = n0 + ci * 16;
+        const bool live = in_img && (c0 + 16 <= p.cout);
+        if (!first && live) fetch(pix, c0, o);
+        first = false;
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.n_tile + ci * 16), v);
+        tmem_ld_wait();
+        if (p.dbg_times && t_s1 == 0) t_s1 = gtime();
+        if (!in_img || c0 >= p.cout) continue;
+        float f[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-      if (live) {
-        if (add_bias) {
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (live) {
+          if (add_bias) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] += s_bias[c0 - n0 + j];
-        }
-        if (p.act) {
-          const float neg = p.act == 2 ? 0.f : 0.2f;  // 1 = LeakyReLU(0.2), 2 = ReLU
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : neg * f[j];
-        }
-        if (p.s0 != 1.f) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] *= p.s0;
-        }
-        if (p.res1_kind != SSR_NONE && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
-          float r[16];
-          expand(cur.r1, p.res1_kind, r);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s1, r[j], f[j]);
-        }
-        if (p.res2_kind != SSR_NONE) {
-          float r[16];
-          expand(cur.r2, p.res2_kind, r);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s2, r[j], f[j]);
-        }
-        // the f32 output is the UNMASKED value (a running gradient sum); the derivative mask only shapes the bf16 copy
-        if (p.out32_mode == SSR_OUT32_NHWC) {
-          float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.out32_stride + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC) {
-          float* dst = p.out_f32 + pix * p.out32_stride + c0;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + j, f[j]);
-        } else if (p.out32_mode == SSR_OUT32_NCHW) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) p.out_f32[(((long)n * p.cout + c0 + j) * p.H + y) * p.W + x] = f[j];
-        }
-        if (p.mask != nullptr && c0 >= p.mask_lo) {
-          float r[16];
-          expand(cur.mk, SSR_BF16, r);
-          const float neg = p.mask_relu ? 0.f : 0.2f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] *= (r[j] > 0.f ? 1.f : neg);
-        }
-        if (p.out_bf16 != nullptr) {
-          uint4 o0, o1;
-          o0.x = pack_bf16(f[0], f[1]);
-          o0.y = pack_bf16(f[2], f[3]);
-          o0.z = pack_bf16(f[4], f[5]);
-          o0.w = pack_bf16(f[6], f[7]);
-          o1.x = pack_bf16(f[8], f[9]);
-          o1.y = pack_bf16(f[10], f[11]);
-          o1.z = pack_bf16(f[12], f[13]);
-          o1.w = pack_bf16(f[14], f[15]);
-          uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.out_stride + c0);
-          dst[0] = o0;
-          dst[1] = o1;
-        }
-      } else {
-        // ragged tail of the channel dimension (cout not a multiple of 16): scalar path
-        for (int j = 0; j < 16; ++j) {
-          const int c = c0 + j;
-          if (c >= p.cout) break;
-          float val = f[j] + s_bias[c - n0];
-          if (p.act) val = val > 0.f ? val : (p.act == 2 ? 0.f : 0.2f * val);
-          val *= p.s0;
-          if (p.res1_cmax == 0 || c < p.res1_cmax) {
-            if (p.res1_kind == SSR_BF16)
-              val += p.s1 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res1)[pix * p.res1_stride + c]);
-            else if (p.res1_kind == SSR_F32)
-              val += p.s1 * reinterpret_cast<const float*>(p.res1)[pix * p.res1_stride + c];
+            for (int j = 0; j < 16; ++j) f[j] += s_bias[ci * 16 + j];
           }
-          if (p.res2_kind == SSR_BF16)
-            val += p.s2 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res2)[pix * p.res2_stride + c]);
-          else if (p.res2_kind == SSR_F32)
-            val += p.s2 * reinterpret_cast<const float*>(p.res2)[pix * p.res2_stride + c];
-          if (p.out32_mode == SSR_OUT32_NHWC)
-            p.out_f32[pix * p.out32_stride + c] = val;
-          else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC)
-            atomicAdd(p.out_f32 + pix * p.out32_stride + c, val);
-          else if (p.out32_mode == SSR_OUT32_NCHW)
-            p.out_f32[(((long)n * p.cout + c) * p.H + y) * p.W + x] = val;
-          if (p.mask != nullptr && c >= p.mask_lo) {
-            const float mv = __bfloat162float(p.mask[pix * p.mask_stride + c]);
-            val *= (mv > 0.f ? 1.f : (p.mask_relu ? 0.f : 0.2f));
+          if (p.act) {
+            const float neg = p.act == 2 ? 0.f : 0.2f;  // 1 = LeakyReLU(0.2), 2 = ReLU
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : neg * f[j];
           }
-          if (p.out_bf16 != nullptr) p.out_bf16[pix * p.out_stride + c] = __float2bfloat16(val);
+          if (p.s0 != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] *= p.s0;
+          }
+          if (use_r1 && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
+            float r[16];
+            expand(o.r1, p.res1_kind, r);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s1, r[j], f[j]);
+          }
+          if (use_r2) {
+            float r[16];
+            expand(o.r2, p.res2_kind, r);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s2, r[j], f[j]);
+          }
+          // the f32 output is the UNMASKED value (a running gradient sum); the derivative mask only shapes the bf16 copy
+          if (p.out32_mode == SSR_OUT32_NHWC) {
+            float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.out32_stride + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC) {
+            float* dst = p.out_f32 + pix * p.out32_stride + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(dst + j, f[j]);
+          } else if (p.out32_mode == SSR_OUT32_NCHW) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) p.out_f32[(((long)n * p.cout + c0 + j) * p.H + y) * p.W + x] = f[j];
+          }
+          if (use_mk && c0 >= p.mask_lo) {
+            float r[16];
+            expand(o.mk, SSR_BF16, r);
+            const float neg = p.mask_relu ? 0.f : 0.2f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] *= (r[j] > 0.f ? 1.f : neg);
+          }
+          if (p.dbg_times && t_s2 == 0) t_s2 = gtime();
+          if (p.out_bf16 != nullptr) {
+            uint4 o0, o1;
+            o0.x = pack_bf16(f[0], f[1]);
+            o0.y = pack_bf16(f[2], f[3]);
+            o0.z = pack_bf16(f[4], f[5]);
+            o0.w = pack_bf16(f[6], f[7]);
+            o1.x = pack_bf16(f[8], f[9]);
+            o1.y = pack_bf16(f[10], f[11]);
+            o1.z = pack_bf16(f[12], f[13]);
+            o1.w = pack_bf16(f[14], f[15]);
+            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.out_stride + c0);
+            dst[0] = o0;
+            dst[1] = o1;
+          }
+          if (p.dbg_times && t_s3 == 0) t_s3 = gtime();
+        } else {
+          // ragged tail of the channel dimension (cout not a multiple of 16): scalar path, fully unrolled so that the
+          // accumulator array is never indexed dynamically (a dynamic index would force it into local memory)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = c0 + j;
+            if (c >= p.cout) continue;
+            float val = f[j] + s_bias[c - n0];
+            if (p.act) val = val > 0.f ? val : (p.act == 2 ? 0.f : 0.2f * val);
+            val *= p.s0;
+            if (p.res1_cmax == 0 || c < p.res1_cmax) {
+              if (p.res1_kind == SSR_BF16)
+                val += p.s1 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res1)[pix * p.res1_stride + c]);
+              else if (p.res1_kind == SSR_F32)
+                val += p.s1 * reinterpret_cast<const float*>(p.res1)[pix * p.res1_stride + c];
+            }
+            if (p.res2_kind == SSR_BF16)
+              val += p.s2 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res2)[pix * p.res2_stride + c]);
+            else if (p.res2_kind == SSR_F32)
+              val += p.s2 * reinterpret_cast<const float*>(p.res2)[pix * p.res2_stride + c];
+            if (p.out32_mode == SSR_OUT32_NHWC)
+              p.out_f32[pix * p.out32_stride + c] = val;
+            else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC)
+              atomicAdd(p.out_f32 + pix * p.out32_stride + c, val);
+            else if (p.out32_mode == SSR_OUT32_NCHW)
+              p.out_f32[(((long)n * p.cout + c) * p.H + y) * p.W + x] = val;
+            if (p.mask != nullptr && c >= p.mask_lo) {
+              const float mv = __bfloat162float(p.mask[pix * p.mask_stride + c]);
+              val *= (mv > 0.f ? 1.f : (p.mask_relu ? 0.f : 0.2f));
+            }
+            if (p.out_bf16 != nullptr) p.out_bf16[pix * p.out_stride + c] = __float2bfloat16(val);
+          }
         }
       }
+    }
+    if (p.dbg_times && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
+      const unsigned long long t_end = gtime();
+      printf("[conv_tc cta0] prologue %llu ns, dep-wait %llu ns, load+mma %llu ns, epilogue %llu ns (iters %d, n_tile %d) | item0: tmem_ld %llu, math %llu, bf16 store %llu ns\n",
+             t_prol - t_start, t_dep - t_prol, t_acc - t_dep, t_end - t_acc, iters, p.n_tile, t_s1 - t_acc, t_s2 - t_s1, t_s3 - t_s2);
     }
   }
 
@@ -539,6 +563,8 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   {
     const char* e = getenv("SSR_DBG_AOFF");
     p.dbg_aoff = e ? atoi(e) : 0;
+    const char* e2 = getenv("SSR_DBG_TIMES");
+    p.dbg_times = e2 ? atoi(e2) : 0;
   }
   if (a->cout % 16 == 0) {
     // vector epilogue alignment contract
