@@ -1,0 +1,256 @@
+// Weight gradient of a 3x3 conv with ALL NINE taps per CTA (tcgen05, sm_100a) -- the fast path of ssr_wgrad_tc for cy <= 64.
+//
+//   dW[ky][kx][cx][cy] += scale * sum_p X[p + (ky-1, kx-1), cx] * dY[p, cy]
+//
+// One TMA box {64 ch, TW+2 cols, TH+2 rows} per 64-channel chunk holds the tile WITH its halo (borders zero-filled by TMA).
+// Because the 128B swizzle of both TMA and the UMMA descriptors is a function of the absolute shared-memory address
+// (probed on the B200, scripts/probe_swizzle.py), an operand window may start at any 128-byte row: tap (ky, kx) of K-step s
+// (16 consecutive pixels of image row ry) is just the start address ((ry+ky)*(TW+2) + 16*hx + kx) * 128 -- so the activation
+// tile is loaded ONCE for nine taps (the first version reloaded it per kx from three CTAs).  Operands are MN-major (one
+// 128-byte row per pixel = per K index); nine f32 accumulators [128 cx, 32 cy] live in 288 TMEM columns; a CTA walks a range
+// of pixel tiles and reduces its partial sums with vector red.global.add.v4.f32.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace ssr {
+
+struct Wg9K {
+  int n_img, H, W, TW, TH, tiles_x, tiles_y, total_tiles, kpr;
+  int cx, cx_rows, cy, out_stride;
+  int stages, splits;
+  uint32_t x_chunk_bytes, x_chunk_alloc, y_bytes, stage_bytes;
+  float* out;
+  float scale;
+};
+
+static constexpr int kW9Threads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kW9Threads, 1)
+wgrad9_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const Wg9K p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* bar_empty = bar_full + p.stages;
+  uint64_t* bar_tmem = bar_empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tmem + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mtile = blockIdx.y;
+  const int n0 = blockIdx.z * 32;
+  const int per = (p.total_tiles + p.splits - 1) / p.splits;
+  const int t_begin = blockIdx.x * per;
+  const int t_end = min(p.total_tiles, t_begin + per);
+  const int iters = t_end - t_begin;
+  if (iters <= 0) return;
+  griddep_launch_dependents();
+  const int nchunks = min(2, (p.cx - mtile * 128 + 63) / 64);
+  const uint32_t x_bytes = 2 * p.x_chunk_alloc;
+  constexpr uint32_t kCols = 512;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmX);
+      prefetch_tmap(&tmY);
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(&bar_full[s], 1);
+        mbar_init(&bar_empty[s], 1);
+      }
+      mbar_init(bar_tmem, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+
+  if (warp == 0) {
+    for (int it = 0; it < iters; ++it) {
+      int t = t_begin + it;
+      const int tx = t % p.tiles_x;
+      t /= p.tiles_x;
+      const int ty = t % p.tiles_y;
+      const int n = t / p.tiles_y;
+      const int x0 = tx * p.TW, y0 = ty * p.TH;
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(&bar_empty[s], ph ^ 1);
+      if (elect_one()) {
+        uint8_t* xs = smem + (size_t)s * p.stage_bytes;
+        mbar_expect_tx(&bar_full[s], nchunks * p.x_chunk_bytes + p.y_bytes);
+        for (int ch = 0; ch < nchunks; ++ch)
+          tma_load_4d(xs + (size_t)ch * p.x_chunk_alloc, &tmX, &bar_full[s], mtile * 128 + ch * 64, x0 - 1, y0 - 1, n);
+        tma_load_4d(xs + x_bytes, &tmY, &bar_full[s], n0, x0, y0, n);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(128u, 32u, 1u, 1u);
+    const int pitch = p.TW + 2;
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(&bar_full[s], ph);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t xs = smem_u32(smem + (size_t)s * p.stage_bytes);
+        const uint64_t da0 = umma_desc(xs, p.x_chunk_alloc, 1024u, 2u);               // X: 128-byte rows, SWIZZLE_128B
+        const uint64_t db0 = umma_desc(xs + x_bytes, 0u, 512u, 4u);                    // dY: 64-byte rows, SWIZZLE_64B
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const int ry = ks / p.kpr, hx = ks - ry * p.kpr;
+          const uint32_t row0 = (uint32_t)(ry * pitch + hx * 16);
+          const uint64_t db = db0 + (uint32_t)(ks * 64);                               // 16 pixels * 64 B >> 4
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint64_t da = da0 + (row0 + (uint32_t)(ky * pitch + kx)) * 8u;     // 128 B >> 4 per pixel row
+              umma_bf16_ss(tmem_base + (uint32_t)((ky * 3 + kx) * 32), da, db, idesc, ks == 0 ? acc : 1u);
+            }
+          }
+        }
+        umma_commit(&bar_empty[s]);
+        if (it == iters - 1) umma_commit(bar_tmem);
+      }
+      __syncwarp();
+      acc = 1;
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int cxi = mtile * 128 + row;
+    const bool valid = cxi < p.cx;
+    mbar_wait(bar_tmem, 0);
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int item = half; item < 18; item += 2) {
+      const int tap = item >> 1, cb = (item & 1) * 16;
+      uint32_t v[16];
+      __syncwarp();
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * 32 + cb), v);
+      tmem_ld_wait();
+      if (!valid) continue;
+      const int c0 = n0 + cb;
+      if (c0 >= p.cy) continue;
+      float* dst = p.out + ((long)tap * p.cx_rows + cxi) * p.out_stride + c0;
+      if (c0 + 16 <= p.cy) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          red_add_v4(dst + 4 * j, p.scale * __uint_as_float(v[4 * j]), p.scale * __uint_as_float(v[4 * j + 1]),
+                     p.scale * __uint_as_float(v[4 * j + 2]), p.scale * __uint_as_float(v[4 * j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j < p.cy) atomicAdd(dst + j, p.scale * __uint_as_float(v[j]));
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kCols);
+  }
+}
+
+static int g_w9_smem = -1;
+
+// returns SSR_OK / error, or 1 when the shape is not eligible (caller falls back to the per-kx kernel)
+int launch_wgrad9(const ssr_wgrad_tc_args* a, cudaStream_t stream) {
+  if (a->r != 3 || a->cy > 64) return 1;
+  int TW = a->w >= 128 ? 128 : a->w;
+  if (TW != 16 && TW != 32 && TW != 64 && TW != 128) return 1;
+  if (a->w % TW) return 1;
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("SSR_WGRAD9");
+    disabled = (e && e[0] == '0') ? 1 : 0;
+  }
+  if (disabled) return 1;
+  if (g_w9_smem < 0) {
+    int dev = 0, v = 0;
+    if (!check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return SSR_E_CUDA;
+    if (!check_cuda(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev), "smem attr")) return SSR_E_CUDA;
+    if (!check_cuda(cudaFuncSetAttribute(wgrad9_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v), "cudaFuncSetAttribute(wgrad9)"))
+      return SSR_E_CUDA;
+    g_w9_smem = v;
+  }
+  Wg9K p{};
+  p.n_img = a->n_img; p.H = a->h; p.W = a->w;
+  p.TW = TW; p.TH = 128 / TW; p.kpr = TW / 16;
+  p.tiles_x = a->w / TW;
+  p.tiles_y = (a->h + p.TH - 1) / p.TH;
+  p.total_tiles = p.tiles_x * p.tiles_y * a->n_img;
+  p.cx = a->cx; p.cx_rows = a->out_cx_rows; p.cy = a->cy; p.out_stride = a->out_stride;
+  SSR_REQUIRE(p.cx_rows >= p.cx && p.out_stride >= p.cy && p.out_stride % 4 == 0, "ssr_wgrad_tc: output layout");
+  SSR_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "ssr_wgrad_tc: out must be 16-byte aligned");
+  p.x_chunk_bytes = (uint32_t)((TW + 2) * (p.TH + 2)) * 128u;
+  // the last tap of the last K-step reads up to ((TH+1)*(TW+2) + TW + 2) rows: keep it inside the chunk allocation
+  p.x_chunk_alloc = (uint32_t)round_up((int)(((p.TH + 2) * (TW + 2) + 16) * 128), 1024);
+  p.y_bytes = (uint32_t)(TW * p.TH * 64);
+  p.stage_bytes = (uint32_t)round_up((int)(2 * p.x_chunk_alloc + p.y_bytes), 1024);
+  int stages = (g_w9_smem - 1280) / (int)p.stage_bytes;
+  if (stages > 4) stages = 4;
+  SSR_REQUIRE(stages >= 1, "ssr_wgrad_tc: stage does not fit shared memory");
+  const int mtiles = (a->cx + 127) / 128;
+  const int halves = (a->cy + 31) / 32;
+  const int units = mtiles * halves;
+  static int target_ctas = -1;
+  if (target_ctas < 0) {
+    const char* e = getenv("SSR_WGRAD_CTAS");
+    target_ctas = e ? atoi(e) : 148;
+  }
+  int splits = a->splits > 0 ? a->splits : (target_ctas + units - 1) / units;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  { int per = (p.total_tiles + splits - 1) / splits; splits = (p.total_tiles + per - 1) / per; if (stages > per) stages = per; }
+  p.splits = splits;
+  p.stages = stages;
+  p.out = a->out;
+  p.scale = a->scale;
+  CUtensorMap tmX, tmY;
+  {
+    uint64_t dims[4] = {(uint64_t)a->cx, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
+    uint64_t str[3] = {(uint64_t)a->x_pix_stride * 2, (uint64_t)a->x_pix_stride * 2 * a->w, (uint64_t)a->x_pix_stride * 2 * a->w * a->h};
+    uint32_t box[4] = {64, (uint32_t)(TW + 2), (uint32_t)(p.TH + 2), 1};
+    if (!encode_tmap_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return SSR_E_CUDA;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)a->cy, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
+    uint64_t str[3] = {(uint64_t)a->dy_pix_stride * 2, (uint64_t)a->dy_pix_stride * 2 * a->w, (uint64_t)a->dy_pix_stride * 2 * a->w * a->h};
+    uint32_t box[4] = {32, (uint32_t)TW, (uint32_t)p.TH, 1};
+    if (!encode_tmap_tiled(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->dy, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return SSR_E_CUDA;
+  }
+  const size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024 + 256;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)splits, (unsigned)mtiles, (unsigned)halves);
+  cfg.blockDim = dim3(kW9Threads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  prof_before(1, stream);
+  if (!check_cuda(cudaLaunchKernelEx(&cfg, wgrad9_tc_kernel, tmX, tmY, p), "wgrad9_tc launch")) return SSR_E_CUDA;
+  prof_after(stream);
+  count_launch();
+  return SSR_OK;
+}
+
+}  // namespace ssr

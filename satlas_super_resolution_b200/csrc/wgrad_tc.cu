@@ -248,6 +248,8 @@ __global__ void bias_grad_groups_kernel(const __nv_bfloat16* __restrict__ dy, in
 
 static int g_w_smem_optin = -1;
 
+int launch_wgrad9(const ssr_wgrad_tc_args* a, cudaStream_t stream);  // wgrad9_tc.cu
+
 }  // namespace ssr
 
 using namespace ssr;
@@ -260,6 +262,11 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
   SSR_REQUIRE(a->cx > 0 && a->cy > 0, "ssr_wgrad_tc: channels");
   SSR_REQUIRE(a->x_pix_stride % 8 == 0 && a->dy_pix_stride % 8 == 0, "ssr_wgrad_tc: strides must be multiples of 8");
   SSR_REQUIRE(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->dy)) & 15) == 0, "ssr_wgrad_tc: alignment");
+  {
+    // fast path: all nine taps from one halo tile per CTA (cy <= 64, power-of-two tile widths)
+    const int rc = launch_wgrad9(a, stream);
+    if (rc <= 0) return rc;
+  }
   if (g_w_smem_optin < 0) {
     int dev = 0, v = 0;
     if (!check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return SSR_E_CUDA;
