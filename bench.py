@@ -66,6 +66,16 @@ def usable_cores():
     return max(1, n)
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel, taken from the committed `ncu --set full` capture of the same step
+    (profiles/ncu_traffic.json, written by scripts/summarize_ncu.py) -- a profiler-side number, never measured in-run."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return {}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -292,8 +302,10 @@ def main():
                      "achieved": ach, "peak": peak_sus, "unit": "TFLOP/s", "frac": ach / peak_sus if ach else None,
                      "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
                      "launches_per_step": int(cnt_cls[0]), "ms_per_step": conv_ms,
-                     "flop_per_launch": FLOP_CONV_TC * B / max(1, cnt_cls[0]), "traffic": None},
-        "roofline_wgrad": {"kernel": "ssr::wgrad_tc_kernel (tcgen05 weight gradient)", "bound": "tensor", "achieved": ach_w,
+                     "flop_per_launch": FLOP_CONV_TC * B / max(1, cnt_cls[0]),
+                     "traffic": ncu_traffic().get("conv_tc_kernel", {}).get("dram_bytes_per_launch"),
+                     "traffic_note": ncu_traffic().get("conv_tc_kernel", {}).get("note")},
+        "roofline_wgrad": {"kernel": "ssr::wgrad9_tc_kernel / wgrad_tc_kernel (tcgen05 weight gradient)", "bound": "tensor", "achieved": ach_w,
                            "peak": peak_sus, "unit": "TFLOP/s", "frac": ach_w / peak_sus if ach_w else None,
                            "launches_per_step": int(cnt_cls[1]), "ms_per_step": wgrad_ms},
         "clocks": sampler.summary(),

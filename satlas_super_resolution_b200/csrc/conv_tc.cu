@@ -41,7 +41,6 @@ struct ConvTcK {
   int out_stride;
   float* out_f32;
   int out32_mode, out32_stride;
-  int dbg_times; // print per-phase globaltimer stamps of CTA 0 (SSR_DBG_TIMES=1)
   int dbg_aoff;  // experiment: extra row offset (x128 B) of the A descriptor, see scripts/probe_swizzle.py
 };
 
@@ -76,17 +75,17 @@ __device__ __forceinline__ void load16_f32(const float* p, float (&f)[16]) {
   }
 }
 
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
+// Persistent, warp-specialised kernel.  CTA c owns M-tile groups c, c + gridDim.x, ...; its three roles run as
+// independent loops coupled only by mbarriers:
+//   warp 0     TMA producer   : streams (chunk, kx) stages for tile after tile (runs ahead across tile boundaries)
+//   warp 1     MMA issuer     : accumulates a tile into TMEM buffer b = tile & 1, then hands it to the epilogue
+//   warps 2..9 epilogue       : drains buffer b (bias / activation / residuals / mask / stores) while the MMAs of the NEXT
+//                               tile already fill buffer b ^ 1 -- prologue, first-load latency and epilogue are paid once
+//                               per CTA instead of once per tile.
 template <int MT, int R>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcK p) {
-  const unsigned long long t_start = p.dbg_times ? gtime() : 0ull;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -94,20 +93,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage_bytes = p.a_alloc + p.b_bytes;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* bar_empty = bar_full + p.stages;
-  uint64_t* bar_tmem = bar_empty + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tmem + 1);
+  uint64_t* bar_acc_full = bar_empty + p.stages;   // [2] accumulator buffer b complete (MMA -> epilogue)
+  uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2] accumulator buffer b drained  (epilogue -> MMA), 8 warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x;
-  t /= p.tiles_x;
-  const int ty = t % p.tiles_y;
-  const int n = t / p.tiles_y;
-  const int x0 = tx * p.TW;
-  const int y0 = ty * (MT * p.TH);
   const int n0 = blockIdx.y * p.n_tile;
 
   // split-K range over the 64-channel chunks
@@ -115,8 +107,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int c_begin = blockIdx.z * per;
   const int c_end = min(p.chunks, c_begin + per);
   const int iters = (c_end - c_begin) * R;
-  if (iters <= 0) return;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.n_img;
+  const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (iters <= 0 || my_tiles <= 0) return;
   griddep_launch_dependents();  // let the next kernel's prologue overlap this kernel (it still waits for our completion)
+  const uint32_t acc_cols = (uint32_t)(MT * p.n_tile);  // TMEM columns of one accumulator buffer
 
   if (warp == 0) {
     if (lane == 0) {
@@ -126,7 +121,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(&bar_full[s], 1);
         mbar_init(&bar_empty[s], 1);
       }
-      mbar_init(bar_tmem, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bar_acc_full[b], 1);
+        mbar_init(&bar_acc_empty[b], 8);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -137,28 +135,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const unsigned long long t_prol = p.dbg_times ? gtime() : 0ull;
   griddep_wait();  // everything above touched only this CTA's smem / TMEM; global memory of earlier kernels is read below
-  const unsigned long long t_dep = p.dbg_times ? gtime() : 0ull;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
-    for (int it = 0; it < iters; ++it) {
-      const int c = c_begin + it / R;
-      const int kx = it - (it / R) * R;
-      const int s = it % p.stages;
-      const uint32_t ph = (it / p.stages) & 1;
-      mbar_wait(&bar_empty[s], ph ^ 1);
-      if (elect_one()) {
-        uint8_t* a_dst = smem + (size_t)s * stage_bytes;
-        uint8_t* b_dst = a_dst + p.a_alloc;
-        mbar_expect_tx(&bar_full[s], p.a_box_bytes + p.b_bytes);
-        tma_load_4d(a_dst, &tmA, &bar_full[s], c * 64, x0 + kx - p.pad, y0 - p.pad, n);
+    int g = 0;  // running stage counter across tiles
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      int t = (int)blockIdx.x + lt * (int)gridDim.x;
+      const int tx = t % p.tiles_x;
+      t /= p.tiles_x;
+      const int ty = t % p.tiles_y;
+      const int n = t / p.tiles_y;
+      const int x0 = tx * p.TW, y0 = ty * (MT * p.TH);
+      for (int it = 0; it < iters; ++it, ++g) {
+        const int c = c_begin + it / R;
+        const int kx = it - (it / R) * R;
+        const int s = g % p.stages;
+        const uint32_t ph = (g / p.stages) & 1;
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        if (elect_one()) {
+          uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+          uint8_t* b_dst = a_dst + p.a_alloc;
+          mbar_expect_tx(&bar_full[s], p.a_box_bytes + p.b_bytes);
+          tma_load_4d(a_dst, &tmA, &bar_full[s], c * 64, x0 + kx - p.pad, y0 - p.pad, n);
 #pragma unroll
-        for (int ky = 0; ky < R; ++ky)
-          tma_load_2d(b_dst + (size_t)ky * p.n_tile * 128, &tmB, &bar_full[s], 0, ((c * R + kx) * R + ky) * p.n_pad + n0);
+          for (int ky = 0; ky < R; ++ky)
+            tma_load_2d(b_dst + (size_t)ky * p.n_tile * 128, &tmB, &bar_full[s], 0, ((c * R + kx) * R + ky) * p.n_pad + n0);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
@@ -167,43 +172,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t a_tap = (uint32_t)(p.TW * 128) >> 4;        // one tile row down  (descriptor address units of 16 B)
     const uint32_t a_mt = (uint32_t)(p.TH * p.TW * 128) >> 4;  // next stacked M tile
     const uint32_t b_tap = (uint32_t)(p.n_tile * 128) >> 4;    // next vertical tap's weight tile
-    uint32_t acc = 0;
-    for (int it = 0; it < iters; ++it) {
-      const int c = c_begin + it / R;
-      const int s = it % p.stages;
-      const uint32_t ph = (it / p.stages) & 1;
-      mbar_wait(&bar_full[s], ph);
+    const uint32_t a_dbg = (uint32_t)(p.dbg_aoff * 128) >> 4;  // hardware probe only (scripts/probe_swizzle.py)
+    int g = 0;
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int b = lt & 1;
+      mbar_wait(&bar_acc_empty[b], ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator buffer
       tc_fence_after_sync();
-      if (elect_one()) {
-        const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint64_t da0 = umma_desc_k128(a_base);
-        const uint64_t db0 = umma_desc_k128(a_base + p.a_alloc);
-        const int ks = min(4, (p.cin - c * 64) >> 4);
-        if (ks == 4) {
+      const uint32_t d_base = tmem_base + (uint32_t)b * acc_cols;
+      uint32_t acc = 0;
+      for (int it = 0; it < iters; ++it, ++g) {
+        const int c = c_begin + it / R;
+        const int s = g % p.stages;
+        const uint32_t ph = (g / p.stages) & 1;
+        mbar_wait(&bar_full[s], ph);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t da0 = umma_desc_k128(a_base) + a_dbg;
+          const uint64_t db0 = umma_desc_k128(a_base + p.a_alloc);
+          const int ks = min(4, (p.cin - c * 64) >> 4);
+          if (ks == 4) {
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
+            for (int m = 0; m < MT; ++m) {
 #pragma unroll
-            for (int ky = 0; ky < R; ++ky) {
+              for (int ky = 0; ky < R; ++ky) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16_ss(tmem_base + (uint32_t)(m * p.n_tile), da0 + (m * a_mt + ky * a_tap + 2 * k),
-                             db0 + (ky * b_tap + 2 * k), idesc, (ky == 0 && k == 0) ? acc : 1u);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_ss(d_base + (uint32_t)(m * p.n_tile), da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
+                               idesc, (ky == 0 && k == 0) ? acc : 1u);
               }
             }
-          }
-        } else {
+          } else {
 #pragma unroll
-          for (int m = 0; m < MT; ++m)
-            for (int ky = 0; ky < R; ++ky)
-              for (int k = 0; k < ks; ++k)
-                umma_bf16_ss(tmem_base + (uint32_t)(m * p.n_tile), da0 + (m * a_mt + ky * a_tap + 2 * k),
-                             db0 + (ky * b_tap + 2 * k), idesc, (ky == 0 && k == 0) ? acc : 1u);
+            for (int m = 0; m < MT; ++m)
+              for (int ky = 0; ky < R; ++ky)
+                for (int k = 0; k < ks; ++k)
+                  umma_bf16_ss(d_base + (uint32_t)(m * p.n_tile), da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
+                               idesc, (ky == 0 && k == 0) ? acc : 1u);
+          }
+          umma_commit(&bar_empty[s]);                              // frees this smem stage once the MMAs above have read it
+          if (it == iters - 1) umma_commit(&bar_acc_full[b]);      // accumulators of this tile complete
         }
-        umma_commit_raw(&bar_empty[s]);  // frees this smem stage once the MMAs above have read it
-        if (it == iters - 1) umma_commit_raw(bar_tmem);  // accumulators complete
+        __syncwarp();
+        acc = 1;
       }
-      __syncwarp();
-      acc = 1;
     }
   } else {
     // ===================== epilogue (warps 2..9: two warps per TMEM lane quarter) =====================
@@ -214,23 +226,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = (warp - 2) >> 2;  // 0: even chunks, 1: odd chunks
     const int m = q * 32 + lane;
     const int et = (int)threadIdx.x - 64;
-    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
     const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
     for (int i = et; i < p.n_tile; i += kThreads - 64) s_bias[i] = (add_bias && n0 + i < p.cout) ? p.bias[n0 + i] : 0.f;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const int tyy = m / p.TW;
     const int txx = m - tyy * p.TW;
-    const int x = x0 + txx;
     const int nchunks = p.n_tile >> 4;
-    int ys[MT];
-    long pixs[MT];
-    bool oks[MT];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      ys[mt] = y0 + mt * p.TH + tyy;
-      pixs[mt] = ((long)n * p.H + ys[mt]) * p.W + x;
-      oks[mt] = (tyy < p.TH) && (ys[mt] < p.H) && (x < p.W);
-    }
     const bool use_r1 = p.res1_kind != SSR_NONE, use_r2 = p.res2_kind != SSR_NONE, use_mk = p.mask != nullptr;
 
     struct Ops {
@@ -284,134 +285,149 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     };
 
-    Ops o;
-    bool first = true;
-    if (half < nchunks && oks[0] && n0 + half * 16 + 16 <= p.cout) fetch(pixs[0], n0 + half * 16, o);   // overlaps the MMAs
-    mbar_wait(bar_tmem, 0);
-    tc_fence_after_sync();
-    const unsigned long long t_acc = p.dbg_times ? gtime() : 0ull;
-    unsigned long long t_s1 = 0, t_s2 = 0, t_s3 = 0;
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      const int y = ys[mt];
-      const long pix = pixs[mt];
-      const bool in_img = oks[mt];
 #pragma unroll 1
-      for (int ci = half; ci < nchunks; ci += 2) {
-        const int c0 = n0 + ci * 16;
-        const bool live = in_img && (c0 + 16 <= p.cout);
-        if (!first && live) fetch(pix, c0, o);
-        first = false;
-        uint32_t v[16];
-        __syncwarp();
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.n_tile + ci * 16), v);
-        tmem_ld_wait();
-        if (p.dbg_times && t_s1 == 0) t_s1 = gtime();
-        if (!in_img || c0 >= p.cout) continue;
-        float f[16];
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      int t = (int)blockIdx.x + lt * (int)gridDim.x;
+      const int tx = t % p.tiles_x;
+      t /= p.tiles_x;
+      const int ty = t % p.tiles_y;
+      const int n = t / p.tiles_y;
+      const int x = tx * p.TW + txx;
+      const int y0 = ty * (MT * p.TH);
+      const int b = lt & 1;
+      const uint32_t d_base = tmem_base + (uint32_t)b * acc_cols;
+      int ys[MT];
+      long pixs[MT];
+      bool oks[MT];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        if (live) {
-          if (add_bias) {
+      for (int mt = 0; mt < MT; ++mt) {
+        ys[mt] = y0 + mt * p.TH + tyy;
+        pixs[mt] = ((long)n * p.H + ys[mt]) * p.W + x;
+        oks[mt] = (tyy < p.TH) && (ys[mt] < p.H) && (x < p.W);
+      }
+      Ops o;
+      bool first = true;
+      if (half < nchunks && oks[0] && n0 + half * 16 + 16 <= p.cout) fetch(pixs[0], n0 + half * 16, o);   // overlaps the MMAs
+      mbar_wait(&bar_acc_full[b], (lt >> 1) & 1);
+      tc_fence_after_sync();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += s_bias[ci * 16 + j];
-          }
-          if (p.act) {
-            const float neg = p.act == 2 ? 0.f : 0.2f;  // 1 = LeakyReLU(0.2), 2 = ReLU
+      for (int mt = 0; mt < MT; ++mt) {
+        const int y = ys[mt];
+        const long pix = pixs[mt];
+        const bool in_img = oks[mt];
+#pragma unroll 1
+        for (int ci = half; ci < nchunks; ci += 2) {
+          const int c0 = n0 + ci * 16;
+          const bool live = in_img && (c0 + 16 <= p.cout);
+          if (!first && live) fetch(pix, c0, o);
+          first = false;
+          uint32_t v[16];
+          __syncwarp();
+          tmem_ld16(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.n_tile + ci * 16), v);
+          tmem_ld_wait();
+          if (!in_img || c0 >= p.cout) continue;
+          float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : neg * f[j];
-          }
-          if (p.s0 != 1.f) {
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (live) {
+            if (add_bias) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] *= p.s0;
-          }
-          if (use_r1 && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
-            float r[16];
-            expand(o.r1, p.res1_kind, r);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s1, r[j], f[j]);
-          }
-          if (use_r2) {
-            float r[16];
-            expand(o.r2, p.res2_kind, r);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s2, r[j], f[j]);
-          }
-          // the f32 output is the UNMASKED value (a running gradient sum); the derivative mask only shapes the bf16 copy
-          if (p.out32_mode == SSR_OUT32_NHWC) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.out32_stride + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC) {
-            float* dst = p.out_f32 + pix * p.out32_stride + c0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(dst + j, f[j]);
-          } else if (p.out32_mode == SSR_OUT32_NCHW) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) p.out_f32[(((long)n * p.cout + c0 + j) * p.H + y) * p.W + x] = f[j];
-          }
-          if (use_mk && c0 >= p.mask_lo) {
-            float r[16];
-            expand(o.mk, SSR_BF16, r);
-            const float neg = p.mask_relu ? 0.f : 0.2f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] *= (r[j] > 0.f ? 1.f : neg);
-          }
-          if (p.dbg_times && t_s2 == 0) t_s2 = gtime();
-          if (p.out_bf16 != nullptr) {
-            uint4 o0, o1;
-            o0.x = pack_bf16(f[0], f[1]);
-            o0.y = pack_bf16(f[2], f[3]);
-            o0.z = pack_bf16(f[4], f[5]);
-            o0.w = pack_bf16(f[6], f[7]);
-            o1.x = pack_bf16(f[8], f[9]);
-            o1.y = pack_bf16(f[10], f[11]);
-            o1.z = pack_bf16(f[12], f[13]);
-            o1.w = pack_bf16(f[14], f[15]);
-            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.out_stride + c0);
-            dst[0] = o0;
-            dst[1] = o1;
-          }
-          if (p.dbg_times && t_s3 == 0) t_s3 = gtime();
-        } else {
-          // ragged tail of the channel dimension (cout not a multiple of 16): scalar path, fully unrolled so that the
-          // accumulator array is never indexed dynamically (a dynamic index would force it into local memory)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = c0 + j;
-            if (c >= p.cout) continue;
-            float val = f[j] + s_bias[c - n0];
-            if (p.act) val = val > 0.f ? val : (p.act == 2 ? 0.f : 0.2f * val);
-            val *= p.s0;
-            if (p.res1_cmax == 0 || c < p.res1_cmax) {
-              if (p.res1_kind == SSR_BF16)
-                val += p.s1 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res1)[pix * p.res1_stride + c]);
-              else if (p.res1_kind == SSR_F32)
-                val += p.s1 * reinterpret_cast<const float*>(p.res1)[pix * p.res1_stride + c];
+              for (int j = 0; j < 16; ++j) f[j] += s_bias[ci * 16 + j];
             }
-            if (p.res2_kind == SSR_BF16)
-              val += p.s2 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res2)[pix * p.res2_stride + c]);
-            else if (p.res2_kind == SSR_F32)
-              val += p.s2 * reinterpret_cast<const float*>(p.res2)[pix * p.res2_stride + c];
-            if (p.out32_mode == SSR_OUT32_NHWC)
-              p.out_f32[pix * p.out32_stride + c] = val;
-            else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC)
-              atomicAdd(p.out_f32 + pix * p.out32_stride + c, val);
-            else if (p.out32_mode == SSR_OUT32_NCHW)
-              p.out_f32[(((long)n * p.cout + c) * p.H + y) * p.W + x] = val;
-            if (p.mask != nullptr && c >= p.mask_lo) {
-              const float mv = __bfloat162float(p.mask[pix * p.mask_stride + c]);
-              val *= (mv > 0.f ? 1.f : (p.mask_relu ? 0.f : 0.2f));
+            if (p.act) {
+              const float neg = p.act == 2 ? 0.f : 0.2f;  // 1 = LeakyReLU(0.2), 2 = ReLU
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : neg * f[j];
             }
-            if (p.out_bf16 != nullptr) p.out_bf16[pix * p.out_stride + c] = __float2bfloat16(val);
+            if (p.s0 != 1.f) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] *= p.s0;
+            }
+            if (use_r1 && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
+              float r[16];
+              expand(o.r1, p.res1_kind, r);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s1, r[j], f[j]);
+            }
+            if (use_r2) {
+              float r[16];
+              expand(o.r2, p.res2_kind, r);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s2, r[j], f[j]);
+            }
+            // the f32 output is the UNMASKED value (a running gradient sum); the derivative mask only shapes the bf16 copy
+            if (p.out32_mode == SSR_OUT32_NHWC) {
+              float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.out32_stride + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC) {
+              float* dst = p.out_f32 + pix * p.out32_stride + c0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) atomicAdd(dst + j, f[j]);
+            } else if (p.out32_mode == SSR_OUT32_NCHW) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) p.out_f32[(((long)n * p.cout + c0 + j) * p.H + y) * p.W + x] = f[j];
+            }
+            if (use_mk && c0 >= p.mask_lo) {
+              float r[16];
+              expand(o.mk, SSR_BF16, r);
+              const float neg = p.mask_relu ? 0.f : 0.2f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] *= (r[j] > 0.f ? 1.f : neg);
+            }
+            if (p.out_bf16 != nullptr) {
+              uint4 o0, o1;
+              o0.x = pack_bf16(f[0], f[1]);
+              o0.y = pack_bf16(f[2], f[3]);
+              o0.z = pack_bf16(f[4], f[5]);
+              o0.w = pack_bf16(f[6], f[7]);
+              o1.x = pack_bf16(f[8], f[9]);
+              o1.y = pack_bf16(f[10], f[11]);
+              o1.z = pack_bf16(f[12], f[13]);
+              o1.w = pack_bf16(f[14], f[15]);
+              uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.out_stride + c0);
+              dst[0] = o0;
+              dst[1] = o1;
+            }
+          } else {
+            // ragged tail of the channel dimension (cout not a multiple of 16): scalar path, fully unrolled so that the
+            // accumulator array is never indexed dynamically (a dynamic index would force it into local memory)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = c0 + j;
+              if (c >= p.cout) continue;
+              float val = f[j] + s_bias[c - n0];
+              if (p.act) val = val > 0.f ? val : (p.act == 2 ? 0.f : 0.2f * val);
+              val *= p.s0;
+              if (p.res1_cmax == 0 || c < p.res1_cmax) {
+                if (p.res1_kind == SSR_BF16)
+                  val += p.s1 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res1)[pix * p.res1_stride + c]);
+                else if (p.res1_kind == SSR_F32)
+                  val += p.s1 * reinterpret_cast<const float*>(p.res1)[pix * p.res1_stride + c];
+              }
+              if (p.res2_kind == SSR_BF16)
+                val += p.s2 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res2)[pix * p.res2_stride + c]);
+              else if (p.res2_kind == SSR_F32)
+                val += p.s2 * reinterpret_cast<const float*>(p.res2)[pix * p.res2_stride + c];
+              if (p.out32_mode == SSR_OUT32_NHWC)
+                p.out_f32[pix * p.out32_stride + c] = val;
+              else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC)
+                atomicAdd(p.out_f32 + pix * p.out32_stride + c, val);
+              else if (p.out32_mode == SSR_OUT32_NCHW)
+                p.out_f32[(((long)n * p.cout + c) * p.H + y) * p.W + x] = val;
+              if (p.mask != nullptr && c >= p.mask_lo) {
+                const float mv = __bfloat162float(p.mask[pix * p.mask_stride + c]);
+                val *= (mv > 0.f ? 1.f : (p.mask_relu ? 0.f : 0.2f));
+              }
+              if (p.out_bf16 != nullptr) p.out_bf16[pix * p.out_stride + c] = __float2bfloat16(val);
+            }
           }
         }
       }
-    }
-    if (p.dbg_times && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
-      const unsigned long long t_end = gtime();
-      printf("[conv_tc cta0] prologue %llu ns, dep-wait %llu ns, load+mma %llu ns, epilogue %llu ns (iters %d, n_tile %d) | item0: tmem_ld %llu, math %llu, bf16 store %llu ns\n",
-             t_prol - t_start, t_dep - t_prol, t_acc - t_dep, t_end - t_acc, iters, p.n_tile, t_s1 - t_acc, t_s2 - t_s1, t_s3 - t_s2);
+      // this warp has finished reading accumulator buffer b: hand it back to the MMA issuer
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
     }
   }
 
@@ -478,7 +494,17 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   p.W = a->w;
   p.R = a->r;
   p.pad = (a->r - 1) / 2;
-  p.TW = a->w >= 128 ? 128 : round_up(a->w, 8);
+  // tile width: narrower tiles have less vertical-halo overhead per pixel (box rows = MT*TH + 2), and every pixel is its own
+  // 128-byte TMA segment anyway, so wide images are cut into 32-column tiles (SSR_CONV_TW overrides for experiments)
+  {
+    static int tw_max = -1;
+    if (tw_max < 0) {
+      const char* e = getenv("SSR_CONV_TW");
+      tw_max = e ? atoi(e) : 32;
+      if (tw_max != 16 && tw_max != 32 && tw_max != 64 && tw_max != 128) tw_max = 32;
+    }
+    p.TW = a->w >= tw_max && a->r == 3 ? tw_max : (a->w >= 128 ? 128 : round_up(a->w, 8));
+  }
   p.TH = 128 / p.TW;
   int mt = a->mt;
   if (mt == 0) {
@@ -505,7 +531,7 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   p.n_tile = a->n_tile ? a->n_tile : (a->n_pad <= 128 ? a->n_pad : 128);
   SSR_REQUIRE(p.n_tile % 16 == 0 && p.n_tile <= 256 && p.n_pad % p.n_tile == 0,
               "ssr_conv_tc: n_tile %d incompatible with n_pad %d", p.n_tile, p.n_pad);
-  SSR_REQUIRE(mt * p.n_tile <= 512, "ssr_conv_tc: mt*n_tile exceeds TMEM");
+  SSR_REQUIRE(2 * mt * p.n_tile <= 512, "ssr_conv_tc: two accumulator buffers of mt*n_tile columns exceed TMEM");
   p.splits = a->splits > 0 ? a->splits : 1;
   if (p.splits > p.chunks) p.splits = p.chunks;
   // make sure no split is empty
@@ -536,7 +562,7 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   if (stages > iters_max) stages = iters_max;
   p.stages = stages;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(mt * p.n_tile)) cols <<= 1;
+  while (cols < (uint32_t)(2 * mt * p.n_tile)) cols <<= 1;   // double-buffered accumulators
   p.tmem_cols = cols;
 
   p.bias = a->bias;
@@ -563,8 +589,6 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   {
     const char* e = getenv("SSR_DBG_AOFF");
     p.dbg_aoff = e ? atoi(e) : 0;
-    const char* e2 = getenv("SSR_DBG_TIMES");
-    p.dbg_times = e2 ? atoi(e2) : 0;
   }
   if (a->cout % 16 == 0) {
     // vector epilogue alignment contract
@@ -599,7 +623,15 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   }
 
   const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
-  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.n_img), (unsigned)(p.n_pad / p.n_tile), (unsigned)p.splits);
+  // persistent: at most one CTA per SM along x, each walking tiles x, x + gridDim.x, ...
+  const int total_tiles = p.tiles_x * p.tiles_y * p.n_img;
+  int ctas_x = total_tiles < g_num_sms ? total_tiles : g_num_sms;
+  {
+    // keep the per-CTA tile counts balanced (e.g. 2048 tiles on 148 SMs -> 14 tiles each on 147 CTAs, not 13.8 ragged)
+    const int waves = (total_tiles + ctas_x - 1) / ctas_x;
+    ctas_x = (total_tiles + waves - 1) / waves;
+  }
+  dim3 grid((unsigned)ctas_x, (unsigned)(p.n_pad / p.n_tile), (unsigned)p.splits);
   auto kern = mt == 1 ? (p.R == 3 ? conv_tc_kernel<1, 3> : conv_tc_kernel<1, 1>) : (p.R == 3 ? conv_tc_kernel<2, 3> : conv_tc_kernel<2, 1>);
   static size_t configured[6] = {0, 0, 0, 0, 0, 0};
   const int cfg_idx = mt * 2 + (p.R == 3 ? 1 : 0);

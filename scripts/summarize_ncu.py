@@ -55,4 +55,24 @@ for k, (h, rr) in rows.items():
     if k >= 3:
         break
 open(out, "w").write("\n".join(lines) + "\n")
+# mean DRAM traffic per captured launch -> profiles/ncu_traffic.json (bench.py's roofline.traffic)
+import json, os
+try:
+    raw2 = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd2 = csv.reader(raw2.splitlines())
+    h2, u2 = next(rd2), next(rd2)
+    ir, iw, ik = h2.index("dram__bytes_read.sum"), h2.index("dram__bytes_write.sum"), h2.index("Kernel Name")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n, kname = 0.0, 0, None
+    for row in rd2:
+        tot += float(row[ir]) * scale.get(u2[ir], 1) + float(row[iw]) * scale.get(u2[iw], 1)
+        n += 1
+        kname = row[ik].split("(")[0].replace("void ", "").split("<")[0].replace("ssr::", "")
+    jpath = os.path.join(os.path.dirname(out), "ncu_traffic.json")
+    data = json.load(open(jpath)) if os.path.exists(jpath) else {}
+    data[kname] = {"dram_bytes_per_launch": tot / max(n, 1), "launches_captured": n, "report": os.path.basename(rep),
+                   "note": "mean dram__bytes_read.sum + dram__bytes_write.sum over the captured launches (cold cache, ncu --set full)"}
+    json.dump(data, open(jpath, "w"), indent=1)
+except Exception as e:  # noqa
+    print("traffic json not updated:", e)
 print("\n".join(lines[:12]))
