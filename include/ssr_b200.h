@@ -186,6 +186,8 @@ typedef struct ssr_wgrad_tc_args {
   int32_t splits; /* 0 = auto */
 } ssr_wgrad_tc_args;
 int ssr_wgrad_tc(const ssr_wgrad_tc_args* args, void* stream);
+/* n independent problems (e.g. the five convs of one ResidualDenseBlock) in one launch where the shapes allow it */
+int ssr_wgrad_tc_batched(const ssr_wgrad_tc_args* args, int32_t n, void* stream);
 int ssr_wgrad_unpack(const float* acc, int32_t cx_rows, int32_t acc_stride, float* grad_oihw, int32_t cout, int32_t cin,
                      int32_t r, float scale, int32_t accumulate, void* stream);
 /* every conv of a network in one launch (device-resident table) */

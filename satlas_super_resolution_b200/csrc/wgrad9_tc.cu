@@ -29,8 +29,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(kW9Threads, 1)
-wgrad9_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const Wg9K p) {
+__device__ __forceinline__ void wgrad9_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const Wg9K& p, int bx, int by, int bz) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -41,10 +40,10 @@ wgrad9_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int mtile = blockIdx.y;
-  const int n0 = blockIdx.z * 32;
+  const int mtile = by;
+  const int n0 = bz * 32;
   const int per = (p.total_tiles + p.splits - 1) / p.splits;
-  const int t_begin = blockIdx.x * per;
+  const int t_begin = bx * per;
   const int t_end = min(p.total_tiles, t_begin + per);
   const int iters = t_end - t_begin;
   if (iters <= 0) return;
@@ -168,10 +167,47 @@ wgrad9_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   }
 }
 
+__global__ void __launch_bounds__(kW9Threads, 1)
+wgrad9_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const Wg9K p) {
+  wgrad9_body(tmX, tmY, p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Horizontal fusion: up to kW9Batch independent weight-gradient problems (the five convs of a ResidualDenseBlock) in ONE launch.
+// Each of these problems alone is latency-bound (one or two pixel tiles per CTA, then the reduction epilogue); batching them
+// pays launch, prologue and first-load latency once instead of five times.
+static constexpr int kW9Batch = 8;
+struct Wg9BatchK {
+  CUtensorMap tmX[kW9Batch];
+  CUtensorMap tmY[kW9Batch];
+  Wg9K k[kW9Batch];
+  int cta_begin[kW9Batch + 1];
+  int mtiles[kW9Batch];
+  int n;
+};
+
+__global__ void __launch_bounds__(kW9Threads, 1) wgrad9_tc_batched_kernel(const __grid_constant__ Wg9BatchK b) {
+  int j = 0;
+  while (j + 1 < b.n && (int)blockIdx.x >= b.cta_begin[j + 1]) ++j;
+  int local = (int)blockIdx.x - b.cta_begin[j];
+  const Wg9K& p = b.k[j];
+  const int bx = local % p.splits;
+  local /= p.splits;
+  const int by = local % b.mtiles[j];
+  const int bz = local / b.mtiles[j];
+  wgrad9_body(b.tmX[j], b.tmY[j], p, bx, by, bz);
+}
+
 static int g_w9_smem = -1;
 
+struct Wg9Prepared {
+  Wg9K p;
+  CUtensorMap tmX, tmY;
+  int mtiles, halves;
+  size_t smem_bytes;
+};
+
 // returns SSR_OK / error, or 1 when the shape is not eligible (caller falls back to the per-kx kernel)
-int launch_wgrad9(const ssr_wgrad_tc_args* a, cudaStream_t stream) {
+static int prepare_wgrad9(const ssr_wgrad_tc_args* a, Wg9Prepared* out) {
   if (a->r != 3 || a->cy > 64) return 1;
   int TW = a->w >= 128 ? 128 : a->w;
   if (TW != 16 && TW != 32 && TW != 64 && TW != 128) return 1;
@@ -187,6 +223,8 @@ int launch_wgrad9(const ssr_wgrad_tc_args* a, cudaStream_t stream) {
     if (!check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return SSR_E_CUDA;
     if (!check_cuda(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev), "smem attr")) return SSR_E_CUDA;
     if (!check_cuda(cudaFuncSetAttribute(wgrad9_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v), "cudaFuncSetAttribute(wgrad9)"))
+      return SSR_E_CUDA;
+    if (!check_cuda(cudaFuncSetAttribute(wgrad9_tc_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v), "cudaFuncSetAttribute(wgrad9b)"))
       return SSR_E_CUDA;
     g_w9_smem = v;
   }
@@ -235,21 +273,80 @@ int launch_wgrad9(const ssr_wgrad_tc_args* a, cudaStream_t stream) {
     uint32_t box[4] = {32, (uint32_t)TW, (uint32_t)p.TH, 1};
     if (!encode_tmap_tiled(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->dy, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return SSR_E_CUDA;
   }
-  const size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024 + 256;
+  out->p = p;
+  out->tmX = tmX;
+  out->tmY = tmY;
+  out->mtiles = mtiles;
+  out->halves = halves;
+  out->smem_bytes = (size_t)stages * p.stage_bytes + 1024 + 256;
+  return SSR_OK;
+}
+
+static cudaLaunchAttribute pdl_attr() {
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  return attr;
+}
+
+int launch_wgrad9(const ssr_wgrad_tc_args* a, cudaStream_t stream) {
+  Wg9Prepared w;
+  const int rc = prepare_wgrad9(a, &w);
+  if (rc != SSR_OK) return rc;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)splits, (unsigned)mtiles, (unsigned)halves);
+  cfg.gridDim = dim3((unsigned)w.p.splits, (unsigned)w.mtiles, (unsigned)w.halves);
   cfg.blockDim = dim3(kW9Threads);
-  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.dynamicSmemBytes = w.smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[1] = {pdl_attr()};
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   prof_before(1, stream);
-  if (!check_cuda(cudaLaunchKernelEx(&cfg, wgrad9_tc_kernel, tmX, tmY, p), "wgrad9_tc launch")) return SSR_E_CUDA;
+  if (!check_cuda(cudaLaunchKernelEx(&cfg, wgrad9_tc_kernel, w.tmX, w.tmY, w.p), "wgrad9_tc launch")) return SSR_E_CUDA;
   prof_after(stream);
   count_launch();
+  return SSR_OK;
+}
+
+// n problems in as few launches as possible; problems that are not eligible for the nine-tap kernel return 1 in `fallback[i]`
+int launch_wgrad9_batched(const ssr_wgrad_tc_args* args, int n, int* fallback, cudaStream_t stream) {
+  int i = 0;
+  while (i < n) {
+    Wg9BatchK b{};
+    size_t smem = 0;
+    int ctas = 0;
+    while (i < n && b.n < kW9Batch) {
+      Wg9Prepared w;
+      const int rc = prepare_wgrad9(&args[i], &w);
+      if (rc < 0) return rc;
+      fallback[i] = rc == 1 ? 1 : 0;
+      if (rc == SSR_OK) {
+        const int j = b.n++;
+        b.k[j] = w.p;
+        b.tmX[j] = w.tmX;
+        b.tmY[j] = w.tmY;
+        b.mtiles[j] = w.mtiles;
+        b.cta_begin[j] = ctas;
+        ctas += w.p.splits * w.mtiles * w.halves;
+        b.cta_begin[j + 1] = ctas;
+        if (w.smem_bytes > smem) smem = w.smem_bytes;
+      }
+      ++i;
+    }
+    if (b.n == 0) continue;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kW9Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1] = {pdl_attr()};
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    prof_before(1, stream);
+    if (!check_cuda(cudaLaunchKernelEx(&cfg, wgrad9_tc_batched_kernel, b), "wgrad9_tc_batched launch")) return SSR_E_CUDA;
+    prof_after(stream);
+    count_launch();
+  }
   return SSR_OK;
 }
 

@@ -249,6 +249,7 @@ __global__ void bias_grad_groups_kernel(const __nv_bfloat16* __restrict__ dy, in
 static int g_w_smem_optin = -1;
 
 int launch_wgrad9(const ssr_wgrad_tc_args* a, cudaStream_t stream);  // wgrad9_tc.cu
+int launch_wgrad9_batched(const ssr_wgrad_tc_args* args, int n, int* fallback, cudaStream_t stream);
 
 }  // namespace ssr
 
@@ -401,4 +402,25 @@ extern "C" int ssr_bias_grad_groups(const void* dy_bf16, int32_t dy_pix_stride, 
       reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dy_pix_stride, npix, c, group_ch, outs_device, scale);
   count_launch();
   return check_last("bias_grad_groups launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_wgrad_tc_batched(const ssr_wgrad_tc_args* args, int32_t n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SSR_REQUIRE(args && n > 0 && n <= 64, "ssr_wgrad_tc_batched: bad args");
+  int fallback[64];
+  for (int i = 0; i < n; ++i) {
+    const ssr_wgrad_tc_args* a = &args[i];
+    SSR_REQUIRE(a->x && a->dy && a->out, "ssr_wgrad_tc_batched: null pointer in problem %d", i);
+    SSR_REQUIRE(a->x_pix_stride % 8 == 0 && a->dy_pix_stride % 8 == 0, "ssr_wgrad_tc_batched: strides must be multiples of 8");
+    SSR_REQUIRE(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->dy)) & 15) == 0, "ssr_wgrad_tc_batched: alignment");
+    fallback[i] = 1;
+  }
+  const int rc = launch_wgrad9_batched(args, n, fallback, stream);
+  if (rc != SSR_OK) return rc;
+  for (int i = 0; i < n; ++i)
+    if (fallback[i]) {
+      const int r2 = ssr_wgrad_tc(&args[i], stream_);
+      if (r2 != SSR_OK) return r2;
+    }
+  return SSR_OK;
 }

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from .ops import Act, PackedConv, Packer, Plan, WgradSet, conv_args, cur_stream, lib, plan_wgrad, round_up
+from .ops import Act, PackedConv, Packer, Plan, WgradSet, conv_args, cur_stream, lib, plan_wgrad, plan_wgrad_batch, round_up
 
 
 class RRDBNetEngine:
@@ -216,9 +216,9 @@ class _Workspace:
         G32 = torch.empty((B, h, w, cw), dtype=torch.float32, device=dev)
         GO32 = torch.empty((B, h, w, nf), dtype=torch.float32, device=dev)
         Dg = Act(B, h, w, cw, dev)
-        gR_b, gO_b = Act(B, h, w, nf, dev), Act(B, h, w, nf, dev)
+        gR_pp, gO_b = [Act(B, h, w, nf, dev), Act(B, h, w, nf, dev)], Act(B, h, w, nf, dev)
         d_first = Act(B, h, w, nf, dev)
-        self._bwd_keep = [gA, gB, d_feat, G32, GO32, Dg, gR_b, gO_b, d_first]
+        self._bwd_keep = [gA, gB, d_feat, G32, GO32, Dg, gR_pp, gO_b, d_first]
 
         def bias_grad(name, dy_ptr, dy_stride, npix, cy, scale=1.0):
             plan.add(lib().ssr_bias_grad, dy_ptr, dy_stride, npix, cy, grads[f"{name}.bias"].data_ptr(), scale)
@@ -279,15 +279,19 @@ class _Workspace:
             cur = self.bufs[i]
             pre = f"body.{blk}.rdb{j + 1}"
             c5 = eng.cv[f"{pre}.conv5"]
+            # the block reads its incoming gradient from gR_in (written by block i+1) and hands its result on in gR_out:
+            # ping-pong, because this block's weight-gradient launch (deferred to the end of the block) still reads gR_in
+            gR_in, gR_out = gR_pp[(i + 1) & 1], gR_pp[i & 1]
             if j == 2:
                 xin, s0, r1, r1s, s1 = gO_b, 0.04, GO32.data_ptr(), nf, 0.2
             else:
-                xin, s0, r1, r1s, s1 = gR_b, 0.2, G32.data_ptr(), cw, 1.0
+                xin, s0, r1, r1s, s1 = gR_in, 0.2, G32.data_ptr(), cw, 1.0
             plan.conv(conv_args(xin.ptr(), B, h, w, nf, nf, c5.packed_dg.data_ptr(), 3, cw, c5.n_pad_dg, s0=s0,
                                 res1=r1, res1_kind=F32, res1_stride=r1s, s1=s1, res1_cmax=nf,
                                 mask=cur.ptr(), mask_stride=cw, mask_lo=nf,
                                 out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(), out32_mode=L.OUT32_NHWC, out32_stride=cw))
-            wgrad(f"{pre}.conv5", cur.ptr(), cw, cw, xin.ptr(), nf, nf, B, h, w, scale=s0)
+            batch = [wg.args(f"{pre}.conv5", cur.ptr(), cw, cw, xin.ptr(), nf, nf, B, h, w, 3, s0)]
+            bias_grad(f"{pre}.conv5", xin.ptr(), nf, B * h * w, nf, s0)
             for k in range(4, 0, -1):
                 ck = eng.cv[f"{pre}.conv{k}"]
                 nk = nf + (k - 1) * g
@@ -301,7 +305,7 @@ class _Workspace:
                 elif j > 0:
                     plan.conv(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
                                         res1=G32.data_ptr(), res1_kind=F32, res1_stride=cw, s1=1.0,
-                                        out=gR_b.ptr(), out_stride=nf, out32=G32.data_ptr(), out32_mode=L.OUT32_NHWC,
+                                        out=gR_out.ptr(), out_stride=nf, out32=G32.data_ptr(), out32_mode=L.OUT32_NHWC,
                                         out32_stride=cw))
                 else:
                     # first block of the RRDB: add the RRDB-level skip gradient and hand over to the previous RRDB
@@ -310,7 +314,9 @@ class _Workspace:
                                         res2=GO32.data_ptr(), res2_kind=F32, res2_stride=nf, s2=1.0,
                                         out=gO_b.ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_NHWC,
                                         out32_stride=nf))
-                wgrad(f"{pre}.conv{k}", cur.ptr(), cw, nk, dyk, cw, g, B, h, w, bias=False)
+                batch.append(wg.args(f"{pre}.conv{k}", cur.ptr(), cw, nk, dyk, cw, g, B, h, w, 3, 1.0))
+            # all five weight gradients of the block in ONE launch (they only need the block's finished dY slots)
+            plan_wgrad_batch(plan, batch)
             plan.add(lib().ssr_bias_grad_groups, Dg.ptr(nf), cw, B * h * w, 4 * g, g, self._bias_ptrs.data_ptr() + 32 * i, 1.0)
         # ---- conv_first: dY = trunk gradient + the long skip (feat = conv_first + conv_body(...))
         plan.add(lib().ssr_axpby, gO_b.ptr(), nf, 1.0, d_feat.ptr(), nf, 1.0, None, 0, 0, d_first.ptr(), nf, B * h * w, nf)

@@ -290,3 +290,11 @@ def rank_slice(n_items, rank, world):
     """contiguous shard of `n_items` independent work items (tiles / chunks) for `rank`: no collective needed"""
     per = (n_items + world - 1) // world
     return range(min(n_items, rank * per), min(n_items, (rank + 1) * per))
+
+
+def plan_wgrad_batch(plan, args_list):
+    """several independent weight-gradient problems -> one ssr_wgrad_tc_batched call"""
+    from ._protos import WgradArgs
+    arr = (WgradArgs * len(args_list))(*args_list)
+    plan.keep.append(arr)
+    plan.calls.append((lib().ssr_wgrad_tc_batched, (arr, len(args_list))))
