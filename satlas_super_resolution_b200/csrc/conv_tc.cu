@@ -468,8 +468,14 @@ static bool device_limits() {
 
 using namespace ssr;
 
+// output channels are cut into equal N tiles of at most 128 (192 -> 2 x 96, 160 -> 2 x 80): no half-empty last tile
+static int balanced_n_tile(int cout) {
+  const int tiles = (cout + 127) / 128;
+  return round_up((cout + tiles - 1) / tiles, 16);
+}
+
 extern "C" int64_t ssr_packed_weight_bytes(int32_t cin, int32_t cout, int32_t r, int32_t* n_pad) {
-  int np = cout <= 128 ? round_up(cout, 16) : round_up(cout, 128);
+  int np = balanced_n_tile(cout) * ((cout + 127) / 128);
   if (n_pad) *n_pad = np;
   int chunks = (cin + 63) / 64;
   return (int64_t)chunks * r * r * np * 64 * 2;
@@ -515,7 +521,7 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
       const char* e = getenv("SSR_CONV_MT");
       forced = e ? atoi(e) : 0;
     }
-    const int nt_guess = a->n_tile ? a->n_tile : (a->n_pad <= 128 ? a->n_pad : 128);
+    const int nt_guess = a->n_tile ? a->n_tile : (a->n_pad <= 128 ? a->n_pad : a->n_pad / ((a->n_pad + 127) / 128));
     const long tiles1 = (long)((a->w + p.TW - 1) / p.TW) * ((a->h + p.TH - 1) / p.TH) * a->n_img;
     mt = 1;
     if (forced == 1 || forced == 2) mt = forced;
@@ -528,7 +534,7 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   p.cin = a->cin;
   p.n_pad = a->n_pad;
   p.cout = a->cout;
-  p.n_tile = a->n_tile ? a->n_tile : (a->n_pad <= 128 ? a->n_pad : 128);
+  p.n_tile = a->n_tile ? a->n_tile : (a->n_pad <= 128 ? a->n_pad : a->n_pad / ((a->n_pad + 127) / 128));
   SSR_REQUIRE(p.n_tile % 16 == 0 && p.n_tile <= 256 && p.n_pad % p.n_tile == 0,
               "ssr_conv_tc: n_tile %d incompatible with n_pad %d", p.n_tile, p.n_pad);
   SSR_REQUIRE(2 * mt * p.n_tile <= 512, "ssr_conv_tc: two accumulator buffers of mt*n_tile columns exceed TMEM");

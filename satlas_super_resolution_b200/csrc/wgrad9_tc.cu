@@ -207,7 +207,7 @@ struct Wg9Prepared {
 };
 
 // returns SSR_OK / error, or 1 when the shape is not eligible (caller falls back to the per-kx kernel)
-static int prepare_wgrad9(const ssr_wgrad_tc_args* a, Wg9Prepared* out) {
+static int prepare_wgrad9(const ssr_wgrad_tc_args* a, Wg9Prepared* out, int target_override = 0) {
   if (a->r != 3 || a->cy > 64) return 1;
   int TW = a->w >= 128 ? 128 : a->w;
   if (TW != 16 && TW != 32 && TW != 64 && TW != 128) return 1;
@@ -253,7 +253,9 @@ static int prepare_wgrad9(const ssr_wgrad_tc_args* a, Wg9Prepared* out) {
     const char* e = getenv("SSR_WGRAD_CTAS");
     target_ctas = e ? atoi(e) : 148;
   }
-  int splits = a->splits > 0 ? a->splits : (target_ctas + units - 1) / units;
+  const int tgt = target_override > 0 ? target_override : target_ctas;
+  int splits = a->splits > 0 ? a->splits : (tgt + units - 1) / units;
+  if (splits < 1) splits = 1;
   if (splits > p.total_tiles) splits = p.total_tiles;
   { int per = (p.total_tiles + splits - 1) / splits; splits = (p.total_tiles + per - 1) / per; if (stages > per) stages = per; }
   p.splits = splits;
@@ -310,6 +312,14 @@ int launch_wgrad9(const ssr_wgrad_tc_args* a, cudaStream_t stream) {
 
 // n problems in as few launches as possible; problems that are not eligible for the nine-tap kernel return 1 in `fallback[i]`
 int launch_wgrad9_batched(const ssr_wgrad_tc_args* args, int n, int* fallback, cudaStream_t stream) {
+  // the batch as a whole should be about `budget` CTAs (a couple of waves): fewer pixel splits per problem = fewer partial
+  // sums to reduce, and the parallelism comes from the n problems instead
+  static int budget = -1;
+  if (budget < 0) {
+    const char* e = getenv("SSR_WGRAD_BATCH_CTAS");
+    budget = e ? atoi(e) : 296;
+  }
+  const int per_problem = budget / (n > 0 ? n : 1) > 8 ? budget / (n > 0 ? n : 1) : 8;
   int i = 0;
   while (i < n) {
     Wg9BatchK b{};
@@ -317,7 +327,7 @@ int launch_wgrad9_batched(const ssr_wgrad_tc_args* args, int n, int* fallback, c
     int ctas = 0;
     while (i < n && b.n < kW9Batch) {
       Wg9Prepared w;
-      const int rc = prepare_wgrad9(&args[i], &w);
+      const int rc = prepare_wgrad9(&args[i], &w, per_problem);
       if (rc < 0) return rc;
       fallback[i] = rc == 1 ? 1 : 0;
       if (rc == SSR_OK) {
