@@ -32,12 +32,17 @@ extern "C" {
 #define SSR_NONE 0
 #define SSR_BF16 1
 #define SSR_F32 2
+/* f32, channel-quad planar: element (pixel p, channel c) at [((c / 4) * P + p) * 4 + c % 4], P = n_img*h*w of the call.
+ * For buffers only epilogues touch (running gradients, the f32 trunk): a warp's 32 pixels x 4 channels are 512
+ * contiguous bytes, where NHWC gives every lane its own cache line.  The pix_stride of such an operand is ignored. */
+#define SSR_F32_PLANAR4 3
 
 /* f32 output modes of ssr_conv_tc */
 #define SSR_OUT32_NONE 0
 #define SSR_OUT32_NHWC 1        /* store   out32[pix*stride + c]              */
 #define SSR_OUT32_NHWC_ATOMIC 2 /* red.add out32[pix*stride + c]  (split-K)   */
 #define SSR_OUT32_NCHW 3        /* store   out32[((n*cout + c)*H + y)*W + x]  */
+#define SSR_OUT32_PLANAR4 4     /* store   out32 in the SSR_F32_PLANAR4 layout */
 
 /* weight packing modes */
 #define SSR_PACK_FWD 0   /* B[n=cout][k=cin], taps as stored          */
@@ -85,7 +90,7 @@ typedef struct ssr_conv_tc_args {
   int32_t act;       /* 1 = LeakyReLU(0.2), 2 = ReLU */
   float s0;
   const void* res1;
-  int32_t res1_kind; /* SSR_NONE / SSR_BF16 / SSR_F32 */
+  int32_t res1_kind; /* SSR_NONE / SSR_BF16 / SSR_F32 / SSR_F32_PLANAR4 */
   int32_t res1_pix_stride;
   float s1;
   const void* res2;
@@ -109,6 +114,17 @@ typedef struct ssr_conv_tc_args {
 } ssr_conv_tc_args;
 
 int ssr_conv_tc(const ssr_conv_tc_args* args, void* stream);
+
+/*
+ * n layers in ONE launch (replaces the five consecutive self.convK(...) calls of ResidualDenseBlock.forward,
+ * ssr/archs/rrdbnet_arch.py:36-43, and autograd's matching five input-gradient convolutions).  Layer i may read
+ * anything layers < i of the same call wrote; all layers share (n_img, h, w, r), have n_pad <= 128 and splits <= 1.
+ * Results are identical to n ssr_conv_tc calls in order; ineligible chains are executed exactly that way.
+ */
+int ssr_conv_tc_chain(const ssr_conv_tc_args* args, int32_t n, void* stream);
+/* diagnostics: with SSR_CHAIN_TIMELINE=1 in the environment every chained launch records clock64 stamps
+ * [cta][layer (5)][8 events]; copies the first n_ctas (<= 512) rows of the LAST launch to host memory (synchronises). */
+int ssr_debug_chain_timeline(long long* host_out, int32_t n_ctas);
 
 /* bytes of a packed weight buffer for (cin, cout, r) -> n_pad is written back */
 int64_t ssr_packed_weight_bytes(int32_t cin, int32_t cout, int32_t r, int32_t* n_pad);

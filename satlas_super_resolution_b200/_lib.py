@@ -9,8 +9,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libssr_b200.so")
 
-SSR_NONE, SSR_BF16, SSR_F32 = 0, 1, 2
-OUT32_NONE, OUT32_NHWC, OUT32_NHWC_ATOMIC, OUT32_NCHW = 0, 1, 2, 3
+SSR_NONE, SSR_BF16, SSR_F32, SSR_F32_PLANAR4 = 0, 1, 2, 3
+OUT32_NONE, OUT32_NHWC, OUT32_NHWC_ATOMIC, OUT32_NCHW, OUT32_PLANAR4 = 0, 1, 2, 3, 4
 PACK_FWD, PACK_DGRAD, PACK_FWD_GEMM, PACK_DGRAD_GEMM = 0, 1, 2, 3
 
 
@@ -58,6 +58,8 @@ def load(build_if_missing=True):
     lib.ssr_launch_count.restype = C.c_int64
     lib.ssr_conv_tc.argtypes = [C.POINTER(ConvTcArgs), C.c_void_p]
     lib.ssr_conv_tc.restype = C.c_int
+    lib.ssr_conv_tc_chain.argtypes = [C.POINTER(ConvTcArgs), C.c_int32, C.c_void_p]
+    lib.ssr_conv_tc_chain.restype = C.c_int
     lib.ssr_packed_weight_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     lib.ssr_packed_weight_bytes.restype = C.c_int64
     lib.ssr_pack_conv_weight.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

@@ -25,6 +25,9 @@ struct ConvTcK {
   int n_tile, n_pad, cout;
   int stages;
   uint32_t a_box_bytes, a_alloc, b_bytes, tmem_cols;
+  uint32_t stage_stride;  // bytes between smem stages (>= a_alloc + b_bytes; the max over the layers of a chain)
+  uint32_t acc_stride;    // TMEM columns between the two accumulator buffers (>= MT * n_tile)
+  int n_loop;             // N tiles one CTA walks itself (1 when gridDim.y spreads them; n_pad / n_tile inside a chain)
   int splits;
   // epilogue
   const float* bias;
@@ -42,6 +45,18 @@ struct ConvTcK {
   float* out_f32;
   int out32_mode, out32_stride;
   int dbg_aoff;  // experiment: extra row offset (x128 B) of the A descriptor, see scripts/probe_swizzle.py
+};
+
+static constexpr int kSyncNone = 0, kSyncGrid = 1, kSyncCluster = 2;
+static constexpr int kMaxChain = 5;   // layers one chained launch may hold (a ResidualDenseBlock)
+struct ConvChainK {
+  CUtensorMap tmA[kMaxChain];
+  CUtensorMap tmB[kMaxChain];
+  ConvTcK k[kMaxChain];
+  int n_layers;
+  int sync_mode;       // kSyncGrid: global arrive counter; kSyncCluster: one image per thread-block cluster, mbarriers in DSMEM
+  unsigned int* sync;  // kSyncGrid only. [2]: arrive counter, done counter (self-resetting)
+  long long* timeline; // diagnostics (SSR_CHAIN_TIMELINE=1): clock64 stamps [cta][layer][8], else NULL
 };
 
 static constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
@@ -82,41 +97,47 @@ __device__ __forceinline__ void load16_f32(const float* p, float (&f)[16]) {
 //   warps 2..9 epilogue       : drains buffer b (bias / activation / residuals / mask / stores) while the MMAs of the NEXT
 //                               tile already fill buffer b ^ 1 -- prologue, first-load latency and epilogue are paid once
 //                               per CTA instead of once per tile.
+//
+// A CHAIN of up to kMaxChain layers (the five convs of a ResidualDenseBlock: each consumes what the previous one wrote) can
+// run inside ONE launch: every role loops over the layers, the producer of layer l+1 waits on a grid-wide arrive counter
+// that the epilogues of layer l bump after their global stores (with the generic->async proxy fence TMA needs), so launch
+// latency, prologue and TMEM allocation are paid once per block instead of once per conv.  All CTAs are co-resident
+// (grid <= SM count, one CTA per SM), which makes the spinning barrier safe.
 template <int MT, int R>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const ConvTcK p) {
+__device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUtensorMap* tmBs, const ConvTcK* ps, const int n_layers,
+                                             const int sync_mode, unsigned int* gsync, long long* timeline = nullptr) {
+#define SSR_STAMP(layer, slot) \
+  do { if (timeline) timeline[((long)blockIdx.x * kMaxChain + (layer)) * 8 + (slot)] = clock64(); } while (0)
+  const ConvTcK& p = ps[0];   // geometry, tiling and the shared-memory ring are identical for every layer of a chain
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  const uint32_t stage_bytes = p.a_alloc + p.b_bytes;
+  const uint32_t stage_bytes = p.stage_stride;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* bar_empty = bar_full + p.stages;
   uint64_t* bar_acc_full = bar_empty + p.stages;   // [2] accumulator buffer b complete (MMA -> epilogue)
   uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2] accumulator buffer b drained  (epilogue -> MMA), 8 warp arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+  uint64_t* bar_layer = bar_acc_empty + 2;         // kSyncCluster: every epilogue warp of the cluster arrives once per layer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_layer + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * p.n_tile;
-
-  // split-K range over the 64-channel chunks
-  const int per = (p.chunks + p.splits - 1) / p.splits;
-  const int c_begin = blockIdx.z * per;
-  const int c_end = min(p.chunks, c_begin + per);
-  const int iters = (c_end - c_begin) * R;
   const int total_tiles = p.tiles_x * p.tiles_y * p.n_img;
   const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  if (iters <= 0 || my_tiles <= 0) return;
+  {
+    // split-K range of the (single-layer) launch; a chain never splits K
+    const int per0 = (p.chunks + p.splits - 1) / p.splits;
+    if (min(p.chunks, (int)blockIdx.z * per0 + per0) - (int)blockIdx.z * per0 <= 0 || my_tiles <= 0) return;
+  }
   griddep_launch_dependents();  // let the next kernel's prologue overlap this kernel (it still waits for our completion)
-  const uint32_t acc_cols = (uint32_t)(MT * p.n_tile);  // TMEM columns of one accumulator buffer
+  const uint32_t acc_cols = p.acc_stride;  // TMEM columns between the two accumulator buffers
 
   if (warp == 0) {
     if (lane == 0) {
-      prefetch_tmap(&tmA);
-      prefetch_tmap(&tmB);
+      prefetch_tmap(&tmAs[0]);
+      prefetch_tmap(&tmBs[0]);
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(&bar_full[s], 1);
         mbar_init(&bar_empty[s], 1);
@@ -125,6 +146,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(&bar_acc_full[b], 1);
         mbar_init(&bar_acc_empty[b], 8);
       }
+      if (sync_mode == kSyncCluster) mbar_init(bar_layer, 8 * cluster_nctarank());
       fence_barrier_init();
     }
     __syncwarp();
@@ -135,86 +157,125 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (sync_mode == kSyncCluster) cluster_sync_all();  // no remote arrive may reach a barrier that is not initialised yet
   griddep_wait();  // everything above touched only this CTA's smem / TMEM; global memory of earlier kernels is read below
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
-    int g = 0;  // running stage counter across tiles
-    for (int lt = 0; lt < my_tiles; ++lt) {
-      int t = (int)blockIdx.x + lt * (int)gridDim.x;
-      const int tx = t % p.tiles_x;
-      t /= p.tiles_x;
-      const int ty = t % p.tiles_y;
-      const int n = t / p.tiles_y;
-      const int x0 = tx * p.TW, y0 = ty * (MT * p.TH);
-      for (int it = 0; it < iters; ++it, ++g) {
-        const int c = c_begin + it / R;
-        const int kx = it - (it / R) * R;
-        const int s = g % p.stages;
-        const uint32_t ph = (g / p.stages) & 1;
-        mbar_wait(&bar_empty[s], ph ^ 1);
-        if (elect_one()) {
-          uint8_t* a_dst = smem + (size_t)s * stage_bytes;
-          uint8_t* b_dst = a_dst + p.a_alloc;
-          mbar_expect_tx(&bar_full[s], p.a_box_bytes + p.b_bytes);
-          tma_load_4d(a_dst, &tmA, &bar_full[s], c * 64, x0 + kx - p.pad, y0 - p.pad, n);
-#pragma unroll
-          for (int ky = 0; ky < R; ++ky)
-            tma_load_2d(b_dst + (size_t)ky * p.n_tile * 128, &tmB, &bar_full[s], 0, ((c * R + kx) * R + ky) * p.n_pad + n0);
+    int g = 0;  // running stage counter across tiles and layers
+    for (int l = 0; l < n_layers; ++l) {
+      const ConvTcK& q = ps[l];
+      const CUtensorMap* tmA = &tmAs[l];
+      const CUtensorMap* tmB = &tmBs[l];
+      const int per = (q.chunks + q.splits - 1) / q.splits;
+      const int c_begin = blockIdx.z * per;
+      const int iters = (min(q.chunks, c_begin + per) - c_begin) * R;
+      if (l > 0) {
+        // layer l-1 has been stored (generic proxy) by every CTA we can depend on: acquire that, then order our TMA
+        // (async proxy) loads behind it
+        if (sync_mode == kSyncCluster) {
+          mbar_wait_cluster(bar_layer, (uint32_t)(l - 1) & 1);
+        } else {
+          const unsigned int want = (unsigned int)l * gridDim.x;
+          if (lane == 0) {
+            while (ld_acquire_gpu(gsync) < want) __nanosleep(64);
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        fence_proxy_async();
+        prefetch_tmap(tmA);
+        prefetch_tmap(tmB);
       }
+      if (lane == 0) SSR_STAMP(l, 0);   // producer: inputs of this layer are ready
+      for (int lt = 0; lt < my_tiles; ++lt) {
+        int t = (int)blockIdx.x + lt * (int)gridDim.x;
+        const int tx = t % q.tiles_x;
+        t /= q.tiles_x;
+        const int ty = t % q.tiles_y;
+        const int n = t / q.tiles_y;
+        const int x0 = tx * q.TW, y0 = ty * (MT * q.TH);
+        for (int nb = 0; nb < q.n_loop; ++nb) {
+        const int n0 = ((int)blockIdx.y * q.n_loop + nb) * q.n_tile;
+        for (int it = 0; it < iters; ++it, ++g) {
+          const int c = c_begin + it / R;
+          const int kx = it - (it / R) * R;
+          const int s = g % q.stages;
+          const uint32_t ph = (g / q.stages) & 1;
+          mbar_wait(&bar_empty[s], ph ^ 1);
+          if (elect_one()) {
+            uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+            uint8_t* b_dst = a_dst + q.a_alloc;
+            mbar_expect_tx(&bar_full[s], q.a_box_bytes + q.b_bytes);
+            tma_load_4d(a_dst, tmA, &bar_full[s], c * 64, x0 + kx - q.pad, y0 - q.pad, n);
+#pragma unroll
+            for (int ky = 0; ky < R; ++ky)
+              tma_load_2d(b_dst + (size_t)ky * q.n_tile * 128, tmB, &bar_full[s], 0, ((c * R + kx) * R + ky) * q.n_pad + n0);
+          }
+          __syncwarp();
+        }
+        }  // N tiles
+      }
+      if (lane == 0) SSR_STAMP(l, 1);   // producer: last stage of this layer issued
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     // Descriptors differ only in their 14-bit start-address field: build one per stage, then add constant offsets.
-    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.n_tile);
     const uint32_t a_tap = (uint32_t)(p.TW * 128) >> 4;        // one tile row down  (descriptor address units of 16 B)
     const uint32_t a_mt = (uint32_t)(p.TH * p.TW * 128) >> 4;  // next stacked M tile
-    const uint32_t b_tap = (uint32_t)(p.n_tile * 128) >> 4;    // next vertical tap's weight tile
     const uint32_t a_dbg = (uint32_t)(p.dbg_aoff * 128) >> 4;  // hardware probe only (scripts/probe_swizzle.py)
-    int g = 0;
-    for (int lt = 0; lt < my_tiles; ++lt) {
-      const int b = lt & 1;
-      mbar_wait(&bar_acc_empty[b], ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator buffer
-      tc_fence_after_sync();
-      const uint32_t d_base = tmem_base + (uint32_t)b * acc_cols;
-      uint32_t acc = 0;
-      for (int it = 0; it < iters; ++it, ++g) {
-        const int c = c_begin + it / R;
-        const int s = g % p.stages;
-        const uint32_t ph = (g / p.stages) & 1;
-        mbar_wait(&bar_full[s], ph);
+    int g = 0, gt = 0;  // running stage / tile counters across layers
+    for (int l = 0; l < n_layers; ++l) {
+      const ConvTcK& q = ps[l];
+      const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)q.n_tile);
+      const uint32_t b_tap = (uint32_t)(q.n_tile * 128) >> 4;    // next vertical tap's weight tile
+      const int per = (q.chunks + q.splits - 1) / q.splits;
+      const int c_begin = blockIdx.z * per;
+      const int iters = (min(q.chunks, c_begin + per) - c_begin) * R;
+      const int items = my_tiles * q.n_loop;  // (pixel tile, N tile) work items of this layer
+      for (int lt = 0; lt < items; ++lt, ++gt) {
+        const int b = gt & 1;
+        mbar_wait(&bar_acc_empty[b], ((gt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator buffer
         tc_fence_after_sync();
-        if (elect_one()) {
-          const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t da0 = umma_desc_k128(a_base) + a_dbg;
-          const uint64_t db0 = umma_desc_k128(a_base + p.a_alloc);
-          const int ks = min(4, (p.cin - c * 64) >> 4);
-          if (ks == 4) {
+        const uint32_t d_base = tmem_base + (uint32_t)b * acc_cols;
+        uint32_t acc = 0;
+        for (int it = 0; it < iters; ++it, ++g) {
+          const int c = c_begin + it / R;
+          const int s = g % q.stages;
+          const uint32_t ph = (g / q.stages) & 1;
+          mbar_wait(&bar_full[s], ph);
+          tc_fence_after_sync();
+          if (lane == 0 && lt == 0 && it == 0) SSR_STAMP(l, 2);                     // MMA: first stage landed
+          if (lane == 0 && lt == items - 1 && it == iters - 1) SSR_STAMP(l, 3);     // MMA: last stage landed
+          if (elect_one()) {
+            const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint64_t da0 = umma_desc_k128(a_base) + a_dbg;
+            const uint64_t db0 = umma_desc_k128(a_base + q.a_alloc);
+            const int ks = min(4, (q.cin - c * 64) >> 4);
+            if (ks == 4) {
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
+              for (int m = 0; m < MT; ++m) {
 #pragma unroll
-              for (int ky = 0; ky < R; ++ky) {
+                for (int ky = 0; ky < R; ++ky) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16_ss(d_base + (uint32_t)(m * p.n_tile), da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
-                               idesc, (ky == 0 && k == 0) ? acc : 1u);
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(d_base + (uint32_t)(m * q.n_tile), da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
+                                 idesc, (ky == 0 && k == 0) ? acc : 1u);
+                }
               }
-            }
-          } else {
+            } else {
 #pragma unroll
-            for (int m = 0; m < MT; ++m)
-              for (int ky = 0; ky < R; ++ky)
-                for (int k = 0; k < ks; ++k)
-                  umma_bf16_ss(d_base + (uint32_t)(m * p.n_tile), da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
-                               idesc, (ky == 0 && k == 0) ? acc : 1u);
+              for (int m = 0; m < MT; ++m)
+                for (int ky = 0; ky < R; ++ky)
+                  for (int k = 0; k < ks; ++k)
+                    umma_bf16_ss(d_base + (uint32_t)(m * q.n_tile), da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
+                                 idesc, (ky == 0 && k == 0) ? acc : 1u);
+            }
+            umma_commit(&bar_empty[s]);                              // frees this smem stage once the MMAs above have read it
+            if (it == iters - 1) umma_commit(&bar_acc_full[b]);      // accumulators of this tile complete
           }
-          umma_commit(&bar_empty[s]);                              // frees this smem stage once the MMAs above have read it
-          if (it == iters - 1) umma_commit(&bar_acc_full[b]);      // accumulators of this tile complete
+          __syncwarp();
+          acc = 1;
         }
-        __syncwarp();
-        acc = 1;
       }
     }
   } else {
@@ -226,13 +287,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = (warp - 2) >> 2;  // 0: even chunks, 1: odd chunks
     const int m = q * 32 + lane;
     const int et = (int)threadIdx.x - 64;
-    const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
-    for (int i = et; i < p.n_tile; i += kThreads - 64) s_bias[i] = (add_bias && n0 + i < p.cout) ? p.bias[n0 + i] : 0.f;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
     const int tyy = m / p.TW;
     const int txx = m - tyy * p.TW;
+    int gt = 0;  // running tile counter across layers (selects the accumulator buffer and its phase)
+#pragma unroll 1
+    for (int l = 0; l < n_layers; ++l) {
+    const ConvTcK& p = ps[l];
+    const int n_base = (int)blockIdx.y * p.n_loop * p.n_tile;   // first output channel this CTA produces
+    const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
+    for (int i = et; i < p.n_loop * p.n_tile; i += kThreads - 64) s_bias[i] = (add_bias && n_base + i < p.cout) ? p.bias[n_base + i] : 0.f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const int nchunks = p.n_tile >> 4;
     const bool use_r1 = p.res1_kind != SSR_NONE, use_r2 = p.res2_kind != SSR_NONE, use_mk = p.mask != nullptr;
+    const long n_pix = (long)p.n_img * p.H * p.W;   // plane stride of the quad-planar f32 operands, in float4
 
     struct Ops {
       uint4 r1[4], r2[4], mk[2];
@@ -243,10 +310,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res1) + pix * p.res1_stride + c0);
           o.r1[0] = s4[0];
           o.r1[1] = s4[1];
-        } else {
+        } else if (p.res1_kind == SSR_F32) {
           const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.res1) + pix * p.res1_stride + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) o.r1[j] = s4[j];
+        } else {
+          // quad-planar f32: the warp's 32 pixels x 4 channels are 512 contiguous bytes
+          const uint4* s4 = reinterpret_cast<const uint4*>(p.res1) + (long)(c0 >> 2) * n_pix + pix;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o.r1[j] = s4[(long)j * n_pix];
         }
       }
       if (use_r2) {
@@ -254,10 +326,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res2) + pix * p.res2_stride + c0);
           o.r2[0] = s4[0];
           o.r2[1] = s4[1];
-        } else {
+        } else if (p.res2_kind == SSR_F32) {
           const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.res2) + pix * p.res2_stride + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) o.r2[j] = s4[j];
+        } else {
+          const uint4* s4 = reinterpret_cast<const uint4*>(p.res2) + (long)(c0 >> 2) * n_pix + pix;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o.r2[j] = s4[(long)j * n_pix];
         }
       }
       if (use_mk && c0 >= p.mask_lo) {
@@ -294,8 +370,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n = t / p.tiles_y;
       const int x = tx * p.TW + txx;
       const int y0 = ty * (MT * p.TH);
-      const int b = lt & 1;
-      const uint32_t d_base = tmem_base + (uint32_t)b * acc_cols;
       int ys[MT];
       long pixs[MT];
       bool oks[MT];
@@ -305,11 +379,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         pixs[mt] = ((long)n * p.H + ys[mt]) * p.W + x;
         oks[mt] = (tyy < p.TH) && (ys[mt] < p.H) && (x < p.W);
       }
+#pragma unroll 1
+      for (int nb = 0; nb < p.n_loop; ++nb, ++gt) {
+      const int n0 = n_base + nb * p.n_tile;
+      const int b = gt & 1;
+      const uint32_t d_base = tmem_base + (uint32_t)b * acc_cols;
       Ops o;
       bool first = true;
       if (half < nchunks && oks[0] && n0 + half * 16 + 16 <= p.cout) fetch(pixs[0], n0 + half * 16, o);   // overlaps the MMAs
-      mbar_wait(&bar_acc_full[b], (lt >> 1) & 1);
+      mbar_wait(&bar_acc_full[b], (gt >> 1) & 1);
       tc_fence_after_sync();
+      if (et == 0 && lt == 0 && nb == 0) SSR_STAMP(l, 4);                            // epilogue: first accumulator complete
+      if (et == 0 && lt == my_tiles - 1 && nb == p.n_loop - 1) SSR_STAMP(l, 5);      // epilogue: last accumulator complete
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         const int y = ys[mt];
@@ -332,7 +413,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (live) {
             if (add_bias) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] += s_bias[ci * 16 + j];
+              for (int j = 0; j < 16; ++j) f[j] += s_bias[c0 - n_base + j];
             }
             if (p.act) {
               const float neg = p.act == 2 ? 0.f : 0.2f;  // 1 = LeakyReLU(0.2), 2 = ReLU
@@ -360,6 +441,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.out32_stride + c0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else if (p.out32_mode == SSR_OUT32_PLANAR4) {
+              float4* dst = reinterpret_cast<float4*>(p.out_f32) + (long)(c0 >> 2) * n_pix + pix;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[(long)j * n_pix] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             } else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC) {
               float* dst = p.out_f32 + pix * p.out32_stride + c0;
 #pragma unroll
@@ -396,7 +481,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 16; ++j) {
               const int c = c0 + j;
               if (c >= p.cout) continue;
-              float val = f[j] + s_bias[c - n0];
+              float val = f[j] + s_bias[c - n_base];
               if (p.act) val = val > 0.f ? val : (p.act == 2 ? 0.f : 0.2f * val);
               val *= p.s0;
               if (p.res1_cmax == 0 || c < p.res1_cmax) {
@@ -404,13 +489,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   val += p.s1 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res1)[pix * p.res1_stride + c]);
                 else if (p.res1_kind == SSR_F32)
                   val += p.s1 * reinterpret_cast<const float*>(p.res1)[pix * p.res1_stride + c];
+                else if (p.res1_kind == SSR_F32_PLANAR4)
+                  val += p.s1 * reinterpret_cast<const float*>(p.res1)[((long)(c >> 2) * n_pix + pix) * 4 + (c & 3)];
               }
               if (p.res2_kind == SSR_BF16)
                 val += p.s2 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res2)[pix * p.res2_stride + c]);
               else if (p.res2_kind == SSR_F32)
                 val += p.s2 * reinterpret_cast<const float*>(p.res2)[pix * p.res2_stride + c];
+              else if (p.res2_kind == SSR_F32_PLANAR4)
+                val += p.s2 * reinterpret_cast<const float*>(p.res2)[((long)(c >> 2) * n_pix + pix) * 4 + (c & 3)];
               if (p.out32_mode == SSR_OUT32_NHWC)
                 p.out_f32[pix * p.out32_stride + c] = val;
+              else if (p.out32_mode == SSR_OUT32_PLANAR4)
+                p.out_f32[((long)(c >> 2) * n_pix + pix) * 4 + (c & 3)] = val;
               else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC)
                 atomicAdd(p.out_f32 + pix * p.out32_stride + c, val);
               else if (p.out32_mode == SSR_OUT32_NCHW)
@@ -428,9 +519,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+      }  // N tiles
     }
+    if (et == 0) SSR_STAMP(l, 6);   // epilogue: this warp's stores of the layer are issued
+    if (sync_mode == kSyncCluster) {
+      // chain, one image per cluster: publish this layer's stores to the TMA loads of the cluster's CTAs (they read our halo
+      // rows), then arrive on every CTA's layer barrier -- a few hundred ns through DSMEM, and no CTA waits for another image
+      if (l + 1 < n_layers) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t nct = cluster_nctarank();
+          for (uint32_t r = 0; r < nct; ++r) mbar_arrive_remote_release(bar_layer, r);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // nobody still reads s_bias of this layer
+      }
+    } else if (sync_mode == kSyncGrid) {
+      // chain over the whole grid: same, through a global arrive counter
+      fence_proxy_async();
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et == 0) {
+        if (l + 1 < n_layers) {
+          red_release_gpu_add(gsync, 1u);
+        } else if (atomicAdd(gsync + 1, 1u) == gridDim.x - 1) {
+          // every CTA has passed every wait: re-arm the counters for the next chained launch on this stream
+          gsync[1] = 0;
+          atomicExch(gsync, 0u);
+        }
+      }
+    }
+    if (et == 0) SSR_STAMP(l, 7);   // epilogue: arrived
+    }  // layers
   }
-
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) {
@@ -438,6 +559,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+}
+
+template <int MT, int R>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcK p) {
+  conv_tc_body<MT, R>(&tmA, &tmB, &p, 1, kSyncNone, nullptr);
+}
+
+template <int MT, int R>
+__global__ void __launch_bounds__(kThreads, 1) conv_chain_kernel(const __grid_constant__ ConvChainK c) {
+  conv_tc_body<MT, R>(c.tmA, c.tmB, c.k, c.n_layers, c.sync_mode, c.sync, c.timeline);
 }
 
 static int g_smem_optin = -1;
@@ -481,8 +613,9 @@ extern "C" int64_t ssr_packed_weight_bytes(int32_t cin, int32_t cout, int32_t r,
   return (int64_t)chunks * r * r * np * 64 * 2;
 }
 
-extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+// validates one layer and fills its kernel parameters + tensor maps; the shared-memory ring and the TMEM budget
+// (stages, stage_stride, acc_stride, tmem_cols) are set afterwards by finalize_ring() -- jointly for the layers of a chain
+static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUtensorMap& tmA, CUtensorMap& tmB, int& mt_out) {
   SSR_REQUIRE(a != nullptr, "ssr_conv_tc: null args");
   SSR_REQUIRE(a->r == 1 || a->r == 3, "ssr_conv_tc: r must be 1 or 3 (got %d)", a->r);
   SSR_REQUIRE(a->n_img > 0 && a->h > 0 && a->w > 0, "ssr_conv_tc: bad geometry");
@@ -494,7 +627,7 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   SSR_REQUIRE(a->w >= 8, "ssr_conv_tc: width < 8 unsupported");
   if (!device_limits()) return SSR_E_CUDA;
 
-  ConvTcK p{};
+  p = ConvTcK{};
   p.n_img = a->n_img;
   p.H = a->h;
   p.W = a->w;
@@ -512,7 +645,7 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
     p.TW = a->w >= tw_max && a->r == 3 ? tw_max : (a->w >= 128 ? 128 : round_up(a->w, 8));
   }
   p.TH = 128 / p.TW;
-  int mt = a->mt;
+  int mt = mt_force ? mt_force : a->mt;
   if (mt == 0) {
     // two stacked M tiles per CTA when one-tile CTAs would spill past a single co-resident wave: the weight tiles
     // and the halo rows are then shared by 256 pixels (less L2 traffic per MMA) and the grid fits the 148 SMs
@@ -556,20 +689,8 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   uint32_t need = (uint32_t)(((mt - 1) * p.TH + p.R - 1) * p.TW) * 128u + 16384u;
   p.a_alloc = (uint32_t)round_up((int)max(p.a_box_bytes, need), 1024);
   p.b_bytes = (uint32_t)(p.R * p.n_tile * 128);
-  const uint32_t stage_bytes = p.a_alloc + p.b_bytes;
-  const int iters_max = ((p.chunks + p.splits - 1) / p.splits) * p.R;
-  const int budget = g_smem_optin - 1024 - 256 - 1024;
-  int stages = budget / (int)stage_bytes;
-  SSR_REQUIRE(stages >= 1, "ssr_conv_tc: stage of %u bytes does not fit shared memory", stage_bytes);
-  // prefer two co-resident CTAs per SM when that still leaves a >= 3 deep pipeline
-  int stages_half = (budget / 2 - 1024) / (int)stage_bytes;
-  if (stages_half >= 3) stages = stages_half;
-  if (stages > 8) stages = 8;
-  if (stages > iters_max) stages = iters_max;
-  p.stages = stages;
-  uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * mt * p.n_tile)) cols <<= 1;   // double-buffered accumulators
-  p.tmem_cols = cols;
+  p.n_loop = 1;
+  mt_out = mt;
 
   p.bias = a->bias;
   p.act = a->act;
@@ -608,8 +729,10 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
     if (p.bias) SSR_REQUIRE((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "ssr_conv_tc: bias alignment");
   }
 
+  if (p.res1_kind == SSR_F32_PLANAR4) SSR_REQUIRE((reinterpret_cast<uintptr_t>(p.res1) & 15) == 0 && a->res1_cmax % 4 == 0, "ssr_conv_tc: res1 alignment");
+  if (p.res2_kind == SSR_F32_PLANAR4) SSR_REQUIRE((reinterpret_cast<uintptr_t>(p.res2) & 15) == 0, "ssr_conv_tc: res2 alignment");
+  if (p.out32_mode == SSR_OUT32_PLANAR4) SSR_REQUIRE((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0, "ssr_conv_tc: out_f32 alignment");
   // tensor maps
-  CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
     uint64_t str[3] = {(uint64_t)a->x_pix_stride * 2, (uint64_t)a->x_pix_stride * 2 * a->w,
@@ -628,43 +751,189 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
       return SSR_E_CUDA;
   }
 
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
-  // persistent: at most one CTA per SM along x, each walking tiles x, x + gridDim.x, ...
+  return SSR_OK;
+}
+
+// one shared-memory ring / TMEM split for all n layers (n == 1: a plain launch); returns the dynamic smem size or 0
+static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
+  uint32_t stage_bytes = 0;
+  int n_tile_max = 0, iters = 0;
+  for (int i = 0; i < n; ++i) {
+    stage_bytes = max(stage_bytes, ps[i].a_alloc + ps[i].b_bytes);
+    n_tile_max = max(n_tile_max, ps[i].n_tile);
+    iters += ((ps[i].chunks + ps[i].splits - 1) / ps[i].splits) * ps[i].R;
+  }
+  const int budget = g_smem_optin - 1024 - 256 - 1024;
+  int stages = budget / (int)stage_bytes;
+  if (stages < 1) {
+    set_error("ssr_conv_tc: stage of %u bytes does not fit shared memory", stage_bytes);
+    return 0;
+  }
+  // prefer two co-resident CTAs per SM when that still leaves a >= 3 deep pipeline
+  int stages_half = (budget / 2 - 1024) / (int)stage_bytes;
+  if (stages_half >= 3 && n == 1) stages = stages_half;
+  if (stages > 8) stages = 8;
+  if (stages > iters) stages = iters;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * mt * n_tile_max)) cols <<= 1;   // double-buffered accumulators
+  for (int i = 0; i < n; ++i) {
+    ps[i].stages = stages;
+    ps[i].stage_stride = stage_bytes;
+    ps[i].acc_stride = (uint32_t)(mt * n_tile_max);
+    ps[i].tmem_cols = cols;
+  }
+  return (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
+}
+
+static int persistent_ctas(const ConvTcK& p) {
+  // at most one CTA per SM along x, each walking tiles x, x + gridDim.x, ...; keep the per-CTA tile counts balanced
+  // (e.g. 2048 tiles on 148 SMs -> 14 tiles each on 147 CTAs, not 13.8 ragged)
   const int total_tiles = p.tiles_x * p.tiles_y * p.n_img;
   int ctas_x = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-  {
-    // keep the per-CTA tile counts balanced (e.g. 2048 tiles on 148 SMs -> 14 tiles each on 147 CTAs, not 13.8 ragged)
-    const int waves = (total_tiles + ctas_x - 1) / ctas_x;
-    ctas_x = (total_tiles + waves - 1) / waves;
-  }
-  dim3 grid((unsigned)ctas_x, (unsigned)(p.n_pad / p.n_tile), (unsigned)p.splits);
-  auto kern = mt == 1 ? (p.R == 3 ? conv_tc_kernel<1, 3> : conv_tc_kernel<1, 1>) : (p.R == 3 ? conv_tc_kernel<2, 3> : conv_tc_kernel<2, 1>);
-  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
-  const int cfg_idx = mt * 2 + (p.R == 3 ? 1 : 0);
-  if (configured[cfg_idx] < smem_bytes) {
-    if (!check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin),
-                    "cudaFuncSetAttribute(conv_tc)"))
+  const int waves = (total_tiles + ctas_x - 1) / ctas_x;
+  return (total_tiles + waves - 1) / waves;
+}
+
+template <typename Kern, typename... Args>
+static int launch_conv(Kern kern, size_t* configured, dim3 grid, int cluster_x, size_t smem_bytes, cudaStream_t stream, const char* what,
+                       Args... args) {
+  if (*configured < smem_bytes) {
+    if (!check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin), "cudaFuncSetAttribute(conv_tc)"))
       return SSR_E_CUDA;
-    configured[cfg_idx] = (size_t)g_smem_optin;
+    *configured = (size_t)g_smem_optin;
   }
   prof_before(0, stream);
-  {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    if (!check_cuda(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p), "conv_tc launch")) return SSR_E_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (!check_cuda(cudaLaunchKernelEx(&cfg, kern, args...), what)) return SSR_E_CUDA;
   prof_after(stream);
   count_launch();
-  if (!check_last("conv_tc launch")) return SSR_E_CUDA;
+  if (!check_last(what)) return SSR_E_CUDA;
   return SSR_OK;
+}
+
+extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ConvTcK p;
+  CUtensorMap tmA, tmB;
+  int mt = 0;
+  if (int rc = prepare_conv(a, 0, p, tmA, tmB, mt)) return rc;
+  const size_t smem_bytes = finalize_ring(&p, 1, mt);
+  if (!smem_bytes) return SSR_E_ARG;
+  dim3 grid((unsigned)persistent_ctas(p), (unsigned)(p.n_pad / p.n_tile), (unsigned)p.splits);
+  auto kern = mt == 1 ? (p.R == 3 ? conv_tc_kernel<1, 3> : conv_tc_kernel<1, 1>) : (p.R == 3 ? conv_tc_kernel<2, 3> : conv_tc_kernel<2, 1>);
+  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+  return launch_conv(kern, &configured[mt * 2 + (p.R == 3 ? 1 : 0)], grid, 1, smem_bytes, stream, "conv_tc launch", tmA, tmB, p);
+}
+
+// diagnostics: with SSR_CHAIN_TIMELINE=1 every chained launch overwrites a [512 CTAs][kMaxChain][8] table of clock64 stamps
+static long long* g_timeline = nullptr;
+static long long* chain_timeline_buffer() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SSR_CHAIN_TIMELINE");
+    on = e ? atoi(e) : 0;
+    if (on && cudaMalloc(&g_timeline, 512 * kMaxChain * 8 * sizeof(long long)) != cudaSuccess) g_timeline = nullptr;
+  }
+  return g_timeline;
+}
+extern "C" int ssr_debug_chain_timeline(long long* host_out, int32_t n_ctas) {
+  SSR_REQUIRE(g_timeline != nullptr, "ssr_debug_chain_timeline: run with SSR_CHAIN_TIMELINE=1");
+  SSR_REQUIRE(n_ctas > 0 && n_ctas <= 512, "ssr_debug_chain_timeline: n_ctas");
+  if (!check_cuda(cudaMemcpy(host_out, g_timeline, (size_t)n_ctas * kMaxChain * 8 * sizeof(long long), cudaMemcpyDeviceToHost), "timeline copy"))
+    return SSR_E_CUDA;
+  return SSR_OK;
+}
+
+// A chain: layers that share the image geometry, each reading what earlier layers of the same call wrote (the five convs
+// of a ResidualDenseBlock, or its five input-gradient convs), executed by ONE launch.
+//   * images of <= 8 tiles (the 32 x 32 training tiles: 4): one thread-block cluster per image, one tile per CTA; a conv only
+//     needs the neighbouring tiles' halo rows, so layers synchronise inside the cluster (DSMEM mbarriers) and images never
+//     wait for each other -- any batch size, no co-residency requirement;
+//   * SSR_CONV_CHAIN=2: larger images through a grid-wide arrive counter (needs the whole grid co-resident: <= one CTA per SM);
+//   * otherwise, or with SSR_CONV_CHAIN=0: n plain launches, with identical results.
+extern "C" int ssr_conv_tc_chain(const ssr_conv_tc_args* a, int32_t n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SSR_REQUIRE(a != nullptr && n >= 1, "ssr_conv_tc_chain: null args");
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("SSR_CONV_CHAIN");
+    enabled = e ? atoi(e) : 1;
+  }
+  bool ok = enabled && n >= 2 && n <= kMaxChain;
+  for (int i = 0; ok && i < n; ++i)
+    ok = a[i].n_img == a[0].n_img && a[i].h == a[0].h && a[i].w == a[0].w && a[i].r == a[0].r && a[i].n_pad <= 256 &&
+         a[i].n_tile == 0 && a[i].splits <= 1 && a[i].mt == a[0].mt;
+  static ConvChainK c;   // 2.3 KB of tensor maps and parameters: built in place, copied by the launch
+  int mt = 0, tiles_per_img = 0;
+  if (ok) {
+    if (!device_limits()) return SSR_E_CUDA;
+    // the widest layer decides how many M tiles a CTA stacks (two accumulator buffers of mt * n_tile TMEM columns)
+    int widest = 0;
+    for (int i = 1; i < n; ++i)
+      if (a[i].n_pad > a[widest].n_pad) widest = i;
+    int mt_w = 0;
+    if (int rc = prepare_conv(&a[widest], 0, c.k[widest], c.tmA[widest], c.tmB[widest], mt_w)) return rc;
+    mt = mt_w;
+    for (int i = 0; i < n; ++i) {
+      int mt_i = 0;
+      if (i != widest)
+        if (int rc = prepare_conv(&a[i], mt, c.k[i], c.tmA[i], c.tmB[i], mt_i)) return rc;
+      c.k[i].n_loop = c.k[i].n_pad / c.k[i].n_tile;
+    }
+    tiles_per_img = c.k[0].tiles_x * c.k[0].tiles_y;
+    const int total = tiles_per_img * c.k[0].n_img;
+    if (tiles_per_img <= 8) c.sync_mode = kSyncCluster;
+    else if (enabled == 2 && total <= 2 * g_num_sms) c.sync_mode = kSyncGrid;
+    else ok = false;
+  }
+  if (!ok) {
+    for (int i = 0; i < n; ++i)
+      if (int rc = ssr_conv_tc(&a[i], stream_)) return rc;
+    return SSR_OK;
+  }
+  const size_t smem_bytes = finalize_ring(c.k, n, mt);
+  if (!smem_bytes) return SSR_E_ARG;
+  c.n_layers = n;
+  c.sync = nullptr;
+  c.timeline = chain_timeline_buffer();
+  dim3 grid(1, 1, 1);
+  int cluster_x = 1;
+  if (c.sync_mode == kSyncCluster) {
+    grid.x = (unsigned)(tiles_per_img * c.k[0].n_img);
+    cluster_x = tiles_per_img;
+  } else {
+    static unsigned int* sync_buf = nullptr;
+    if (!sync_buf) {
+      if (!check_cuda(cudaMalloc(&sync_buf, 2 * sizeof(unsigned int)), "cudaMalloc(chain sync)")) return SSR_E_CUDA;
+      if (!check_cuda(cudaMemsetAsync(sync_buf, 0, 2 * sizeof(unsigned int), stream), "cudaMemset(chain sync)")) return SSR_E_CUDA;
+    }
+    c.sync = sync_buf;
+    grid.x = (unsigned)min(persistent_ctas(c.k[0]), g_num_sms);
+  }
+  const int R = c.k[0].R;
+  auto kern = mt == 1 ? (R == 3 ? conv_chain_kernel<1, 3> : conv_chain_kernel<1, 1>) : (R == 3 ? conv_chain_kernel<2, 3> : conv_chain_kernel<2, 1>);
+  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+  return launch_conv(kern, &configured[mt * 2 + (R == 3 ? 1 : 0)], grid, cluster_x, smem_bytes, stream, "conv_tc chain launch", c);
 }
 
 // ------------------------------------------------------------------ weight packing

@@ -144,35 +144,37 @@ class _Workspace:
         b0 = self.rdb_buf(0)
         plan.conv(conv_args(self.in0.ptr(), B, h, w, self.in0.stride, eng.cin_pad, c.packed.data_ptr(), 3, c.cout, c.n_pad,
                             bias=bptr(c), out=b0.ptr(0), out_stride=b0.stride,
-                            out32=self.trunk_of(0).data_ptr(), out32_mode=L.OUT32_NHWC, out32_stride=nf))
+                            out32=self.trunk_of(0).data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf))
         n_rdb = 3 * nb
         for i in range(n_rdb):
             blk, j = divmod(i, 3)
             cur = self.rdb_buf(i)
             nxt = self.rdb_buf(i + 1) if i + 1 < n_rdb else self.body_out
             t_cur, t_nxt = self.trunk_of(i), self.trunk_of(i + 1)
+            block = []   # the five convs of the dense block run as one chained launch
             for k in range(1, 5):
                 c = eng.cv[f"body.{blk}.rdb{j + 1}.conv{k}"]
                 cin = nf + (k - 1) * g
-                plan.conv(conv_args(cur.ptr(0), B, h, w, cur.stride, cin, c.packed.data_ptr(), 3, c.cout, c.n_pad,
-                                    bias=bptr(c), act=1, out=cur.ptr(cin), out_stride=cur.stride))
+                block.append(conv_args(cur.ptr(0), B, h, w, cur.stride, cin, c.packed.data_ptr(), 3, c.cout, c.n_pad,
+                                       bias=bptr(c), act=1, out=cur.ptr(cin), out_stride=cur.stride))
             c = eng.cv[f"body.{blk}.rdb{j + 1}.conv5"]
             if j < 2:
-                plan.conv(conv_args(cur.ptr(0), B, h, w, cur.stride, nf + 4 * g, c.packed.data_ptr(), 3, c.cout, c.n_pad,
-                                    bias=bptr(c), s0=0.2, res1=t_cur.data_ptr(), res1_kind=L.SSR_F32, res1_stride=nf, s1=1.0,
+                block.append(conv_args(cur.ptr(0), B, h, w, cur.stride, nf + 4 * g, c.packed.data_ptr(), 3, c.cout, c.n_pad,
+                                    bias=bptr(c), s0=0.2, res1=t_cur.data_ptr(), res1_kind=L.SSR_F32_PLANAR4, res1_stride=nf, s1=1.0,
                                     out=nxt.ptr(0), out_stride=nxt.stride,
-                                    out32=t_nxt.data_ptr(), out32_mode=L.OUT32_NHWC, out32_stride=nf))
+                                    out32=t_nxt.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf))
             else:
                 t_blk = self.trunk_of(3 * blk)
                 # (x5*0.2 + x_rdb3)*0.2 + x_rrdb
-                plan.conv(conv_args(cur.ptr(0), B, h, w, cur.stride, nf + 4 * g, c.packed.data_ptr(), 3, c.cout, c.n_pad,
-                                    bias=bptr(c), s0=0.04, res1=t_cur.data_ptr(), res1_kind=L.SSR_F32, res1_stride=nf, s1=0.2,
-                                    res2=t_blk.data_ptr(), res2_kind=L.SSR_F32, res2_stride=nf, s2=1.0,
+                block.append(conv_args(cur.ptr(0), B, h, w, cur.stride, nf + 4 * g, c.packed.data_ptr(), 3, c.cout, c.n_pad,
+                                    bias=bptr(c), s0=0.04, res1=t_cur.data_ptr(), res1_kind=L.SSR_F32_PLANAR4, res1_stride=nf, s1=0.2,
+                                    res2=t_blk.data_ptr(), res2_kind=L.SSR_F32_PLANAR4, res2_stride=nf, s2=1.0,
                                     out=nxt.ptr(0), out_stride=nxt.stride,
-                                    out32=t_nxt.data_ptr(), out32_mode=L.OUT32_NHWC, out32_stride=nf))
+                                    out32=t_nxt.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf))
+            plan.chain(block)
         c = eng.cv["conv_body"]
         plan.conv(conv_args(self.body_out.ptr(), B, h, w, nf, nf, c.packed.data_ptr(), 3, c.cout, c.n_pad, bias=bptr(c),
-                            res1=self.trunk_of(0).data_ptr(), res1_kind=L.SSR_F32, res1_stride=nf, s1=1.0,
+                            res1=self.trunk_of(0).data_ptr(), res1_kind=L.SSR_F32_PLANAR4, res1_stride=nf, s1=1.0,
                             out=self.feat.ptr(), out_stride=nf))
         src = self.feat
         hh, ww = h, w
@@ -207,7 +209,7 @@ class _Workspace:
         cw = nf + 4 * g
         dev = eng.device
         wg = eng.wg
-        F32 = L.SSR_F32
+        F32 = L.SSR_F32_PLANAR4   # the running f32 gradients are epilogue-only buffers: quad-planar, coalesced per warp
         plan = Plan()
         grads = eng.grads
         self.d_last = Act(B, H, W, 16, dev)
@@ -271,7 +273,7 @@ class _Workspace:
         # ---- conv_body
         c = eng.cv["conv_body"]
         plan.conv(conv_args(d_feat.ptr(), B, h, w, nf, nf, c.packed_dg.data_ptr(), 3, nf, c.n_pad_dg,
-                            out=gO_b.ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_NHWC, out32_stride=nf))
+                            out=gO_b.ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf))
         wgrad("conv_body", self.body_out.ptr(), nf, nf, d_feat.ptr(), nf, nf, B, h, w)
         # ---- the trunk, last block first
         for i in range(3 * nb - 1, -1, -1):
@@ -286,35 +288,37 @@ class _Workspace:
                 xin, s0, r1, r1s, s1 = gO_b, 0.04, GO32.data_ptr(), nf, 0.2
             else:
                 xin, s0, r1, r1s, s1 = gR_in, 0.2, G32.data_ptr(), cw, 1.0
-            plan.conv(conv_args(xin.ptr(), B, h, w, nf, nf, c5.packed_dg.data_ptr(), 3, cw, c5.n_pad_dg, s0=s0,
+            # the five input-gradient convs of the block: one chained launch (each reads the dY slot the previous one wrote)
+            dchain = [conv_args(xin.ptr(), B, h, w, nf, nf, c5.packed_dg.data_ptr(), 3, cw, c5.n_pad_dg, s0=s0,
                                 res1=r1, res1_kind=F32, res1_stride=r1s, s1=s1, res1_cmax=nf,
                                 mask=cur.ptr(), mask_stride=cw, mask_lo=nf,
-                                out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(), out32_mode=L.OUT32_NHWC, out32_stride=cw))
+                                out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=cw)]
             batch = [wg.args(f"{pre}.conv5", cur.ptr(), cw, cw, xin.ptr(), nf, nf, B, h, w, 3, s0)]
-            bias_grad(f"{pre}.conv5", xin.ptr(), nf, B * h * w, nf, s0)
             for k in range(4, 0, -1):
                 ck = eng.cv[f"{pre}.conv{k}"]
                 nk = nf + (k - 1) * g
                 dyk = Dg.ptr(nk)
                 if k > 1:
-                    plan.conv(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
+                    dchain.append(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
                                         res1=G32.data_ptr(), res1_kind=F32, res1_stride=cw, s1=1.0,
                                         mask=cur.ptr(), mask_stride=cw, mask_lo=nf,
-                                        out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(), out32_mode=L.OUT32_NHWC,
+                                        out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(), out32_mode=L.OUT32_PLANAR4,
                                         out32_stride=cw))
                 elif j > 0:
-                    plan.conv(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
+                    dchain.append(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
                                         res1=G32.data_ptr(), res1_kind=F32, res1_stride=cw, s1=1.0,
-                                        out=gR_out.ptr(), out_stride=nf, out32=G32.data_ptr(), out32_mode=L.OUT32_NHWC,
+                                        out=gR_out.ptr(), out_stride=nf, out32=G32.data_ptr(), out32_mode=L.OUT32_PLANAR4,
                                         out32_stride=cw))
                 else:
                     # first block of the RRDB: add the RRDB-level skip gradient and hand over to the previous RRDB
-                    plan.conv(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
+                    dchain.append(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
                                         res1=G32.data_ptr(), res1_kind=F32, res1_stride=cw, s1=1.0,
                                         res2=GO32.data_ptr(), res2_kind=F32, res2_stride=nf, s2=1.0,
-                                        out=gO_b.ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_NHWC,
+                                        out=gO_b.ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_PLANAR4,
                                         out32_stride=nf))
                 batch.append(wg.args(f"{pre}.conv{k}", cur.ptr(), cw, nk, dyk, cw, g, B, h, w, 3, 1.0))
+            plan.chain(dchain)
+            bias_grad(f"{pre}.conv5", xin.ptr(), nf, B * h * w, nf, s0)
             # all five weight gradients of the block in ONE launch (they only need the block's finished dY slots)
             plan_wgrad_batch(plan, batch)
             plan.add(lib().ssr_bias_grad_groups, Dg.ptr(nf), cw, B * h * w, 4 * g, g, self._bias_ptrs.data_ptr() + 32 * i, 1.0)

@@ -54,6 +54,12 @@ class Plan:
         self.keep.append(args)
         self.calls.append((lib().ssr_conv_tc, (C.byref(args),)))
 
+    def chain(self, args_list):
+        """consecutive convs over one image geometry, each reading what the previous ones wrote: ONE launch (ssr_conv_tc_chain)"""
+        arr = (L.ConvTcArgs * len(args_list))(*args_list)
+        self.keep.append(arr)
+        self.calls.append((lib().ssr_conv_tc_chain, (arr, len(args_list))))
+
     def extend(self, other):
         self.calls.extend(other.calls)
         self.keep.extend(other.keep)

@@ -268,3 +268,158 @@ def test_bad_args_fail_loudly():
     rc = lib.ssr_conv_tc(C.byref(a), None)
     assert rc == -1
     assert b"r must be" in lib.ssr_last_error()
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (32, 32, 32), (3, 24, 40)])
+def test_chain_equals_plain_launches(B, H, W):
+    """ssr_conv_tc_chain (five dense-block convs in ONE launch, grid-wide arrive/wait between layers) must be
+    bit-identical to the same five ssr_conv_tc calls; run three times (barrier phases / counters must re-arm)."""
+    L, lib = _lib()
+    nf, g = 64, 32
+    cw = nf + 4 * g
+    torch.manual_seed(B * 1000 + H)
+    x0 = torch.randn(B, H, W, nf) * 0.5
+    ws, packs, biases = [], [], []
+    for k in range(5):
+        cin, cout = nf + k * g, (g if k < 4 else nf)
+        wk = torch.randn(cout, cin, 3, 3) * (1.0 / (3.0 * cin ** 0.5))
+        packed, n_pad = pack_weight(L, lib, wk, L.PACK_FWD, k_pad=(cin + 63) // 64 * 64)
+        packs.append((packed, n_pad, cin, cout))
+        biases.append((torch.randn(cout) * 0.1).cuda())
+    trunk = torch.randn(B, H, W, nf).cuda()
+
+    def make(buf, nxt, t32):
+        arr = (L.ConvTcArgs * 5)()
+        for k in range(5):
+            packed, n_pad, cin, cout = packs[k]
+            a = arr[k]
+            a.x, a.n_img, a.h, a.w, a.x_pix_stride, a.cin = buf.data_ptr(), B, H, W, cw, cin
+            a.w_packed, a.r, a.cout, a.n_pad = packed.data_ptr(), 3, cout, n_pad
+            a.bias = biases[k].data_ptr()
+            if k < 4:
+                a.act, a.s0 = 1, 1.0
+                a.out_bf16, a.out_pix_stride = buf.data_ptr() + 2 * cin, cw
+            else:
+                a.act, a.s0 = 0, 0.2
+                a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = trunk.data_ptr(), L.SSR_F32, nf, 1.0
+                a.out_bf16, a.out_pix_stride = nxt.data_ptr(), nf
+                a.out_f32, a.out32_mode, a.out32_pix_stride = t32.data_ptr(), L.OUT32_NHWC, nf
+        return arr
+
+    def fresh():
+        buf = torch.zeros(B, H, W, cw, dtype=torch.bfloat16, device="cuda")
+        buf[..., :nf] = x0.cuda().to(torch.bfloat16)
+        return buf, torch.zeros(B, H, W, nf, dtype=torch.bfloat16, device="cuda"), torch.zeros(B, H, W, nf, device="cuda")
+
+    s = torch.cuda.current_stream().cuda_stream
+    buf_a, nxt_a, t_a = fresh()
+    arr = make(buf_a, nxt_a, t_a)
+    for k in range(5):
+        L.check(lib.ssr_conv_tc(C.byref(arr[k]), s))
+    torch.cuda.synchronize()
+    assert nxt_a.float().abs().max() > 0
+    for _ in range(3):
+        buf_b, nxt_b, t_b = fresh()
+        arr_b = make(buf_b, nxt_b, t_b)
+        n0 = lib.ssr_launch_count()
+        L.check(lib.ssr_conv_tc_chain(arr_b, 5, s))
+        torch.cuda.synchronize()
+        # 32 x 32 images are 4 (or 8) tiles: one cluster per image, a single launch; 24 x 40 is 12 tiles: plain launches
+        assert lib.ssr_launch_count() - n0 == (1 if (H, W) == (32, 32) else 5)
+        assert torch.equal(buf_a, buf_b)
+        assert torch.equal(nxt_a, nxt_b)
+        assert torch.equal(t_a, t_b)
+
+
+@pytest.mark.parametrize("B", [2, 32])
+def test_chain_wide_layers_in_place_gradient(B):
+    """the input-gradient chain of a dense block: N = 192, 160, 128, 96, 64 output channels (several N tiles per CTA),
+    a running f32 gradient read and rewritten in place, derivative masks -- chained launch == five plain launches, bit for bit"""
+    L, lib = _lib()
+    H = W = 32
+    nf, g = 64, 32
+    cw = nf + 4 * g
+    torch.manual_seed(7 + B)
+    xin = (torch.randn(B, H, W, nf) * 0.5).cuda().to(torch.bfloat16)
+    cur = torch.randn(B, H, W, cw).cuda().to(torch.bfloat16)          # forward activations -> LeakyReLU derivative mask
+    g32_0 = torch.randn(B, H, W, cw).cuda() * 0.1
+    layers = []
+    for k in range(5, 0, -1):
+        nk = nf + (k - 1) * g                      # output channels of this layer; it reads the g-channel dY slot at nk
+        cin = nf if k == 5 else g
+        wk = torch.randn(nk, cin, 3, 3) * (1.0 / (3.0 * cin ** 0.5))
+        packed, n_pad = pack_weight(L, lib, wk, L.PACK_FWD, k_pad=64)
+        layers.append((k, nk, cin, packed, n_pad))
+
+    def make(dg, G32, gout):
+        arr = (L.ConvTcArgs * 5)()
+        for i, (k, nk, cin, packed, n_pad) in enumerate(layers):
+            a = arr[i]
+            a.x = xin.data_ptr() if k == 5 else dg.data_ptr() + 2 * nk
+            a.x_pix_stride = nf if k == 5 else cw
+            a.n_img, a.h, a.w, a.cin = B, H, W, cin
+            a.w_packed, a.r, a.cout, a.n_pad = packed.data_ptr(), 3, nk, n_pad
+            a.s0 = 0.2 if k == 5 else 1.0
+            a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = G32.data_ptr(), L.SSR_F32, cw, 1.0
+            if k == 5:
+                a.res1_cmax = nf
+            a.out_f32, a.out32_mode, a.out32_pix_stride = G32.data_ptr(), L.OUT32_NHWC, cw
+            if k > 1:
+                a.mask, a.mask_pix_stride, a.mask_lo = cur.data_ptr(), cw, nf
+                a.out_bf16, a.out_pix_stride = dg.data_ptr(), cw
+            else:
+                a.out_bf16, a.out_pix_stride = gout.data_ptr(), nf
+        return arr
+
+    def fresh():
+        return (torch.zeros(B, H, W, cw, dtype=torch.bfloat16, device="cuda"), g32_0.clone(),
+                torch.zeros(B, H, W, nf, dtype=torch.bfloat16, device="cuda"))
+
+    s = torch.cuda.current_stream().cuda_stream
+    ref = fresh()
+    arr = make(*ref)
+    for i in range(5):
+        L.check(lib.ssr_conv_tc(C.byref(arr[i]), s))
+    torch.cuda.synchronize()
+    assert ref[2].float().abs().max() > 0
+    for _ in range(3):
+        got = fresh()
+        arr_b = make(*got)
+        n0 = lib.ssr_launch_count()
+        L.check(lib.ssr_conv_tc_chain(arr_b, 5, s))
+        torch.cuda.synchronize()
+        assert lib.ssr_launch_count() - n0 == 1
+        for r, o in zip(ref, got):
+            assert torch.equal(r, o)
+
+
+@pytest.mark.parametrize("cout", [64, 20])
+def test_planar4_f32_operands_match_nhwc(cout):
+    """SSR_F32_PLANAR4 residual + SSR_OUT32_PLANAR4 output hold exactly the values of the NHWC f32 forms (layout only)"""
+    L, lib = _lib()
+    B, H, W, cin = 2, 32, 32, 64
+    P = B * H * W
+    torch.manual_seed(cout)
+    x = (torch.randn(B, H, W, cin) * 0.5).cuda().to(torch.bfloat16)
+    wk = torch.randn(cout, cin, 3, 3) * 0.05
+    packed, n_pad = pack_weight(L, lib, wk, L.PACK_FWD)
+    cq = (cout + 3) // 4 * 4
+    res = torch.randn(P, cq).cuda()
+    res_planar = res.view(P, cq // 4, 4).permute(1, 0, 2).contiguous()
+    s = torch.cuda.current_stream().cuda_stream
+
+    def run(planar):
+        a = L.ConvTcArgs()
+        a.x, a.n_img, a.h, a.w, a.x_pix_stride, a.cin = x.data_ptr(), B, H, W, cin, cin
+        a.w_packed, a.r, a.cout, a.n_pad, a.s0 = packed.data_ptr(), 3, cout, n_pad, 0.5
+        out = torch.zeros(cq // 4, P, 4, device="cuda") if planar else torch.zeros(P, cq, device="cuda")
+        a.res1 = (res_planar if planar else res).data_ptr()
+        a.res1_kind, a.res1_pix_stride, a.s1 = (L.SSR_F32_PLANAR4 if planar else L.SSR_F32), cq, 1.5
+        a.out_f32, a.out32_mode, a.out32_pix_stride = out.data_ptr(), (L.OUT32_PLANAR4 if planar else L.OUT32_NHWC), cq
+        L.check(lib.ssr_conv_tc(C.byref(a), s))
+        torch.cuda.synchronize()
+        return out.permute(1, 0, 2).reshape(P, cq) if planar else out
+
+    nhwc, planar = run(False), run(True)
+    assert nhwc.abs().max() > 0
+    assert torch.equal(nhwc[:, :cout], planar[:, :cout])
