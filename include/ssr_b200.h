@@ -111,6 +111,11 @@ typedef struct ssr_conv_tc_args {
   int32_t mt;     /* 128-pixel M tiles per CTA: 1 or 2 */
   int32_t splits; /* split the cin chunks over this many CTAs (needs SSR_OUT32_NHWC_ATOMIC) */
   int32_t res1_cmax; /* res1 is added only to channels < res1_cmax (0 = all); multiple of 16 */
+  int32_t out_lo;    /* out_bf16 (and mask) only cover channels >= out_lo (multiple of 16): an input-gradient conv of a dense
+                      * block adds into all its f32 channels but only its top slot is read again as bf16 */
+  float* bias_grad;  /* bias_grad[c - out_lo] += bias_grad_scale * sum_p (the value out_bf16 receives), or NULL: the bf16 output
+                      * of an input-gradient conv is the dY of the conv below it, its pixel sum that conv's bias gradient */
+  float bias_grad_scale;
 } ssr_conv_tc_args;
 
 int ssr_conv_tc(const ssr_conv_tc_args* args, void* stream);

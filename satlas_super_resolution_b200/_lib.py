@@ -32,6 +32,7 @@ class ConvTcArgs(C.Structure):
         ("out_bf16", C.c_void_p), ("out_pix_stride", C.c_int32),
         ("out_f32", C.c_void_p), ("out32_mode", C.c_int32), ("out32_pix_stride", C.c_int32),
         ("n_tile", C.c_int32), ("mt", C.c_int32), ("splits", C.c_int32), ("res1_cmax", C.c_int32),
+        ("out_lo", C.c_int32), ("bias_grad", C.c_void_p), ("bias_grad_scale", C.c_float),
     ]
 
 

@@ -44,6 +44,9 @@ struct ConvTcK {
   int out_stride;
   float* out_f32;
   int out32_mode, out32_stride;
+  int out_lo;          // the bf16 output (and its bias-gradient sum) only covers channels >= out_lo
+  float* bgrad;        // bgrad[c - out_lo] += bgrad_scale * sum over pixels of the bf16-path value, or NULL
+  float bgrad_scale;
   int dbg_aoff;  // experiment: extra row offset (x128 B) of the A descriptor, see scripts/probe_swizzle.py
 };
 
@@ -120,7 +123,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
   uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2] accumulator buffer b drained  (epilogue -> MMA), 8 warp arrivals
   uint64_t* bar_layer = bar_acc_empty + 2;         // kSyncCluster: every epilogue warp of the cluster arrives once per layer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_layer + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [256] bias of the layer's output channels
+  float* s_bg = s_bias + 256;                                // [256] per-CTA bias-gradient partial sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -295,7 +299,10 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
     const ConvTcK& p = ps[l];
     const int n_base = (int)blockIdx.y * p.n_loop * p.n_tile;   // first output channel this CTA produces
     const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
-    for (int i = et; i < p.n_loop * p.n_tile; i += kThreads - 64) s_bias[i] = (add_bias && n_base + i < p.cout) ? p.bias[n_base + i] : 0.f;
+    for (int i = et; i < p.n_loop * p.n_tile; i += kThreads - 64) {
+      s_bias[i] = (add_bias && n_base + i < p.cout) ? p.bias[n_base + i] : 0.f;
+      s_bg[i] = 0.f;
+    }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const int nchunks = p.n_tile >> 4;
     const bool use_r1 = p.res1_kind != SSR_NONE, use_r2 = p.res2_kind != SSR_NONE, use_mk = p.mask != nullptr;
@@ -336,7 +343,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
           for (int j = 0; j < 4; ++j) o.r2[j] = s4[(long)j * n_pix];
         }
       }
-      if (use_mk && c0 >= p.mask_lo) {
+      if (use_mk && c0 >= p.mask_lo && c0 >= p.out_lo) {
         const uint4* s4 = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_stride + c0);
         o.mk[0] = s4[0];
         o.mk[1] = s4[1];
@@ -406,7 +413,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
           __syncwarp();
           tmem_ld16(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.n_tile + ci * 16), v);
           tmem_ld_wait();
-          if (!in_img || c0 >= p.cout) continue;
+          const bool wr16 = c0 >= p.out_lo;                    // this chunk has a bf16 output (warp-uniform)
+          const bool sum_bg = (p.bgrad != nullptr) && wr16;     // ... whose per-channel pixel sums are a bias gradient
+          if (!sum_bg && (!in_img || c0 >= p.cout)) continue;
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
@@ -453,14 +462,14 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
 #pragma unroll
               for (int j = 0; j < 16; ++j) p.out_f32[(((long)n * p.cout + c0 + j) * p.H + y) * p.W + x] = f[j];
             }
-            if (use_mk && c0 >= p.mask_lo) {
+            if (use_mk && c0 >= p.mask_lo && wr16) {
               float r[16];
               expand(o.mk, SSR_BF16, r);
               const float neg = p.mask_relu ? 0.f : 0.2f;
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] *= (r[j] > 0.f ? 1.f : neg);
             }
-            if (p.out_bf16 != nullptr) {
+            if (p.out_bf16 != nullptr && wr16) {
               uint4 o0, o1;
               o0.x = pack_bf16(f[0], f[1]);
               o0.y = pack_bf16(f[2], f[3]);
@@ -474,7 +483,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
               dst[0] = o0;
               dst[1] = o1;
             }
-          } else {
+          } else if (in_img && c0 < p.cout) {
             // ragged tail of the channel dimension (cout not a multiple of 16): scalar path, fully unrolled so that the
             // accumulator array is never indexed dynamically (a dynamic index would force it into local memory)
 #pragma unroll
@@ -510,8 +519,36 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
                 const float mv = __bfloat162float(p.mask[pix * p.mask_stride + c]);
                 val *= (mv > 0.f ? 1.f : (p.mask_relu ? 0.f : 0.2f));
               }
-              if (p.out_bf16 != nullptr) p.out_bf16[pix * p.out_stride + c] = __float2bfloat16(val);
+              if (p.out_bf16 != nullptr && c >= p.out_lo) p.out_bf16[pix * p.out_stride + c] = __float2bfloat16(val);
             }
+          }
+          if (sum_bg) {
+            // per-channel sum over the warp's 32 pixels: a transposing butterfly (16 values -> 1 per lane in 16 shuffles),
+            // then one shared-memory atomic per channel; the CTA adds its partial sums to global memory once per layer
+            if (!live) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = 0.f;
+            }
+            float g8[8], g4[4], g2[2];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float keep = (lane & 16) ? f[j + 8] : f[j], send = (lane & 16) ? f[j] : f[j + 8];
+              g8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float keep = (lane & 8) ? g8[j + 4] : g8[j], send = (lane & 8) ? g8[j] : g8[j + 4];
+              g4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float keep = (lane & 4) ? g4[j + 2] : g4[j], send = (lane & 4) ? g4[j] : g4[j + 2];
+              g2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            float g1 = ((lane & 2) ? g2[1] : g2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 2) ? g2[0] : g2[1], 2);
+            g1 += __shfl_xor_sync(0xffffffffu, g1, 1);
+            const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if ((lane & 1) == 0) atomicAdd(&s_bg[c0 - n_base + ch], g1);
           }
         }
       }
@@ -520,6 +557,13 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
       }  // N tiles
+    }
+    if (p.bgrad != nullptr) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = et; i < p.n_loop * p.n_tile; i += kThreads - 64) {
+        const int c = n_base + i;
+        if (c >= p.out_lo && c < p.cout) atomicAdd(p.bgrad + (c - p.out_lo), p.bgrad_scale * s_bg[i]);
+      }
     }
     if (et == 0) SSR_STAMP(l, 6);   // epilogue: this warp's stores of the layer are issued
     if (sync_mode == kSyncCluster) {
@@ -713,6 +757,11 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
   p.out_f32 = a->out_f32;
   p.out32_mode = a->out_f32 ? a->out32_mode : SSR_OUT32_NONE;
   p.out32_stride = a->out32_pix_stride;
+  p.out_lo = a->out_lo;
+  p.bgrad = a->bias_grad;
+  p.bgrad_scale = a->bias_grad_scale;
+  SSR_REQUIRE(a->out_lo >= 0 && a->out_lo % 16 == 0, "ssr_conv_tc: out_lo must be a multiple of 16");
+  if (a->bias_grad) SSR_REQUIRE(a->cout % 16 == 0 && a->splits <= 1, "ssr_conv_tc: bias_grad needs cout %% 16 == 0 and no split-K");
   {
     const char* e = getenv("SSR_DBG_AOFF");
     p.dbg_aoff = e ? atoi(e) : 0;
@@ -763,7 +812,7 @@ static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
     n_tile_max = max(n_tile_max, ps[i].n_tile);
     iters += ((ps[i].chunks + ps[i].splits - 1) / ps[i].splits) * ps[i].R;
   }
-  const int budget = g_smem_optin - 1024 - 256 - 1024;
+  const int budget = g_smem_optin - 1024 - 256 - 2048;
   int stages = budget / (int)stage_bytes;
   if (stages < 1) {
     set_error("ssr_conv_tc: stage of %u bytes does not fit shared memory", stage_bytes);
@@ -782,7 +831,7 @@ static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
     ps[i].acc_stride = (uint32_t)(mt * n_tile_max);
     ps[i].tmem_cols = cols;
   }
-  return (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
+  return (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias, bias-gradient sums*/;
 }
 
 static int persistent_ctas(const ConvTcK& p) {

@@ -230,12 +230,10 @@ class _Workspace:
             if bias:
                 bias_grad(name, dy_ptr, dy_stride, BB * HH * WW, cy, scale)
 
-        # one table of bias-gradient pointers per dense block: the four 32-channel dY slots of Dg in ONE launch
-        ptr_rows = []
-        for i in range(3 * nb):
+        def bgrad_ptr(i, k):
+            """bias gradient of conv k of dense block i (accumulated by the epilogue of the conv that produces its dY)"""
             blk, j = divmod(i, 3)
-            ptr_rows.append([grads[f"body.{blk}.rdb{j + 1}.conv{k}.bias"].data_ptr() for k in range(1, 5)])
-        self._bias_ptrs = torch.tensor(ptr_rows, dtype=torch.int64, device=dev)
+            return grads[f"body.{blk}.rdb{j + 1}.conv{k}.bias"].data_ptr()
 
         # ---- tail: conv_last <- conv_hr <- conv_up_n ... conv_up1
         c = eng.cv["conv_last"]
@@ -273,7 +271,8 @@ class _Workspace:
         # ---- conv_body
         c = eng.cv["conv_body"]
         plan.conv(conv_args(d_feat.ptr(), B, h, w, nf, nf, c.packed_dg.data_ptr(), 3, nf, c.n_pad_dg,
-                            out=gO_b.ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf))
+                            out=gO_b.ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf,
+                            bias_grad=bgrad_ptr(3 * nb - 1, 5), bias_grad_scale=0.04))
         wgrad("conv_body", self.body_out.ptr(), nf, nf, d_feat.ptr(), nf, nf, B, h, w)
         # ---- the trunk, last block first
         for i in range(3 * nb - 1, -1, -1):
@@ -288,10 +287,13 @@ class _Workspace:
                 xin, s0, r1, r1s, s1 = gO_b, 0.04, GO32.data_ptr(), nf, 0.2
             else:
                 xin, s0, r1, r1s, s1 = gR_in, 0.2, G32.data_ptr(), cw, 1.0
-            # the five input-gradient convs of the block: one chained launch (each reads the dY slot the previous one wrote)
+            # The five input-gradient convs of the block: one chained launch (each reads the dY slot the previous one wrote).
+            # Every layer adds into ALL its f32 channels (G32) but only its top g-channel slot is read again as bf16 -- it is
+            # the finished dY of the conv below, so the masked bf16 store is limited to that slot (out_lo) and its pixel
+            # sum is accumulated as that conv's bias gradient on the way out.
             dchain = [conv_args(xin.ptr(), B, h, w, nf, nf, c5.packed_dg.data_ptr(), 3, cw, c5.n_pad_dg, s0=s0,
                                 res1=r1, res1_kind=F32, res1_stride=r1s, s1=s1, res1_cmax=nf,
-                                mask=cur.ptr(), mask_stride=cw, mask_lo=nf,
+                                mask=cur.ptr(), mask_stride=cw, mask_lo=cw - g, out_lo=cw - g, bias_grad=bgrad_ptr(i, 4),
                                 out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=cw)]
             batch = [wg.args(f"{pre}.conv5", cur.ptr(), cw, cw, xin.ptr(), nf, nf, B, h, w, 3, s0)]
             for k in range(4, 0, -1):
@@ -301,27 +303,27 @@ class _Workspace:
                 if k > 1:
                     dchain.append(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
                                         res1=G32.data_ptr(), res1_kind=F32, res1_stride=cw, s1=1.0,
-                                        mask=cur.ptr(), mask_stride=cw, mask_lo=nf,
+                                        mask=cur.ptr(), mask_stride=cw, mask_lo=nk - g, out_lo=nk - g,
+                                        bias_grad=bgrad_ptr(i, k - 1),
                                         out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(), out32_mode=L.OUT32_PLANAR4,
                                         out32_stride=cw))
                 elif j > 0:
                     dchain.append(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
                                         res1=G32.data_ptr(), res1_kind=F32, res1_stride=cw, s1=1.0,
                                         out=gR_out.ptr(), out_stride=nf, out32=G32.data_ptr(), out32_mode=L.OUT32_PLANAR4,
-                                        out32_stride=cw))
+                                        out32_stride=cw, bias_grad=bgrad_ptr(i - 1, 5), bias_grad_scale=0.2))
                 else:
                     # first block of the RRDB: add the RRDB-level skip gradient and hand over to the previous RRDB
                     dchain.append(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
                                         res1=G32.data_ptr(), res1_kind=F32, res1_stride=cw, s1=1.0,
                                         res2=GO32.data_ptr(), res2_kind=F32, res2_stride=nf, s2=1.0,
                                         out=gO_b.ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_PLANAR4,
-                                        out32_stride=nf))
+                                        out32_stride=nf, bias_grad=bgrad_ptr(i - 1, 5) if i > 0 else None,
+                                        bias_grad_scale=0.04))
                 batch.append(wg.args(f"{pre}.conv{k}", cur.ptr(), cw, nk, dyk, cw, g, B, h, w, 3, 1.0))
             plan.chain(dchain)
-            bias_grad(f"{pre}.conv5", xin.ptr(), nf, B * h * w, nf, s0)
             # all five weight gradients of the block in ONE launch (they only need the block's finished dY slots)
             plan_wgrad_batch(plan, batch)
-            plan.add(lib().ssr_bias_grad_groups, Dg.ptr(nf), cw, B * h * w, 4 * g, g, self._bias_ptrs.data_ptr() + 32 * i, 1.0)
         # ---- conv_first: dY = trunk gradient + the long skip (feat = conv_first + conv_body(...))
         plan.add(lib().ssr_axpby, gO_b.ptr(), nf, 1.0, d_feat.ptr(), nf, 1.0, None, 0, 0, d_first.ptr(), nf, B * h * w, nf)
         wgrad("conv_first", self.in0.ptr(), self.in0.stride, eng.cin_pad, d_first.ptr(), nf, nf, B, h, w)

@@ -140,7 +140,7 @@ def conv_args(x_ptr, B, H, W, x_stride, cin, w_ptr, r, cout, n_pad, bias=None, a
               res2=None, res2_kind=L.SSR_BF16, res2_stride=0, s2=0.0,
               mask=None, mask_stride=0, mask_lo=0, mask_relu=0,
               out=None, out_stride=0, out32=None, out32_mode=L.OUT32_NONE, out32_stride=0,
-              n_tile=0, mt=0, splits=0, res1_cmax=0):
+              n_tile=0, mt=0, splits=0, res1_cmax=0, out_lo=0, bias_grad=None, bias_grad_scale=1.0):
     a = L.ConvTcArgs()
     a.x, a.n_img, a.h, a.w, a.x_pix_stride, a.cin = x_ptr, B, H, W, x_stride, cin
     a.w_packed, a.r, a.cout, a.n_pad = w_ptr, r, cout, n_pad
@@ -157,6 +157,9 @@ def conv_args(x_ptr, B, H, W, x_stride, cin, w_ptr, r, cout, n_pad, bias=None, a
     if out32 is not None:
         a.out_f32, a.out32_mode, a.out32_pix_stride = out32, out32_mode, out32_stride
     a.n_tile, a.mt, a.splits, a.res1_cmax = n_tile, mt, splits, res1_cmax
+    a.out_lo = out_lo
+    if bias_grad is not None:
+        a.bias_grad, a.bias_grad_scale = bias_grad, bias_grad_scale
     return a
 
 

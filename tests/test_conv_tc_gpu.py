@@ -351,7 +351,7 @@ def test_chain_wide_layers_in_place_gradient(B):
         packed, n_pad = pack_weight(L, lib, wk, L.PACK_FWD, k_pad=64)
         layers.append((k, nk, cin, packed, n_pad))
 
-    def make(dg, G32, gout):
+    def make(dg, G32, gout, bg):
         arr = (L.ConvTcArgs * 5)()
         for i, (k, nk, cin, packed, n_pad) in enumerate(layers):
             a = arr[i]
@@ -360,12 +360,14 @@ def test_chain_wide_layers_in_place_gradient(B):
             a.n_img, a.h, a.w, a.cin = B, H, W, cin
             a.w_packed, a.r, a.cout, a.n_pad = packed.data_ptr(), 3, nk, n_pad
             a.s0 = 0.2 if k == 5 else 1.0
-            a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = G32.data_ptr(), L.SSR_F32, cw, 1.0
+            a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = G32.data_ptr(), L.SSR_F32_PLANAR4, cw, 1.0
             if k == 5:
                 a.res1_cmax = nf
-            a.out_f32, a.out32_mode, a.out32_pix_stride = G32.data_ptr(), L.OUT32_NHWC, cw
+            a.out_f32, a.out32_mode, a.out32_pix_stride = G32.data_ptr(), L.OUT32_PLANAR4, cw
+            # only the top g-channel slot is stored as (masked) bf16; its pixel sums go to row i of bg, scaled
+            a.bias_grad, a.bias_grad_scale = bg.data_ptr() + 4 * 64 * i, 0.5
             if k > 1:
-                a.mask, a.mask_pix_stride, a.mask_lo = cur.data_ptr(), cw, nf
+                a.mask, a.mask_pix_stride, a.mask_lo, a.out_lo = cur.data_ptr(), cw, nk - g, nk - g
                 a.out_bf16, a.out_pix_stride = dg.data_ptr(), cw
             else:
                 a.out_bf16, a.out_pix_stride = gout.data_ptr(), nf
@@ -373,7 +375,7 @@ def test_chain_wide_layers_in_place_gradient(B):
 
     def fresh():
         return (torch.zeros(B, H, W, cw, dtype=torch.bfloat16, device="cuda"), g32_0.clone(),
-                torch.zeros(B, H, W, nf, dtype=torch.bfloat16, device="cuda"))
+                torch.zeros(B, H, W, nf, dtype=torch.bfloat16, device="cuda"), torch.zeros(5, 64, device="cuda"))
 
     s = torch.cuda.current_stream().cuda_stream
     ref = fresh()
@@ -382,6 +384,13 @@ def test_chain_wide_layers_in_place_gradient(B):
         L.check(lib.ssr_conv_tc(C.byref(arr[i]), s))
     torch.cuda.synchronize()
     assert ref[2].float().abs().max() > 0
+    # the fused bias gradient = scale * pixel sum of what the bf16 output received (f32 values before the bf16 rounding)
+    for i, (k, nk, cin, packed, n_pad) in enumerate(layers):
+        slot = ref[0][..., nk - g:nk] if k > 1 else ref[2]
+        want = 0.5 * slot.float().sum(dim=(0, 1, 2))
+        got_bg = ref[3][i, :want.numel()]
+        assert torch.allclose(got_bg, want, rtol=2e-2, atol=2e-2 * want.abs().max().item()), (k, (got_bg - want).abs().max())
+    assert ref[0][..., :nf].float().abs().max() == 0   # below every layer's out_lo: never stored as bf16
     for _ in range(3):
         got = fresh()
         arr_b = make(*got)
@@ -389,8 +398,9 @@ def test_chain_wide_layers_in_place_gradient(B):
         L.check(lib.ssr_conv_tc_chain(arr_b, 5, s))
         torch.cuda.synchronize()
         assert lib.ssr_launch_count() - n0 == 1
-        for r, o in zip(ref, got):
+        for r, o in zip(ref[:3], got[:3]):
             assert torch.equal(r, o)
+        assert torch.allclose(ref[3], got[3], rtol=1e-4, atol=1e-4 * ref[3].abs().max().item())   # atomics: order differs
 
 
 @pytest.mark.parametrize("cout", [64, 20])
