@@ -186,9 +186,11 @@ int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, int32_t n_l
 
 /* ---------------------------------------------------------------------------------------------------
  * Weight gradient on tensor cores (MN-major operands straight from the NHWC buffers).
- *   out[(ky*R + kx)][cx][cy] += scale * sum_p x[p + (ky-pad, kx-pad), cx] * dy[p, cy]      (f32, red.add)
- * `out` is [R*R][out_cx_rows][out_stride] f32 and must be zeroed by the caller before the first
- * accumulation; ssr_wgrad_unpack scatters it into the OIHW gradient of nn.Conv2d.weight.
+ *   out(ky*R + kx, cx, cy) += scale * sum_p x[p + (ky-pad, kx-pad), cx] * dy[p, cy]      (f32, red.add.v4)
+ * `out` is an f32 scratch accumulator of R*R * out_cx_rows * out_stride floats (out_stride = cy rounded up to 4), stored
+ * channel-quad planar so that the reduction of a warp's 32 cx rows is 512 contiguous bytes:
+ *   element (tap, cx, cy) at [((cy / 4) * R*R*out_cx_rows + tap*out_cx_rows + cx) * 4 + cy % 4].
+ * The caller zeroes it before the first accumulation; ssr_wgrad_unpack scatters it into the OIHW gradient of nn.Conv2d.weight.
  * Replaces the wgrad half of autograd for every nn.Conv2d of rrdbnet_arch.py / discriminator_arch.py.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct ssr_wgrad_tc_args {

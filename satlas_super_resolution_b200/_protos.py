@@ -48,6 +48,7 @@ PROTOS = {
     "ssr_u8_to_f32": (C.c_int, [vp, vp, i64, f32, vp]),
     "ssr_adam_tick": (C.c_int, [vp, vp]),
     "ssr_adam_ema": (C.c_int, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, f32, vp, vp]),
+    "ssr_debug_chain_timeline": (C.c_int, [vp, i32]),
     "ssr_wgrad_tc": (C.c_int, [C.POINTER(WgradArgs), vp]),
     "ssr_wgrad_tc_batched": (C.c_int, [C.POINTER(WgradArgs), i32, vp]),
     "ssr_wgrad_unpack": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, f32, i32, vp]),

@@ -25,11 +25,8 @@ struct Wg9K {
 
 static constexpr int kW9Threads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
-__device__ __forceinline__ void wgrad9_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const Wg9K& p, int bx, int by, int bz) {
+__device__ __forceinline__ void wgrad9_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const Wg9K& p, int bx, int by, int bz, int splits) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -42,7 +39,7 @@ __device__ __forceinline__ void wgrad9_body(const CUtensorMap& tmX, const CUtens
   const int lane = threadIdx.x & 31;
   const int mtile = by;
   const int n0 = bz * 32;
-  const int per = (p.total_tiles + p.splits - 1) / p.splits;
+  const int per = (p.total_tiles + splits - 1) / splits;
   const int t_begin = bx * per;
   const int t_end = min(p.total_tiles, t_begin + per);
   const int iters = t_end - t_begin;
@@ -144,17 +141,15 @@ __device__ __forceinline__ void wgrad9_body(const CUtensorMap& tmX, const CUtens
       if (!valid) continue;
       const int c0 = n0 + cb;
       if (c0 >= p.cy) continue;
-      float* dst = p.out + ((long)tap * p.cx_rows + cxi) * p.out_stride + c0;
-      if (c0 + 16 <= p.cy) {
+      // accumulator layout [cy / 4][9 taps * cx_rows][4]: the warp's 32 consecutive cx rows are 512 contiguous bytes per
+      // channel quad (channels past cy inside the last quad receive exact zeros: their dY columns are TMA zero fill)
+      const long plane = 9L * p.cx_rows * 4;
+      float* dst = p.out + (long)(c0 >> 2) * plane + ((long)tap * p.cx_rows + cxi) * 4;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          red_add_v4(dst + 4 * j, p.scale * __uint_as_float(v[4 * j]), p.scale * __uint_as_float(v[4 * j + 1]),
+      for (int j = 0; j < 4; ++j)
+        if (c0 + 4 * j < p.out_stride)
+          red_add_v4(dst + j * plane, p.scale * __uint_as_float(v[4 * j]), p.scale * __uint_as_float(v[4 * j + 1]),
                      p.scale * __uint_as_float(v[4 * j + 2]), p.scale * __uint_as_float(v[4 * j + 3]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j < p.cy) atomicAdd(dst + j, p.scale * __uint_as_float(v[j]));
-      }
     }
   }
 
@@ -169,32 +164,32 @@ __device__ __forceinline__ void wgrad9_body(const CUtensorMap& tmX, const CUtens
 
 __global__ void __launch_bounds__(kW9Threads, 1)
 wgrad9_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const Wg9K p) {
-  wgrad9_body(tmX, tmY, p, blockIdx.x, blockIdx.y, blockIdx.z);
+  wgrad9_body(tmX, tmY, p, blockIdx.x, blockIdx.y, blockIdx.z, p.splits);
 }
 
-// Horizontal fusion: up to kW9Batch independent weight-gradient problems (the five convs of a ResidualDenseBlock) in ONE launch.
-// Each of these problems alone is latency-bound (one or two pixel tiles per CTA, then the reduction epilogue); batching them
-// pays launch, prologue and first-load latency once instead of five times.
+// Horizontal fusion: up to kW9Batch independent weight-gradient problems (the five convs of a ResidualDenseBlock) in ONE launch
+// of about one CTA per SM.  A problem splits into units (128 cx rows x 32 cy columns of output); every unit gets a share of
+// the CTAs proportional to its work (pixel tiles; the MMA operand reads dominate), so all CTAs finish together and each pays
+// prologue, first-load latency and the reduction epilogue once for a long run of pixel tiles.
 static constexpr int kW9Batch = 8;
+static constexpr int kW9Units = 32;
+struct Wg9Unit {
+  short prob, by, bz, pad_;
+  int splits, cta_begin;
+};
 struct Wg9BatchK {
   CUtensorMap tmX[kW9Batch];
   CUtensorMap tmY[kW9Batch];
   Wg9K k[kW9Batch];
-  int cta_begin[kW9Batch + 1];
-  int mtiles[kW9Batch];
-  int n;
+  Wg9Unit u[kW9Units];
+  int n_units;
 };
 
 __global__ void __launch_bounds__(kW9Threads, 1) wgrad9_tc_batched_kernel(const __grid_constant__ Wg9BatchK b) {
   int j = 0;
-  while (j + 1 < b.n && (int)blockIdx.x >= b.cta_begin[j + 1]) ++j;
-  int local = (int)blockIdx.x - b.cta_begin[j];
-  const Wg9K& p = b.k[j];
-  const int bx = local % p.splits;
-  local /= p.splits;
-  const int by = local % b.mtiles[j];
-  const int bz = local / b.mtiles[j];
-  wgrad9_body(b.tmX[j], b.tmY[j], p, bx, by, bz);
+  while (j + 1 < b.n_units && (int)blockIdx.x >= b.u[j + 1].cta_begin) ++j;
+  const Wg9Unit& u = b.u[j];
+  wgrad9_body(b.tmX[u.prob], b.tmY[u.prob], b.k[u.prob], (int)blockIdx.x - u.cta_begin, u.by, u.bz, u.splits);
 }
 
 static int g_w9_smem = -1;
@@ -312,38 +307,86 @@ int launch_wgrad9(const ssr_wgrad_tc_args* a, cudaStream_t stream) {
 
 // n problems in as few launches as possible; problems that are not eligible for the nine-tap kernel return 1 in `fallback[i]`
 int launch_wgrad9_batched(const ssr_wgrad_tc_args* args, int n, int* fallback, cudaStream_t stream) {
-  // the batch as a whole should be about `budget` CTAs (a couple of waves): fewer pixel splits per problem = fewer partial
-  // sums to reduce, and the parallelism comes from the n problems instead
   static int budget = -1;
   if (budget < 0) {
     const char* e = getenv("SSR_WGRAD_BATCH_CTAS");
-    budget = e ? atoi(e) : 296;
+    budget = e ? atoi(e) : 0;
+    if (budget <= 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&budget, cudaDevAttrMultiProcessorCount, dev);   // one wave: one CTA per SM
+    }
   }
-  const int per_problem = budget / (n > 0 ? n : 1) > 8 ? budget / (n > 0 ? n : 1) : 8;
   int i = 0;
   while (i < n) {
-    Wg9BatchK b{};
+    static Wg9BatchK b;
+    b.n_units = 0;
+    int n_prob = 0;
     size_t smem = 0;
-    int ctas = 0;
-    while (i < n && b.n < kW9Batch) {
+    double cost[kW9Units];
+    double total_cost = 0;
+    while (i < n && n_prob < kW9Batch) {
       Wg9Prepared w;
-      const int rc = prepare_wgrad9(&args[i], &w, per_problem);
+      const int rc = prepare_wgrad9(&args[i], &w, 1);
       if (rc < 0) return rc;
       fallback[i] = rc == 1 ? 1 : 0;
       if (rc == SSR_OK) {
-        const int j = b.n++;
+        if (b.n_units + w.mtiles * w.halves > kW9Units) break;   // next launch takes it
+        const int j = n_prob++;
         b.k[j] = w.p;
         b.tmX[j] = w.tmX;
         b.tmY[j] = w.tmY;
-        b.mtiles[j] = w.mtiles;
-        b.cta_begin[j] = ctas;
-        ctas += w.p.splits * w.mtiles * w.halves;
-        b.cta_begin[j + 1] = ctas;
+        for (int bz = 0; bz < w.halves; ++bz)
+          for (int by = 0; by < w.mtiles; ++by) {
+            Wg9Unit& u = b.u[b.n_units];
+            u.prob = (short)j;
+            u.by = (short)by;
+            u.bz = (short)bz;
+            // a pixel tile costs 72 MMAs whose shared-memory operand reads (4 KB of X per MMA) bound the SM whatever the
+            // number of valid cx rows; units that stream one 64-channel chunk instead of two are a little cheaper
+            const int ch = w.p.cx - by * 128 < 128 ? w.p.cx - by * 128 : 128;   // valid X channels of this unit
+            cost[b.n_units] = (double)w.p.total_tiles * (ch > 64 ? 1.0 : 0.85);
+            total_cost += cost[b.n_units];
+            ++b.n_units;
+          }
         if (w.smem_bytes > smem) smem = w.smem_bytes;
       }
       ++i;
     }
-    if (b.n == 0) continue;
+    if (b.n_units == 0) continue;
+    // CTAs per unit, proportional to cost; leftovers go to the units with the most work per CTA
+    int used = 0;
+    for (int u = 0; u < b.n_units; ++u) {
+      int sp = (int)(budget * cost[u] / total_cost);
+      const int tiles = b.k[b.u[u].prob].total_tiles;
+      if (sp < 1) sp = 1;
+      if (sp > tiles) sp = tiles;
+      b.u[u].splits = sp;
+      used += sp;
+    }
+    while (used < budget) {
+      int best = -1;
+      double best_load = 0;
+      for (int u = 0; u < b.n_units; ++u) {
+        const double load = cost[u] / b.u[u].splits;
+        if (b.u[u].splits < b.k[b.u[u].prob].total_tiles && load > best_load) {
+          best_load = load;
+          best = u;
+        }
+      }
+      if (best < 0) break;
+      ++b.u[best].splits;
+      ++used;
+    }
+    int ctas = 0;
+    for (int u = 0; u < b.n_units; ++u) {
+      // no empty split: per = ceil(tiles / splits), splits = ceil(tiles / per)
+      const int tiles = b.k[b.u[u].prob].total_tiles;
+      const int per = (tiles + b.u[u].splits - 1) / b.u[u].splits;
+      b.u[u].splits = (tiles + per - 1) / per;
+      b.u[u].cta_begin = ctas;
+      ctas += b.u[u].splits;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)ctas);
     cfg.blockDim = dim3(kW9Threads);

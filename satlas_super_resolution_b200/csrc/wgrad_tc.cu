@@ -144,9 +144,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const bool valid = cxi < p.cx;
     mbar_wait(bar_tmem, 0);
     tc_fence_after_sync();
+    // accumulator layout [cy / 4][R*R taps * cx_rows][4]: 32 consecutive cx rows of one channel quad are 512 contiguous bytes
+    const long plane = (long)R * R * p.cx_rows * 4;
 #pragma unroll 1
     for (int ky = 0; ky < R; ++ky) {
-      float* dst = p.out + ((long)(ky * R + kx) * p.cx_rows + cxi) * p.out_stride + n0;
+      float* dst = p.out + ((long)(ky * R + kx) * p.cx_rows + cxi) * 4;
 #pragma unroll 1
       for (int cb = 0; cb < p.n_tile; cb += 16) {
         uint32_t v[16];
@@ -155,8 +157,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         tmem_ld_wait();
         if (!valid) continue;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (n0 + cb + j < p.cy) atomicAdd(dst + cb + j, p.scale * __uint_as_float(v[j]));
+        for (int j = 0; j < 4; ++j) {
+          const int co = n0 + cb + 4 * j;   // channels past cy inside the last quad get exact zeros (TMA zero fill of dY)
+          if (co < p.out_stride)
+            red_add_v4(dst + (long)(co >> 2) * plane, p.scale * __uint_as_float(v[4 * j]), p.scale * __uint_as_float(v[4 * j + 1]),
+                       p.scale * __uint_as_float(v[4 * j + 2]), p.scale * __uint_as_float(v[4 * j + 3]));
+        }
       }
     }
   }
@@ -170,7 +176,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
-// out[taps][cx_rows][stride] (f32) -> grad OIHW [cy][cx][R][R] += scale * out
+// acc[cy / 4][taps * cx_rows][4] (f32) -> grad OIHW [cy][cx][R][R] += scale * acc
 __global__ void wgrad_unpack_kernel(const float* __restrict__ acc, int cx_rows, int stride, float* __restrict__ grad,
                                     int cy, int cx, int r, float scale, int accumulate) {
   const long total = (long)cy * cx * r * r;
@@ -182,7 +188,7 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ acc, int cx_rows, 
     t /= r;
     const int ci = t % cx;
     const int co = t / cx;
-    const float v = scale * acc[((long)(kyy * r + kxx) * cx_rows + ci) * stride + co];
+    const float v = scale * acc[((long)(co >> 2) * (r * r * cx_rows) + (long)(kyy * r + kxx) * cx_rows + ci) * 4 + (co & 3)];
     if (accumulate) grad[i] += v; else grad[i] = v;
   }
 }
@@ -205,7 +211,7 @@ __global__ void wgrad_unpack_batched_kernel(const UnpackDesc* __restrict__ descs
     t /= d.r;
     const int ci = t % d.cin;
     const int co = t / d.cin;
-    const float v = d.scale * d.acc[((long)(kyy * d.r + kxx) * d.cx_rows + ci) * d.acc_stride + co];
+    const float v = d.scale * d.acc[((long)(co >> 2) * (d.r * d.r * d.cx_rows) + (long)(kyy * d.r + kxx) * d.cx_rows + ci) * 4 + (co & 3)];
     if (d.accumulate) d.grad[i] += v; else d.grad[i] = v;
   }
 }
@@ -289,7 +295,8 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
   p.tiles_y = (a->h + p.TH - 1) / p.TH;
   p.total_tiles = p.tiles_x * p.tiles_y * a->n_img;
   p.cx = a->cx; p.cx_rows = a->out_cx_rows; p.cy = a->cy; p.out_stride = a->out_stride;
-  SSR_REQUIRE(p.cx_rows >= p.cx && p.out_stride >= p.cy, "ssr_wgrad_tc: output too small");
+  SSR_REQUIRE(p.cx_rows >= p.cx && p.out_stride >= p.cy && p.out_stride % 4 == 0, "ssr_wgrad_tc: output too small / cy stride not a multiple of 4");
+  SSR_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "ssr_wgrad_tc: out must be 16-byte aligned");
   if (a->cy <= 32) { p.n_tile = 32; p.y_blocks = 1; p.y_rowbytes = 64; }
   else if (a->cy <= 64) { p.n_tile = 64; p.y_blocks = 1; p.y_rowbytes = 128; }
   else { p.n_tile = 128; p.y_blocks = 2; p.y_rowbytes = 128; }

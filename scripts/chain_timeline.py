@@ -13,7 +13,6 @@ import torch  # noqa: E402
 from satlas_super_resolution_b200 import _lib as L  # noqa: E402
 
 lib = L.load()
-lib.ssr_debug_chain_timeline.argtypes = [C.c_void_p, C.c_int32]
 B, H, W, nf, g = 32, 32, 32, 64, 32
 cw = nf + 4 * g
 EVENTS = ["in-ready", "last-issue", "stage0-full", "stageN-full", "acc0-full", "accN-full", "stores-out", "arrived"]
@@ -47,9 +46,9 @@ def fwd_chain():
         if k < 4:
             a.act, a.s0, a.out_bf16, a.out_pix_stride = 1, 1.0, buf.data_ptr() + 2 * cin, cw
         else:
-            a.s0, a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = 0.2, trunk.data_ptr(), L.SSR_F32, nf, 1.0
+            a.s0, a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = 0.2, trunk.data_ptr(), L.SSR_F32_PLANAR4, nf, 1.0
             a.out_bf16, a.out_pix_stride = nxt.data_ptr(), nf
-            a.out_f32, a.out32_mode, a.out32_pix_stride = t32.data_ptr(), L.OUT32_NHWC, nf
+            a.out_f32, a.out32_mode, a.out32_pix_stride = t32.data_ptr(), L.OUT32_PLANAR4, nf
     return arr, keep
 
 
@@ -60,7 +59,8 @@ def dgrad_chain():
     G32 = torch.zeros(B, H, W, cw, device="cuda")
     gout = torch.zeros(B, H, W, nf, dtype=torch.bfloat16, device="cuda")
     arr = (L.ConvTcArgs * 5)()
-    keep = [xin, cur, dg, G32, gout]
+    bg = torch.zeros(5, 64, device="cuda")
+    keep = [xin, cur, dg, G32, gout, bg]
     for i, k in enumerate(range(5, 0, -1)):
         nk = nf + (k - 1) * g
         cin = nf if k == 5 else g
@@ -72,12 +72,13 @@ def dgrad_chain():
         a.n_img, a.h, a.w, a.cin = B, H, W, cin
         a.w_packed, a.r, a.cout, a.n_pad = packed.data_ptr(), 3, nk, n_pad
         a.s0 = 0.2 if k == 5 else 1.0
-        a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = G32.data_ptr(), L.SSR_F32, cw, 1.0
+        a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = G32.data_ptr(), L.SSR_F32_PLANAR4, cw, 1.0
         if k == 5:
             a.res1_cmax = nf
-        a.out_f32, a.out32_mode, a.out32_pix_stride = G32.data_ptr(), L.OUT32_NHWC, cw
+        a.out_f32, a.out32_mode, a.out32_pix_stride = G32.data_ptr(), L.OUT32_PLANAR4, cw
+        a.bias_grad, a.bias_grad_scale = bg.data_ptr() + 256 * i, 1.0
         if k > 1:
-            a.mask, a.mask_pix_stride, a.mask_lo = cur.data_ptr(), cw, nf
+            a.mask, a.mask_pix_stride, a.mask_lo, a.out_lo = cur.data_ptr(), cw, nk - g, nk - g
             a.out_bf16, a.out_pix_stride = dg.data_ptr(), cw
         else:
             a.out_bf16, a.out_pix_stride = gout.data_ptr(), nf
