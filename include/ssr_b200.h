@@ -43,6 +43,10 @@ extern "C" {
 #define SSR_OUT32_NHWC_ATOMIC 2 /* red.add out32[pix*stride + c]  (split-K)   */
 #define SSR_OUT32_NCHW 3        /* store   out32[((n*cout + c)*H + y)*W + x]  */
 #define SSR_OUT32_PLANAR4 4     /* store   out32 in the SSR_F32_PLANAR4 layout */
+/* out32 (planar) is ALSO res1 (res1 == out_f32, SSR_F32_PLANAR4, s1 == 1): a running sum.  Channels that produce a
+ * bf16 output (>= out_lo) are read, added and stored as with SSR_OUT32_PLANAR4; all others are accumulated with a
+ * vector reduction (red.global.add.v4.f32) -- no dependent load in the epilogue.  One writer per element: deterministic. */
+#define SSR_OUT32_PLANAR4_ACC 5
 
 /* weight packing modes */
 #define SSR_PACK_FWD 0   /* B[n=cout][k=cin], taps as stored          */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libssr_b200.so")
 
 SSR_NONE, SSR_BF16, SSR_F32, SSR_F32_PLANAR4 = 0, 1, 2, 3
-OUT32_NONE, OUT32_NHWC, OUT32_NHWC_ATOMIC, OUT32_NCHW, OUT32_PLANAR4 = 0, 1, 2, 3, 4
+OUT32_NONE, OUT32_NHWC, OUT32_NHWC_ATOMIC, OUT32_NCHW, OUT32_PLANAR4, OUT32_PLANAR4_ACC = 0, 1, 2, 3, 4, 5
 PACK_FWD, PACK_DGRAD, PACK_FWD_GEMM, PACK_DGRAD_GEMM = 0, 1, 2, 3
 
 

@@ -168,7 +168,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
     int g = 0;  // running stage counter across tiles and layers
     for (int l = 0; l < n_layers; ++l) {
-      const ConvTcK& q = ps[l];
+      const ConvTcK q = ps[l];   // by value: registers, not parameter-space loads repeated after every asm memory clobber
       const CUtensorMap* tmA = &tmAs[l];
       const CUtensorMap* tmB = &tmBs[l];
       const int per = (q.chunks + q.splits - 1) / q.splits;
@@ -229,7 +229,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
     const uint32_t a_dbg = (uint32_t)(p.dbg_aoff * 128) >> 4;  // hardware probe only (scripts/probe_swizzle.py)
     int g = 0, gt = 0;  // running stage / tile counters across layers
     for (int l = 0; l < n_layers; ++l) {
-      const ConvTcK& q = ps[l];
+      const ConvTcK q = ps[l];
       const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)q.n_tile);
       const uint32_t b_tap = (uint32_t)(q.n_tile * 128) >> 4;    // next vertical tap's weight tile
       const int per = (q.chunks + q.splits - 1) / q.splits;
@@ -296,7 +296,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
     int gt = 0;  // running tile counter across layers (selects the accumulator buffer and its phase)
 #pragma unroll 1
     for (int l = 0; l < n_layers; ++l) {
-    const ConvTcK& p = ps[l];
+    // a private copy of the layer's parameters: the compiler keeps the used fields in registers; through the reference every
+    // p.field inside the item loop was an indexed parameter load again (asm memory clobbers forbid hoisting them)
+    const ConvTcK p = ps[l];
     const int n_base = (int)blockIdx.y * p.n_loop * p.n_tile;   // first output channel this CTA produces
     const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
     for (int i = et; i < p.n_loop * p.n_tile; i += kThreads - 64) {
@@ -307,12 +309,13 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
     const int nchunks = p.n_tile >> 4;
     const bool use_r1 = p.res1_kind != SSR_NONE, use_r2 = p.res2_kind != SSR_NONE, use_mk = p.mask != nullptr;
     const long n_pix = (long)p.n_img * p.H * p.W;   // plane stride of the quad-planar f32 operands, in float4
+    const bool acc_mode = p.out32_mode == SSR_OUT32_PLANAR4_ACC;   // out32 is the running sum res1 itself
 
     struct Ops {
       uint4 r1[4], r2[4], mk[2];
     };
     auto fetch = [&](long pix, int c0, Ops& o) {
-      if (use_r1 && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
+      if (use_r1 && (p.res1_cmax == 0 || c0 < p.res1_cmax) && !(acc_mode && c0 < p.out_lo)) {
         if (p.res1_kind == SSR_BF16) {
           const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res1) + pix * p.res1_stride + c0);
           o.r1[0] = s4[0];
@@ -325,7 +328,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
           // quad-planar f32: the warp's 32 pixels x 4 channels are 512 contiguous bytes
           const uint4* s4 = reinterpret_cast<const uint4*>(p.res1) + (long)(c0 >> 2) * n_pix + pix;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o.r1[j] = s4[(long)j * n_pix];
+          for (int j = 0; j < 4; ++j) o.r1[j] = __ldcg(s4 + (long)j * n_pix);   // L2: other layers update it with reductions
         }
       }
       if (use_r2) {
@@ -433,7 +436,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] *= p.s0;
             }
-            if (use_r1 && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
+            const bool has_r1 = use_r1 && (p.res1_cmax == 0 || c0 < p.res1_cmax);
+            const bool lazy = acc_mode && has_r1 && !wr16;   // nobody needs the sum now: add into it with a reduction below
+            if (has_r1 && !lazy) {
               float r[16];
               expand(o.r1, p.res1_kind, r);
 #pragma unroll
@@ -450,10 +455,14 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
               float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.out32_stride + c0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            } else if (p.out32_mode == SSR_OUT32_PLANAR4) {
+            } else if (p.out32_mode == SSR_OUT32_PLANAR4 || (acc_mode && !lazy)) {
               float4* dst = reinterpret_cast<float4*>(p.out_f32) + (long)(c0 >> 2) * n_pix + pix;
 #pragma unroll
               for (int j = 0; j < 4; ++j) dst[(long)j * n_pix] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else if (acc_mode) {
+              float* dst = p.out_f32 + ((long)(c0 >> 2) * n_pix + pix) * 4;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) red_add_v4(dst + (long)j * n_pix * 4, f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             } else if (p.out32_mode == SSR_OUT32_NHWC_ATOMIC) {
               float* dst = p.out_f32 + pix * p.out32_stride + c0;
 #pragma unroll
@@ -780,7 +789,11 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
 
   if (p.res1_kind == SSR_F32_PLANAR4) SSR_REQUIRE((reinterpret_cast<uintptr_t>(p.res1) & 15) == 0 && a->res1_cmax % 4 == 0, "ssr_conv_tc: res1 alignment");
   if (p.res2_kind == SSR_F32_PLANAR4) SSR_REQUIRE((reinterpret_cast<uintptr_t>(p.res2) & 15) == 0, "ssr_conv_tc: res2 alignment");
-  if (p.out32_mode == SSR_OUT32_PLANAR4) SSR_REQUIRE((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0, "ssr_conv_tc: out_f32 alignment");
+  if (p.out32_mode == SSR_OUT32_PLANAR4 || p.out32_mode == SSR_OUT32_PLANAR4_ACC)
+    SSR_REQUIRE((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0, "ssr_conv_tc: out_f32 alignment");
+  if (p.out32_mode == SSR_OUT32_PLANAR4_ACC)
+    SSR_REQUIRE(p.res1_kind == SSR_F32_PLANAR4 && p.res1 == (const void*)p.out_f32 && p.s1 == 1.f && a->cout % 16 == 0 && p.splits == 1,
+                "ssr_conv_tc: SSR_OUT32_PLANAR4_ACC needs res1 == out_f32 (planar), s1 == 1, cout %% 16 == 0, no split-K");
   // tensor maps
   {
     uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};

@@ -294,7 +294,8 @@ class _Workspace:
             dchain = [conv_args(xin.ptr(), B, h, w, nf, nf, c5.packed_dg.data_ptr(), 3, cw, c5.n_pad_dg, s0=s0,
                                 res1=r1, res1_kind=F32, res1_stride=r1s, s1=s1, res1_cmax=nf,
                                 mask=cur.ptr(), mask_stride=cw, mask_lo=cw - g, out_lo=cw - g, bias_grad=bgrad_ptr(i, 4),
-                                out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=cw)]
+                                out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(),
+                                out32_mode=L.OUT32_PLANAR4_ACC if j < 2 else L.OUT32_PLANAR4, out32_stride=cw)]
             batch = [wg.args(f"{pre}.conv5", cur.ptr(), cw, cw, xin.ptr(), nf, nf, B, h, w, 3, s0)]
             for k in range(4, 0, -1):
                 ck = eng.cv[f"{pre}.conv{k}"]
@@ -305,7 +306,7 @@ class _Workspace:
                                         res1=G32.data_ptr(), res1_kind=F32, res1_stride=cw, s1=1.0,
                                         mask=cur.ptr(), mask_stride=cw, mask_lo=nk - g, out_lo=nk - g,
                                         bias_grad=bgrad_ptr(i, k - 1),
-                                        out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(), out32_mode=L.OUT32_PLANAR4,
+                                        out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(), out32_mode=L.OUT32_PLANAR4_ACC,
                                         out32_stride=cw))
                 elif j > 0:
                     dchain.append(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,

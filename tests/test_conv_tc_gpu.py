@@ -351,7 +351,7 @@ def test_chain_wide_layers_in_place_gradient(B):
         packed, n_pad = pack_weight(L, lib, wk, L.PACK_FWD, k_pad=64)
         layers.append((k, nk, cin, packed, n_pad))
 
-    def make(dg, G32, gout, bg):
+    def make(dg, G32, gout, bg, acc=False):
         arr = (L.ConvTcArgs * 5)()
         for i, (k, nk, cin, packed, n_pad) in enumerate(layers):
             a = arr[i]
@@ -363,7 +363,8 @@ def test_chain_wide_layers_in_place_gradient(B):
             a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = G32.data_ptr(), L.SSR_F32_PLANAR4, cw, 1.0
             if k == 5:
                 a.res1_cmax = nf
-            a.out_f32, a.out32_mode, a.out32_pix_stride = G32.data_ptr(), L.OUT32_PLANAR4, cw
+            # acc: channels without a bf16 output are added into the running sum with vector reductions (same values)
+            a.out_f32, a.out32_mode, a.out32_pix_stride = G32.data_ptr(), (L.OUT32_PLANAR4_ACC if acc and k > 1 else L.OUT32_PLANAR4), cw
             # only the top g-channel slot is stored as (masked) bf16; its pixel sums go to row i of bg, scaled
             a.bias_grad, a.bias_grad_scale = bg.data_ptr() + 4 * 64 * i, 0.5
             if k > 1:
@@ -393,7 +394,7 @@ def test_chain_wide_layers_in_place_gradient(B):
     assert ref[0][..., :nf].float().abs().max() == 0   # below every layer's out_lo: never stored as bf16
     for _ in range(3):
         got = fresh()
-        arr_b = make(*got)
+        arr_b = make(*got, acc=(_ > 0))     # first pass: same modes as the reference; then the reduction form
         n0 = lib.ssr_launch_count()
         L.check(lib.ssr_conv_tc_chain(arr_b, 5, s))
         torch.cuda.synchronize()
