@@ -1,3 +1,5 @@
+# Round profile (run under gpurun): ncu launch list of one eager step + full captures of the chained conv kernel (one forward, one
+# input-gradient launch) and the batched weight gradient; summarise with scripts/summarize_launches.py / summarize_ncu.py into profiles/.
 set -x
 mkdir -p gpurun_out
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 1500 --csv --log-file gpurun_out/launches_r1g.csv python scripts/profile_step.py 32 > gpurun_out/ncu_list.log 2>&1
