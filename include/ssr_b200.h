@@ -131,6 +131,18 @@ int ssr_conv_tc(const ssr_conv_tc_args* args, void* stream);
  * Results are identical to n ssr_conv_tc calls in order; ineligible chains are executed exactly that way.
  */
 int ssr_conv_tc_chain(const ssr_conv_tc_args* args, int32_t n, void* stream);
+/*
+ * Chain whose layers add into ONE f32 accumulator per pixel that stays in tensor memory for the whole launch (the five
+ * input-gradient convs of a ResidualDenseBlock: autograd's running gradient of the dense buffer).  Layer i adds its cout_i
+ * channels at channel offset 0 (cout_0 is the widest); after the add it EMITS the channels >= out_lo_i of the running sum:
+ * v = sum + s1*res1 + s2*res2 -> out_f32 (unmasked), mask -> out_bf16, bias_grad.  Channels below out_lo_i stay in tensor
+ * memory and are never stored; layer i+1 must satisfy cout_{i+1} <= out_lo_i.  Every layer: s0 == 1 (fold scales into the
+ * packed weights), no bias / activation, cout % 16 == 0.  Needs images of <= 8 pixel tiles (ssr_conv_tc_chain_acc_supported);
+ * there is no plain-launch fallback -- unsupported shapes return SSR_E_ARG.
+ */
+int ssr_conv_tc_chain_acc(const ssr_conv_tc_args* args, int32_t n, void* stream);
+/* 1 if ssr_conv_tc_chain_acc can run this geometry (host arithmetic only, no device needed), else 0 */
+int ssr_conv_tc_chain_acc_supported(int32_t n_img, int32_t h, int32_t w, int32_t widest_cout);
 /* diagnostics: with SSR_CHAIN_TIMELINE=1 in the environment every chained launch records clock64 stamps
  * [cta][layer (5)][8 events]; copies the first n_ctas (<= 512) rows of the LAST launch to host memory (synchronises). */
 int ssr_debug_chain_timeline(long long* host_out, int32_t n_ctas);

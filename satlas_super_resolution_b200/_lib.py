@@ -61,6 +61,10 @@ def load(build_if_missing=True):
     lib.ssr_conv_tc.restype = C.c_int
     lib.ssr_conv_tc_chain.argtypes = [C.POINTER(ConvTcArgs), C.c_int32, C.c_void_p]
     lib.ssr_conv_tc_chain.restype = C.c_int
+    lib.ssr_conv_tc_chain_acc.argtypes = [C.POINTER(ConvTcArgs), C.c_int32, C.c_void_p]
+    lib.ssr_conv_tc_chain_acc.restype = C.c_int
+    lib.ssr_conv_tc_chain_acc_supported.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.ssr_conv_tc_chain_acc_supported.restype = C.c_int
     lib.ssr_packed_weight_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     lib.ssr_packed_weight_bytes.restype = C.c_int64
     lib.ssr_pack_conv_weight.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

@@ -27,6 +27,7 @@ struct ConvTcK {
   uint32_t a_box_bytes, a_alloc, b_bytes, tmem_cols;
   uint32_t stage_stride;  // bytes between smem stages (>= a_alloc + b_bytes; the max over the layers of a chain)
   uint32_t acc_stride;    // TMEM columns between the two accumulator buffers (>= MT * n_tile)
+  int acc_w;              // > 0: chain with ONE f32 accumulator of acc_w channels per pixel that stays in TMEM for all layers
   int n_loop;             // N tiles one CTA walks itself (1 when gridDim.y spreads them; n_pad / n_tile inside a chain)
   int splits;
   // epilogue
@@ -236,12 +237,15 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       const int c_begin = blockIdx.z * per;
       const int iters = (min(q.chunks, c_begin + per) - c_begin) * R;
       const int items = my_tiles * q.n_loop;  // (pixel tile, N tile) work items of this layer
+      // TMEM-resident accumulator (acc_w > 0): channel c of M tile m is column m * acc_w + c in EVERY layer; layer 0 initialises,
+      // later layers add; nothing is handed back by the epilogue (a layer only writes columns below the slot being drained)
+      const uint32_t m_cols = q.acc_w ? (uint32_t)q.acc_w : (uint32_t)q.n_tile;
       for (int lt = 0; lt < items; ++lt, ++gt) {
-        const int b = gt & 1;
-        mbar_wait(&bar_acc_empty[b], ((gt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator buffer
+        const int b = q.acc_w ? 0 : (gt & 1);
+        if (!q.acc_w) mbar_wait(&bar_acc_empty[b], ((gt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator buffer
         tc_fence_after_sync();
-        const uint32_t d_base = tmem_base + (uint32_t)b * acc_cols;
-        uint32_t acc = 0;
+        const uint32_t d_base = q.acc_w ? tmem_base + (uint32_t)((lt % q.n_loop) * q.n_tile) : tmem_base + (uint32_t)b * acc_cols;
+        uint32_t acc = (q.acc_w && l > 0) ? 1u : 0u;
         for (int it = 0; it < iters; ++it, ++g) {
           const int c = c_begin + it / R;
           const int s = g % q.stages;
@@ -262,7 +266,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
                 for (int ky = 0; ky < R; ++ky) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_bf16_ss(d_base + (uint32_t)(m * q.n_tile), da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
+                    umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
                                  idesc, (ky == 0 && k == 0) ? acc : 1u);
                 }
               }
@@ -271,11 +275,12 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
               for (int m = 0; m < MT; ++m)
                 for (int ky = 0; ky < R; ++ky)
                   for (int k = 0; k < ks; ++k)
-                    umma_bf16_ss(d_base + (uint32_t)(m * q.n_tile), da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
+                    umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
                                  idesc, (ky == 0 && k == 0) ? acc : 1u);
             }
             umma_commit(&bar_empty[s]);                              // frees this smem stage once the MMAs above have read it
-            if (it == iters - 1) umma_commit(&bar_acc_full[b]);      // accumulators of this tile complete
+            // accumulators of this tile complete (TMEM-resident form: once per layer, after its last N tile)
+            if (it == iters - 1 && (!q.acc_w || lt == items - 1)) umma_commit(&bar_acc_full[b]);
           }
           __syncwarp();
           acc = 1;
@@ -306,7 +311,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       s_bg[i] = 0.f;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const int nchunks = p.n_tile >> 4;
+    // TMEM-resident accumulator: one pass per layer over the chunks that are emitted (>= out_lo), whatever the N tiling of the MMAs
+    const int nchunks = p.acc_w ? ((p.cout + 15) >> 4) : (p.n_tile >> 4);
+    const int ci_first = (p.acc_w ? (p.out_lo >> 4) : 0) + half;
+    const int n_loop_e = p.acc_w ? 1 : p.n_loop;
+    const uint32_t m_cols = p.acc_w ? (uint32_t)p.acc_w : (uint32_t)p.n_tile;
     const bool use_r1 = p.res1_kind != SSR_NONE, use_r2 = p.res2_kind != SSR_NONE, use_mk = p.mask != nullptr;
     const long n_pix = (long)p.n_img * p.H * p.W;   // plane stride of the quad-planar f32 operands, in float4
     const bool acc_mode = p.out32_mode == SSR_OUT32_PLANAR4_ACC;   // out32 is the running sum res1 itself
@@ -390,31 +399,31 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
         oks[mt] = (tyy < p.TH) && (ys[mt] < p.H) && (x < p.W);
       }
 #pragma unroll 1
-      for (int nb = 0; nb < p.n_loop; ++nb, ++gt) {
+      for (int nb = 0; nb < n_loop_e; ++nb, ++gt) {
       const int n0 = n_base + nb * p.n_tile;
-      const int b = gt & 1;
-      const uint32_t d_base = tmem_base + (uint32_t)b * acc_cols;
+      const int b = p.acc_w ? 0 : (gt & 1);
+      const uint32_t d_base = p.acc_w ? tmem_base : tmem_base + (uint32_t)b * acc_cols;
       Ops o;
       bool first = true;
-      if (half < nchunks && oks[0] && n0 + half * 16 + 16 <= p.cout) fetch(pixs[0], n0 + half * 16, o);   // overlaps the MMAs
-      mbar_wait(&bar_acc_full[b], (gt >> 1) & 1);
+      if (ci_first < nchunks && oks[0] && n0 + ci_first * 16 + 16 <= p.cout) fetch(pixs[0], n0 + ci_first * 16, o);   // overlaps the MMAs
+      mbar_wait(&bar_acc_full[b], p.acc_w ? (uint32_t)(l & 1) : (uint32_t)((gt >> 1) & 1));
       tc_fence_after_sync();
       if (et == 0 && lt == 0 && nb == 0) SSR_STAMP(l, 4);                            // epilogue: first accumulator complete
-      if (et == 0 && lt == my_tiles - 1 && nb == p.n_loop - 1) SSR_STAMP(l, 5);      // epilogue: last accumulator complete
+      if (et == 0 && lt == my_tiles - 1 && nb == n_loop_e - 1) SSR_STAMP(l, 5);      // epilogue: last accumulator complete
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         const int y = ys[mt];
         const long pix = pixs[mt];
         const bool in_img = oks[mt];
 #pragma unroll 1
-        for (int ci = half; ci < nchunks; ci += 2) {
+        for (int ci = ci_first; ci < nchunks; ci += 2) {
           const int c0 = n0 + ci * 16;
           const bool live = in_img && (c0 + 16 <= p.cout);
           if (!first && live) fetch(pix, c0, o);
           first = false;
           uint32_t v[16];
           __syncwarp();
-          tmem_ld16(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.n_tile + ci * 16), v);
+          tmem_ld16(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mt * m_cols + (uint32_t)(ci * 16), v);
           tmem_ld_wait();
           const bool wr16 = c0 >= p.out_lo;                    // this chunk has a bf16 output (warp-uniform)
           const bool sum_bg = (p.bgrad != nullptr) && wr16;     // ... whose per-channel pixel sums are a bias gradient
@@ -564,7 +573,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       // this warp has finished reading accumulator buffer b: hand it back to the MMA issuer
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+      if (lane == 0 && !p.acc_w) mbar_arrive(&bar_acc_empty[b]);
       }  // N tiles
     }
     if (p.bgrad != nullptr) {
@@ -743,6 +752,7 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
   p.a_alloc = (uint32_t)round_up((int)max(p.a_box_bytes, need), 1024);
   p.b_bytes = (uint32_t)(p.R * p.n_tile * 128);
   p.n_loop = 1;
+  p.acc_w = 0;
   mt_out = mt;
 
   p.bias = a->bias;
@@ -837,7 +847,9 @@ static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
   if (stages > 8) stages = 8;
   if (stages > iters) stages = iters;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * mt * n_tile_max)) cols <<= 1;   // double-buffered accumulators
+  const uint32_t need_cols = ps[0].acc_w ? (uint32_t)(mt * ps[0].acc_w)      // one TMEM-resident accumulator for the whole chain
+                                         : (uint32_t)(2 * mt * n_tile_max);  // double-buffered accumulators
+  while (cols < need_cols) cols <<= 1;
   for (int i = 0; i < n; ++i) {
     ps[i].stages = stages;
     ps[i].stage_stride = stage_bytes;
@@ -933,7 +945,7 @@ extern "C" int ssr_debug_chain_timeline(long long* host_out, int32_t n_ctas) {
 //     wait for each other -- any batch size, no co-residency requirement;
 //   * SSR_CONV_CHAIN=2: larger images through a grid-wide arrive counter (needs the whole grid co-resident: <= one CTA per SM);
 //   * otherwise, or with SSR_CONV_CHAIN=0: n plain launches, with identical results.
-extern "C" int ssr_conv_tc_chain(const ssr_conv_tc_args* a, int32_t n, void* stream_) {
+static int conv_chain_impl(const ssr_conv_tc_args* a, int32_t n, void* stream_, bool tmem_acc) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SSR_REQUIRE(a != nullptr && n >= 1, "ssr_conv_tc_chain: null args");
   static int enabled = -1;
@@ -965,8 +977,22 @@ extern "C" int ssr_conv_tc_chain(const ssr_conv_tc_args* a, int32_t n, void* str
     tiles_per_img = c.k[0].tiles_x * c.k[0].tiles_y;
     const int total = tiles_per_img * c.k[0].n_img;
     if (tiles_per_img <= 8) c.sync_mode = kSyncCluster;
-    else if (enabled == 2 && total <= 2 * g_num_sms) c.sync_mode = kSyncGrid;
+    else if (enabled == 2 && total <= 2 * g_num_sms && !tmem_acc) c.sync_mode = kSyncGrid;
     else ok = false;
+  }
+  if (tmem_acc) {
+    // The running sum of all layers stays in tensor memory: what a layer does not emit (channels < out_lo) is never stored.
+    // That has no plain-launch equivalent, so the shape must be chainable and the layers must nest.
+    SSR_REQUIRE(ok, "ssr_conv_tc_chain_acc: needs 2..%d layers over images of at most 8 pixel tiles (SSR_CONV_CHAIN != 0)", kMaxChain);
+    const int acc_w = c.k[0].n_pad;
+    SSR_REQUIRE(mt * acc_w <= 512, "ssr_conv_tc_chain_acc: %d stacked tiles x %d channels exceed tensor memory", mt, acc_w);
+    for (int i = 0; i < n; ++i) {
+      SSR_REQUIRE(a[i].s0 == 1.f && a[i].act == 0 && a[i].bias == nullptr, "ssr_conv_tc_chain_acc: layer %d must be a pure sum (s0 == 1, no bias / activation)", i);
+      SSR_REQUIRE(a[i].cout % 16 == 0 && a[i].n_pad <= acc_w, "ssr_conv_tc_chain_acc: layer %d: cout must be a multiple of 16 and <= the first layer's", i);
+      SSR_REQUIRE(a[i].out32_mode != SSR_OUT32_NHWC_ATOMIC && a[i].out32_mode != SSR_OUT32_PLANAR4_ACC, "ssr_conv_tc_chain_acc: layer %d: out32 mode", i);
+      if (i > 0) SSR_REQUIRE(a[i].n_pad <= a[i - 1].out_lo, "ssr_conv_tc_chain_acc: layer %d writes channels layer %d is still emitting", i, i - 1);
+      c.k[i].acc_w = acc_w;
+    }
   }
   if (!ok) {
     for (int i = 0; i < n; ++i)
@@ -996,6 +1022,22 @@ extern "C" int ssr_conv_tc_chain(const ssr_conv_tc_args* a, int32_t n, void* str
   auto kern = mt == 1 ? (R == 3 ? conv_chain_kernel<1, 3> : conv_chain_kernel<1, 1>) : (R == 3 ? conv_chain_kernel<2, 3> : conv_chain_kernel<2, 1>);
   static size_t configured[6] = {0, 0, 0, 0, 0, 0};
   return launch_conv(kern, &configured[mt * 2 + (R == 3 ? 1 : 0)], grid, cluster_x, smem_bytes, stream, "conv_tc chain launch", c);
+}
+
+extern "C" int ssr_conv_tc_chain(const ssr_conv_tc_args* a, int32_t n, void* stream) { return conv_chain_impl(a, n, stream, false); }
+extern "C" int ssr_conv_tc_chain_acc(const ssr_conv_tc_args* a, int32_t n, void* stream) { return conv_chain_impl(a, n, stream, true); }
+
+// host-side arithmetic only: can ssr_conv_tc_chain_acc run this geometry?  (images of <= 8 pixel tiles, accumulator fits TMEM)
+extern "C" int ssr_conv_tc_chain_acc_supported(int32_t n_img, int32_t h, int32_t w, int32_t widest_cout) {
+  if (n_img <= 0 || h <= 0 || w < 8 || widest_cout <= 0) return 0;
+  const char* e = getenv("SSR_CONV_CHAIN");
+  if (e && atoi(e) == 0) return 0;
+  const int tw = w >= 32 ? 32 : round_up(w, 8), th = 128 / tw;
+  const int n_pad = balanced_n_tile(widest_cout) * ((widest_cout + 127) / 128);
+  const long tiles1 = (long)((w + tw - 1) / tw) * ((h + th - 1) / th) * n_img;
+  const int mt = (h >= 2 * th && tiles1 >= 200 && n_pad / ((n_pad + 127) / 128) * 2 <= 512) ? 2 : 1;
+  const int per_img = ((w + tw - 1) / tw) * ((h + mt * th - 1) / (mt * th));
+  return per_img <= 8 && mt * n_pad <= 512 ? 1 : 0;
 }
 
 // ------------------------------------------------------------------ weight packing

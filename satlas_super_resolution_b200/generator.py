@@ -8,6 +8,8 @@ writes straight into channels [0, num_feat) of the NEXT block's buffer.
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -45,6 +47,15 @@ class RRDBNetEngine:
         mk("conv_hr", nf)
         mk("conv_last", nf)
         self.cv = cv
+        # SSR_DGRAD_TMEM=1: the dense-block input-gradient chain keeps its running sum in tensor memory
+        # (ssr_conv_tc_chain_acc).  Its layers are pure sums, so conv5's 0.2 (0.04 for the third block of an RRDB) is folded into the
+        # packed input-gradient weights.  Off by default until it has been measured on the GPU.
+        self.dgrad_tmem = want_grad and os.environ.get("SSR_DGRAD_TMEM", "0") == "1"
+        if self.dgrad_tmem:
+            for i in range(num_block):
+                for j in (1, 2, 3):
+                    cv[f"body.{i}.rdb{j}.conv5"].dg_inv_scale = torch.full((1,), 25.0 if j == 3 else 5.0, dtype=torch.float32,
+                                                                           device=self.device)
         self.packer = Packer(list(cv.values()), self.device)
         self._ws = {}
         # gradients: `grads` maps parameter name -> f32 tensor of the parameter's shape (views of a flat buffer)
@@ -275,6 +286,7 @@ class _Workspace:
                             bias_grad=bgrad_ptr(3 * nb - 1, 5), bias_grad_scale=0.04))
         wgrad("conv_body", self.body_out.ptr(), nf, nf, d_feat.ptr(), nf, nf, B, h, w)
         # ---- the trunk, last block first
+        tmem_chain = bool(eng.dgrad_tmem and lib().ssr_conv_tc_chain_acc_supported(B, h, w, cw))
         for i in range(3 * nb - 1, -1, -1):
             blk, j = divmod(i, 3)
             cur = self.bufs[i]
@@ -287,6 +299,38 @@ class _Workspace:
                 xin, s0, r1, r1s, s1 = gO_b, 0.04, GO32.data_ptr(), nf, 0.2
             else:
                 xin, s0, r1, r1s, s1 = gR_in, 0.2, G32.data_ptr(), cw, 1.0
+            if tmem_chain:
+                # running sum in tensor memory: layer k emits only its finished dY slot (masked bf16 + bias gradient); the last
+                # layer emits the block-input gradient = sum + incoming gradient(s).  G32 shrinks to the 64 trunk channels.
+                s0w = 0.04 if j == 2 else 0.2
+                achain = [conv_args(xin.ptr(), B, h, w, nf, nf, c5.packed_dg.data_ptr(), 3, cw, c5.n_pad_dg,
+                                    mask=cur.ptr(), mask_stride=cw, mask_lo=cw - g, out_lo=cw - g, bias_grad=bgrad_ptr(i, 4),
+                                    out=Dg.ptr(), out_stride=cw)]
+                batch = [wg.args(f"{pre}.conv5", cur.ptr(), cw, cw, xin.ptr(), nf, nf, B, h, w, 3, s0w)]
+                for k in range(4, 0, -1):
+                    ck = eng.cv[f"{pre}.conv{k}"]
+                    nk = nf + (k - 1) * g
+                    dyk = Dg.ptr(nk)
+                    if k > 1:
+                        achain.append(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
+                                                mask=cur.ptr(), mask_stride=cw, mask_lo=nk - g, out_lo=nk - g,
+                                                bias_grad=bgrad_ptr(i, k - 1), out=Dg.ptr(), out_stride=cw))
+                    else:
+                        res = dict(res1=GO32.data_ptr(), res1_kind=F32, res1_stride=nf, s1=0.2) if j == 2 else \
+                            dict(res1=G32.data_ptr(), res1_kind=F32, res1_stride=cw, s1=1.0)
+                        if j == 0:
+                            res.update(res2=GO32.data_ptr(), res2_kind=F32, res2_stride=nf, s2=1.0)
+                        dst, dst32 = (gO_b, GO32) if j == 0 else (gR_out, G32)
+                        achain.append(conv_args(dyk, B, h, w, cw, g, ck.packed_dg.data_ptr(), 3, nk, ck.n_pad_dg,
+                                                out=dst.ptr(), out_stride=nf, out32=dst32.data_ptr(), out32_mode=L.OUT32_PLANAR4,
+                                                out32_stride=nf, bias_grad=bgrad_ptr(i - 1, 5) if i > 0 else None,
+                                                bias_grad_scale=0.04 if j == 0 else 0.2, **res))
+                    batch.append(wg.args(f"{pre}.conv{k}", cur.ptr(), cw, nk, dyk, cw, g, B, h, w, 3, 1.0))
+                plan.chain_acc(achain)
+                plan_wgrad_batch(plan, batch)
+                continue
+            if eng.dgrad_tmem:
+                s0 = 1.0   # the factor lives in the packed weights (see RRDBNetEngine.__init__); the wgrad scale below keeps it
             # The five input-gradient convs of the block: one chained launch (each reads the dY slot the previous one wrote).
             # Every layer adds into ALL its f32 channels (G32) but only its top g-channel slot is read again as bf16 -- it is
             # the finished dY of the conv below, so the masked bf16 store is limited to that slot (out_lo) and its pixel
@@ -296,7 +340,7 @@ class _Workspace:
                                 mask=cur.ptr(), mask_stride=cw, mask_lo=cw - g, out_lo=cw - g, bias_grad=bgrad_ptr(i, 4),
                                 out=Dg.ptr(), out_stride=cw, out32=G32.data_ptr(),
                                 out32_mode=L.OUT32_PLANAR4_ACC if j < 2 else L.OUT32_PLANAR4, out32_stride=cw)]
-            batch = [wg.args(f"{pre}.conv5", cur.ptr(), cw, cw, xin.ptr(), nf, nf, B, h, w, 3, s0)]
+            batch = [wg.args(f"{pre}.conv5", cur.ptr(), cw, cw, xin.ptr(), nf, nf, B, h, w, 3, 0.04 if j == 2 else 0.2)]
             for k in range(4, 0, -1):
                 ck = eng.cv[f"{pre}.conv{k}"]
                 nk = nf + (k - 1) * g

@@ -60,6 +60,12 @@ class Plan:
         self.keep.append(arr)
         self.calls.append((lib().ssr_conv_tc_chain, (arr, len(args_list))))
 
+    def chain_acc(self, args_list):
+        """input-gradient chain whose running sum stays in tensor memory (ssr_conv_tc_chain_acc)"""
+        arr = (L.ConvTcArgs * len(args_list))(*args_list)
+        self.keep.append(arr)
+        self.calls.append((lib().ssr_conv_tc_chain_acc, (arr, len(args_list))))
+
     def extend(self, other):
         self.calls.extend(other.calls)
         self.keep.extend(other.keep)
@@ -110,7 +116,9 @@ class PackedConv:
             d = PackDesc()
             d.w = self.weight.data_ptr()
             d.dst = self.packed_dg.data_ptr()
-            d.inv_scale = self.inv_scale.data_ptr() if self.inv_scale is not None else None
+            # dg_inv_scale: the input-gradient operand may carry a constant factor (1 / dg_inv_scale) of its own
+            dg_inv = getattr(self, "dg_inv_scale", None)
+            d.inv_scale = dg_inv.data_ptr() if dg_inv is not None else (self.inv_scale.data_ptr() if self.inv_scale is not None else None)
             d.cout, d.cin, d.r, d.mode, d.k_pad, d.n_pad = (self.cout, self.cin, self.r, L.PACK_DGRAD, self.k_pad_dg,
                                                             self.n_pad_dg)
             out.append(d)

@@ -404,6 +404,85 @@ def test_chain_wide_layers_in_place_gradient(B):
         assert torch.allclose(ref[3], got[3], rtol=1e-4, atol=1e-4 * ref[3].abs().max().item())   # atomics: order differs
 
 
+@pytest.mark.parametrize("B", [2, 32])
+def test_chain_acc_running_sum_in_tensor_memory(B):
+    """ssr_conv_tc_chain_acc: the five input-gradient layers add into ONE accumulator that never leaves tensor memory; each layer
+    emits only its top 32-channel slot, the last one the 64 block-input channels plus the incoming gradient.  Reference = the
+    same layers as plain launches accumulating through an f32 buffer in global memory (f32 summation order differs: tolerance)."""
+    L, lib = _lib()
+    H = W = 32
+    nf, g = 64, 32
+    cw = nf + 4 * g
+    P = B * H * W
+    assert lib.ssr_conv_tc_chain_acc_supported(B, H, W, cw) == 1
+    assert lib.ssr_conv_tc_chain_acc_supported(B, 128, 128, cw) == 0
+    torch.manual_seed(11 + B)
+    xin = (torch.randn(B, H, W, nf) * 0.5).cuda().to(torch.bfloat16)
+    cur = torch.randn(B, H, W, cw).cuda().to(torch.bfloat16)
+    incoming = (torch.randn(nf // 4, P, 4) * 0.3).cuda()          # planar f32 gradient arriving from the block above
+    layers = []
+    for k in range(5, 0, -1):
+        nk = nf + (k - 1) * g
+        cin = nf if k == 5 else g
+        wk = torch.randn(nk, cin, 3, 3) * (1.0 / (3.0 * cin ** 0.5))
+        packed, n_pad = pack_weight(L, lib, wk, L.PACK_FWD, k_pad=64)
+        layers.append((k, nk, cin, packed, n_pad))
+
+    def make(dg, G32, gout, bg, acc):
+        arr = (L.ConvTcArgs * 5)()
+        for i, (k, nk, cin, packed, n_pad) in enumerate(layers):
+            a = arr[i]
+            a.x = xin.data_ptr() if k == 5 else dg.data_ptr() + 2 * nk
+            a.x_pix_stride = nf if k == 5 else cw
+            a.n_img, a.h, a.w, a.cin = B, H, W, cin
+            a.w_packed, a.r, a.cout, a.n_pad, a.s0 = packed.data_ptr(), 3, nk, n_pad, 1.0
+            a.bias_grad, a.bias_grad_scale = bg.data_ptr() + 4 * 64 * i, 0.5
+            if k > 1:
+                a.mask, a.mask_pix_stride, a.mask_lo, a.out_lo = cur.data_ptr(), cw, nk - g, nk - g
+                a.out_bf16, a.out_pix_stride = dg.data_ptr(), cw
+            else:
+                a.out_bf16, a.out_pix_stride = gout.data_ptr(), nf
+            if acc:
+                if k == 1:   # only the last layer touches global f32 memory: sum + incoming -> out32
+                    a.res1, a.res1_kind, a.s1 = incoming.data_ptr(), L.SSR_F32_PLANAR4, 1.0
+                    a.out_f32, a.out32_mode = G32.data_ptr(), L.OUT32_PLANAR4
+            else:
+                # plain launches: the running sum lives in G32 (planar, cw channels); it starts as `incoming` in channels [0, nf)
+                if k == 5:
+                    a.res1, a.res1_kind, a.s1, a.res1_cmax = G32.data_ptr(), L.SSR_F32_PLANAR4, 1.0, nf
+                else:
+                    a.res1, a.res1_kind, a.s1 = G32.data_ptr(), L.SSR_F32_PLANAR4, 1.0
+                a.out_f32, a.out32_mode = G32.data_ptr(), L.OUT32_PLANAR4
+        return arr
+
+    def fresh():
+        G32 = torch.zeros(cw // 4, P, 4, device="cuda")
+        return (torch.zeros(B, H, W, cw, dtype=torch.bfloat16, device="cuda"), G32,
+                torch.zeros(B, H, W, nf, dtype=torch.bfloat16, device="cuda"), torch.zeros(5, 64, device="cuda"))
+
+    s = torch.cuda.current_stream().cuda_stream
+    ref = fresh()
+    ref[1][:nf // 4].copy_(incoming)
+    arr = make(*ref, acc=False)
+    for i in range(5):
+        L.check(lib.ssr_conv_tc(C.byref(arr[i]), s))
+    torch.cuda.synchronize()
+    for _ in range(2):
+        got = fresh()
+        arr_b = make(*got, acc=True)
+        n0 = lib.ssr_launch_count()
+        L.check(lib.ssr_conv_tc_chain_acc(arr_b, 5, s))
+        torch.cuda.synchronize()
+        assert lib.ssr_launch_count() - n0 == 1
+        scale = ref[0][..., nf:].float().abs().max().item()
+        assert (ref[0][..., nf:].float() - got[0][..., nf:].float()).abs().max().item() <= 2 ** -7 * scale      # the four dY slots
+        assert rel_err(got[2].float().cpu(), ref[2].float().cpu()) < 2 ** -7                                      # block-input gradient, bf16
+        # ... and f32: a dY slot that rounds to the other bf16 neighbour (different f32 summation order) moves later layers slightly
+        assert rel_err(got[1][:nf // 4].cpu(), ref[1][:nf // 4].cpu()) < 2e-3
+        assert got[1][nf // 4:].abs().max() == 0                                                                    # nothing else leaves TMEM
+        assert torch.allclose(ref[3], got[3], rtol=1e-3, atol=1e-3 * ref[3].abs().max().item())                    # bias gradients
+
+
 @pytest.mark.parametrize("cout", [64, 20])
 def test_planar4_f32_operands_match_nhwc(cout):
     """SSR_F32_PLANAR4 residual + SSR_OUT32_PLANAR4 output hold exactly the values of the NHWC f32 forms (layout only)"""

@@ -25,7 +25,8 @@ def test_library_builds_loads_and_exports_the_header():
     assert len(names) >= 35
     for n in names:
         assert hasattr(lib, n), f"libssr_b200.so does not export {n}"
-    bound = set(_protos.PROTOS) | {"ssr_last_error", "ssr_abi_version", "ssr_launch_count", "ssr_conv_tc", "ssr_conv_tc_chain",
+    bound = set(_protos.PROTOS) | {"ssr_last_error", "ssr_abi_version", "ssr_launch_count", "ssr_conv_tc", "ssr_conv_tc_chain", "ssr_conv_tc_chain_acc",
+                                   "ssr_conv_tc_chain_acc_supported",
                                    "ssr_packed_weight_bytes", "ssr_pack_conv_weight"}
     assert set(names) <= bound, f"no ctypes prototype for {set(names) - bound}"
     assert lib.ssr_abi_version() == 1

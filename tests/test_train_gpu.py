@@ -162,10 +162,12 @@ def _g_setup(num_block, B, seed=5):
     return p, x, d_out
 
 
-@pytest.mark.parametrize("num_block", [1, 3])
-def test_generator_backward(num_block):
+@pytest.mark.parametrize("num_block,tmem", [(1, False), (3, False), (3, True)])
+def test_generator_backward(num_block, tmem, monkeypatch):
+    """tmem: the dense-block input-gradient chain keeps its running sum in tensor memory (SSR_DGRAD_TMEM=1)"""
     from oracle import nets
     from satlas_super_resolution_b200.generator import RRDBNetEngine
+    monkeypatch.setenv("SSR_DGRAD_TMEM", "1" if tmem else "0")
     B = 2
     p, x, d_out = _g_setup(num_block, B)
     with torch.no_grad():
@@ -173,6 +175,7 @@ def test_generator_backward(num_block):
     pc = {k: v.cuda().contiguous() for k, v in p.items()}
     grads = {k: torch.zeros_like(v) for k, v in pc.items()}
     eng = RRDBNetEngine(pc, 24, 3, num_block=num_block, want_grad=True, grads=grads)
+    assert eng.dgrad_tmem == tmem
     eng.repack()
     out = eng.forward(x.cuda().contiguous(), train=True)
     eng.backward(d_out.cuda().contiguous(), B, 32, 32)
