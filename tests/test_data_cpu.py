@@ -1,0 +1,187 @@
+"""CPU tests of the packed-shard data path (satlas_super_resolution_b200/data.py).
+
+A small synthetic S2-NAIP tree (PNG files, written with cv2) exercises every branch of the sample assembly: a NAIP chip with a
+black pixel (rejected), Sentinel-2 frames with black pixels (used only to fill up), a chip with too few frames, a missing band
+file, the random-crop augmentation, `train_samples` sub-sampling and `old_naip_path`.  With the same `random` seed
+  * the shard reader returns the same tensors as the PNG reader of the same class, and
+  * -- when /root/reference is present -- both return what the UNMODIFIED reference `S2NAIPDataset` returns,
+    item by item, including the indices it skips to.
+"""
+import os
+import random
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+cv2 = pytest.importorskip("cv2")
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+N_S2 = 4
+
+
+def _write_png(path, chw):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    a = np.ascontiguousarray(np.transpose(chw, (1, 2, 0)))
+    assert cv2.imwrite(path, a[..., ::-1] if a.shape[2] == 3 else a[..., 0])
+
+
+def make_tree(root, with_old=False):
+    rng = np.random.default_rng(5)
+    chips = [f"{10 + i}_{20 + i}" for i in range(7)]
+    for i, chip in enumerate(chips):
+        hr = rng.integers(1, 256, (3, 128, 128), dtype=np.uint8)
+        if i == 2:
+            hr[:, 5, 7] = 0                                   # a black pixel: the reference skips this datapoint
+        _write_png(os.path.join(root, "naip", "2020", chip, f"{chip}.png"), hr)
+        if with_old:
+            _write_png(os.path.join(root, "old_naip", "2017", f"{chip}.png"), rng.integers(1, 256, (3, 128, 128), dtype=np.uint8))
+        # chip 4 has fewer frames than requested; chip 3 (no b08.png) has exactly n_s2_images frames -- the reference's zero
+        # stand-in for a missing band has n_s2_images frames, so it only concatenates with a series of that length
+        T = 3 if i == 4 else (N_S2 if i == 3 else 7)
+        tci = rng.integers(1, 256, (3, T * 32, 32), dtype=np.uint8)
+        if i in (1, 5):
+            for t in ((0, 2, 3, 6) if i == 1 else (1,)):      # chip 1: only 3 clean frames left -> bad ones fill up
+                tci[:, t * 32 + 3, 4] = 0
+        _write_png(os.path.join(root, "s2", chip, "tci.png"), tci)
+        if i != 3:                                            # chip 3 lacks the extra band: zeros of n_s2_images frames
+            _write_png(os.path.join(root, "s2", chip, "b08.png"), rng.integers(1, 256, (1, T * 32, 32), dtype=np.uint8))
+    return chips
+
+
+def opts(root, **kw):
+    o = dict(phase="train", n_s2_images=N_S2, scale=4, sentinel2_path=os.path.join(root, "s2"), naip_path=os.path.join(root, "naip"),
+             s2_bands=["b08", "tci"])
+    o.update(kw)
+    return o
+
+
+def collect(ds, seed):
+    random.seed(seed)
+    out = []
+    for i in range(len(ds)):
+        s = ds[i]
+        out.append({k: (v.clone() if torch.is_tensor(v) else v) for k, v in s.items()})
+    return out
+
+
+def assert_same(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x["Index"] == y["Index"] and x["Chip"] == y["Chip"] and x["Phase"] == y["Phase"]
+        for k in ("lr", "hr", "old_hr"):
+            assert (k in x) == (k in y)
+            if k in x:
+                assert x[k].dtype == torch.uint8 and x[k].shape == y[k].shape and torch.equal(x[k], y[k]), k
+
+
+REFERENCE_CHECK = r"""
+import importlib, os, random, sys, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+from satlas_super_resolution_b200 import dropin
+dropin.install()                      # registry / scandir stand-ins for the absent basicsr; seeds sys.modules (hence the subprocess)
+sys.path.insert(0, {ref!r})
+ref_cls = importlib.import_module("ssr.data.s2-naip_dataset").S2NAIPDataset
+import test_data_cpu as t
+from satlas_super_resolution_b200.data import S2NAIPShardDataset
+tree, prefix, extra = {tree!r}, {prefix!r}, {extra!r}
+def build(cls, **kw):
+    random.seed(99)
+    return cls(t.opts(tree, **extra, **kw))
+ref = t.collect(build(ref_cls), 1234)
+ours = t.collect(build(S2NAIPShardDataset, shard_path=prefix), 1234)
+t.assert_same(ref, ours)
+print("REFERENCE-OK", len(ref))
+"""
+
+
+def check_against_reference(tree, prefix, extra):
+    """the unmodified reference S2NAIPDataset on the PNG tree vs our shard reader, same seeds, in a fresh interpreter"""
+    if not os.path.isdir(os.path.join(REF, "ssr", "data")):
+        return False
+    code = REFERENCE_CHECK.format(root=ROOT, ref=REF, tree=tree, prefix=prefix, extra=extra)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "REFERENCE-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    return True
+
+
+@pytest.mark.parametrize("variant", ["plain", "rand_crop", "subset", "old_hr"])
+def test_shard_reader_matches_png_reader_and_reference(tmp_path, variant):
+    from satlas_super_resolution_b200.data import S2NAIPShardDataset, pack_s2naip
+    root = str(tmp_path)
+    make_tree(root, with_old=(variant == "old_hr"))
+    extra = {}
+    if variant == "rand_crop":
+        extra["rand_crop"] = True
+    if variant == "subset":
+        extra["train_samples"] = 5
+    if variant == "old_hr":
+        extra["old_naip_path"] = os.path.join(root, "old_naip")
+    prefix = os.path.join(root, "shard0")
+    assert pack_s2naip(opts(root, **extra), prefix) == 7
+
+    def build(cls, **kw):
+        random.seed(99)                                       # `train_samples` draws from the global state at construction
+        return cls(opts(root, **extra, **kw))
+
+    png = collect(build(S2NAIPShardDataset), 1234)
+    shard = collect(build(S2NAIPShardDataset, shard_path=prefix), 1234)
+    assert_same(png, shard)
+    s0 = shard[0]
+    assert s0["lr"].shape == (N_S2 * 4, 32, 32) and s0["hr"].shape == (3, 128, 128)
+    # the datapoint with the black NAIP pixel is never returned; the one with too few frames neither
+    assert all(s["Chip"] not in ("12_22", "14_24") for s in shard)
+    check_against_reference(root, prefix, extra)
+
+
+def test_frame_choice_prefers_clean_frames(tmp_path):
+    from satlas_super_resolution_b200.data import S2NAIPShardDataset, has_black_pixels, pack_s2naip
+    root = str(tmp_path)
+    make_tree(root)
+    prefix = os.path.join(root, "s")
+    pack_s2naip(opts(root), prefix)
+    ds = S2NAIPShardDataset(opts(root, shard_path=prefix))
+    random.seed(3)
+    by_chip = {}
+    for i in range(len(ds)):
+        s = ds[i]
+        by_chip.setdefault(s["Chip"], s)
+    # chip 15_25 has one bad frame out of 7: the 4 chosen frames are all clean (channels: t * 4 + c, TCI first)
+    lr = by_chip["15_25"]["lr"].view(N_S2, 4, 32, 32)
+    assert not any(has_black_pixels(f[:3]) for f in lr)
+    # chip 11_21 has only 3 clean frames: exactly one chosen frame carries a black pixel
+    lr = by_chip["11_21"]["lr"].view(N_S2, 4, 32, 32)
+    assert sum(bool(has_black_pixels(f[:3])) for f in lr) == 1
+    # chip 13_23 lacks b08.png: that channel is all zeros, TCI is not
+    lr = by_chip["13_23"]["lr"].view(N_S2, 4, 32, 32)
+    assert lr[:, 3].abs().max() == 0 and lr[:, :3].max() > 0
+
+
+def test_shard_guards_and_batcher(tmp_path):
+    from satlas_super_resolution_b200.data import PinnedBatcher, S2NAIPShardDataset, pack_s2naip
+    from satlas_super_resolution_b200.registry import DATASET_REGISTRY
+    assert DATASET_REGISTRY.get("S2NAIPShardDataset") is S2NAIPShardDataset
+    root = str(tmp_path)
+    make_tree(root)
+    prefix = os.path.join(root, "s")
+    pack_s2naip(opts(root), prefix)
+    with pytest.raises(ValueError, match="bands"):
+        S2NAIPShardDataset(opts(root, shard_path=prefix, s2_bands=["tci"]))
+    with pytest.raises(ValueError, match="old_naip_path"):
+        S2NAIPShardDataset(opts(root, shard_path=prefix, old_naip_path=os.path.join(root, "nowhere")))
+    with pytest.raises(NotImplementedError):
+        S2NAIPShardDataset(opts(root, shard_path=prefix, osm_objs_path="x.json"))
+    ds = S2NAIPShardDataset(opts(root, shard_path=prefix))
+    random.seed(0)
+    pb = PinnedBatcher(ds, 3, pin=False)
+    random.seed(7)
+    b = pb.batch([0, 1, 5])
+    random.seed(7)
+    want = [ds[i] for i in (0, 1, 5)]
+    assert b["lr"].shape == (3, N_S2 * 4, 32, 32) and b["hr"].shape == (3, 3, 128, 128)
+    for i, s in enumerate(want):
+        assert torch.equal(b["lr"][i], s["lr"]) and torch.equal(b["hr"][i], s["hr"])
+    w = ds.get_tile_weight_sampler({"10_20": 5.0})
+    assert len(list(iter(w))) == len(ds)
