@@ -21,7 +21,6 @@ namespace ssr {
 struct ConvTcK {
   int n_img, H, W, R, pad;
   int TW, TH, tiles_x, tiles_y;
-  int pitch;   // shared-memory rows per tile row: TW, or more in the SSR_DBG_PITCH hardware probe (8-pixel tiles only)
   int chunks, cin;
   int n_tile, n_pad, cout;
   int stages;
@@ -226,11 +225,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     // Descriptors differ only in their 14-bit start-address field: build one per stage, then add constant offsets.
-    const uint32_t a_tap = (uint32_t)(p.pitch * 128) >> 4;        // one tile row down  (descriptor address units of 16 B)
-    const uint32_t a_mt = (uint32_t)(p.TH * p.pitch * 128) >> 4;  // next stacked M tile
-    // stride between the 8-row groups of the M = 128 operand window: contiguous (1024 B) unless a tile row is 8 pixels inside a
-    // wider shared-memory row (probe: is the 128B swizzle still purely address-based then?)
-    const uint32_t a_sbo = p.pitch == p.TW ? 1024u : (uint32_t)p.pitch * 128u;
+    const uint32_t a_tap = (uint32_t)(p.TW * 128) >> 4;        // one tile row down  (descriptor address units of 16 B)
+    const uint32_t a_mt = (uint32_t)(p.TH * p.TW * 128) >> 4;  // next stacked M tile
     const uint32_t a_dbg = (uint32_t)(p.dbg_aoff * 128) >> 4;  // hardware probe only (scripts/probe_swizzle.py)
     int g = 0, gt = 0;  // running stage / tile counters across layers
     for (int l = 0; l < n_layers; ++l) {
@@ -260,7 +256,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
           if (lane == 0 && lt == items - 1 && it == iters - 1) SSR_STAMP(l, 3);     // MMA: last stage landed
           if (elect_one()) {
             const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-            const uint64_t da0 = umma_desc(a_base, 16u, a_sbo, 2u) + a_dbg;
+            const uint64_t da0 = umma_desc_k128(a_base) + a_dbg;
             const uint64_t db0 = umma_desc_k128(a_base + q.a_alloc);
             const int ks = min(4, (q.cin - c * 64) >> 4);
             if (ks == 4) {
@@ -706,21 +702,11 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
     if (tw_max < 0) {
       const char* e = getenv("SSR_CONV_TW");
       tw_max = e ? atoi(e) : 32;
-      if (tw_max != 8 && tw_max != 16 && tw_max != 32 && tw_max != 64 && tw_max != 128) tw_max = 32;
+      if (tw_max != 16 && tw_max != 32 && tw_max != 64 && tw_max != 128) tw_max = 32;
     }
     p.TW = a->w >= tw_max && a->r == 3 ? tw_max : (a->w >= 128 ? 128 : round_up(a->w, 8));
   }
   p.TH = 128 / p.TW;
-  {
-    // hardware probe (scripts/probe_sbo.sh): 8-pixel tile rows inside wider shared-memory rows, SBO = pitch * 128 B
-    static int extra = -1;
-    if (extra < 0) {
-      const char* e = getenv("SSR_DBG_PITCH");
-      extra = e ? atoi(e) : 0;
-      if (extra < 0 || extra > 8) extra = 0;
-    }
-    p.pitch = p.TW + (p.TW == 8 && a->r == 3 ? extra : 0);
-  }
   int mt = mt_force ? mt_force : a->mt;
   if (mt == 0) {
     // two stacked M tiles per CTA when one-tile CTAs would spill past a single co-resident wave: the weight tiles
@@ -760,9 +746,9 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
                 "ssr_conv_tc: split-K needs a pure atomic f32 epilogue");
 
   const int rows = mt * p.TH + p.R - 1;
-  p.a_box_bytes = (uint32_t)p.pitch * rows * 128u;
+  p.a_box_bytes = (uint32_t)p.TW * rows * 128u;
   // the M=128 operand window of the last tap may run past the box when TW*TH < 128: keep it inside the stage
-  uint32_t need = (uint32_t)(((mt - 1) * p.TH + p.R - 1) * p.pitch) * 128u + (p.pitch == p.TW ? 16384u : (uint32_t)(15 * p.pitch + 8) * 128u);
+  uint32_t need = (uint32_t)(((mt - 1) * p.TH + p.R - 1) * p.TW) * 128u + 16384u;
   p.a_alloc = (uint32_t)round_up((int)max(p.a_box_bytes, need), 1024);
   p.b_bytes = (uint32_t)(p.R * p.n_tile * 128);
   p.n_loop = 1;
@@ -823,7 +809,7 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
     uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
     uint64_t str[3] = {(uint64_t)a->x_pix_stride * 2, (uint64_t)a->x_pix_stride * 2 * a->w,
                        (uint64_t)a->x_pix_stride * 2 * a->w * a->h};
-    uint32_t box[4] = {64, (uint32_t)p.pitch, (uint32_t)rows, 1};
+    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)rows, 1};
     if (!encode_tmap_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x, dims, str, box,
                            CU_TENSOR_MAP_SWIZZLE_128B))
       return SSR_E_CUDA;
