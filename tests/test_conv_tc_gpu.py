@@ -478,7 +478,7 @@ def test_chain_acc_running_sum_in_tensor_memory(B):
         assert (ref[0][..., nf:].float() - got[0][..., nf:].float()).abs().max().item() <= 2 ** -7 * scale      # the four dY slots
         assert rel_err(got[2].float().cpu(), ref[2].float().cpu()) < 2 ** -7                                      # block-input gradient, bf16
         # ... and f32: a dY slot that rounds to the other bf16 neighbour (different f32 summation order) moves later layers slightly
-        assert rel_err(got[1][:nf // 4].cpu(), ref[1][:nf // 4].cpu()) < 2e-3
+        assert rel_err(got[1][:nf // 4].cpu(), ref[1][:nf // 4].cpu()) < 5e-3   # measured 4e-4 at B = 2
         assert got[1][nf // 4:].abs().max() == 0                                                                    # nothing else leaves TMEM
         assert torch.allclose(ref[3], got[3], rtol=1e-3, atol=1e-3 * ref[3].abs().max().item())                    # bias gradients
 
