@@ -171,6 +171,10 @@ int ssr_pack_conv_weight(const float* w_oihw, int32_t cout, int32_t cin, int32_t
 int ssr_ingest_nchw(const void* src, int32_t src_kind, void* dst_bf16, int32_t dst_pix_stride, int32_t b, int32_t c,
                     int32_t h, int32_t w, int32_t c_pad, float scale, const float* mean, const float* inv_std,
                     void* stream);
+/* The same with pixel_unshuffle(x, factor) fused (ssr/archs/arch_util.py:769-785, called at rrdbnet_arch.py:117-120 for
+ * scale 1 / 2): dst[n, y, x, c*f*f + i*f + j] = src[n, c, y*f + i, x*f + j] * scale, dst is [b, h/f, w/f, c_pad]. */
+int ssr_ingest_nchw_unshuffle(const float* src, void* dst_bf16, int32_t dst_pix_stride, int32_t b, int32_t c, int32_t h, int32_t w,
+                              int32_t factor, int32_t c_pad, float scale, void* stream);
 /* NHWC bf16 channel slice -> planar NCHW f32 (dst = or += src*scale) */
 int ssr_egress_nchw(const void* src_bf16, int32_t src_pix_stride, float* dst, int32_t b, int32_t c, int32_t h, int32_t w,
                     float scale, int32_t accumulate, const float* ch_scale /* [c] or NULL */, void* stream);
@@ -271,6 +275,11 @@ int ssr_bce_logits(const float* x, int64_t n, float target, float weight, float*
 int ssr_disc_input(const float* img, int32_t ci, const void* lr, int32_t lr_pix_stride, int32_t cl, int32_t factor, void* out,
                    int32_t out_pix_stride, int32_t b, int32_t h, int32_t w, void* stream);
 
+/* the same with a third group appended: [img | nearest(lr) | extra] -- `extra` (planar f32 [b, ce, h, w]) is the old_hr image of
+ * ssr_esrgan_model.py:112-114, 171-174, 202-207 */
+int ssr_disc_input_ex(const float* img, int32_t ci, const void* lr, int32_t lr_pix_stride, int32_t cl, int32_t factor,
+                      const float* extra, int32_t ce, void* out, int32_t out_pix_stride, int32_t b, int32_t h, int32_t w, void* stream);
+
 /* torch.nn.utils.spectral_norm, batched over the 8 normalised convs of the discriminator (device-resident table) */
 typedef struct ssr_sn_desc {
   const float* w; /* weight_orig viewed [rows = cout][cols = cin*k*k] */
@@ -294,6 +303,8 @@ int ssr_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64
                  float weight_decay, int32_t step, float ema_decay, float grad_scale,
                  const float* dev_hyper /* device [lr, 1-b1^t, sqrt(1-b2^t), t, b1, b2] overriding lr/step (graph replay), or NULL */,
                  void* stream);
+/* basicsr model_ema alone (ssr_esrgan_model.py:230-231 on an iteration without a generator step): ema = decay*ema + (1-decay)*p */
+int ssr_ema_update(float* ema, const float* p, int64_t n, float decay, void* stream);
 /* t += 1 and refresh the two bias corrections in a device-resident hyper block (recorded inside the step's CUDA graph) */
 int ssr_adam_tick(float* hyper_dev, void* stream);
 

@@ -42,6 +42,9 @@ PROTOS = {
     "ssr_l1_loss": (C.c_int, [vp, vp, i64, f32, vp, vp, i32, vp]),
     "ssr_bce_logits": (C.c_int, [vp, i64, f32, f32, vp, vp, vp, vp]),
     "ssr_disc_input": (C.c_int, [vp, i32, vp, i32, i32, i32, vp, i32, i32, i32, i32, vp]),
+    "ssr_disc_input_ex": (C.c_int, [vp, i32, vp, i32, i32, i32, vp, i32, vp, i32, i32, i32, i32, vp]),
+    "ssr_ema_update": (C.c_int, [vp, vp, i64, f32, vp]),
+    "ssr_ingest_nchw_unshuffle": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp]),
     "ssr_spectral_norm": (C.c_int, [vp, i32, i32, f32, vp]),
     "ssr_spectral_norm_bwd": (C.c_int, [vp, i32, vp]),
     "ssr_usm_sharp": (C.c_int, [vp, vp, vp, i32, i32, i32, vp, i32, f32, f32, vp]),

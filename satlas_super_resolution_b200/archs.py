@@ -106,7 +106,7 @@ class _GeneratorFn(torch.autograd.Function):
         if mod._weights_dirty():
             eng.repack()
         if need_grad:
-            ws, token = mod._acquire(B, h, w)
+            ws, token = mod._acquire(B, h // eng.unshuffle, w // eng.unshuffle)
             ctx.token, ctx.ws = token, ws
             out = eng.forward(x.contiguous(), train=True, ws=ws)
         else:
@@ -159,8 +159,7 @@ class SSR_RRDBNet(_FlatModule):
         self._ensure_flat()
         if self._engine is None:
             from .generator import RRDBNetEngine
-            self._engine = RRDBNetEngine(self._flat.views(), self.num_in_ch * (4 if self.scale == 2 else 16 if self.scale == 1 else 1),
-                                         self.num_out_ch, scale=self.scale if self.scale >= 4 else 4, num_feat=self.num_feat,
+            self._engine = RRDBNetEngine(self._flat.views(), self.num_in_ch, self.num_out_ch, scale=self.scale, num_feat=self.num_feat,
                                          num_block=self.num_block, num_grow_ch=self.num_grow_ch, want_grad=True,
                                          grads=self._flat_grad.views())
             self._packed_version = None
@@ -195,8 +194,6 @@ class SSR_RRDBNet(_FlatModule):
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("SSR_RRDBNet: the B200 engine has no CPU path (input must be a CUDA tensor)")
-        if self.scale in (1, 2):
-            raise NotImplementedError("scale 1 / 2 (pixel_unshuffle front-end, rrdbnet_arch.py:117-120) is not built yet")
         if x.requires_grad and torch.is_grad_enabled():
             raise NotImplementedError("SSR_RRDBNet: the gradient w.r.t. the low-res input is never needed on the path and is not built")
         anchor = self._anchor if any(p.requires_grad for p in self.parameters()) else self._anchor.detach()
@@ -225,6 +222,10 @@ class _DiscFn(torch.autograd.Function):
         L.check(lib().ssr_ingest_nchw(x.contiguous().data_ptr(), L.SSR_F32, ws.x_in.ptr(), ws.x_in.stride, B, Cc, H, W,
                                       eng.cin_pad, 1.0, None, None, s))
         logits = eng.forward(ws, training=mod.training, stream=s)
+        # sigma, u, v and the packed W / sigma operands are engine state that every forward overwrites (torch's spectral_norm
+        # clones them per forward): remember which forward this graph belongs to
+        mod._fwd_serial = getattr(mod, "_fwd_serial", 0) + 1
+        ctx.serial = mod._fwd_serial
         ctx.mod, ctx.ws, ctx.token = mod, ws, token
         ctx.wgrad, ctx.dinput, ctx.x_shape = anchor.requires_grad, x.requires_grad, (B, Cc, H, W)
         return logits.clone()
@@ -233,6 +234,10 @@ class _DiscFn(torch.autograd.Function):
     def backward(ctx, d_logits):
         mod, ws = ctx.mod, ctx.ws
         eng = mod._get_engine()
+        if ctx.serial != mod._fwd_serial:
+            raise RuntimeError("SSR_UNetDiscriminatorSN: backward of a forward that is no longer the latest one -- the spectral-norm "
+                               "state (sigma, u, v, packed W / sigma) has been overwritten by a newer forward.  Call backward() after "
+                               "each forward (as ssr_esrgan_model.py:215-227 does), not after several.")
         if ctx.wgrad:
             mod._attach_grads()
         eng.backward(ws, d_logits.contiguous(), need_wgrad=ctx.wgrad, need_dinput=ctx.dinput)

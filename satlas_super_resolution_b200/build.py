@@ -20,6 +20,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC",
     "-shared",
+    "--threads", "0",
 ]
 
 

@@ -21,12 +21,18 @@ namespace ssr {
 struct ConvTcK {
   int n_img, H, W, R, pad;
   int TW, TH, tiles_x, tiles_y;
+  int pitch;   // shared-memory rows per tile row: TW, or more in the SSR_DBG_PITCH hardware probe (8-pixel tiles only)
   int chunks, cin;
   int n_tile, n_pad, cout;
   int stages;
   uint32_t a_box_bytes, a_alloc, b_bytes, tmem_cols;
   uint32_t stage_stride;  // bytes between smem stages (>= a_alloc + b_bytes; the max over the layers of a chain)
   uint32_t acc_stride;    // TMEM columns between the two accumulator buffers (>= MT * n_tile)
+  // Resident dense block (forward chain, SSR_CONV_RESIDENT=1): the 192-channel tile WITH its halo stays in shared memory for all
+  // layers; only weights stream.  res_out_ch = channel offset of this layer's output inside the tile (-1: not written back)
+  int resident, res_out_ch, res_in_chunks;
+  int res_in_lo;          // channel offset of this layer's INPUT inside the tile (0 forward; the dY slot of an input-gradient layer)
+  uint32_t chunk_alloc;   // bytes of one 64-channel chunk of the resident tile ((TW+2) x (MT*TH+2) rows of 128 B, 1 KB aligned)
   int acc_w;              // > 0: chain with ONE f32 accumulator of acc_w channels per pixel that stays in TMEM for all layers
   int n_loop;             // N tiles one CTA walks itself (1 when gridDim.y spreads them; n_pad / n_tile inside a chain)
   int splits;
@@ -52,6 +58,7 @@ struct ConvTcK {
 };
 
 static constexpr int kSyncNone = 0, kSyncGrid = 1, kSyncCluster = 2;
+static constexpr int kResChunks = 3;   // 64-channel chunks of a resident dense-block tile (192 channels)
 static constexpr int kMaxChain = 5;   // layers one chained launch may hold (a ResidualDenseBlock)
 struct ConvChainK {
   CUtensorMap tmA[kMaxChain];
@@ -118,12 +125,15 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
   const uint32_t stage_bytes = p.stage_stride;
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* const dense = smem;                                                         // resident tile (if any) first,
+  uint8_t* const ring = smem + (p.resident ? (size_t)kResChunks * p.chunk_alloc : 0);  // then the stage ring
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * stage_bytes);
   uint64_t* bar_empty = bar_full + p.stages;
   uint64_t* bar_acc_full = bar_empty + p.stages;   // [2] accumulator buffer b complete (MMA -> epilogue)
   uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2] accumulator buffer b drained  (epilogue -> MMA), 8 warp arrivals
   uint64_t* bar_layer = bar_acc_empty + 2;         // kSyncCluster: every epilogue warp of the cluster arrives once per layer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_layer + 1);
+  uint64_t* bar_x = bar_layer + 1;                 // resident tile: the block input has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_x + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [256] bias of the layer's output channels
   float* s_bg = s_bias + 256;                                // [256] per-CTA bias-gradient partial sums
 
@@ -152,11 +162,20 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
         mbar_init(&bar_acc_empty[b], 8);
       }
       if (sync_mode == kSyncCluster) mbar_init(bar_layer, 8 * cluster_nctarank());
+      mbar_init(bar_x, 1);
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
+  }
+  if (p.resident) {
+    // the chunks the block input does not fill start as zeros: image borders stay zero, interior halo columns are written by
+    // the neighbour CTAs (DSMEM) layer by layer.  Generic-proxy stores, later read by the tensor core: proxy fence.
+    uint4* z = reinterpret_cast<uint4*>(dense + (size_t)p.res_in_chunks * p.chunk_alloc);
+    const int n16 = (int)(((size_t)(kResChunks - p.res_in_chunks) * p.chunk_alloc) >> 4);
+    for (int i = (int)threadIdx.x; i < n16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -175,7 +194,20 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       const int per = (q.chunks + q.splits - 1) / q.splits;
       const int c_begin = blockIdx.z * per;
       const int iters = (min(q.chunks, c_begin + per) - c_begin) * R;
-      if (l > 0) {
+      if (q.resident) {
+        // only weights stream (they do not depend on earlier layers: no wait); the block input is loaded once, with its halo
+        if (l == 0 && elect_one()) {
+          int t0 = (int)blockIdx.x;
+          const int tx0 = t0 % q.tiles_x;
+          t0 /= q.tiles_x;
+          const int ty0 = t0 % q.tiles_y;
+          mbar_expect_tx(bar_x, (uint32_t)q.res_in_chunks * q.a_box_bytes);
+          for (int c = 0; c < q.res_in_chunks; ++c)
+            tma_load_4d(dense + (size_t)c * q.chunk_alloc, tmA, bar_x, c * 64, tx0 * q.TW - q.pad, ty0 * (MT * q.TH) - q.pad, t0 / q.tiles_y);
+        }
+        __syncwarp();
+        if (l > 0) prefetch_tmap(tmB);
+      } else if (l > 0) {
         // layer l-1 has been stored (generic proxy) by every CTA we can depend on: acquire that, then order our TMA
         // (async proxy) loads behind it
         if (sync_mode == kSyncCluster) {
@@ -208,10 +240,10 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
           const uint32_t ph = (g / q.stages) & 1;
           mbar_wait(&bar_empty[s], ph ^ 1);
           if (elect_one()) {
-            uint8_t* a_dst = smem + (size_t)s * stage_bytes;
-            uint8_t* b_dst = a_dst + q.a_alloc;
-            mbar_expect_tx(&bar_full[s], q.a_box_bytes + q.b_bytes);
-            tma_load_4d(a_dst, tmA, &bar_full[s], c * 64, x0 + kx - q.pad, y0 - q.pad, n);
+            uint8_t* a_dst = ring + (size_t)s * stage_bytes;
+            uint8_t* b_dst = a_dst + q.a_alloc;   // resident: a_alloc == 0, the stage holds weights only
+            mbar_expect_tx(&bar_full[s], (q.resident ? 0u : q.a_box_bytes) + q.b_bytes);
+            if (!q.resident) tma_load_4d(a_dst, tmA, &bar_full[s], c * 64, x0 + kx - q.pad, y0 - q.pad, n);
 #pragma unroll
             for (int ky = 0; ky < R; ++ky)
               tma_load_2d(b_dst + (size_t)ky * q.n_tile * 128, tmB, &bar_full[s], 0, ((c * R + kx) * R + ky) * q.n_pad + n0);
@@ -225,8 +257,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     // Descriptors differ only in their 14-bit start-address field: build one per stage, then add constant offsets.
-    const uint32_t a_tap = (uint32_t)(p.TW * 128) >> 4;        // one tile row down  (descriptor address units of 16 B)
-    const uint32_t a_mt = (uint32_t)(p.TH * p.TW * 128) >> 4;  // next stacked M tile
+    const uint32_t a_tap = (uint32_t)(p.pitch * 128) >> 4;        // one tile row down  (descriptor address units of 16 B)
+    const uint32_t a_mt = (uint32_t)(p.TH * p.pitch * 128) >> 4;  // next stacked M tile
+    // stride between the 8-row groups of the M = 128 operand window: contiguous (1024 B) unless a tile row is 8 pixels inside a
+    // wider shared-memory row (probe: is the 128B swizzle still purely address-based then?)
+    const uint32_t a_sbo = p.pitch == p.TW ? 1024u : (uint32_t)p.pitch * 128u;
     const uint32_t a_dbg = (uint32_t)(p.dbg_aoff * 128) >> 4;  // hardware probe only (scripts/probe_swizzle.py)
     int g = 0, gt = 0;  // running stage / tile counters across layers
     for (int l = 0; l < n_layers; ++l) {
@@ -237,6 +272,13 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       const int c_begin = blockIdx.z * per;
       const int iters = (min(q.chunks, c_begin + per) - c_begin) * R;
       const int items = my_tiles * q.n_loop;  // (pixel tile, N tile) work items of this layer
+      if (q.resident) {
+        // the tile this layer reads is complete when the block input has landed (layer 0) / when every epilogue warp of the
+        // cluster has written layer l-1's channels, including the halo columns they push into our shared memory
+        if (l == 0) mbar_wait(bar_x, 0);
+        else mbar_wait_cluster(bar_layer, (uint32_t)(l - 1) & 1);
+        fence_proxy_async();
+      }
       // TMEM-resident accumulator (acc_w > 0): channel c of M tile m is column m * acc_w + c in EVERY layer; layer 0 initialises,
       // later layers add; nothing is handed back by the epilogue (a layer only writes columns below the slot being drained)
       const uint32_t m_cols = q.acc_w ? (uint32_t)q.acc_w : (uint32_t)q.n_tile;
@@ -255,9 +297,13 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
           if (lane == 0 && lt == 0 && it == 0) SSR_STAMP(l, 2);                     // MMA: first stage landed
           if (lane == 0 && lt == items - 1 && it == iters - 1) SSR_STAMP(l, 3);     // MMA: last stage landed
           if (elect_one()) {
-            const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-            const uint64_t da0 = umma_desc_k128(a_base) + a_dbg;
-            const uint64_t db0 = umma_desc_k128(a_base + q.a_alloc);
+            const uint32_t st_base = smem_u32(ring + (size_t)s * stage_bytes);
+            // resident: the operand window of tap (ky, kx) starts (ky * pitch + kx) rows into the halo tile of chunk c
+            // (an input that starts inside a chunk -- a 32-channel dY slot -- begins at K step (res_in_lo % 64) / 16 of its rows)
+            const uint32_t a_base = q.resident ? smem_u32(dense + (size_t)((q.res_in_lo >> 6) + c) * q.chunk_alloc) : st_base;
+            const uint64_t da0 = umma_desc(a_base, 16u, a_sbo, 2u) + a_dbg +
+                                 (q.resident ? (uint32_t)((it - (it / R) * R) * 8 + ((q.res_in_lo & 63) >> 4) * 2) : 0u);
+            const uint64_t db0 = umma_desc_k128(st_base + q.a_alloc);
             const int ks = min(4, (q.cin - c * 64) >> 4);
             if (ks == 4) {
 #pragma unroll
@@ -487,7 +533,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] *= (r[j] > 0.f ? 1.f : neg);
             }
-            if (p.out_bf16 != nullptr && wr16) {
+            const bool to_tile = p.resident && p.res_out_ch >= 0;   // the next layers read this output from shared memory
+            if ((p.out_bf16 != nullptr && wr16) || to_tile) {
               uint4 o0, o1;
               o0.x = pack_bf16(f[0], f[1]);
               o0.y = pack_bf16(f[2], f[3]);
@@ -497,9 +544,37 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
               o1.y = pack_bf16(f[10], f[11]);
               o1.z = pack_bf16(f[12], f[13]);
               o1.w = pack_bf16(f[14], f[15]);
-              uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.out_stride + c0);
-              dst[0] = o0;
-              dst[1] = o1;
+              if (p.out_bf16 != nullptr && wr16) {
+                uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.out_stride + c0);
+                dst[0] = o0;
+                dst[1] = o1;
+              }
+              if (to_tile) {
+                // resident tile: row = (y + 1) * pitch + (x + 1), 128 B per row and 64-channel chunk, 16-byte pieces XOR-swizzled
+                // with the row index (the layout TMA SWIZZLE_128B writes and the K-major UMMA descriptor reads)
+                const int dc = p.res_out_ch + (c0 - n_base);
+                const uint32_t chunk_base = smem_u32(dense + (size_t)(dc >> 6) * p.chunk_alloc);
+                const uint32_t j0 = (uint32_t)(dc & 63) >> 3;
+                const int yl = mt * p.TH + tyy;
+                const uint32_t row = (uint32_t)((yl + 1) * p.pitch + txx + 1);
+                st_shared_v4(chunk_base + row * 128u + ((j0 ^ (row & 7u)) << 4), o0);
+                st_shared_v4(chunk_base + row * 128u + (((j0 + 1u) ^ (row & 7u)) << 4), o1);
+                // the strips left and right of ours read our edge columns as their halo: push them into the neighbours' tiles
+                const uint32_t rank = cluster_ctarank();
+                int peer = -1;
+                uint32_t prow = 0;
+                if (txx == 0 && rank > 0) {
+                  peer = (int)rank - 1;
+                  prow = (uint32_t)((yl + 1) * p.pitch + p.TW + 1);
+                } else if (txx == p.TW - 1 && rank + 1 < cluster_nctarank()) {
+                  peer = (int)rank + 1;
+                  prow = (uint32_t)((yl + 1) * p.pitch);
+                }
+                if (peer >= 0) {
+                  st_shared_cluster_v4(chunk_base + prow * 128u + ((j0 ^ (prow & 7u)) << 4), (uint32_t)peer, o0);
+                  st_shared_cluster_v4(chunk_base + prow * 128u + (((j0 + 1u) ^ (prow & 7u)) << 4), (uint32_t)peer, o1);
+                }
+              }
             }
           } else if (in_img && c0 < p.cout) {
             // ragged tail of the channel dimension (cout not a multiple of 16): scalar path, fully unrolled so that the
@@ -677,7 +752,8 @@ extern "C" int64_t ssr_packed_weight_bytes(int32_t cin, int32_t cout, int32_t r,
 
 // validates one layer and fills its kernel parameters + tensor maps; the shared-memory ring and the TMEM budget
 // (stages, stage_stride, acc_stride, tmem_cols) are set afterwards by finalize_ring() -- jointly for the layers of a chain
-static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUtensorMap& tmA, CUtensorMap& tmB, int& mt_out) {
+static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUtensorMap& tmA, CUtensorMap& tmB, int& mt_out,
+                        bool halo_tile = false) {
   SSR_REQUIRE(a != nullptr, "ssr_conv_tc: null args");
   SSR_REQUIRE(a->r == 1 || a->r == 3, "ssr_conv_tc: r must be 1 or 3 (got %d)", a->r);
   SSR_REQUIRE(a->n_img > 0 && a->h > 0 && a->w > 0, "ssr_conv_tc: bad geometry");
@@ -702,11 +778,23 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
     if (tw_max < 0) {
       const char* e = getenv("SSR_CONV_TW");
       tw_max = e ? atoi(e) : 32;
-      if (tw_max != 16 && tw_max != 32 && tw_max != 64 && tw_max != 128) tw_max = 32;
+      if (tw_max != 8 && tw_max != 16 && tw_max != 32 && tw_max != 64 && tw_max != 128) tw_max = 32;
     }
     p.TW = a->w >= tw_max && a->r == 3 ? tw_max : (a->w >= 128 ? 128 : round_up(a->w, 8));
+    if (halo_tile) p.TW = 8;   // resident dense block: 8-pixel strips, the tile keeps its halo columns in shared memory
   }
   p.TH = 128 / p.TW;
+  {
+    // hardware probe (scripts/probe_sbo.sh): 8-pixel tile rows inside wider shared-memory rows, SBO = pitch * 128 B
+    static int extra = -1;
+    if (extra < 0) {
+      const char* e = getenv("SSR_DBG_PITCH");
+      extra = e ? atoi(e) : 0;
+      if (extra < 0 || extra > 8) extra = 0;
+    }
+    p.pitch = p.TW + (p.TW == 8 && a->r == 3 ? extra : 0);
+    if (halo_tile) p.pitch = p.TW + 2;
+  }
   int mt = mt_force ? mt_force : a->mt;
   if (mt == 0) {
     // two stacked M tiles per CTA when one-tile CTAs would spill past a single co-resident wave: the weight tiles
@@ -746,13 +834,18 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
                 "ssr_conv_tc: split-K needs a pure atomic f32 epilogue");
 
   const int rows = mt * p.TH + p.R - 1;
-  p.a_box_bytes = (uint32_t)p.TW * rows * 128u;
+  p.a_box_bytes = (uint32_t)p.pitch * rows * 128u;
   // the M=128 operand window of the last tap may run past the box when TW*TH < 128: keep it inside the stage
-  uint32_t need = (uint32_t)(((mt - 1) * p.TH + p.R - 1) * p.TW) * 128u + 16384u;
+  uint32_t need = (uint32_t)(((mt - 1) * p.TH + p.R - 1) * p.pitch) * 128u + (p.pitch == p.TW ? 16384u : (uint32_t)(15 * p.pitch + 8) * 128u);
   p.a_alloc = (uint32_t)round_up((int)max(p.a_box_bytes, need), 1024);
   p.b_bytes = (uint32_t)(p.R * p.n_tile * 128);
   p.n_loop = 1;
   p.acc_w = 0;
+  p.resident = 0;
+  p.res_out_ch = -1;
+  p.res_in_chunks = 0;
+  p.res_in_lo = 0;
+  p.chunk_alloc = 0;
   mt_out = mt;
 
   p.bias = a->bias;
@@ -809,7 +902,7 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
     uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
     uint64_t str[3] = {(uint64_t)a->x_pix_stride * 2, (uint64_t)a->x_pix_stride * 2 * a->w,
                        (uint64_t)a->x_pix_stride * 2 * a->w * a->h};
-    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)rows, 1};
+    uint32_t box[4] = {64, (uint32_t)p.pitch, (uint32_t)rows, 1};
     if (!encode_tmap_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x, dims, str, box,
                            CU_TENSOR_MAP_SWIZZLE_128B))
       return SSR_E_CUDA;
@@ -828,6 +921,7 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
 
 // one shared-memory ring / TMEM split for all n layers (n == 1: a plain launch); returns the dynamic smem size or 0
 static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
+  const size_t dense_bytes = ps[0].resident ? (size_t)kResChunks * ps[0].chunk_alloc : 0;   // resident tile in front of the ring
   uint32_t stage_bytes = 0;
   int n_tile_max = 0, iters = 0;
   for (int i = 0; i < n; ++i) {
@@ -835,7 +929,7 @@ static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
     n_tile_max = max(n_tile_max, ps[i].n_tile);
     iters += ((ps[i].chunks + ps[i].splits - 1) / ps[i].splits) * ps[i].R;
   }
-  const int budget = g_smem_optin - 1024 - 256 - 2048;
+  const int budget = g_smem_optin - 1024 - 256 - 2048 - (int)dense_bytes;
   int stages = budget / (int)stage_bytes;
   if (stages < 1) {
     set_error("ssr_conv_tc: stage of %u bytes does not fit shared memory", stage_bytes);
@@ -856,7 +950,7 @@ static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
     ps[i].acc_stride = (uint32_t)(mt * n_tile_max);
     ps[i].tmem_cols = cols;
   }
-  return (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias, bias-gradient sums*/;
+  return dense_bytes + (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias, bias-gradient sums*/;
 }
 
 static int persistent_ctas(const ConvTcK& p) {
@@ -959,6 +1053,37 @@ static int conv_chain_impl(const ssr_conv_tc_args* a, int32_t n, void* stream_, 
          a[i].n_tile == 0 && a[i].splits <= 1 && a[i].mt == a[0].mt;
   static ConvChainK c;   // 2.3 KB of tensor maps and parameters: built in place, copied by the launch
   int mt = 0, tiles_per_img = 0;
+  // Resident dense block (experimental, SSR_CONV_RESIDENT=1): every layer reads channels [0, cin_i) of ONE buffer and all but
+  // the last append their output at channel cin_i -- ResidualDenseBlock.forward.  The 192-channel tile of an 8-pixel strip
+  // (with halo) then stays in shared memory for all layers and only weights stream.
+  static int resident_on = -1;
+  if (resident_on < 0) {
+    const char* e = getenv("SSR_CONV_RESIDENT");
+    resident_on = e ? atoi(e) : 0;
+  }
+  bool resident = ok && resident_on && a[0].r == 3 && a[0].h <= 32 && a[0].w <= 64 && a[0].mt == 0;
+  int res_in_lo[kMaxChain] = {0, 0, 0, 0, 0};
+  if (!tmem_acc) {
+    for (int i = 0; resident && i < n; ++i) {
+      resident = a[i].x == a[0].x && a[i].x_pix_stride == a[0].x_pix_stride && a[i].n_pad <= 128 && a[i].cin <= 64 * kResChunks &&
+                 (i == 0 || a[i].cin == a[i - 1].cin + a[i - 1].cout);
+      if (resident && i + 1 < n)
+        resident = a[i].cout % 16 == 0 && a[i].out_pix_stride == a[0].x_pix_stride &&
+                   a[i].out_bf16 == (void*)((char*)const_cast<void*>(a[0].x) + 2 * (size_t)a[i].cin);
+    }
+  } else {
+    // input-gradient chain (running sum in tensor memory): layer 0 reads the incoming gradient (<= 64 channels -> chunk 0 of the
+    // tile); layer i >= 1 reads the slot layer i-1 just emitted, which lives in the gradient buffer at its absolute channel --
+    // the tile uses the same channel numbering, so an emitted channel c goes to tile channel c (res_out_ch = 0)
+    resident = resident && a[0].cin <= 64;
+    for (int i = 1; resident && i < n; ++i) {
+      res_in_lo[i] = a[i - 1].out_lo;
+      resident = a[i - 1].out_bf16 != nullptr && a[i].x == (void*)((char*)a[i - 1].out_bf16 + 2 * (size_t)a[i - 1].out_lo) &&
+                 a[i].x_pix_stride == a[i - 1].out_pix_stride && a[i].cin == a[i - 1].cout - a[i - 1].out_lo &&
+                 a[i - 1].out_lo >= 64 && a[i - 1].cout <= 64 * kResChunks && (a[i - 1].out_lo & 63) + a[i].cin <= 64 &&
+                 a[i - 1].out_lo % 16 == 0;
+    }
+  }
   if (ok) {
     if (!device_limits()) return SSR_E_CUDA;
     // the widest layer decides how many M tiles a CTA stacks (two accumulator buffers of mt * n_tile TMEM columns)
@@ -966,13 +1091,34 @@ static int conv_chain_impl(const ssr_conv_tc_args* a, int32_t n, void* stream_, 
     for (int i = 1; i < n; ++i)
       if (a[i].n_pad > a[widest].n_pad) widest = i;
     int mt_w = 0;
-    if (int rc = prepare_conv(&a[widest], 0, c.k[widest], c.tmA[widest], c.tmB[widest], mt_w)) return rc;
+    if (int rc = prepare_conv(&a[widest], resident ? 2 : 0, c.k[widest], c.tmA[widest], c.tmB[widest], mt_w, resident)) return rc;
     mt = mt_w;
     for (int i = 0; i < n; ++i) {
       int mt_i = 0;
       if (i != widest)
-        if (int rc = prepare_conv(&a[i], mt, c.k[i], c.tmA[i], c.tmB[i], mt_i)) return rc;
+        if (int rc = prepare_conv(&a[i], mt, c.k[i], c.tmA[i], c.tmB[i], mt_i, resident)) return rc;
       c.k[i].n_loop = c.k[i].n_pad / c.k[i].n_tile;
+    }
+    if (resident && c.k[0].tiles_y != 1) {
+      // taller than one strip: vertical halos would need an exchange too -- redo the layers in the standard layout
+      resident = false;
+      for (int i = 0; i < n; ++i) {
+        int mt_i = 0;
+        if (int rc = prepare_conv(&a[i], i == 0 ? 0 : mt, c.k[i], c.tmA[i], c.tmB[i], mt_i)) return rc;
+        if (i == 0) mt = mt_i;
+        c.k[i].n_loop = c.k[i].n_pad / c.k[i].n_tile;
+      }
+    }
+    if (resident) {
+      const uint32_t chunk_alloc = (uint32_t)round_up((int)c.k[0].a_box_bytes, 1024);   // (TW+2) x (MT*TH+2) rows of 128 B
+      for (int i = 0; i < n; ++i) {
+        c.k[i].resident = 1;
+        c.k[i].chunk_alloc = chunk_alloc;
+        c.k[i].a_alloc = 0;                                   // stages carry weights only
+        c.k[i].res_in_chunks = (a[0].cin + 63) / 64;
+        c.k[i].res_in_lo = res_in_lo[i];
+        c.k[i].res_out_ch = i + 1 < n ? (tmem_acc ? 0 : a[i].cin) : -1;
+      }
     }
     tiles_per_img = c.k[0].tiles_x * c.k[0].tiles_y;
     const int total = tiles_per_img * c.k[0].n_img;

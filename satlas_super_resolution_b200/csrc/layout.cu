@@ -56,6 +56,43 @@ __global__ void nchw_to_nhwc_bf16_kernel(const T* __restrict__ src, __nv_bfloat1
   }
 }
 
+// ---------------------------------------------------------------- ingest with pixel_unshuffle (space-to-depth)
+// pixel_unshuffle(x, s) of ssr/archs/arch_util.py:769-785 (the scale 1 / 2 front end of SSR_RRDBNet, rrdbnet_arch.py:117-120):
+// out[n, c*s*s + i*s + j, y, x] = in[n, c, y*s + i, x*s + j], written NHWC bf16.  One thread per (output pixel, 8-channel group).
+__global__ void nchw_unshuffle_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int C,
+                                                   int H, int W, int s, int dst_stride, int c_pad, float scale) {
+  const int h = H / s, w = W / s, ss = s * s;
+  const long hw_out = (long)h * w;
+  const int groups = c_pad / 8;
+  const long total = (long)B * hw_out * groups;
+  const int C_out = C * ss;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i % ((long)B * hw_out);
+    const int g = (int)(i / ((long)B * hw_out));
+    const long n = pix / hw_out;
+    const long r = pix - n * hw_out;
+    const int y = (int)(r / w), x = (int)(r - (long)y * w);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = g * 8 + j;
+      float f = 0.f;
+      if (co < C_out) {
+        const int c = co / ss, ij = co - c * ss;
+        f = src[((n * C + c) * H + (y * s + ij / s)) * (long)W + (x * s + ij % s)] * scale;
+      }
+      v[j] = f;
+    }
+    uint4 o;
+    __nv_bfloat162 hh;
+    hh = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&hh);
+    hh = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&hh);
+    hh = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&hh);
+    hh = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&hh);
+    *reinterpret_cast<uint4*>(dst + pix * dst_stride + g * 8) = o;
+  }
+}
+
 // ---------------------------------------------------------------- egress: NHWC bf16 -> planar f32
 __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, int src_stride,
                                              float* __restrict__ dst, int B, int C, int H, int W, float scale,
@@ -373,6 +410,20 @@ extern "C" int ssr_ingest_nchw(const void* src, int32_t src_kind /*0 = u8, 2 = f
     SSR_REQUIRE(false, "ssr_ingest_nchw: src_kind must be 0 (u8) or 2 (f32)");
   count_launch();
   return check_last("ingest launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_ingest_nchw_unshuffle(const float* src, void* dst_bf16, int32_t dst_pix_stride, int32_t b, int32_t c, int32_t h,
+                                         int32_t w, int32_t factor, int32_t c_pad, float scale, void* stream) {
+  SSR_REQUIRE(src && dst_bf16, "ssr_ingest_nchw_unshuffle: null pointer");
+  SSR_REQUIRE(factor >= 1 && h % factor == 0 && w % factor == 0, "ssr_ingest_nchw_unshuffle: size not divisible by the factor");
+  SSR_REQUIRE(c_pad % 8 == 0 && c_pad >= c * factor * factor && dst_pix_stride % 8 == 0 && dst_pix_stride >= c_pad,
+              "ssr_ingest_nchw_unshuffle: c_pad/stride");
+  SSR_REQUIRE((reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0, "ssr_ingest_nchw_unshuffle: dst alignment");
+  const long total = (long)b * (h / factor) * (w / factor) * (c_pad / 8);
+  nchw_unshuffle_to_nhwc_bf16_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), b, c, h,
+                                                                                         w, factor, dst_pix_stride, c_pad, scale);
+  count_launch();
+  return check_last("ingest unshuffle launch") ? SSR_OK : SSR_E_CUDA;
 }
 
 extern "C" int ssr_egress_nchw(const void* src_bf16, int32_t src_pix_stride, float* dst, int32_t b, int32_t c, int32_t h,

@@ -53,6 +53,24 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(v));
   return v;
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t v;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(v));
+  return v;
+}
+// 16-byte stores into this CTA's / a peer CTA's shared memory (distributed shared memory; the address is the LOCAL address of the
+// same location, mapped into the peer's window with mapa)
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_shared_cluster_v4(uint32_t local_addr, uint32_t cta_rank, uint4 v) {
+  asm volatile(
+      "{\n.reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "st.shared::cluster.v4.b32 [ra], {%2, %3, %4, %5};\n}" ::"r"(local_addr),
+      "r"(cta_rank), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+      : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }

@@ -291,26 +291,42 @@ __global__ void bce_logits_kernel(const float* __restrict__ x, long n, float tar
 }
 
 // ------------------------------------------------------------------ discriminator input assembly
-// out[n, y, x, :] = [ img[n, 0:ci, y, x] (planar f32) | lr[n, y/f, x/f, 0:cl] (NHWC bf16, nearest x f) | 0 ... ]
-// = torch.cat((output | gt, F.interpolate(lr, scale_factor=4)), 1) of ssr_esrgan_model.py:133,176,208-210.
+// out[n, y, x, :] = [ img[n, 0:ci, y, x] (planar f32) | lr[n, y/f, x/f, 0:cl] (NHWC bf16, nearest x f) | extra[n, 0:ce, y, x] (planar f32) | 0 ... ]
+// = torch.cat((output | gt, F.interpolate(lr, scale_factor=4), old_hr), 1) of ssr_esrgan_model.py:133,171-176,202-210.
+// One thread per pixel: the planar reads are coalesced across the warp (consecutive pixels), the NHWC row of the pixel
+// (out_stride bf16, a multiple of 8) leaves as consecutive 16-byte stores.
 __global__ void disc_input_kernel(const float* __restrict__ img, int ci, const __nv_bfloat16* __restrict__ lr, int lr_stride, int cl,
-                                  int f, __nv_bfloat16* __restrict__ out, int out_stride, int B, int H, int W) {
+                                  int f, const float* __restrict__ extra, int ce, __nv_bfloat16* __restrict__ out, int out_stride,
+                                  int B, int H, int W) {
   const long HW = (long)H * W;
-  const long total = (long)B * HW * out_stride;
+  const long total = (long)B * HW;
   const int h = H / f, w = W / f;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % out_stride);
-    const long pix = i / out_stride;
+  const int groups = out_stride >> 3;
+  for (long pix = blockIdx.x * (long)blockDim.x + threadIdx.x; pix < total; pix += (long)gridDim.x * blockDim.x) {
     const long n = pix / HW;
     const long hw = pix - n * HW;
-    float v = 0.f;
-    if (c < ci) {
-      v = img[(n * ci + c) * HW + hw];
-    } else if (c < ci + cl) {
-      const int y = (int)(hw / W), x = (int)(hw % W);
-      v = __bfloat162float(lr[((n * h + y / f) * w + x / f) * (long)lr_stride + (c - ci)]);
+    const int y = (int)(hw / W), x = (int)(hw - (long)y * W);
+    const __nv_bfloat16* lrp = cl ? lr + ((n * h + y / f) * w + x / f) * (long)lr_stride : nullptr;
+    uint4* dst = reinterpret_cast<uint4*>(out + pix * out_stride);
+    for (int g = 0; g < groups; ++g) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        float t = 0.f;
+        if (c < ci) t = img[(n * ci + c) * HW + hw];
+        else if (c < ci + cl) t = __bfloat162float(lrp[c - ci]);
+        else if (c < ci + cl + ce) t = extra[(n * ce + (c - ci - cl)) * HW + hw];
+        v[j] = t;
+      }
+      uint4 o;
+      __nv_bfloat162 hh;
+      hh = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&hh);
+      hh = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&hh);
+      hh = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&hh);
+      hh = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&hh);
+      dst[g] = o;
     }
-    out[i] = __float2bfloat16(v);
   }
 }
 
@@ -489,6 +505,12 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
   }
 }
 
+// basicsr model_ema on an iteration without a generator step (net_d_iters > 1 / net_d_init_iters): ema = decay*ema + (1-decay)*p
+__global__ void ema_update_kernel(float* __restrict__ ema, const float* __restrict__ p, long n, float decay) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    ema[i] = decay * ema[i] + (1.f - decay) * p[i];
+}
+
 // hyper = [lr, 1 - b1^t, sqrt(1 - b2^t), t, b1, b2]: advance t on the device (CUDA-graph replays cannot take new kernel
 // arguments, and a host-staged copy could be overwritten by a CPU that runs several steps ahead)
 __global__ void adam_tick_kernel(float* __restrict__ hyper) {
@@ -576,15 +598,22 @@ extern "C" int ssr_bce_logits(const float* x, int64_t n, float target, float wei
   return LAUNCH_OK("bce_logits");
 }
 
-extern "C" int ssr_disc_input(const float* img, int32_t ci, const void* lr, int32_t lr_pix_stride, int32_t cl, int32_t factor, void* out,
-                              int32_t out_pix_stride, int32_t b, int32_t h, int32_t w, void* stream) {
-  SSR_REQUIRE(img && out && (cl == 0 || lr) && ci + cl <= out_pix_stride, "ssr_disc_input: bad args");
-  SSR_REQUIRE(cl == 0 || (h % factor == 0 && w % factor == 0), "ssr_disc_input: size not divisible by factor");
-  const long total = (long)b * h * w * out_pix_stride;
-  disc_input_kernel<<<grid_for2(total, 256), 256, 0, STREAM(stream)>>>(img, ci, reinterpret_cast<const __nv_bfloat16*>(lr), lr_pix_stride,
-                                                                      cl, factor > 0 ? factor : 1,
+extern "C" int ssr_disc_input_ex(const float* img, int32_t ci, const void* lr, int32_t lr_pix_stride, int32_t cl, int32_t factor,
+                                 const float* extra, int32_t ce, void* out, int32_t out_pix_stride, int32_t b, int32_t h, int32_t w,
+                                 void* stream) {
+  SSR_REQUIRE(img && out && (cl == 0 || lr) && (ce == 0 || extra) && ci + cl + ce <= out_pix_stride, "ssr_disc_input: bad args");
+  SSR_REQUIRE(out_pix_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "ssr_disc_input: out must be 16-byte aligned rows");
+  SSR_REQUIRE(cl == 0 || (factor > 0 && h % factor == 0 && w % factor == 0), "ssr_disc_input: size not divisible by factor");
+  const long total = (long)b * h * w;
+  disc_input_kernel<<<grid_for2(total, 128), 128, 0, STREAM(stream)>>>(img, ci, reinterpret_cast<const __nv_bfloat16*>(lr), lr_pix_stride,
+                                                                      cl, factor > 0 ? factor : 1, extra, ce,
                                                                       reinterpret_cast<__nv_bfloat16*>(out), out_pix_stride, b, h, w);
   return LAUNCH_OK("disc_input");
+}
+
+extern "C" int ssr_disc_input(const float* img, int32_t ci, const void* lr, int32_t lr_pix_stride, int32_t cl, int32_t factor, void* out,
+                              int32_t out_pix_stride, int32_t b, int32_t h, int32_t w, void* stream) {
+  return ssr_disc_input_ex(img, ci, lr, lr_pix_stride, cl, factor, nullptr, 0, out, out_pix_stride, b, h, w, stream);
 }
 
 extern "C" int ssr_spectral_norm(const ssr_sn_desc* descs_device, int32_t n_layers, int32_t power_iteration, float eps, void* stream) {
@@ -660,6 +689,12 @@ extern "C" int ssr_adam_ema(float* p, const float* g, float* m, float* v, float*
   adam_ema_kernel<<<grid_for2(n, 256), 256, 0, STREAM(stream)>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
                                                                  (float)sqrt(bc2), ema_decay, grad_scale, dev_hyper);
   return LAUNCH_OK("adam_ema");
+}
+
+extern "C" int ssr_ema_update(float* ema, const float* p, int64_t n, float decay, void* stream) {
+  SSR_REQUIRE(ema && p && n > 0, "ssr_ema_update: bad args");
+  ema_update_kernel<<<grid_for2(n, 256), 256, 0, STREAM(stream)>>>(ema, p, n, decay);
+  return LAUNCH_OK("ema_update");
 }
 
 extern "C" int ssr_adam_tick(float* hyper_dev, void* stream) {

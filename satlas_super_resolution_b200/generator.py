@@ -19,17 +19,22 @@ from .ops import Act, PackedConv, Packer, Plan, WgradSet, conv_args, cur_stream,
 class RRDBNetEngine:
     def __init__(self, params, num_in_ch, num_out_ch=3, scale=4, num_feat=64, num_block=23, num_grow_ch=32,
                  want_grad=True, grads=None):
-        if scale not in (4, 8, 16):
-            raise NotImplementedError("RRDBNetEngine: scale 1/2 (pixel_unshuffle front-end) is not built yet")
+        if scale not in (1, 2, 4, 8, 16):
+            raise ValueError(f"RRDBNetEngine: scale {scale} (the reference builds 1, 2, 4, 8, 16: rrdbnet_arch.py:92-109)")
         if num_feat % 16 or num_grow_ch % 16:
             raise ValueError("num_feat and num_grow_ch must be multiples of 16")
         self.p = params
         self.device = next(iter(params.values())).device
         self.cin, self.cout, self.scale = num_in_ch, num_out_ch, scale
         self.nf, self.nb, self.g = num_feat, num_block, num_grow_ch
-        self.cin_pad = round_up(num_in_ch, 16)
+        # scale 2 / 1: pixel_unshuffle(x, 2 / 4) in front of conv_first (rrdbnet_arch.py:95-98, 117-120), fused into the ingest
+        self.unshuffle = {1: 4, 2: 2}.get(scale, 1)
+        self.cin_eff = num_in_ch * self.unshuffle ** 2
+        if params["conv_first.weight"].shape[1] != self.cin_eff:
+            raise ValueError(f"conv_first.weight has {params['conv_first.weight'].shape[1]} input channels, expected {self.cin_eff}")
+        self.cin_pad = round_up(self.cin_eff, 16)
         self.want_grad = want_grad
-        self.n_up = {4: 2, 8: 3, 16: 4}[scale]
+        self.n_up = {1: 2, 2: 2, 4: 2, 8: 3, 16: 4}[scale]
         nf, g = self.nf, self.g
         cv = {}
 
@@ -85,19 +90,26 @@ class RRDBNetEngine:
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
         B, Cc, h, w = x.shape
         assert Cc == self.cin
+        f = self.unshuffle
+        if h % f or w % f:
+            raise ValueError(f"scale {self.scale}: input {h}x{w} is not divisible by the pixel_unshuffle factor {f}")
         if ws is None:
-            ws = self.workspace(B, h, w, train)
+            ws = self.workspace(B, h // f, w // f, train)
         s = stream if stream is not None else cur_stream()
-        L.check(lib().ssr_ingest_nchw(x.data_ptr(), L.SSR_F32, ws.in0.ptr(), ws.in0.stride, B, Cc, h, w, self.cin_pad,
-                                      1.0, None, None, s))
+        if f == 1:
+            L.check(lib().ssr_ingest_nchw(x.data_ptr(), L.SSR_F32, ws.in0.ptr(), ws.in0.stride, B, Cc, h, w, self.cin_pad,
+                                          1.0, None, None, s))
+        else:
+            L.check(lib().ssr_ingest_nchw_unshuffle(x.data_ptr(), ws.in0.ptr(), ws.in0.stride, B, Cc, h, w, f, self.cin_pad, 1.0, s))
         ws.fwd.run(s)
         return ws.out
 
     def backward(self, d_out, B, h, w, stream=None, ws=None):
-        """d_out: f32 NCHW gradient of the forward output; accumulates into self.grads (weights and biases)."""
+        """d_out: f32 NCHW gradient of the forward output; accumulates into self.grads (weights and biases).
+        h, w: height / width of the forward INPUT."""
         assert self.wg is not None, "engine built without gradient buffers"
         if ws is None:
-            ws = self.workspace(B, h, w, True)
+            ws = self.workspace(B, h // self.unshuffle, w // self.unshuffle, True)
         s = stream if stream is not None else cur_stream()
         if ws.bwd is None:
             ws.bwd = ws._build_backward(self)

@@ -19,9 +19,11 @@ from .registry import LOSS_REGISTRY, _register
 class _L1Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target, weight):
+        need = ctx.needs_input_grad[0]          # of the caller's tensor: the casts below return plain copies inside forward
+        ctx.in_dtype = pred.dtype
         pred, target = pred.contiguous().float(), target.contiguous().float()
         loss = torch.zeros(1, dtype=torch.float32, device=pred.device)
-        grad = torch.empty_like(pred) if pred.requires_grad or torch.is_grad_enabled() else None
+        grad = torch.empty_like(pred) if need else None
         L.check(lib().ssr_l1_loss(pred.data_ptr(), target.data_ptr(), pred.numel(), weight, loss.data_ptr(),
                                   grad.data_ptr() if grad is not None else None, 0, cur_stream()))
         ctx.grad = grad
@@ -29,7 +31,7 @@ class _L1Fn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return (ctx.grad * g if ctx.grad is not None else None), None, None
+        return ((ctx.grad * g).to(ctx.in_dtype) if ctx.grad is not None else None), None, None
 
 
 class L1Loss(nn.Module):
@@ -80,39 +82,39 @@ class GANLoss(nn.Module):
 class _PercepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gt, mod):
+        need = ctx.needs_input_grad[0]
+        ctx.in_dtype = x.dtype
         x, gt = x.contiguous().float(), gt.contiguous().float()
         loss = torch.zeros(1, dtype=torch.float32, device=x.device)
-        dx = torch.zeros_like(x) if x.requires_grad else None
+        dx = torch.zeros_like(x) if need else None
         mod.engine(x.device).loss_and_grad(x, gt, loss, dx, cur_stream())
         ctx.dx = dx
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
-        return (ctx.dx * g if ctx.dx is not None else None), None, None
+        return ((ctx.dx * g).to(ctx.in_dtype) if ctx.dx is not None else None), None, None
 
 
 class PerceptualLoss(nn.Module):
     """basicsr PerceptualLoss(layer_weights, vgg_type='vgg19', use_input_norm, range_norm, perceptual_weight, style_weight=0,
-    criterion='l1').  VGG19 weights: `experiments/pretrained_models/vgg19-dcbb9e9d.pth` when present (the file basicsr looks
-    for), else seeded random weights (offline)."""
-
-    VGG_PATH = "experiments/pretrained_models/vgg19-dcbb9e9d.pth"
+    criterion='l1').  VGG19 weights: the torchvision checkpoint vgg19-dcbb9e9d.pth (weights.vgg19_search_paths()); when it is
+    absent construction of the engine RAISES unless `vgg_seed` (or $SSR_VGG_RANDOM_SEED) explicitly asks for seeded random
+    weights (tests / benchmarks offline)."""
 
     def __init__(self, layer_weights, vgg_type="vgg19", use_input_norm=True, range_norm=False, perceptual_weight=1.0,
-                 style_weight=0.0, criterion="l1", vgg_seed=0):
+                 style_weight=0.0, criterion="l1", vgg_seed=None, vgg_path=None):
         super().__init__()
         if vgg_type != "vgg19" or criterion != "l1" or style_weight:
             raise NotImplementedError("PerceptualLoss: only vgg19 / l1 / style_weight=0 (the shipped config) is built")
         self.layer_weights, self.perceptual_weight = dict(layer_weights), perceptual_weight
-        self.use_input_norm, self.range_norm, self.vgg_seed = use_input_norm, range_norm, vgg_seed
+        self.use_input_norm, self.range_norm, self.vgg_seed, self.vgg_path = use_input_norm, range_norm, vgg_seed, vgg_path
         self._engine = None
 
     def engine(self, device):
         if self._engine is None:
-            import os
             from .vgg import PerceptualEngine
-            sd = weights.vgg19_state(self.vgg_seed, self.VGG_PATH if os.path.exists(self.VGG_PATH) else None)
+            sd = weights.resolve_vgg19_state(self.vgg_seed, self.vgg_path)
             self._engine = PerceptualEngine({k: v.to(device) for k, v in sd.items()}, self.layer_weights, self.perceptual_weight,
                                             self.use_input_norm, self.range_norm)
         return self._engine

@@ -56,13 +56,21 @@ class SSRESRGANModel:
             raise RuntimeError("SSRESRGANModel (B200 engine): num_gpu == 0 / CPU execution is not available")
         rank = int(os.environ.get("LOCAL_RANK", 0))
         self.device = torch.device("cuda", rank if opt.get("dist") else torch.cuda.current_device())
-        train_opt = opt.get("train", {})
+        train_opt = opt.get("train") or {}
         # ---- networks (registry-built, reference key schema); the trainer then owns their storage
         self.net_g = build_network(opt["network_g"])
         self._load_if_given(self.net_g, "pretrain_network_g", "param_key_g", "strict_load_g", "params")
-        self.net_d = build_network(opt["network_d"]) if "network_d" in opt else None
-        if self.net_d is not None:
-            self._load_if_given(self.net_d, "pretrain_network_d", "param_key_d", "strict_load_d", "params")
+        self.log_dict = OrderedDict()
+        self.optimizers, self.schedulers = [], []
+        self.trainer = None
+        if not self.is_train:
+            # basicsr SRModel with is_train False builds net_g only (no D, losses, optimizers, EMA copy): forward-only engine
+            self.net_g.to(self.device).eval()
+            return
+        if "network_d" not in opt:
+            raise ValueError("SSRESRGANModel (is_train): the option file has no network_d")
+        self.net_d = build_network(opt["network_d"])
+        self._load_if_given(self.net_d, "pretrain_network_d", "param_key_d", "strict_load_d", "params")
         for unsupported in ("ldl_opt", "ssim_opt", "clip_opt"):
             if train_opt.get(unsupported):
                 raise NotImplementedError(f"train.{unsupported}: this loss is outside the built hot path (SURVEY.md section 2 rows 5, 13)")
@@ -70,12 +78,21 @@ class SSRESRGANModel:
         if gan and gan.get("gan_type", "vanilla") != "vanilla":
             raise NotImplementedError("only gan_type 'vanilla' is built")
         optim_g = dict(train_opt.get("optim_g", {"type": "Adam", "lr": 1e-4, "betas": [0.9, 0.99]}))
-        if optim_g.get("type", "Adam") != "Adam":
-            raise NotImplementedError("only Adam is built (esrgan_s2naip_urban.yml:98-107)")
-        vgg_path = losses.PerceptualLoss.VGG_PATH
-        vgg_sd = weights.vgg19_state(0, vgg_path if os.path.exists(vgg_path) else None) if per else None
+        optim_d = dict(train_opt.get("optim_d", optim_g))
+        for o in (optim_g, optim_d):
+            if o.get("type", "Adam") != "Adam":
+                raise NotImplementedError("only Adam is built (esrgan_s2naip_urban.yml:98-107)")
+            extra = set(o) - {"type", "lr", "betas", "weight_decay", "eps"}
+            if extra:
+                raise NotImplementedError(f"Adam options {sorted(extra)} are not built")
+        if optim_g.get("eps", 1e-8) != 1e-8 or optim_d.get("eps", 1e-8) != 1e-8:
+            raise NotImplementedError("Adam eps other than 1e-8 is not built")
+        vgg_sd = weights.resolve_vgg19_state(per.get("vgg_seed", opt.get("vgg_seed")), per.get("vgg_path")) if per else None
         cfg = dict(network_g=dict(num_in_ch=self.net_g.num_in_ch, num_block=self.net_g.num_block, scale=self.net_g.scale),
                    ema_decay=train_opt.get("ema_decay", 0), lr=optim_g.get("lr", 1e-4), betas=tuple(optim_g.get("betas", (0.9, 0.99))),
+                   weight_decay=optim_g.get("weight_decay", 0.0),
+                   lr_d=optim_d.get("lr", 1e-4), betas_d=tuple(optim_d.get("betas", (0.9, 0.99))),
+                   weight_decay_d=optim_d.get("weight_decay", 0.0),
                    pixel_weight=pix.get("loss_weight", 1.0) if pix else 0.0, gan_weight=gan.get("loss_weight", 0.1),
                    perceptual=bool(per), layer_weights=per.get("layer_weights"), perceptual_weight=per.get("perceptual_weight", 1.0),
                    use_input_norm=per.get("use_input_norm", True), range_norm=per.get("range_norm", False),
@@ -86,6 +103,7 @@ class SSRESRGANModel:
         if per and not cfg["layer_weights"]:
             raise ValueError("perceptual_opt needs layer_weights")
         pg = torch.distributed.group.WORLD if (opt.get("dist") and torch.distributed.is_initialized()) else None
+        # ESRGANTrainer broadcasts rank 0's parameters / buffers / EMA to every rank (what DDP does at construction)
         self.trainer = ESRGANTrainer(self.net_g.state_dict(), self.net_d.state_dict(), vgg_sd, cfg, device=self.device,
                                      process_group=pg)
         tr = self.trainer
@@ -112,7 +130,6 @@ class SSRESRGANModel:
             raise NotImplementedError("only MultiStepLR is built (esrgan_s2naip_urban.yml:109-112)")
         self._milestones, self._gamma = list(sched.get("milestones", [])), sched.get("gamma", 0.5)
         self._sched_iter = 0
-        self.log_dict = OrderedDict()
         self.net_g.train()
         self.net_d.train()
 
@@ -149,12 +166,12 @@ class SSRESRGANModel:
 
     def feed_data(self, data):
         """ssr_esrgan_model.py:104-117 -- data['lr'] uint8 [B, T*C, h, w], data['hr'] uint8 [B, 3, H, W]"""
-        if "old_hr" in data:
-            raise NotImplementedError("old_hr discriminator conditioning (SURVEY.md 8f row 4) is not built yet")
-        if "hr" not in data:
+        if "hr" not in data or self.trainer is None:
             self.lr = (data["lr"].to(self.device).float() / 255).contiguous()
+            if "hr" in data:
+                self.gt = (data["hr"].to(self.device).float() / 255).contiguous()
             return
-        self.trainer.feed_data(data["lr"], data["hr"])
+        self.trainer.feed_data(data["lr"], data["hr"], data.get("old_hr"))
         self.lr, self.gt, self.gt_usm = self.trainer.lr, self.trainer.gt, self.trainer.gt_usm
 
     def optimize_parameters(self, current_iter):
@@ -167,8 +184,13 @@ class SSRESRGANModel:
         return self.log_dict
 
     def test(self):
-        """ssr_esrgan_model.py:235-244"""
-        self.output = self.trainer.test(self.lr)
+        """ssr_esrgan_model.py:235-244: net_g_ema (eval) when it exists, else net_g in eval mode"""
+        if self.trainer is not None:
+            self.output = self.trainer.test(self.lr)
+            return
+        with torch.no_grad():
+            self.net_g.eval()
+            self.output = self.net_g(self.lr)
 
     def get_current_visuals(self):
         out = OrderedDict(lr=self.lr.detach().cpu(), result=self.output.detach().cpu())

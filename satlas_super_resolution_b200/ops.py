@@ -303,6 +303,18 @@ def allreduce_sum_(flat, process_group=None):
     return flat
 
 
+def broadcast_from_rank0_(tensors, process_group=None):
+    """in-place broadcast of every tensor from the group's rank 0 (what DistributedDataParallel does to parameters and
+    buffers when it wraps a module)"""
+    import torch.distributed as dist
+    if process_group is None and not (dist.is_available() and dist.is_initialized()):
+        return tensors
+    src = dist.get_global_rank(process_group, 0) if process_group is not None else 0
+    for t in tensors:
+        dist.broadcast(t, src=src, group=process_group)
+    return tensors
+
+
 def rank_slice(n_items, rank, world):
     """contiguous shard of `n_items` independent work items (tiles / chunks) for `rank`: no collective needed"""
     per = (n_items + world - 1) // world

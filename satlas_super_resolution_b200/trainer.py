@@ -118,6 +118,7 @@ class ESRGANTrainer:
                                       cfg.get("perceptual_weight", 1.0), cfg.get("use_input_norm", True),
                                       cfg.get("range_norm", False))
         self.feed_disc_lr = cfg.get("feed_disc_lr", True)
+        self.old_hr_ch = 0   # set by feed_data when the batch carries an `old_hr` image (ssr_esrgan_model.py:112-114)
         self.l1_gt_usm = cfg.get("l1_gt_usm", True)
         self.percep_gt_usm = cfg.get("percep_gt_usm", True)
         self.gan_gt_usm = cfg.get("gan_gt_usm", False)
@@ -125,8 +126,13 @@ class ESRGANTrainer:
         self.net_d_init_iters = cfg.get("net_d_init_iters", 0)
         lr = cfg.get("lr", 1e-4)
         betas = tuple(cfg.get("betas", (0.9, 0.99)))
-        self.opt_g = FusedAdamState(self.gbuf, self.ggrad, lr, betas, ema=self.gema, ema_decay=self.ema_decay)
-        self.opt_d = FusedAdamState(self.dbuf, self.dgrad, lr, betas)
+        # train.optim_d has its own lr / betas / weight_decay (esrgan_s2naip_urban.yml:103-107); default = optim_g's
+        self.opt_g = FusedAdamState(self.gbuf, self.ggrad, lr, betas, weight_decay=cfg.get("weight_decay", 0.0),
+                                    ema=self.gema, ema_decay=self.ema_decay)
+        self.opt_d = FusedAdamState(self.dbuf, self.dgrad, cfg.get("lr_d", lr), tuple(cfg.get("betas_d", betas)),
+                                    weight_decay=cfg.get("weight_decay_d", cfg.get("weight_decay", 0.0)))
+        if self.pg is not None:
+            self.sync_replicas()
         self.loss_dev = torch.zeros(8, dtype=torch.float32, device=dev)
         self.usm_taps = (C_float_array(gaussian_taps(51, 0)), 51)
         self._io = {}
@@ -135,6 +141,20 @@ class ESRGANTrainer:
         self._last_mode = "eager"
         self.use_graph = bool(cfg.get("cuda_graph", False))
         self.log_dict = OrderedDict()
+
+    def replicated_tensors(self):
+        """everything DistributedDataParallel broadcasts from rank 0 at construction (parameters and buffers) plus the EMA copy"""
+        out = [self.gbuf.flat, self.dbuf.flat] + [self.d_uv[k] for k in sorted(self.d_uv)]
+        if self.gema is not None:
+            out.append(self.gema.flat)
+        return out
+
+    def sync_replicas(self):
+        """The reference seeds every rank with manual_seed + rank (ssr/utils/options.py:81) and relies on DDP broadcasting rank 0's
+        parameters and buffers when the wrapper is built (basicsr model_to_device, ssr_esrgan_model.py:54): do the same, so
+        replicas that were initialised differently start -- and, applying the same averaged gradients, stay -- identical."""
+        from .ops import broadcast_from_rank0_
+        broadcast_from_rank0_(self.replicated_tensors(), self.pg)
 
     # ------------------------------------------------------------------ data
     def _io_for(self, B, C_lr, h, w, H, W):
@@ -147,6 +167,8 @@ class ESRGANTrainer:
                       lr=torch.empty((B, C_lr, h, w), dtype=torch.float32, device=dev),
                       gt=torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
                       gt_usm=torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
+                      old_u8=torch.empty((B, 3, H, W), dtype=torch.uint8, device=dev),
+                      old_hr=torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
                       usm_scratch=torch.empty((3, B, 3, H, W), dtype=torch.float32, device=dev),
                       d_out=torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
                       d_logits=torch.empty((B, 1, H, W), dtype=torch.float32, device=dev))
@@ -154,15 +176,28 @@ class ESRGANTrainer:
         return io
 
     @torch.no_grad()
-    def feed_data(self, lr_u8, hr_u8, stream=None):
-        """ssr_esrgan_model.py:104-117: uint8 -> float / 255 (+ USM-sharpened ground truth).  lr_u8 / hr_u8 may be host
-        (pinned) or device uint8 tensors; the H2D copy is part of this call."""
+    def feed_data(self, lr_u8, hr_u8, old_hr_u8=None, stream=None):
+        """ssr_esrgan_model.py:104-117: uint8 -> float / 255 (+ USM-sharpened ground truth, + the optional `old_hr` image the
+        discriminator is conditioned on).  The uint8 tensors may be host (pinned) or device tensors; the H2D copy is part of
+        this call."""
         s = stream if stream is not None else cur_stream()
         B, C_lr, h, w = lr_u8.shape
         H, W = hr_u8.shape[-2:]
         io = self._io_for(B, C_lr, h, w, H, W)
         io["lr_u8"].copy_(lr_u8, non_blocking=True)
         io["hr_u8"].copy_(hr_u8, non_blocking=True)
+        old_ch = 0
+        if old_hr_u8 is not None:
+            io["old_u8"].copy_(old_hr_u8, non_blocking=True)
+            old_ch = 3
+        if old_ch != self.old_hr_ch:
+            self.old_hr_ch = old_ch      # the recorded step changes shape: re-warm / re-capture
+            self._warm.clear()
+            self._graphs.clear()
+        want = 3 + (C_lr if self.feed_disc_lr else 0) + old_ch
+        if want != self.d_in_ch:
+            raise ValueError(f"network_d.num_in_ch is {self.d_in_ch} but the discriminator input has {want} channels "
+                             f"(3 image + {C_lr if self.feed_disc_lr else 0} low-res + {old_ch} old_hr)")
         self._feed_kernels(io, s)
         self.io = io
         self.lr, self.gt, self.gt_usm = io["lr"], io["gt"], io["gt_usm"]
@@ -171,6 +206,8 @@ class ESRGANTrainer:
         lb = lib()
         L.check(lb.ssr_u8_to_f32(io["lr_u8"].data_ptr(), io["lr"].data_ptr(), io["lr"].numel(), 1.0 / 255.0, s))
         L.check(lb.ssr_u8_to_f32(io["hr_u8"].data_ptr(), io["gt"].data_ptr(), io["gt"].numel(), 1.0 / 255.0, s))
+        if self.old_hr_ch:
+            L.check(lb.ssr_u8_to_f32(io["old_u8"].data_ptr(), io["old_hr"].data_ptr(), io["old_hr"].numel(), 1.0 / 255.0, s))
         B, _, H, W = io["gt"].shape
         taps, n = self.usm_taps
         L.check(lb.ssr_usm_sharp(io["gt"].data_ptr(), io["gt_usm"].data_ptr(), io["usm_scratch"].data_ptr(), B * 3, H, W, taps, n,
@@ -194,15 +231,18 @@ class ESRGANTrainer:
         loss = self.loss_dev
         lp = lambda i: loss.data_ptr() + 4 * i
         d_out, d_logits = io["d_out"], io["d_logits"]
-        gws = self.G.workspace(B, h, w, True)
+        gws = self.G.workspace(B, h // self.G.unshuffle, w // self.G.unshuffle, True)
         dws = self.D.workspace(B, H, W)
         n_logit = B * H * W
         cl = C_lr if self.feed_disc_lr else 0
         f = H // h
 
+        ce = self.old_hr_ch
+
         def disc_in(img):
-            L.check(lb.ssr_disc_input(img.data_ptr(), 3, gws.in0.ptr() if cl else None, gws.in0.stride, cl, f, dws.x_in.ptr(),
-                                      dws.x_in.stride, B, H, W, s))
+            # torch.cat((img, lr_resized, old_hr), 1) -- ssr_esrgan_model.py:171-178, 202-213 -- written straight as NHWC bf16
+            L.check(lb.ssr_disc_input_ex(img.data_ptr(), 3, gws.in0.ptr() if cl else None, gws.in0.stride, cl, f,
+                                         io["old_hr"].data_ptr() if ce else None, ce, dws.x_in.ptr(), dws.x_in.stride, B, H, W, s))
 
         if phase == 1:
             loss.zero_()
@@ -224,6 +264,9 @@ class ESRGANTrainer:
             out = self.output
             if do_g:
                 self.opt_g.step(1.0 / self.world, s, from_device=graph_mode)
+            elif self.gema is not None:
+                # model_ema runs every iteration in the reference (:230-231), also when the generator step is skipped
+                L.check(lb.ssr_ema_update(self.gema.flat.data_ptr(), self.gbuf.flat.data_ptr(), self.gbuf.numel, self.ema_decay, s))
             self.dgrad.flat.zero_()
             disc_in(gan_gt)
             logits = self.D.forward(dws, training=True, stream=s)
@@ -247,6 +290,7 @@ class ESRGANTrainer:
 
     def optimize_parameters(self, current_iter=1):
         do_g = (current_iter % self.net_d_iters == 0) and (current_iter > self.net_d_init_iters)
+        self._last_do_g = do_g
         key = (id(self.io), do_g)
         if not self.use_graph or key not in self._warm:
             # eager: also the mandatory first pass per shape (allocates workspaces, sets kernel attributes)
@@ -299,6 +343,8 @@ class ESRGANTrainer:
         for i, k in enumerate(LOSS_KEYS):
             if k == "l_g_percep" and self.P is None:
                 continue
+            if k.startswith("l_g_") and not getattr(self, "_last_do_g", True):
+                continue      # no generator step this iteration (net_d_iters / net_d_init_iters): the reference logs no l_g_*
             log[k] = vals[i]
         if self.world > 1:
             t = torch.tensor(list(log.values()), device=self.device)
@@ -329,8 +375,8 @@ class ESRGANTrainer:
         """ssr_esrgan_model.py:235-244: EMA generator in eval mode."""
         if self.G_ema is None:
             src = self.gema if self.gema is not None else self.gbuf
-            self.G_ema = RRDBNetEngine(src.views(), self.num_in_ch, 3, scale=self.scale, num_block=self.num_block,
-                                       want_grad=False)
+            self.G_ema = RRDBNetEngine(src.views(), self.num_in_ch, self.G.cout, scale=self.scale, num_feat=self.G.nf,
+                                       num_block=self.num_block, num_grow_ch=self.G.g, want_grad=False)
         self.G_ema.repack()
         x = lr if lr is not None else self.lr
         self.output = self.G_ema.forward(x.contiguous(), train=False).clone()

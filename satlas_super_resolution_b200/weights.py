@@ -94,3 +94,40 @@ def vgg19_state(seed=0, pretrained_path=None):
         sd[f"{name}.weight"] = torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / (cout * 9))
         sd[f"{name}.bias"] = torch.zeros(cout)
     return sd
+
+
+VGG19_FILE = "vgg19-dcbb9e9d.pth"
+
+
+def vgg19_search_paths():
+    """where the torchvision VGG19 checkpoint may live: $SSR_VGG19_PATH, the path basicsr looks at first (relative to the
+    working directory), and the torch hub cache torchvision downloads into"""
+    import os
+    out = []
+    if os.environ.get("SSR_VGG19_PATH"):
+        out.append(os.environ["SSR_VGG19_PATH"])
+    out.append(os.path.join("experiments", "pretrained_models", VGG19_FILE))
+    hub = os.environ.get("TORCH_HOME") or os.path.join(os.path.expanduser("~"), ".cache", "torch")
+    out.append(os.path.join(hub, "hub", "checkpoints", VGG19_FILE))
+    return out
+
+
+def resolve_vgg19_state(vgg_seed=None, path=None):
+    """VGG19 weights for the perceptual loss.  basicsr loads the ImageNet checkpoint (downloading it when absent); a perceptual
+    term on random features is meaningless for real training, so a missing checkpoint is an ERROR here unless the caller opted
+    into seeded random weights explicitly (`vgg_seed` option / $SSR_VGG_RANDOM_SEED -- what tests and benchmarks use offline)."""
+    import os
+    import warnings
+    for cand in ([path] if path else []) + vgg19_search_paths():
+        if cand and os.path.exists(cand):
+            return vgg19_state(pretrained_path=cand)
+    if vgg_seed is None and os.environ.get("SSR_VGG_RANDOM_SEED") is not None:
+        vgg_seed = int(os.environ["SSR_VGG_RANDOM_SEED"])
+    if vgg_seed is None:
+        raise FileNotFoundError(
+            f"PerceptualLoss: {VGG19_FILE} not found (searched {vgg19_search_paths()}).  Put the torchvision VGG19 checkpoint at one "
+            "of these paths or set SSR_VGG19_PATH; for tests / benchmarks without it pass vgg_seed=<int> (perceptual_opt.vgg_seed) "
+            "or set SSR_VGG_RANDOM_SEED to use seeded RANDOM weights.")
+    warnings.warn(f"PerceptualLoss: {VGG19_FILE} not found -- using seeded RANDOM VGG19 weights (seed {vgg_seed}); "
+                  "the perceptual term is not meaningful for real training", RuntimeWarning, stacklevel=2)
+    return vgg19_state(seed=vgg_seed)

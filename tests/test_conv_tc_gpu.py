@@ -513,3 +513,17 @@ def test_planar4_f32_operands_match_nhwc(cout):
     nhwc, planar = run(False), run(True)
     assert nhwc.abs().max() > 0
     assert torch.equal(nhwc[:, :cout], planar[:, :cout])
+
+
+def test_resident_dense_block_chain_in_subprocess():
+    """SSR_CONV_RESIDENT=1: the forward dense-block chain keeps the 192-channel tile (8-pixel strips, halo columns exchanged
+    through distributed shared memory) resident and streams only weights.  Same accumulation order as the plain launches, so
+    the chain tests must still hold bit for bit.  Environment switches are read once per process: run them in a child."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SSR_CONV_RESIDENT="1")
+    # chain_acc: the input-gradient form -- running sum in tensor memory AND the dY slots resident in the tile
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", "chain_equals_plain or chain_acc"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -130,7 +130,7 @@ def _opt(tmp_path, nb=2):
                   "perceptual_opt": dict(type="PerceptualLoss", layer_weights={"conv1_2": 0.1, "conv2_2": 0.1, "conv3_4": 1,
                                                                                 "conv4_4": 1, "conv5_4": 1},
                                          vgg_type="vgg19", use_input_norm=True, perceptual_weight=1.0, style_weight=0,
-                                         range_norm=False, criterion="l1"),
+                                         range_norm=False, criterion="l1", vgg_seed=0),
                   "gan_opt": dict(type="GANLoss", gan_type="vanilla", real_label_val=1.0, fake_label_val=0.0, loss_weight=0.1),
                   "net_d_iters": 1, "net_d_init_iters": 0},
     }
@@ -159,7 +159,7 @@ def test_model_from_opt_matches_reference_style_step(tmp_path):
     net_d.load_state_dict(model.net_d.state_dict())
     net_g, net_d = net_g.cuda().train(), net_d.cuda().train()
     cri_pix, cri_gan = L1Loss(1.0), GANLoss("vanilla", loss_weight=0.1)
-    cri_per = PerceptualLoss(opt["train"]["perceptual_opt"]["layer_weights"])
+    cri_per = PerceptualLoss(opt["train"]["perceptual_opt"]["layer_weights"], vgg_seed=0)
     opt_g = torch.optim.Adam(net_g.parameters(), lr=1e-4, betas=(0.9, 0.99))
     opt_d = torch.optim.Adam(net_d.parameters(), lr=1e-4, betas=(0.9, 0.99))
 
