@@ -1,23 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- img-pairs/s of the 8-frame ESRGAN 4x training step (BASELINE.json configs[1]) on N B200s.
+"""bench.py -- BASELINE.json's metric on N B200s: img-pairs/s of the 8-frame ESRGAN 4x training step (configs[1]; [2] with
+--gpus 8; [3] with --bands 12) and MPix/s of 16x16-chunk grid inference (configs[4], --mode infer).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl engine|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--mode train|infer] [--bands 3|12] [--impl engine|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
-A "step" = feed_data kernels (uint8 -> float/255, USM sharpen) + SSRESRGANModel.optimize_parameters
-(ssr/models/ssr_esrgan_model.py:104-233: G forward, L1 + VGG19-perceptual + 0.1*GAN losses through the frozen D,
-G backward + Adam + EMA, D real/fake forward+backward + Adam) on one synthetic batch of B pairs per GPU
-(lr uint8 [B,24,32,32], hr uint8 [B,3,128,128]), random-init weights (no checkpoints offline).
+train: a "step" = SSRESRGANModel.feed_data kernels (uint8 -> float/255, USM sharpen) + optimize_parameters
+(ssr/models/ssr_esrgan_model.py:104-233: G forward, L1 + VGG19-perceptual + 0.1*GAN losses through the frozen D, G backward +
+Adam + EMA, D real/fake forward+backward + Adam) on one synthetic batch of B pairs per GPU (lr uint8 [B,24|96,32,32], hr uint8
+[B,3,128,128]), random-init weights (no checkpoints offline).  The model is built the way ssr/train.py builds it:
+build_model(opt) -> MODEL_REGISTRY['SSRESRGANModel'].
   value : pairs/s, whole job, inputs already resident in HBM, device-timed (CUDA events, max over ranks)
-  e2e   : same through the public call sequence with HOST (pinned) uint8 batches: H2D copy inside the timed region,
-          loss scalars read back (D2H) every step
-  roofline     : the dominant kernel (ssr_conv_tc: every conv forward / input-gradient of G, D, VGG), algorithmic conv
-                 FLOPs per step / its summed device time, measured with per-launch CUDA events in one extra eager step
-  cpu_baseline : the CPU restatement of the reference step (oracle/step.py, torch fp32) on this box's host cores
---impl reference: the reference's own CPU path for the same step.  The reference (pure Python on basicsr, which is not
-installable offline) cannot run here, so this arm times the oracle port of it ("kind": "port") with all host threads.
+  e2e   : the plugin call sequence model.feed_data({'lr','hr'} HOST pinned uint8) / model.optimize_parameters(it) /
+          model.get_current_log(): H2D copy inside the timed region, loss scalars read back (D2H) every step
+  roofline          : the dominant kernel, conv_chain_kernel (a ResidualDenseBlock's five convs / five input-gradient convs per
+                      launch), algorithmic FLOPs / summed device time (per-launch CUDA events in one extra eager step)
+  roofline_kernels  : the same for the single-launch conv kernel and the two weight-gradient kernels
+  cpu_baseline      : the CPU restatement of the reference step (oracle/step.py, torch fp32) on this box's host cores
+  The default run also measures the other two things BASELINE.json's metric names and attaches them to the same line:
+  "infer" (grid inference MPix/s, configs[4]) and "train_12band" (configs[3] on this many GPUs) -- skip with --no-extras.
+infer (--mode infer as the headline): one 2048^2 tile = 256 chunks [24,32,32] per GPU and step through infer.infer_grid
+(batched forward, clamp -> uint8 -> stitch on the GPU); e2e = pinned host chunks in, uint8 canvas copied back to the host.
+--impl reference: the reference's own CPU path.  The reference (pure Python on basicsr, which is not installable offline)
+cannot run here, so this arm times the oracle port of it ("kind": "port") with all host threads.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -30,11 +38,19 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# work model, BASELINE.md section 3 (FLOP = 2*MAC, convs only, per img-pair, RGB 8-frame)
-F_G, F_D, F_V, F_FIRST, F_C0 = 36.7390e9, 13.4134e9, 12.7402e9, 0.0283e9, 0.5096e9
-FLOP_STEP = 3 * F_G - F_FIRST + 8 * F_D - 2 * F_C0 + 3 * F_V           # 254.70 GFLOP
-FLOP_WGRAD = F_G + 2 * F_D                                              # weight gradients (ssr_wgrad_tc)
-FLOP_CONV_TC = FLOP_STEP - FLOP_WGRAD                                   # forward + input-gradient convs (ssr_conv_tc)
+# work model, BASELINE.md section 3 (FLOP = 2*MAC, convs only, per img-pair): {bands: (F_G, F_D, F_V, f_first, f_c0)}
+WORK = {3: (36.7390e9, 13.4134e9, 12.7402e9, 0.0283e9, 0.5096e9), 12: (36.8239e9, 14.7723e9, 12.7402e9, 0.1132e9, 1.8686e9)}
+F_RDB = 2 * 1024 * 9 * (64 * 32 + 96 * 32 + 128 * 32 + 160 * 32 + 192 * 64)      # one ResidualDenseBlock, per image: 0.4907 GFLOP
+N_RDB = 69
+MPIX_TILE = 2048 * 2048 / 1e6
+PROFILE_CLASSES = 5   # include/ssr_b200.h: 0 conv single, 1 wgrad single, 2 chain fwd, 3 chain dgrad, 4 wgrad9 batched
+
+
+def flops(bands):
+    fg, fd, fv, ffirst, fc0 = WORK[bands]
+    step = 3 * fg - ffirst + 8 * fd - 2 * fc0 + 3 * fv
+    wgrad = fg + 2 * fd
+    return dict(step=step, wgrad=wgrad, conv=step - wgrad, infer_per_chunk=fg)
 
 
 def env_int(name, default):
@@ -66,15 +82,6 @@ def usable_cores():
     return max(1, n)
 
 
-def _dominant_traffic():
-    """DRAM bytes per launch of the kernel that dominates class 0 (the chained launch: 58 % of the conv time, 138 of 239 launches)"""
-    t = ncu_traffic()
-    e = dict(t.get("conv_chain_kernel") or t.get("conv_tc_kernel") or {})
-    if "note" in e and "conv_chain_kernel" in t:
-        e["note"] = "conv_chain_kernel: " + e["note"]
-    return e
-
-
 def ncu_traffic():
     """DRAM bytes per launch of the dominant kernel, taken from the committed `ncu --set full` capture of the same step
     (profiles/ncu_traffic.json, written by scripts/summarize_ncu.py) -- a profiler-side number, never measured in-run."""
@@ -90,8 +97,8 @@ def measured_peaks():
     if os.path.exists(path):
         with open(path) as fh:
             d = json.load(fh)
-        return d.get("bf16_tflops_sustained", 1379.2), d.get("bf16_tflops", 1660.0), "measured"
-    return 1400.0, 1590.0, "fallback"
+        return d.get("bf16_tflops_sustained", 1379.2), d.get("bf16_tflops", 1660.0), "measured (MEASURED_PEAKS.json)"
+    return 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler(threading.Thread):
@@ -126,29 +133,55 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synthetic_batch(B, seed):
+def synthetic_batch(B, seed, bands=3):
     g = torch.Generator().manual_seed(seed)
-    lr = torch.randint(1, 256, (B, 24, 32, 32), generator=g, dtype=torch.uint8)
+    lr = torch.randint(1, 256, (B, 8 * bands, 32, 32), generator=g, dtype=torch.uint8)
     hr = torch.randint(1, 256, (B, 3, 128, 128), generator=g, dtype=torch.uint8)
     return lr, hr
 
 
-CONFIG = {"workload": "ESRGAN 8-S2-frame RGB training (RRDBNet-23 + UNetDiscriminatorSN, 4x), synthetic 32x32 tiles",
-          "losses": "L1(1.0) + VGG19 perceptual(conv1_2..5_4) + 0.1*GAN(vanilla), Adam 1e-4, EMA 0.999, USM gt",
-          "num_in_ch_g": 24, "num_in_ch_d": 27}
+def train_config(bands):
+    cin = 8 * bands
+    return {"workload": f"ESRGAN 8-S2-frame {'RGB' if bands == 3 else '12-band'} training (RRDBNet-23 + UNetDiscriminatorSN, 4x), "
+                        "synthetic 32x32 tiles",
+            "losses": "L1(1.0) + VGG19 perceptual(conv1_2..5_4) + 0.1*GAN(vanilla), Adam 1e-4, EMA 0.999, USM gt",
+            "num_in_ch_g": cin, "num_in_ch_d": cin + 3}
+
+
+def model_opt(bands, graph, dist):
+    """the corrected esrgan_s2naip_urban.yml (num_in_ch 24|96 and 27|99, feed_disc_lr) as build_model's opt"""
+    cin = 8 * bands
+    return {
+        "name": "bench", "model_type": "SSRESRGANModel", "scale": 4, "num_gpu": 1, "is_train": True, "dist": dist, "manual_seed": 0,
+        "l1_gt_usm": True, "percep_gt_usm": True, "gan_gt_usm": False, "feed_disc_lr": True, "cuda_graph": graph,
+        "network_g": dict(type="SSR_RRDBNet", num_in_ch=cin, num_out_ch=3, num_feat=64, num_block=23, num_grow_ch=32),
+        "network_d": dict(type="SSR_UNetDiscriminatorSN", num_in_ch=cin + 3, num_feat=64, skip_connection=True),
+        "path": {},
+        "train": {"ema_decay": 0.999,
+                  "optim_g": dict(type="Adam", lr=1e-4, weight_decay=0, betas=[0.9, 0.99]),
+                  "optim_d": dict(type="Adam", lr=1e-4, weight_decay=0, betas=[0.9, 0.99]),
+                  "scheduler": dict(type="MultiStepLR", milestones=[400000], gamma=0.5),
+                  "pixel_opt": dict(type="L1Loss", loss_weight=1.0, reduction="mean"),
+                  "perceptual_opt": dict(type="PerceptualLoss", layer_weights={"conv1_2": 0.1, "conv2_2": 0.1, "conv3_4": 1, "conv4_4": 1,
+                                                                                "conv5_4": 1}, vgg_type="vgg19", use_input_norm=True,
+                                         perceptual_weight=1.0, style_weight=0, range_norm=False, criterion="l1",
+                                         vgg_seed=2),   # seeded random VGG19: the ImageNet file cannot be fetched offline
+                  "gan_opt": dict(type="GANLoss", gan_type="vanilla", real_label_val=1.0, fake_label_val=0.0, loss_weight=0.1),
+                  "net_d_iters": 1, "net_d_init_iters": 0},
+    }
 
 
 # ---------------------------------------------------------------------------------------------- CPU arms
-def cpu_step_time(batch, iters, warm, threads):
+def cpu_step_time(batch, iters, warm, threads, bands=3):
     """the oracle restatement of the reference step (torch fp32) on the host cores; returns s/iter"""
     from oracle import losses, nets
     from oracle.step import OracleESRGAN
     torch.set_num_threads(threads)
-    gp = nets.rrdbnet_init(24, 3, seed=0)
-    dp = nets.unet_disc_init(27, seed=1)
+    gp = nets.rrdbnet_init(8 * bands, 3, seed=0)
+    dp = nets.unet_disc_init(8 * bands + 3, seed=1)
     vp = losses.vgg19_init(seed=2)
     orc = OracleESRGAN(gp, dp, vp, dict(ema_decay=0.999, lr=1e-4))
-    lr, hr = synthetic_batch(batch, 0)
+    lr, hr = synthetic_batch(batch, 0, bands)
     times = []
     for i in range(warm + iters):
         t0 = time.perf_counter()
@@ -160,36 +193,233 @@ def cpu_step_time(batch, iters, warm, threads):
     return sum(times) / len(times)
 
 
+def cpu_infer_time(chunks, iters, warm, threads):
+    """the reference generator forward (oracle/nets.py = rrdbnet_arch.py:116-137) on `chunks` 32x32 chunks under no_grad; s/iter"""
+    from oracle import nets
+    torch.set_num_threads(threads)
+    gp = nets.rrdbnet_init(24, 3, seed=0)
+    x = synthetic_batch(chunks, 0)[0].float() / 255
+    times = []
+    with torch.no_grad():
+        for i in range(warm + iters):
+            t0 = time.perf_counter()
+            out = nets.rrdbnet_forward(gp, x)
+            (out.clamp(0, 1) * 255).to(torch.uint8)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    return sum(times) / len(times)
+
+
+CPU_TRAIN_BATCH = 8     # BASELINE.md section 4: 8-frame full step, B = 8 (CPU throughput is flat in B)
+CPU_INFER_CHUNKS = 16   # BASELINE.md section 4 (4): G forward under no_grad, B = 16 chunks
+
+
+def cpu_baseline(mode, bands, steps, warm):
+    threads = usable_cores()
+    if mode == "infer":
+        t = cpu_infer_time(CPU_INFER_CHUNKS, steps, warm, threads)
+        val = CPU_INFER_CHUNKS * 128 * 128 / 1e6 / t
+        return dict(value=val, unit="MPix/s", cores=threads, kind="port", t=t, steps=steps, batch=CPU_INFER_CHUNKS,
+                    sample=f"{steps} timed generator forwards of {CPU_INFER_CHUNKS} chunks [24,32,32] (oracle/nets.py, torch fp32 CPU, all host "
+                           f"threads) after {warm} warm-up")
+    t = cpu_step_time(CPU_TRAIN_BATCH, steps, warm, threads, bands)
+    return dict(value=CPU_TRAIN_BATCH / t, unit="img-pairs/s", cores=threads, kind="port", t=t, steps=steps, batch=CPU_TRAIN_BATCH,
+                sample=f"{steps} timed optimize_parameters steps of {CPU_TRAIN_BATCH} pairs (oracle/step.py, torch fp32 CPU, all host threads) "
+                       f"after {warm} warm-up; the reference itself needs basicsr, which is absent offline")
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = usable_cores()
-    batch = 2
     steps = max(1, min(args.steps, 3))
-    t = cpu_step_time(batch, steps, 1 if args.warmup > 0 else 0, threads)
-    val = batch / t
-    line = {"impl": "reference", "metric": "img-pairs/sec 8-frame ESRGAN 4x train", "value": val, "unit": "img-pairs/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3,
+    warm = 1 if args.warmup > 0 else 0
+    cb = cpu_baseline(args.mode, args.bands, steps, warm)
+    t = cb.pop("t")
+    cb.pop("steps")
+    batch = cb.pop("batch")
+    metric = "infer MPix/s (16x16-chunk grid inference, 8-frame RRDBNet-23)" if args.mode == "infer" else "img-pairs/sec 8-frame ESRGAN 4x train"
+    cfg = dict(workload="ssr/infer_grid.py 16x16-chunk stitched inference, 8-frame model") if args.mode == "infer" else train_config(args.bands)
+    line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": cb["unit"],
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(CONFIG, batch_per_step=batch),
-            "cpu_baseline": {"value": val, "unit": "img-pairs/s", "cores": threads, "kind": "port",
-                             "sample": f"{steps} full optimize_parameters steps of {batch} pairs (oracle/step.py, torch fp32 CPU); "
-                                       "the reference itself needs basicsr, which is absent offline"},
-            "e2e": {"value": val, "unit": "img-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": dict(cfg, batch_per_step=batch),
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------- engine arm
+class Harness:
+    def __init__(self, world):
+        self.world = world
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, k):
+        """k calls of fn between barrier + synchronize on both sides, device-timed, max over ranks -> total ms"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if self.world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item()
+
+
+def roofline_entry(kernel, flop, ms, count, peak, peak_src, extra=None):
+    ach = flop / (ms / 1e3) / 1e12 if ms > 0 else None
+    d = {"kernel": kernel, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if ach else None,
+         "peak_source": peak_src, "launches_per_step": int(count), "ms_per_step": ms,
+         "flop_per_launch": flop / max(1, count), "us_per_launch": ms * 1e3 / max(1, count)}
+    if extra:
+        d.update(extra)
+    return d
+
+
+def measure_train(args, bands, rank, world, local, lib, L, harness, steps, warmup):
+    from satlas_super_resolution_b200.ops import cur_stream
+    from satlas_super_resolution_b200.registry import build_model
+    B = args.batch
+    torch.manual_seed(rank)            # ssr/utils/options.py:81 seeds every rank with manual_seed + rank; rank 0's init is broadcast
+    model = build_model(model_opt(bands, not args.no_graph, world > 1))
+    tr = model.trainer
+    lr_h, hr_h = synthetic_batch(B, rank, bands)
+    data = {"lr": lr_h.pin_memory(), "hr": hr_h.pin_memory()}
+    it = [0]
+
+    def step_resident():
+        it[0] += 1
+        tr._feed_kernels(tr.io, cur_stream())
+        model.optimize_parameters(it[0])
+
+    def step_e2e():
+        it[0] += 1
+        model.feed_data(data)
+        model.optimize_parameters(it[0])
+        return model.get_current_log()
+
+    log(f"model built ({bands} bands)")
+    model.feed_data(data)
+    for i in range(warmup):
+        step_resident()
+        torch.cuda.synchronize()
+        log(f"warm-up step {i} done")
+    ms_total = harness.timed(step_resident, steps)
+    log(f"resident timing done: {ms_total / steps:.2f} ms/step")
+    ms_e2e = harness.timed(step_e2e, steps)
+    log(f"e2e timing done: {ms_e2e / steps:.2f} ms/step")
+    # ---- one eager, instrumented step: per-launch CUDA events around the tensor-core kernels (graph replays do not pass
+    # through the host entry points, so launches are also counted here)
+    tr.use_graph = False
+    tr._warm.clear()
+    L.check(lib.ssr_profile_start())
+    l0 = lib.ssr_launch_count()
+    step_resident()
+    launches = lib.ssr_launch_count() - l0
+    ms_cls = (ctypes.c_double * PROFILE_CLASSES)()
+    cnt_cls = (ctypes.c_int64 * PROFILE_CLASSES)()
+    L.check(lib.ssr_profile_stop(ms_cls, cnt_cls, PROFILE_CLASSES))
+    tr.use_graph = not args.no_graph
+    return dict(B=B, ms_step=ms_total / steps, ms_e2e=ms_e2e / steps, launches=int(launches), ms_cls=list(ms_cls), cnt_cls=list(cnt_cls),
+                h2d=int(lr_h.numel() + hr_h.numel()), model=model)
+
+
+def train_rooflines(m, bands, peak, peak_src):
+    f = flops(bands)
+    B = m["B"]
+    ms, cnt = m["ms_cls"], m["cnt_cls"]
+    chain_flop = N_RDB * F_RDB * B
+    traffic = ncu_traffic()
+    t_chain = dict(traffic.get("conv_chain_kernel") or {})
+    main = roofline_entry("ssr::conv_chain_kernel (one ResidualDenseBlock per launch: its five forward convs, or its five input-gradient "
+                          "convs; tcgen05 implicit GEMM)", 2 * chain_flop, ms[2] + ms[3], cnt[2] + cnt[3], peak, peak_src,
+                          dict(traffic=t_chain.get("dram_bytes_per_launch"), traffic_note=t_chain.get("note"),
+                               forward=roofline_entry("conv_chain_kernel, forward", chain_flop, ms[2], cnt[2], peak, peak_src),
+                               input_gradient=roofline_entry("conv_chain_kernel, input gradient", chain_flop, ms[3], cnt[3], peak, peak_src)))
+    others = {
+        "conv_tc_kernel": roofline_entry("ssr::conv_tc_kernel (single-launch convs: G head / tail, D, VGG19; forward + input gradient)",
+                                         f["conv"] * B - 2 * chain_flop, ms[0], cnt[0], peak, peak_src),
+        "wgrad9_tc_batched_kernel": roofline_entry("ssr::wgrad9_tc_batched_kernel (five weight gradients of a dense block per launch)",
+                                                   chain_flop, ms[4], cnt[4], peak, peak_src),
+        "wgrad_tc_kernels": roofline_entry("ssr::wgrad9_tc_kernel / wgrad_tc_kernel (weight gradients outside the trunk)",
+                                           f["wgrad"] * B - chain_flop, ms[1], cnt[1], peak, peak_src),
+        "all_conv_fwd_dgrad": roofline_entry("every forward / input-gradient conv", f["conv"] * B, ms[0] + ms[2] + ms[3], cnt[0] + cnt[2] + cnt[3],
+                                             peak, peak_src),
+    }
+    return main, others
+
+
+def measure_infer(args, rank, world, harness, steps, warmup):
+    from satlas_super_resolution_b200 import weights
+    from satlas_super_resolution_b200.archs import SSR_RRDBNet
+    from satlas_super_resolution_b200.infer import infer_grid
+    net = SSR_RRDBNet(24, 3)
+    net.load_state_dict(weights.rrdbnet_state(24, 3, seed=0))
+    net = net.cuda().eval()
+    # weak scaling: every rank stitches its own tile (tiles are independent -- replicas, no collective: ssr/infer_grid.py:46-85)
+    lr_h = synthetic_batch(256, 1000 + rank)[0].pin_memory()
+    lr_d = lr_h.cuda()
+    host_canvas = torch.empty((2048, 2048, 3), dtype=torch.uint8).pin_memory()
+
+    def step_resident():
+        infer_grid(net, lr_d, batch=args.infer_batch)
+
+    def step_e2e():
+        host_canvas.copy_(infer_grid(net, lr_h, batch=args.infer_batch), non_blocking=True)
+
+    for _ in range(warmup):
+        step_resident()
+    ms = harness.timed(step_resident, steps) / steps
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = harness.timed(step_e2e, steps) / steps
+    from satlas_super_resolution_b200 import _lib as L
+    lib = L.load()
+    l0 = lib.ssr_launch_count()
+    step_resident()
+    torch.cuda.synchronize()
+    return dict(ms_step=ms, ms_e2e=ms_e2e, launches=int(lib.ssr_launch_count() - l0), h2d=int(lr_h.numel()), d2h=int(host_canvas.numel()))
+
+
+def infer_block(m, world, peak, peak_src, steps, warmup):
+    f = flops(3)
+    val = world * MPIX_TILE / (m["ms_step"] / 1e3)
+    tflops = 256 * f["infer_per_chunk"] / (m["ms_step"] / 1e3) / 1e12
+    return {"metric": "infer MPix/s (16x16-chunk grid inference, 8-frame RRDBNet-23)", "value": val, "unit": "MPix/s",
+            "ms_per_step": m["ms_step"], "steps": steps, "warmup": warmup,
+            "config": {"workload": "ssr/infer_grid.py: one 2048^2 tile (256 chunks [24,32,32] -> 128x128, stitched) per GPU and step",
+                       "chunks_per_gpu_per_step": 256, "parallelism": f"replicas x{world} (independent tiles, no collective)"},
+            "e2e": {"value": world * MPIX_TILE / (m["ms_e2e"] / 1e3), "unit": "MPix/s", "h2d_bytes_per_step": m["h2d"],
+                    "d2h_bytes_per_step": m["d2h"]},
+            "gpu_launches_per_step": m["launches"],
+            "roofline": {"kernel": "generator forward (conv_chain_kernel + conv_tc_kernel)", "bound": "tensor", "achieved": tflops, "peak": peak,
+                         "unit": "TFLOP/s", "frac": tflops / peak, "peak_source": peak_src,
+                         "flop_per_step": 256 * f["infer_per_chunk"], "note": "2.2424 TFLOP per output MPix (BASELINE.md section 3)"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32, help="pairs per GPU per step (reference batch_size_per_gpu: 32)")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--bands", type=int, default=3, choices=[3, 12], help="3 = RGB (24-channel G input), 12 = all Sentinel-2 bands (96)")
+    ap.add_argument("--infer-batch", type=int, default=256, help="chunks per generator forward in --mode infer")
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="train mode: skip the attached inference / 12-band measurements")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
@@ -198,135 +428,94 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     torch.cuda.set_device(local)
-    pg = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
-        pg = torch.distributed.group.WORLD
 
     from satlas_super_resolution_b200 import _lib as L
-    from satlas_super_resolution_b200 import weights
-    from satlas_super_resolution_b200.ops import cur_stream
-    from satlas_super_resolution_b200.trainer import ESRGANTrainer
     lib = L.load()
-    B = args.batch
-    cfg = dict(ema_decay=0.999, lr=1e-4, network_g=dict(num_in_ch=24, num_block=23), cuda_graph=not args.no_graph)
-    # identical replicas on every rank (seeded init); each rank draws its own batch (manual_seed + rank, options.py:81)
-    tr = ESRGANTrainer(weights.rrdbnet_state(24, 3, seed=0), weights.unet_disc_state(27, seed=1), weights.vgg19_state(seed=2),
-                       cfg, device=f"cuda:{local}", process_group=pg)
-    lr_h, hr_h = synthetic_batch(B, rank)
-    lr_h, hr_h = lr_h.pin_memory(), hr_h.pin_memory()
-    stream = torch.cuda.current_stream()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    it = [0]
-
-    def step_resident():
-        it[0] += 1
-        tr._feed_kernels(tr.io, cur_stream())
-        tr.optimize_parameters(it[0])
-
-    def step_e2e():
-        it[0] += 1
-        tr.feed_data(lr_h, hr_h)
-        tr.optimize_parameters(it[0])
-        return tr.get_current_log()
-
-    # ---- warm-up (eager first pass allocates workspaces; the next ones capture + replay the CUDA graph)
-    log("trainer built")
-    tr.feed_data(lr_h, hr_h)
-    for i in range(args.warmup):
-        step_resident()
-        torch.cuda.synchronize()
-        log(f"warm-up step {i} done")
-    barrier()
-
-    def timed(fn, k):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for _ in range(k):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-        return ms.item()
-
+    harness = Harness(world)
+    peak_sus, peak_burst, peak_src = measured_peaks()
+    peak_note = f"{peak_src}: bf16_tflops_sustained (kernels timed inside a long step)"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = lib.ssr_launch_count()
-    ms_total = timed(step_resident, args.steps)
-    log(f"resident timing done: {ms_total / args.steps:.2f} ms/step")
-    # launches per step: graph replays do not pass through the host entry points, so count one eager step below
-    ms_e2e = timed(step_e2e, args.steps)
+
+    if args.mode == "infer":
+        m = measure_infer(args, rank, world, harness, args.steps, args.warmup)
+        sampler.stop_flag = True
+        if rank == 0:
+            blk = infer_block(m, world, peak_sus, peak_note, args.steps, args.warmup)
+            line = {"metric": blk["metric"], "value": blk["value"], "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": m["ms_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "bf16", "data": "synthetic",
+                    "config": dict(blk["config"], l2="256 chunks stream ~0.9 GB of activations per step, far above the 126 MB L2"),
+                    "e2e": blk["e2e"], "gpu_launches": m["launches"] * args.steps, "gpu_launches_per_step": m["launches"],
+                    "roofline": blk["roofline"], "clocks": sampler.summary()}
+            if not args.no_cpu_baseline:
+                cb = cpu_baseline("infer", 3, 2, 1)
+                for k in ("t", "steps", "batch"):
+                    cb.pop(k)
+                line["cpu_baseline"] = cb
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    bands = args.bands
+    m = measure_train(args, bands, rank, world, local, lib, L, harness, args.steps, args.warmup)
     sampler.stop_flag = True
-    log(f"e2e timing done: {ms_e2e / args.steps:.2f} ms/step")
-
-    # ---- one eager, instrumented step: per-launch CUDA events around the two tensor-core kernels
-    tr.use_graph = False
-    tr._warm.clear()
-    L.check(lib.ssr_profile_start())
-    l0 = lib.ssr_launch_count()
-    step_resident()
-    launches_per_step = lib.ssr_launch_count() - l0
-    import ctypes
-    ms_cls = (ctypes.c_double * 2)()
-    cnt_cls = (ctypes.c_int64 * 2)()
-    L.check(lib.ssr_profile_stop(ms_cls, cnt_cls, 2))
-    log(f"instrumented step: conv_tc {ms_cls[0]:.2f} ms / {cnt_cls[0]} launches, wgrad_tc {ms_cls[1]:.2f} ms / {cnt_cls[1]} launches")
-
+    clocks = sampler.summary() if rank == 0 else None
+    extras = {}
+    if not args.no_extras:
+        # the other two halves of BASELINE.json's metric, measured in the same run (shorter: they are attachments, not the headline)
+        k = max(3, min(args.steps, 10))
+        del m["model"]
+        torch.cuda.empty_cache()
+        mi = measure_infer(args, rank, world, harness, k, 3)
+        if rank == 0:
+            extras["infer"] = infer_block(mi, world, peak_sus, peak_note, k, 3)
+        other = 12 if bands == 3 else 3
+        mo = measure_train(args, other, rank, world, local, lib, L, harness, k, 3)
+        if rank == 0:
+            fo = flops(other)
+            main_o, _ = train_rooflines(mo, other, peak_sus, peak_note)
+            extras["train_12band" if other == 12 else "train_rgb"] = {
+                "metric": "img-pairs/sec 8-frame ESRGAN 4x train", "value": mo["B"] * world / (mo["ms_step"] / 1e3), "unit": "img-pairs/s",
+                "ms_per_step": mo["ms_step"], "steps": k, "warmup": 3, "config": dict(train_config(other), batch_per_gpu=mo["B"]),
+                "e2e": {"value": mo["B"] * world / (mo["ms_e2e"] / 1e3), "unit": "img-pairs/s", "h2d_bytes_per_step": mo["h2d"],
+                        "d2h_bytes_per_step": 32},
+                "step_tflops": fo["step"] * mo["B"] / (mo["ms_step"] / 1e3) / 1e12, "gpu_launches_per_step": mo["launches"],
+                "roofline": main_o}
+        del mo
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
         return
-    ms_step = ms_total / args.steps
-    value = B * world / (ms_step / 1e3)
-    e2e_val = B * world / (ms_e2e / args.steps / 1e3)
-    peak_sus, peak_burst, peak_src = measured_peaks()
-    conv_ms, wgrad_ms = ms_cls[0], ms_cls[1]
-    ach = FLOP_CONV_TC * B / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
-    ach_w = FLOP_WGRAD * B / (wgrad_ms / 1e3) / 1e12 if wgrad_ms > 0 else None
+    f = flops(bands)
+    B = m["B"]
+    value = B * world / (m["ms_step"] / 1e3)
+    main_r, other_r = train_rooflines(m, bands, peak_sus, peak_note)
     line = {
         "metric": "img-pairs/sec 8-frame ESRGAN 4x train", "value": value, "unit": "img-pairs/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": dict(CONFIG, batch_per_gpu=B, global_batch=B * world, parallelism=f"dp{world}",
-                       cuda_graph=not args.no_graph,
+        "config": dict(train_config(bands), batch_per_gpu=B, global_batch=B * world, parallelism=f"dp{world}",
+                       cuda_graph=not args.no_graph, api="build_model(opt) -> SSRESRGANModel.feed_data / optimize_parameters / get_current_log",
                        l2="no explicit flush: one step streams >10 GB of activations/gradients, far above the 126 MB L2"),
-        "e2e": {"value": e2e_val, "unit": "img-pairs/s", "h2d_bytes_per_step": int(lr_h.numel() + hr_h.numel()),
-                "d2h_bytes_per_step": 32},
-        "gpu_launches": int(launches_per_step * args.steps),
-        "gpu_launches_per_step": int(launches_per_step),
-        "step_flop_fraction_of_peak": FLOP_STEP * B / (ms_step / 1e3) / 1e12 / peak_sus,
-        "step_tflops": FLOP_STEP * B / (ms_step / 1e3) / 1e12,
-        "roofline": {"kernel": "ssr::conv_chain_kernel / conv_tc_kernel (one tcgen05 implicit-GEMM body: forward + input gradient; "
-                               "a dense block's five convs per chained launch)", "bound": "tensor",
-                     "achieved": ach, "peak": peak_sus, "unit": "TFLOP/s", "frac": ach / peak_sus if ach else None,
-                     "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
-                     "launches_per_step": int(cnt_cls[0]), "ms_per_step": conv_ms,
-                     "flop_per_launch": FLOP_CONV_TC * B / max(1, cnt_cls[0]),
-                     "traffic": _dominant_traffic().get("dram_bytes_per_launch"),
-                     "traffic_note": _dominant_traffic().get("note")},
-        "roofline_wgrad": {"kernel": "ssr::wgrad9_tc_kernel / wgrad_tc_kernel (tcgen05 weight gradient)", "bound": "tensor", "achieved": ach_w,
-                           "peak": peak_sus, "unit": "TFLOP/s", "frac": ach_w / peak_sus if ach_w else None,
-                           "launches_per_step": int(cnt_cls[1]), "ms_per_step": wgrad_ms},
-        "clocks": sampler.summary(),
+        "e2e": {"value": B * world / (m["ms_e2e"] / 1e3), "unit": "img-pairs/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 32},
+        "gpu_launches": m["launches"] * args.steps, "gpu_launches_per_step": m["launches"],
+        "step_flop_fraction_of_peak": f["step"] * B / (m["ms_step"] / 1e3) / 1e12 / peak_sus,
+        "step_tflops": f["step"] * B / (m["ms_step"] / 1e3) / 1e12,
+        "roofline": main_r, "roofline_kernels": other_r, "clocks": clocks,
     }
+    line.update(extras)
     if not args.no_cpu_baseline:
-        threads = usable_cores()
-        log(f"cpu baseline on {threads} threads")
-        t = cpu_step_time(2, 2, 1, threads)
-        line["cpu_baseline"] = {"value": 2 / t, "unit": "img-pairs/s", "cores": threads, "kind": "port",
-                                "sample": "2 timed optimize_parameters steps of 2 pairs (oracle/step.py, torch fp32 CPU, all host "
-                                          "threads) after 1 warm-up"}
+        log(f"cpu baseline on {usable_cores()} threads")
+        cb = cpu_baseline("train", bands, 2, 1)
+        for k in ("t", "steps", "batch"):
+            cb.pop(k)
+        line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -58,8 +58,11 @@ const char* ssr_last_error(void);
 int ssr_abi_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t ssr_launch_count(void);
-/* per-launch CUDA-event timing of the two tensor-core kernels (class 0 = ssr_conv_tc, 1 = ssr_wgrad_tc) for the
- * roofline figure: start, run the step eagerly, stop -> total ms and launch count per class (synchronises). */
+/* per-launch CUDA-event timing of the tensor-core kernels for the roofline figures: start, run the step eagerly, stop ->
+ * total ms and launch count per class (synchronises).  Classes: 0 = single-launch conv (conv_tc_kernel), 1 = weight gradient
+ * (wgrad_tc / wgrad9_tc, one problem per launch), 2 = dense-block forward chain (conv_chain_kernel), 3 = dense-block
+ * input-gradient chain (conv_chain_kernel), 4 = batched dense-block weight gradient (wgrad9_tc_batched_kernel). */
+#define SSR_PROFILE_CLASSES 5
 int ssr_profile_start(void);
 int ssr_profile_stop(double* ms, int64_t* count, int32_t n_classes);
 
@@ -129,6 +132,10 @@ int ssr_conv_tc(const ssr_conv_tc_args* args, void* stream);
  * ssr/archs/rrdbnet_arch.py:36-43, and autograd's matching five input-gradient convolutions).  Layer i may read
  * anything layers < i of the same call wrote; all layers share (n_img, h, w, r), have n_pad <= 128 and splits <= 1.
  * Results are identical to n ssr_conv_tc calls in order; ineligible chains are executed exactly that way.
+ * A chain with the channel pattern of a ResidualDenseBlock (layer i reads channels [0, 64 + 32 i) of ONE buffer and appends its
+ * 32 outputs there; f32 operands channel-quad planar) over 32-row images runs with the 192-channel tile resident in shared
+ * memory: activations are loaded once, halo columns travel through distributed shared memory, only weights stream.  In that
+ * form the intermediate layers may pass out_bf16 == NULL (inference: x1..x4 are never written to global memory).
  */
 int ssr_conv_tc_chain(const ssr_conv_tc_args* args, int32_t n, void* stream);
 /*
@@ -143,6 +150,9 @@ int ssr_conv_tc_chain(const ssr_conv_tc_args* args, int32_t n, void* stream);
 int ssr_conv_tc_chain_acc(const ssr_conv_tc_args* args, int32_t n, void* stream);
 /* 1 if ssr_conv_tc_chain_acc can run this geometry (host arithmetic only, no device needed), else 0 */
 int ssr_conv_tc_chain_acc_supported(int32_t n_img, int32_t h, int32_t w, int32_t widest_cout);
+/* diagnostics: how many chains ran as the shared-memory-resident dense-block kernel (32-row images, 8 | w <= 64, the channel pattern
+ * of ResidualDenseBlock; SSR_CONV_RESIDENT=0 disables it) */
+int64_t ssr_debug_resident_launches(void);
 /* diagnostics: with SSR_CHAIN_TIMELINE=1 in the environment every chained launch records clock64 stamps
  * [cta][layer (5)][8 events]; copies the first n_ctas (<= 512) rows of the LAST launch to host memory (synchronises). */
 int ssr_debug_chain_timeline(long long* host_out, int32_t n_ctas);
@@ -307,6 +317,22 @@ int ssr_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64
 int ssr_ema_update(float* ema, const float* p, int64_t n, float decay, void* stream);
 /* t += 1 and refresh the two bias corrections in a device-resident hyper block (recorded inside the step's CUDA graph) */
 int ssr_adam_tick(float* hyper_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Validation metrics (ssr/models/ssr_esrgan_model.py:269-352 computes them per image on the host).
+ * ------------------------------------------------------------------------------------------------- */
+/* basicsr tensor2img(rgb2bgr, uint8, min_max=(0,1)): uint8(round_half_even(clamp(v, 0, 1) * 255)), f32 NCHW -> u8 HWC per image */
+int ssr_f32_nchw_to_u8_hwc(const float* src, void* dst_u8, int32_t b, int32_t c, int32_t h, int32_t w, int32_t reverse_channels,
+                           void* stream);
+/* exact integer sums behind PSNR (max_offset 0; basicsr calculate_psnr) and cPSNR (max_offset 8; ssr/metrics/cpsnr.py:7-59): for
+ * image n, offset (ro, co) in [0, max_offset]^2, channel ch over the cropped window: d = a[y+ro, x+co] - b[y+M-ro, x+M-co],
+ * out[((n*(M+1)^2 + ro*(M+1)+co)*c + ch)*2 + {0,1}] = {sum d, sum d^2} (int64).  a, b: uint8 HWC batches. */
+int ssr_u8_shift_diff_sums(const void* a_u8, const void* b_u8, int32_t b, int32_t h, int32_t w, int32_t c, int32_t crop_border,
+                           int32_t max_offset, long long* out, void* stream);
+/* basicsr calculate_ssim: out[n*c + ch] += sum over the valid (h-2cb-10) x (w-2cb-10) region of the SSIM map (float64, caller
+ * zeroes out and divides); window11_device = cv2.getGaussianKernel(11, 1.5) as 11 doubles in device memory */
+int ssr_u8_ssim_sums(const void* a_u8, const void* b_u8, int32_t b, int32_t h, int32_t w, int32_t c, int32_t crop_border,
+                     const double* window11_device, double* out, void* stream);
 
 #ifdef __cplusplus
 }

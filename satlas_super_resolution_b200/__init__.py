@@ -5,7 +5,7 @@ Importing the package registers SSR_RRDBNet / SSR_UNetDiscriminatorSN (ARCH_REGI
 library is loaded on first use and there is no CPU fallback.
 """
 from . import registry  # noqa: F401
-from . import archs, data, losses, models  # noqa: F401
+from . import archs, data, losses, metrics, models  # noqa: F401
 from .registry import ARCH_REGISTRY, LOSS_REGISTRY, MODEL_REGISTRY, build_loss, build_model, build_network  # noqa: F401
 
 __all__ = ["ARCH_REGISTRY", "LOSS_REGISTRY", "MODEL_REGISTRY", "build_network", "build_loss", "build_model"]

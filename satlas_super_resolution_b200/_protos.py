@@ -45,6 +45,9 @@ PROTOS = {
     "ssr_disc_input_ex": (C.c_int, [vp, i32, vp, i32, i32, i32, vp, i32, vp, i32, i32, i32, i32, vp]),
     "ssr_ema_update": (C.c_int, [vp, vp, i64, f32, vp]),
     "ssr_ingest_nchw_unshuffle": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp]),
+    "ssr_f32_nchw_to_u8_hwc": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    "ssr_u8_shift_diff_sums": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "ssr_u8_ssim_sums": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "ssr_spectral_norm": (C.c_int, [vp, i32, i32, f32, vp]),
     "ssr_spectral_norm_bwd": (C.c_int, [vp, i32, vp]),
     "ssr_usm_sharp": (C.c_int, [vp, vp, vp, i32, i32, i32, vp, i32, f32, f32, vp]),
@@ -52,6 +55,7 @@ PROTOS = {
     "ssr_adam_tick": (C.c_int, [vp, vp]),
     "ssr_adam_ema": (C.c_int, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, f32, vp, vp]),
     "ssr_debug_chain_timeline": (C.c_int, [vp, i32]),
+    "ssr_debug_resident_launches": (C.c_int64, []),
     "ssr_wgrad_tc": (C.c_int, [C.POINTER(WgradArgs), vp]),
     "ssr_wgrad_tc_batched": (C.c_int, [C.POINTER(WgradArgs), i32, vp]),
     "ssr_wgrad_unpack": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, f32, i32, vp]),

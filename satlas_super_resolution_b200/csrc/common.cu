@@ -132,7 +132,7 @@ int ssr_profile_start(void) {
   ssr::g_prof_on = true;
   return SSR_OK;
 }
-// ms[c] / count[c] for c = 0 (ssr_conv_tc), 1 (ssr_wgrad_tc); synchronises the device
+// ms[c] / count[c] per profile class (see ssr_b200.h); synchronises the device
 int ssr_profile_stop(double* ms, int64_t* count, int32_t n_classes) {
   ssr::g_prof_on = false;
   if (!ssr::check_cuda(cudaDeviceSynchronize(), "profile sync")) return SSR_E_CUDA;

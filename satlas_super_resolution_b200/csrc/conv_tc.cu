@@ -21,15 +21,15 @@ namespace ssr {
 struct ConvTcK {
   int n_img, H, W, R, pad;
   int TW, TH, tiles_x, tiles_y;
-  int pitch;   // shared-memory rows per tile row: TW, or more in the SSR_DBG_PITCH hardware probe (8-pixel tiles only)
+  int pitch;   // shared-memory rows per tile row: TW, or TW + 2 for the halo tile of the resident dense block
   int chunks, cin;
   int n_tile, n_pad, cout;
   int stages;
   uint32_t a_box_bytes, a_alloc, b_bytes, tmem_cols;
   uint32_t stage_stride;  // bytes between smem stages (>= a_alloc + b_bytes; the max over the layers of a chain)
   uint32_t acc_stride;    // TMEM columns between the two accumulator buffers (>= MT * n_tile)
-  // Resident dense block (forward chain, SSR_CONV_RESIDENT=1): the 192-channel tile WITH its halo stays in shared memory for all
-  // layers; only weights stream.  res_out_ch = channel offset of this layer's output inside the tile (-1: not written back)
+  // Resident dense block (rdb_resident_kernel): the 192-channel tile WITH its halo stays in shared memory for all layers;
+  // only weights stream.  res_out_ch = channel offset of this layer's output inside the tile (-1: not written back)
   int resident, res_out_ch, res_in_chunks;
   int res_in_lo;          // channel offset of this layer's INPUT inside the tile (0 forward; the dY slot of an input-gradient layer)
   uint32_t chunk_alloc;   // bytes of one 64-channel chunk of the resident tile ((TW+2) x (MT*TH+2) rows of 128 B, 1 KB aligned)
@@ -54,7 +54,6 @@ struct ConvTcK {
   int out_lo;          // the bf16 output (and its bias-gradient sum) only covers channels >= out_lo
   float* bgrad;        // bgrad[c - out_lo] += bgrad_scale * sum over pixels of the bf16-path value, or NULL
   float bgrad_scale;
-  int dbg_aoff;  // experiment: extra row offset (x128 B) of the A descriptor, see scripts/probe_swizzle.py
 };
 
 static constexpr int kSyncNone = 0, kSyncGrid = 1, kSyncCluster = 2;
@@ -125,15 +124,12 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
   const uint32_t stage_bytes = p.stage_stride;
-  uint8_t* const dense = smem;                                                         // resident tile (if any) first,
-  uint8_t* const ring = smem + (p.resident ? (size_t)kResChunks * p.chunk_alloc : 0);  // then the stage ring
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * stage_bytes);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* bar_empty = bar_full + p.stages;
   uint64_t* bar_acc_full = bar_empty + p.stages;   // [2] accumulator buffer b complete (MMA -> epilogue)
   uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2] accumulator buffer b drained  (epilogue -> MMA), 8 warp arrivals
   uint64_t* bar_layer = bar_acc_empty + 2;         // kSyncCluster: every epilogue warp of the cluster arrives once per layer
-  uint64_t* bar_x = bar_layer + 1;                 // resident tile: the block input has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_x + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_layer + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [256] bias of the layer's output channels
   float* s_bg = s_bias + 256;                                // [256] per-CTA bias-gradient partial sums
 
@@ -162,20 +158,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
         mbar_init(&bar_acc_empty[b], 8);
       }
       if (sync_mode == kSyncCluster) mbar_init(bar_layer, 8 * cluster_nctarank());
-      mbar_init(bar_x, 1);
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
-  }
-  if (p.resident) {
-    // the chunks the block input does not fill start as zeros: image borders stay zero, interior halo columns are written by
-    // the neighbour CTAs (DSMEM) layer by layer.  Generic-proxy stores, later read by the tensor core: proxy fence.
-    uint4* z = reinterpret_cast<uint4*>(dense + (size_t)p.res_in_chunks * p.chunk_alloc);
-    const int n16 = (int)(((size_t)(kResChunks - p.res_in_chunks) * p.chunk_alloc) >> 4);
-    for (int i = (int)threadIdx.x; i < n16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    fence_proxy_async();
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -194,20 +181,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       const int per = (q.chunks + q.splits - 1) / q.splits;
       const int c_begin = blockIdx.z * per;
       const int iters = (min(q.chunks, c_begin + per) - c_begin) * R;
-      if (q.resident) {
-        // only weights stream (they do not depend on earlier layers: no wait); the block input is loaded once, with its halo
-        if (l == 0 && elect_one()) {
-          int t0 = (int)blockIdx.x;
-          const int tx0 = t0 % q.tiles_x;
-          t0 /= q.tiles_x;
-          const int ty0 = t0 % q.tiles_y;
-          mbar_expect_tx(bar_x, (uint32_t)q.res_in_chunks * q.a_box_bytes);
-          for (int c = 0; c < q.res_in_chunks; ++c)
-            tma_load_4d(dense + (size_t)c * q.chunk_alloc, tmA, bar_x, c * 64, tx0 * q.TW - q.pad, ty0 * (MT * q.TH) - q.pad, t0 / q.tiles_y);
-        }
-        __syncwarp();
-        if (l > 0) prefetch_tmap(tmB);
-      } else if (l > 0) {
+      if (l > 0) {
         // layer l-1 has been stored (generic proxy) by every CTA we can depend on: acquire that, then order our TMA
         // (async proxy) loads behind it
         if (sync_mode == kSyncCluster) {
@@ -240,10 +214,10 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
           const uint32_t ph = (g / q.stages) & 1;
           mbar_wait(&bar_empty[s], ph ^ 1);
           if (elect_one()) {
-            uint8_t* a_dst = ring + (size_t)s * stage_bytes;
-            uint8_t* b_dst = a_dst + q.a_alloc;   // resident: a_alloc == 0, the stage holds weights only
-            mbar_expect_tx(&bar_full[s], (q.resident ? 0u : q.a_box_bytes) + q.b_bytes);
-            if (!q.resident) tma_load_4d(a_dst, tmA, &bar_full[s], c * 64, x0 + kx - q.pad, y0 - q.pad, n);
+            uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+            uint8_t* b_dst = a_dst + q.a_alloc;
+            mbar_expect_tx(&bar_full[s], q.a_box_bytes + q.b_bytes);
+            tma_load_4d(a_dst, tmA, &bar_full[s], c * 64, x0 + kx - q.pad, y0 - q.pad, n);
 #pragma unroll
             for (int ky = 0; ky < R; ++ky)
               tma_load_2d(b_dst + (size_t)ky * q.n_tile * 128, tmB, &bar_full[s], 0, ((c * R + kx) * R + ky) * q.n_pad + n0);
@@ -257,12 +231,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     // Descriptors differ only in their 14-bit start-address field: build one per stage, then add constant offsets.
-    const uint32_t a_tap = (uint32_t)(p.pitch * 128) >> 4;        // one tile row down  (descriptor address units of 16 B)
-    const uint32_t a_mt = (uint32_t)(p.TH * p.pitch * 128) >> 4;  // next stacked M tile
-    // stride between the 8-row groups of the M = 128 operand window: contiguous (1024 B) unless a tile row is 8 pixels inside a
-    // wider shared-memory row (probe: is the 128B swizzle still purely address-based then?)
-    const uint32_t a_sbo = p.pitch == p.TW ? 1024u : (uint32_t)p.pitch * 128u;
-    const uint32_t a_dbg = (uint32_t)(p.dbg_aoff * 128) >> 4;  // hardware probe only (scripts/probe_swizzle.py)
+    const uint32_t a_tap = (uint32_t)(p.TW * 128) >> 4;        // one tile row down  (descriptor address units of 16 B)
+    const uint32_t a_mt = (uint32_t)(p.TH * p.TW * 128) >> 4;  // next stacked M tile
     int g = 0, gt = 0;  // running stage / tile counters across layers
     for (int l = 0; l < n_layers; ++l) {
       const ConvTcK q = ps[l];
@@ -272,13 +242,6 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       const int c_begin = blockIdx.z * per;
       const int iters = (min(q.chunks, c_begin + per) - c_begin) * R;
       const int items = my_tiles * q.n_loop;  // (pixel tile, N tile) work items of this layer
-      if (q.resident) {
-        // the tile this layer reads is complete when the block input has landed (layer 0) / when every epilogue warp of the
-        // cluster has written layer l-1's channels, including the halo columns they push into our shared memory
-        if (l == 0) mbar_wait(bar_x, 0);
-        else mbar_wait_cluster(bar_layer, (uint32_t)(l - 1) & 1);
-        fence_proxy_async();
-      }
       // TMEM-resident accumulator (acc_w > 0): channel c of M tile m is column m * acc_w + c in EVERY layer; layer 0 initialises,
       // later layers add; nothing is handed back by the epilogue (a layer only writes columns below the slot being drained)
       const uint32_t m_cols = q.acc_w ? (uint32_t)q.acc_w : (uint32_t)q.n_tile;
@@ -297,13 +260,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
           if (lane == 0 && lt == 0 && it == 0) SSR_STAMP(l, 2);                     // MMA: first stage landed
           if (lane == 0 && lt == items - 1 && it == iters - 1) SSR_STAMP(l, 3);     // MMA: last stage landed
           if (elect_one()) {
-            const uint32_t st_base = smem_u32(ring + (size_t)s * stage_bytes);
-            // resident: the operand window of tap (ky, kx) starts (ky * pitch + kx) rows into the halo tile of chunk c
-            // (an input that starts inside a chunk -- a 32-channel dY slot -- begins at K step (res_in_lo % 64) / 16 of its rows)
-            const uint32_t a_base = q.resident ? smem_u32(dense + (size_t)((q.res_in_lo >> 6) + c) * q.chunk_alloc) : st_base;
-            const uint64_t da0 = umma_desc(a_base, 16u, a_sbo, 2u) + a_dbg +
-                                 (q.resident ? (uint32_t)((it - (it / R) * R) * 8 + ((q.res_in_lo & 63) >> 4) * 2) : 0u);
-            const uint64_t db0 = umma_desc_k128(st_base + q.a_alloc);
+            const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint64_t da0 = umma_desc_k128(a_base);
+            const uint64_t db0 = umma_desc_k128(a_base + q.a_alloc);
             const int ks = min(4, (q.cin - c * 64) >> 4);
             if (ks == 4) {
 #pragma unroll
@@ -533,8 +492,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] *= (r[j] > 0.f ? 1.f : neg);
             }
-            const bool to_tile = p.resident && p.res_out_ch >= 0;   // the next layers read this output from shared memory
-            if ((p.out_bf16 != nullptr && wr16) || to_tile) {
+            if (p.out_bf16 != nullptr && wr16) {
               uint4 o0, o1;
               o0.x = pack_bf16(f[0], f[1]);
               o0.y = pack_bf16(f[2], f[3]);
@@ -544,37 +502,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
               o1.y = pack_bf16(f[10], f[11]);
               o1.z = pack_bf16(f[12], f[13]);
               o1.w = pack_bf16(f[14], f[15]);
-              if (p.out_bf16 != nullptr && wr16) {
-                uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.out_stride + c0);
-                dst[0] = o0;
-                dst[1] = o1;
-              }
-              if (to_tile) {
-                // resident tile: row = (y + 1) * pitch + (x + 1), 128 B per row and 64-channel chunk, 16-byte pieces XOR-swizzled
-                // with the row index (the layout TMA SWIZZLE_128B writes and the K-major UMMA descriptor reads)
-                const int dc = p.res_out_ch + (c0 - n_base);
-                const uint32_t chunk_base = smem_u32(dense + (size_t)(dc >> 6) * p.chunk_alloc);
-                const uint32_t j0 = (uint32_t)(dc & 63) >> 3;
-                const int yl = mt * p.TH + tyy;
-                const uint32_t row = (uint32_t)((yl + 1) * p.pitch + txx + 1);
-                st_shared_v4(chunk_base + row * 128u + ((j0 ^ (row & 7u)) << 4), o0);
-                st_shared_v4(chunk_base + row * 128u + (((j0 + 1u) ^ (row & 7u)) << 4), o1);
-                // the strips left and right of ours read our edge columns as their halo: push them into the neighbours' tiles
-                const uint32_t rank = cluster_ctarank();
-                int peer = -1;
-                uint32_t prow = 0;
-                if (txx == 0 && rank > 0) {
-                  peer = (int)rank - 1;
-                  prow = (uint32_t)((yl + 1) * p.pitch + p.TW + 1);
-                } else if (txx == p.TW - 1 && rank + 1 < cluster_nctarank()) {
-                  peer = (int)rank + 1;
-                  prow = (uint32_t)((yl + 1) * p.pitch);
-                }
-                if (peer >= 0) {
-                  st_shared_cluster_v4(chunk_base + prow * 128u + ((j0 ^ (prow & 7u)) << 4), (uint32_t)peer, o0);
-                  st_shared_cluster_v4(chunk_base + prow * 128u + (((j0 + 1u) ^ (prow & 7u)) << 4), (uint32_t)peer, o1);
-                }
-              }
+              uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.out_stride + c0);
+              dst[0] = o0;
+              dst[1] = o1;
             }
           } else if (in_img && c0 < p.cout) {
             // ragged tail of the channel dimension (cout not a multiple of 16): scalar path, fully unrolled so that the
@@ -709,6 +639,460 @@ __global__ void __launch_bounds__(kThreads, 1) conv_chain_kernel(const __grid_co
   conv_tc_body<MT, R>(c.tmA, c.tmB, c.k, c.n_layers, c.sync_mode, c.sync, c.timeline);
 }
 
+// =====================================================================================================================
+// Resident dense block: the five convs of a ResidualDenseBlock (ACC = false; ssr/archs/rrdbnet_arch.py:37-44) or its five
+// input-gradient convs (ACC = true; autograd's backward of the same lines) in ONE launch whose activation tile never
+// leaves the SM.
+//
+//   * one thread-block cluster per image, one CTA per 8-pixel-wide strip (8 x 32 pixels = two stacked M = 128 tiles of
+//     8 x 16); the strip's 192-channel tile lives in shared memory WITH a one-pixel halo on every side: 3 chunks (64
+//     channels = one 128-byte swizzled row per pixel) x 34 rows x 10 pixels.  A row of the M = 128 operand window is 8
+//     consecutive pixels, so the window of tap (ky, kx) is 16 groups of 8 rows starting (ky * 10 + kx) rows into the chunk
+//     with SBO = 1280 B: all nine taps read the SAME bytes through descriptor offsets (the 128B swizzle is a function of the
+//     absolute shared-memory address, probed on the B200: profiles/r02_probe_sbo.md).  Nothing of the activations is ever
+//     re-loaded; only weights stream through the TMA ring (and they do not depend on earlier layers, so the producer runs
+//     ahead across layer boundaries).
+//   * the block input is loaded ONCE by TMA (image borders zero-filled); every layer's epilogue writes its bf16 output
+//     into the swizzled tile (st.shared) and pushes its edge columns into the neighbour strips' halo columns through
+//     distributed shared memory (st.shared::cluster), THEN arrives (release.cluster) on the layer barrier of every CTA of
+//     the cluster, and only after that issues the global stores training needs (x1..x4 for the backward pass) -- the
+//     release does not wait for global memory, and the next layer's MMAs run under those stores.
+//   * forward: layer l+1's input channels [0, 64 + 32 (l-1)) do NOT depend on layer l.  The MMA warp issues those chunks
+//     into the other TMEM accumulator buffer while layer l's epilogue is still draining, and waits for the cluster barrier
+//     only in front of the LAST 64-channel chunk (same accumulation order as five plain launches: bit-identical).
+//   * input gradient (ACC): the running sum of all five transposed convs stays in tensor memory (channel c of M tile m is
+//     column m * 192 + c); a layer emits only its finished 32-channel dY slot (masked, bf16) into the tile -- where the next
+//     layer reads it as its operand, K steps (slot % 64) / 16 .. of chunk slot / 64 -- and into global memory for the weight
+//     gradient; the last layer emits the 64 block-input channels with the incoming gradients added.
+//
+//     The tile of the ACC form is only two chunks: the incoming gradient, and ONE chunk whose two 32-channel halves the dY
+//     slots ping-pong through (a slot is read by the next layer only), which leaves room for a deeper weight ring.
+//
+// Roles as in conv_tc_body: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue.  The unit of the weight stream is a
+// "triple": the three vertical taps of one (64-channel chunk, kx) -- 24 (12 for a 32-channel tail) MMAs with constant
+// descriptor offsets, issued by one elected lane; a ring stage holds as many consecutive triples of the current N tile as fit.
+static constexpr int kRPitch = 10, kRTH = 16;                  // tile row = 8 pixels + 2 halo pixels; rows per M tile
+static constexpr uint32_t kRChunk = 44032;                     // 10 x 34 rows of 128 B = 43520, rounded up to 1 KB
+static constexpr uint32_t kRStageFwd = 24576;                  // one triple of a 64-wide layer, two of a 32-wide one
+static constexpr uint32_t kRStageAcc = 32768;                  // one triple of an N tile of up to 80 channels
+static constexpr uint32_t kRTapRow = kRPitch * 128 / 16;       // descriptor units (16 B): one tile row down
+static constexpr uint32_t kRMt = kRTH * kRPitch * 128 / 16;    // ... the second M tile
+
+// the 3 vertical taps of one (chunk, kx) for both stacked M tiles: accumulation order (ky, k) per M tile, as conv_tc_body
+template <int KS>
+__device__ __forceinline__ void rdb_issue_triple(uint32_t d0, uint32_t m_cols, uint64_t da, uint64_t db, uint32_t b_tap, uint32_t idesc,
+                                                 uint32_t first) {
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int k = 0; k < KS; ++k)
+        umma_bf16_ss(d0 + (uint32_t)m * m_cols, da + (uint32_t)(m * kRMt + ky * kRTapRow + 2 * k), db + (uint32_t)(ky * b_tap + 2 * k), idesc,
+                     (ky == 0 && k == 0) ? first : 1u);
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_constant__ ConvChainK cc) {
+  const ConvTcK* ps = cc.k;
+  const int n_layers = cc.n_layers;
+  long long* timeline = cc.timeline;
+  const ConvTcK& p = ps[0];
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  constexpr int kTileChunks = ACC ? 2 : kResChunks;
+  constexpr uint32_t kRStage = ACC ? kRStageAcc : kRStageFwd;
+  uint8_t* const dense = smem;
+  uint8_t* const ring = smem + (size_t)kTileChunks * kRChunk;
+  const int stages = p.stages;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(ring + (size_t)stages * kRStage);
+  uint64_t* bar_empty = bar_full + stages;
+  uint64_t* bar_acc_full = bar_empty + stages;     // [2]
+  uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2], 8 warp arrivals
+  uint64_t* bar_layer = bar_acc_empty + 2;         // every epilogue warp of the cluster arrives once per layer
+  uint64_t* bar_x = bar_layer + 1;                 // the block input has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_x + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [256]
+  float* s_bg = s_bias + 256;                                // [256]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tx = (int)blockIdx.x % p.tiles_x;      // strip of the image = rank in the cluster
+  const int img = (int)blockIdx.x / p.tiles_x;
+  griddep_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&cc.tmA[0]);
+      prefetch_tmap(&cc.tmB[0]);
+      for (int s = 0; s < stages; ++s) {
+        mbar_init(&bar_full[s], 1);
+        mbar_init(&bar_empty[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bar_acc_full[b], 1);
+        mbar_init(&bar_acc_empty[b], 8);
+      }
+      mbar_init(bar_layer, 8 * cluster_nctarank());
+      mbar_init(bar_x, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  {
+    // the chunks the block input does not fill start as zeros: image borders stay zero, interior halo columns are written by
+    // the neighbour CTAs layer by layer.  Generic-proxy stores that the tensor core reads later: proxy fence.
+    uint4* z = reinterpret_cast<uint4*>(dense + (size_t)p.res_in_chunks * kRChunk);
+    const int n16 = (int)(((size_t)(kTileChunks - p.res_in_chunks) * kRChunk) >> 4);
+    for (int i = (int)threadIdx.x; i < n16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster_sync_all();   // no remote store / arrive may reach shared memory that is not initialised yet
+  griddep_wait();       // everything above touched only this CTA's smem / TMEM
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_expect_tx(bar_x, (uint32_t)p.res_in_chunks * p.a_box_bytes);
+      for (int c = 0; c < p.res_in_chunks; ++c)
+        tma_load_4d(dense + (size_t)c * kRChunk, &cc.tmA[0], bar_x, c * 64, tx * 8 - 1, -1, img);
+    }
+    __syncwarp();
+    int g = 0;
+    for (int l = 0; l < n_layers; ++l) {
+      const ConvTcK q = ps[l];
+      const CUtensorMap* tmB = &cc.tmB[l];
+      if (l > 0) prefetch_tmap(tmB);
+      const uint32_t tap_bytes = (uint32_t)q.n_tile * 128u;
+      const int gps = max(1, (int)(kRStage / (3u * tap_bytes)));   // triples per stage
+      const int n_tr = 3 * q.chunks;                               // triples of one N tile, order (chunk, kx)
+      for (int nb = 0; nb < q.n_loop; ++nb) {
+        for (int tr0 = 0; tr0 < n_tr; tr0 += gps, ++g) {
+          const int nt = min(gps, n_tr - tr0) * 3;                 // taps in this stage
+          const int s = g % stages;
+          mbar_wait(&bar_empty[s], ((g / stages) & 1) ^ 1);
+          if (elect_one()) {
+            uint8_t* dst = ring + (size_t)s * kRStage;
+            mbar_expect_tx(&bar_full[s], (uint32_t)nt * tap_bytes);
+            for (int j = 0; j < nt; ++j)   // packed rows: ((chunk * 3 + kx) * 3 + ky) * n_pad + n
+              tma_load_2d(dst + (size_t)j * tap_bytes, tmB, &bar_full[s], 0, (tr0 * 3 + j) * q.n_pad + nb * q.n_tile);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int g = 0;
+    const uint32_t acc_cols = p.acc_stride;
+    const uint32_t dense_addr = smem_u32(dense);
+    const uint32_t ring_addr = smem_u32(ring);
+#pragma unroll 1
+    for (int l = 0; l < n_layers; ++l) {
+      const ConvTcK q = ps[l];
+      const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)q.n_tile);
+      const uint32_t b_tap = (uint32_t)q.n_tile * 8u;              // one tap's weight tile, descriptor units
+      const int gps = max(1, (int)(kRStage / (3u * (uint32_t)q.n_tile * 128u)));
+      const int n_tr = 3 * q.chunks;
+      const int b = ACC ? 0 : (l & 1);
+      const uint32_t m_cols = ACC ? (uint32_t)q.acc_w : (uint32_t)q.n_tile;
+      // the first triple that reads what layer l-1 wrote: the whole input (ACC: the dY slot), or the last 64-channel chunk
+      const int tr_dep = (ACC || l == 0) ? 0 : 3 * (q.chunks - 1);
+      // operand window of (chunk 0, kx 0, ky 0): chunk res_in_lo / 64 of the tile, K steps from (res_in_lo % 64) / 16
+      const uint64_t da_layer = umma_desc(dense_addr + (uint32_t)(q.res_in_lo >> 6) * kRChunk, 16u, kRPitch * 128u, 2u) +
+                                (uint32_t)((q.res_in_lo & 63) >> 4) * 2u;
+      const int ks_tail = ((q.cin - 64 * (q.chunks - 1)) >> 4);    // K steps of the last chunk: 4, or 2 for a 32-channel tail
+      if (!ACC) {
+        mbar_wait(&bar_acc_empty[b], (uint32_t)(((l >> 1) & 1) ^ 1));   // layer l-2's epilogue has drained this buffer
+        tc_fence_after_sync();
+      }
+#pragma unroll 1
+      for (int nb = 0; nb < q.n_loop; ++nb) {
+        const uint32_t d_base = ACC ? tmem_base + (uint32_t)(nb * q.n_tile) : tmem_base + (uint32_t)b * acc_cols;
+#pragma unroll 1
+        for (int tr0 = 0; tr0 < n_tr; tr0 += gps, ++g) {
+          const int s = g % stages;
+          mbar_wait(&bar_full[s], (uint32_t)(g / stages) & 1);
+          tc_fence_after_sync();
+          if (lane == 0 && nb == 0 && tr0 == 0) SSR_STAMP(l, 2);                            // first weights landed
+          if (lane == 0 && nb == q.n_loop - 1 && tr0 + gps >= n_tr) SSR_STAMP(l, 3);        // last weights landed
+          const uint64_t db_stage = umma_desc_k128(ring_addr + (uint32_t)s * kRStage);
+#pragma unroll 1
+          for (int jj = 0; jj < gps; ++jj) {
+            const int tr = tr0 + jj;
+            if (tr >= n_tr) break;
+            if (nb == 0 && tr == tr_dep) {
+              if (l == 0) mbar_wait(bar_x, 0);
+              else mbar_wait_cluster(bar_layer, (uint32_t)(l - 1) & 1);
+              fence_proxy_async();
+              tc_fence_after_sync();
+              if (lane == 0) SSR_STAMP(l, 0);   // inputs of this layer complete
+            }
+            if (elect_one()) {
+              const int c = tr / 3, kx = tr - 3 * c;
+              const uint64_t da = da_layer + (uint32_t)(c * (int)(kRChunk >> 4) + kx * 8);
+              const uint64_t db = db_stage + (uint32_t)(jj * 3) * b_tap;
+              const uint32_t first = (tr == 0 && !(ACC && l > 0)) ? 0u : 1u;   // ACC: layer 0 initialises, later layers add
+              if (c + 1 < q.chunks || ks_tail == 4) rdb_issue_triple<4>(d_base, m_cols, da, db, b_tap, idesc, first);
+              else rdb_issue_triple<2>(d_base, m_cols, da, db, b_tap, idesc, first);
+              if (jj == gps - 1 || tr == n_tr - 1) umma_commit(&bar_empty[s]);
+              if (tr == n_tr - 1 && (!ACC || nb == q.n_loop - 1)) umma_commit(&bar_acc_full[b]);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9: two warps per TMEM lane quarter) =====================
+    const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int m = qd * 32 + lane;
+    const int et = (int)threadIdx.x - 64;
+    const int tyy = m >> 3;          // row inside the M tile (0..15)
+    const int txx = m & 7;           // pixel inside the strip
+    const int x = tx * 8 + txx;
+    const long n_pix = (long)p.n_img * p.H * p.W;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t n_rank = cluster_nctarank();
+#pragma unroll 1
+    for (int l = 0; l < n_layers; ++l) {
+      const ConvTcK p = ps[l];
+      const bool add_bias = p.bias != nullptr;
+      const int n_out = ACC ? p.cout : p.n_tile;
+      for (int i = et; i < 256; i += kThreads - 64) {
+        s_bias[i] = (add_bias && i < p.cout) ? p.bias[i] : 0.f;
+        s_bg[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int nchunks = n_out >> 4;
+      const int ci_first = (ACC ? (p.out_lo >> 4) : 0) + half;
+      const int b = ACC ? 0 : (l & 1);
+      const uint32_t m_cols = ACC ? (uint32_t)p.acc_w : (uint32_t)p.n_tile;
+      const uint32_t d_base = ACC ? tmem_base : tmem_base + (uint32_t)b * p.acc_stride;
+      const bool use_r1 = p.res1_kind != SSR_NONE, use_r2 = p.res2_kind != SSR_NONE, use_mk = p.mask != nullptr;
+      const bool to_tile = p.res_out_ch >= 0;
+      const float neg_act = p.act == 2 ? 0.f : 0.2f;
+
+      struct Ops {
+        uint4 r1[4], r2[4], mk[2];
+      };
+      auto fetch_mask = [&](long pix, int c0, uint4 (&mk)[2]) {
+        if (use_mk && c0 >= p.mask_lo && c0 >= p.out_lo) {
+          const uint4* s4 = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_stride + c0);
+          mk[0] = s4[0];
+          mk[1] = s4[1];
+        }
+      };
+      auto fetch = [&](long pix, int c0, Ops& o) {
+        if (use_r1 && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
+          const uint4* s4 = reinterpret_cast<const uint4*>(p.res1) + (long)(c0 >> 2) * n_pix + pix;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o.r1[j] = __ldcg(s4 + (long)j * n_pix);
+        }
+        if (use_r2) {
+          const uint4* s4 = reinterpret_cast<const uint4*>(p.res2) + (long)(c0 >> 2) * n_pix + pix;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o.r2[j] = __ldcg(s4 + (long)j * n_pix);
+        }
+        fetch_mask(pix, c0, o.mk);
+      };
+      auto expand_f32 = [](const uint4* src, float (&r)[16]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          r[4 * j] = __uint_as_float(src[j].x);
+          r[4 * j + 1] = __uint_as_float(src[j].y);
+          r[4 * j + 2] = __uint_as_float(src[j].z);
+          r[4 * j + 3] = __uint_as_float(src[j].w);
+        }
+      };
+      // one work item = 32 pixels (this warp's TMEM lanes) x 16 channels of M tile mt; returns the packed bf16 result
+      auto item = [&](int mt, int ci, const uint4* r1, const uint4* r2, const uint4* mk, long pix, uint4& o0, uint4& o1) {
+        const int c0 = ci * 16;
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(d_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)mt * m_cols + (uint32_t)c0, v);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (add_bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] += s_bias[c0 + j];
+        }
+        if (p.act) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : neg_act * f[j];
+        }
+        if (p.s0 != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] *= p.s0;
+        }
+        if (use_r1 && (p.res1_cmax == 0 || c0 < p.res1_cmax)) {
+          float r[16];
+          expand_f32(r1, r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s1, r[j], f[j]);
+        }
+        if (use_r2) {
+          float r[16];
+          expand_f32(r2, r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaf(p.s2, r[j], f[j]);
+        }
+        if (p.out32_mode == SSR_OUT32_PLANAR4) {   // the f32 output is the UNMASKED value
+          float4* dst = reinterpret_cast<float4*>(p.out_f32) + (long)(c0 >> 2) * n_pix + pix;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[(long)j * n_pix] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+        if (use_mk && c0 >= p.mask_lo) {
+          const uint32_t u[8] = {mk[0].x, mk[0].y, mk[0].z, mk[0].w, mk[1].x, mk[1].y, mk[1].z, mk[1].w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            f[2 * j] *= (bf16_lo(u[j]) > 0.f ? 1.f : 0.2f);
+            f[2 * j + 1] *= (bf16_hi(u[j]) > 0.f ? 1.f : 0.2f);
+          }
+        }
+        o0.x = pack_bf16(f[0], f[1]);
+        o0.y = pack_bf16(f[2], f[3]);
+        o0.z = pack_bf16(f[4], f[5]);
+        o0.w = pack_bf16(f[6], f[7]);
+        o1.x = pack_bf16(f[8], f[9]);
+        o1.y = pack_bf16(f[10], f[11]);
+        o1.z = pack_bf16(f[12], f[13]);
+        o1.w = pack_bf16(f[14], f[15]);
+        if (p.bgrad != nullptr) {
+          // per-channel sum over the warp's 32 pixels (a transposing butterfly), one shared-memory atomic per channel
+          float g8[8], g4[4], g2[2];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float keep = (lane & 16) ? f[j + 8] : f[j], send = (lane & 16) ? f[j] : f[j + 8];
+            g8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float keep = (lane & 8) ? g8[j + 4] : g8[j], send = (lane & 8) ? g8[j] : g8[j + 4];
+            g4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float keep = (lane & 4) ? g4[j + 2] : g4[j], send = (lane & 4) ? g4[j] : g4[j + 2];
+            g2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+          float g1 = ((lane & 2) ? g2[1] : g2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 2) ? g2[0] : g2[1], 2);
+          g1 += __shfl_xor_sync(0xffffffffu, g1, 1);
+          const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          if ((lane & 1) == 0) atomicAdd(&s_bg[c0 + ch], g1);
+        }
+      };
+
+      long pixs[2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) pixs[mt] = ((long)img * p.H + (mt * kRTH + tyy)) * p.W + x;
+      Ops o;
+      uint4 mk2[2][2];
+      if (to_tile) {   // a tile layer has no residual operands; its two masks (ACC) are fetched while the MMAs run
+        fetch_mask(pixs[0], ci_first * 16, mk2[0]);
+        fetch_mask(pixs[1], ci_first * 16, mk2[1]);
+      } else if (ci_first < nchunks) {
+        fetch(pixs[0], ci_first * 16, o);
+      }
+      mbar_wait(&bar_acc_full[b], ACC ? (uint32_t)(l & 1) : (uint32_t)((l >> 1) & 1));
+      tc_fence_after_sync();
+      if (et == 0) SSR_STAMP(l, 5);   // accumulators complete
+      if (to_tile) {
+        // ---- a layer the next ones read from shared memory: exactly one 16-channel chunk per warp and M tile.  Tile first
+        // (own rows + the neighbours' halo columns), then the cluster barrier, then global memory.
+        const int ci = ci_first;
+        const int dc = p.res_out_ch + (ACC ? half : ci) * 16;      // channel inside the tile (ACC: the slot's ping-pong half)
+        const uint32_t chunk_base = smem_u32(dense + (size_t)(dc >> 6) * kRChunk);
+        const uint32_t j0 = (uint32_t)(dc & 63) >> 3;              // 16-byte piece of the 128-byte row
+        uint4 keep[2][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          item(mt, ci, nullptr, nullptr, mk2[mt], pixs[mt], keep[mt][0], keep[mt][1]);
+          const uint32_t yl = (uint32_t)(mt * kRTH + tyy);
+          const uint32_t row = (yl + 1u) * kRPitch + (uint32_t)txx + 1u;
+          st_shared_v4(chunk_base + row * 128u + ((j0 ^ (row & 7u)) << 4), keep[mt][0]);
+          st_shared_v4(chunk_base + row * 128u + (((j0 + 1u) ^ (row & 7u)) << 4), keep[mt][1]);
+          int peer = -1;
+          uint32_t prow = 0;
+          if (txx == 0 && rank > 0) {
+            peer = (int)rank - 1;
+            prow = (yl + 1u) * kRPitch + 9u;
+          } else if (txx == 7 && rank + 1 < n_rank) {
+            peer = (int)rank + 1;
+            prow = (yl + 1u) * kRPitch;
+          }
+          if (peer >= 0) {
+            st_shared_cluster_v4(chunk_base + prow * 128u + ((j0 ^ (prow & 7u)) << 4), (uint32_t)peer, keep[mt][0]);
+            st_shared_cluster_v4(chunk_base + prow * 128u + (((j0 + 1u) ^ (prow & 7u)) << 4), (uint32_t)peer, keep[mt][1]);
+          }
+        }
+        tc_fence_before_sync();
+        fence_proxy_async();        // our generic-proxy stores (local and remote) before the tensor core's reads of them
+        __syncwarp();
+        if (lane == 0) {
+          if (!ACC) mbar_arrive(&bar_acc_empty[b]);
+          for (uint32_t r = 0; r < n_rank; ++r) mbar_arrive_remote_release(bar_layer, r);
+        }
+        if (et == 0) SSR_STAMP(l, 7);   // arrived
+        if (p.out_bf16 != nullptr) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pixs[mt] * p.out_stride + ci * 16);
+            dst[0] = keep[mt][0];
+            dst[1] = keep[mt][1];
+          }
+        }
+      } else {
+        // ---- the last layer: everything goes to global memory (f32 trunk / running gradient, bf16 copy for the next block)
+        bool first = true;
+#pragma unroll 1
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll 1
+          for (int ci = ci_first; ci < nchunks; ci += 2) {
+            if (!first) fetch(pixs[mt], ci * 16, o);
+            first = false;
+            uint4 o0, o1;
+            item(mt, ci, o.r1, o.r2, o.mk, pixs[mt], o0, o1);
+            if (p.out_bf16 != nullptr && ci * 16 >= p.out_lo) {
+              uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pixs[mt] * p.out_stride + ci * 16);
+              dst[0] = o0;
+              dst[1] = o1;
+            }
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0 && !ACC) mbar_arrive(&bar_acc_empty[b]);
+      }
+      if (et == 0) SSR_STAMP(l, 6);   // stores issued
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // s_bg complete; nobody still reads s_bias of this layer
+      if (p.bgrad != nullptr) {
+        for (int i = et; i < n_out; i += kThreads - 64)
+          if (i >= p.out_lo) atomicAdd(p.bgrad + (i - p.out_lo), p.bgrad_scale * s_bg[i]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // ... before the next layer zeroes s_bg
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // no CTA may exit while a peer can still push halo columns into its shared memory
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 static int g_smem_optin = -1;
 static int g_num_sms = 0;
 
@@ -784,17 +1168,9 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
     if (halo_tile) p.TW = 8;   // resident dense block: 8-pixel strips, the tile keeps its halo columns in shared memory
   }
   p.TH = 128 / p.TW;
-  {
-    // hardware probe (scripts/probe_sbo.sh): 8-pixel tile rows inside wider shared-memory rows, SBO = pitch * 128 B
-    static int extra = -1;
-    if (extra < 0) {
-      const char* e = getenv("SSR_DBG_PITCH");
-      extra = e ? atoi(e) : 0;
-      if (extra < 0 || extra > 8) extra = 0;
-    }
-    p.pitch = p.TW + (p.TW == 8 && a->r == 3 ? extra : 0);
-    if (halo_tile) p.pitch = p.TW + 2;
-  }
+  // resident dense block: the tile keeps one halo column on each side in shared memory (rows of TW + 2 pixels); the M = 128
+  // operand window is then 16 groups of 8 rows at SBO = pitch * 128 B (probed on the B200, profiles/r02_probe_sbo.md)
+  p.pitch = halo_tile ? p.TW + 2 : p.TW;
   int mt = mt_force ? mt_force : a->mt;
   if (mt == 0) {
     // two stacked M tiles per CTA when one-tile CTAs would spill past a single co-resident wave: the weight tiles
@@ -874,10 +1250,6 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
   p.bgrad_scale = a->bias_grad_scale;
   SSR_REQUIRE(a->out_lo >= 0 && a->out_lo % 16 == 0, "ssr_conv_tc: out_lo must be a multiple of 16");
   if (a->bias_grad) SSR_REQUIRE(a->cout % 16 == 0 && a->splits <= 1, "ssr_conv_tc: bias_grad needs cout %% 16 == 0 and no split-K");
-  {
-    const char* e = getenv("SSR_DBG_AOFF");
-    p.dbg_aoff = e ? atoi(e) : 0;
-  }
   if (a->cout % 16 == 0) {
     // vector epilogue alignment contract
     if (p.out_bf16) SSR_REQUIRE(p.out_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0, "ssr_conv_tc: out_bf16 alignment");
@@ -921,7 +1293,6 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
 
 // one shared-memory ring / TMEM split for all n layers (n == 1: a plain launch); returns the dynamic smem size or 0
 static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
-  const size_t dense_bytes = ps[0].resident ? (size_t)kResChunks * ps[0].chunk_alloc : 0;   // resident tile in front of the ring
   uint32_t stage_bytes = 0;
   int n_tile_max = 0, iters = 0;
   for (int i = 0; i < n; ++i) {
@@ -929,7 +1300,7 @@ static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
     n_tile_max = max(n_tile_max, ps[i].n_tile);
     iters += ((ps[i].chunks + ps[i].splits - 1) / ps[i].splits) * ps[i].R;
   }
-  const int budget = g_smem_optin - 1024 - 256 - 2048 - (int)dense_bytes;
+  const int budget = g_smem_optin - 1024 - 256 - 2048;
   int stages = budget / (int)stage_bytes;
   if (stages < 1) {
     set_error("ssr_conv_tc: stage of %u bytes does not fit shared memory", stage_bytes);
@@ -950,7 +1321,7 @@ static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
     ps[i].acc_stride = (uint32_t)(mt * n_tile_max);
     ps[i].tmem_cols = cols;
   }
-  return dense_bytes + (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias, bias-gradient sums*/;
+  return (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias, bias-gradient sums*/;
 }
 
 static int persistent_ctas(const ConvTcK& p) {
@@ -964,13 +1335,13 @@ static int persistent_ctas(const ConvTcK& p) {
 
 template <typename Kern, typename... Args>
 static int launch_conv(Kern kern, size_t* configured, dim3 grid, int cluster_x, size_t smem_bytes, cudaStream_t stream, const char* what,
-                       Args... args) {
+                       int prof_class, Args... args) {
   if (*configured < smem_bytes) {
     if (!check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin), "cudaFuncSetAttribute(conv_tc)"))
       return SSR_E_CUDA;
     *configured = (size_t)g_smem_optin;
   }
-  prof_before(0, stream);
+  prof_before(prof_class, stream);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kThreads);
@@ -1010,7 +1381,7 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   dim3 grid((unsigned)persistent_ctas(p), (unsigned)(p.n_pad / p.n_tile), (unsigned)p.splits);
   auto kern = mt == 1 ? (p.R == 3 ? conv_tc_kernel<1, 3> : conv_tc_kernel<1, 1>) : (p.R == 3 ? conv_tc_kernel<2, 3> : conv_tc_kernel<2, 1>);
   static size_t configured[6] = {0, 0, 0, 0, 0, 0};
-  return launch_conv(kern, &configured[mt * 2 + (p.R == 3 ? 1 : 0)], grid, 1, smem_bytes, stream, "conv_tc launch", tmA, tmB, p);
+  return launch_conv(kern, &configured[mt * 2 + (p.R == 3 ? 1 : 0)], grid, 1, smem_bytes, stream, "conv_tc launch", 0, tmA, tmB, p);
 }
 
 // diagnostics: with SSR_CHAIN_TIMELINE=1 every chained launch overwrites a [512 CTAs][kMaxChain][8] table of clock64 stamps
@@ -1039,6 +1410,107 @@ extern "C" int ssr_debug_chain_timeline(long long* host_out, int32_t n_ctas) {
 //     wait for each other -- any batch size, no co-residency requirement;
 //   * SSR_CONV_CHAIN=2: larger images through a grid-wide arrive counter (needs the whole grid co-resident: <= one CTA per SM);
 //   * otherwise, or with SSR_CONV_CHAIN=0: n plain launches, with identical results.
+static int64_t g_resident_launches = 0;
+extern "C" int64_t ssr_debug_resident_launches(void) { return g_resident_launches; }
+
+// Resident dense block (rdb_resident_kernel): does this chain have the shape of ResidualDenseBlock.forward (every layer reads
+// channels [0, cin_i) of ONE buffer, all but the last append 32 channels at cin_i) or of its input-gradient chain with the
+// running sum in tensor memory (layer i+1 reads the 32-channel dY slot layer i emitted)?  32-row images cut into 8-pixel
+// strips, one cluster per image.  Returns 1 when launched, 0 when the shape does not qualify, < 0 on error.
+static int rdb_resident_launch(const ssr_conv_tc_args* a, int32_t n, cudaStream_t stream, bool tmem_acc) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SSR_CONV_RESIDENT");
+    on = e ? atoi(e) : 1;
+  }
+  if (!on || n < 2 || n > kMaxChain) return 0;
+  const int h = a[0].h, w = a[0].w;
+  if (a[0].r != 3 || h != 32 || w < 8 || w > 64 || (w & 7) || a[0].cin != 64) return 0;
+  for (int i = 0; i < n; ++i) {
+    const ssr_conv_tc_args& L = a[i];
+    const bool last = i + 1 == n;
+    if (L.n_img != a[0].n_img || L.h != h || L.w != w || L.r != 3 || L.n_tile != 0 || L.splits > 1 || L.mt != 0) return 0;
+    if (L.cout % 16 || L.out32_mode == SSR_OUT32_NHWC || L.out32_mode == SSR_OUT32_NHWC_ATOMIC || L.out32_mode == SSR_OUT32_NCHW ||
+        L.out32_mode == SSR_OUT32_PLANAR4_ACC)
+      return 0;
+    if ((L.res1 && L.res1_kind != SSR_F32_PLANAR4) || (L.res2 && L.res2_kind != SSR_F32_PLANAR4) || L.mask_relu) return 0;
+    if (!last && (L.res1 || L.res2 || L.out_f32)) return 0;
+    if (last && (L.cout != 64 || L.out_lo != 0)) return 0;
+    if (!tmem_acc) {
+      // forward: layer i reads [0, 64 + 32 i) of the dense buffer and appends its 32 channels there (or nowhere: inference)
+      if (L.x != a[0].x || L.x_pix_stride != a[0].x_pix_stride || L.cin != 64 + 32 * i || L.mask || L.bias_grad || L.out_lo) return 0;
+      if (!last && (L.cout != 32 || (L.out_bf16 && (L.out_pix_stride != L.x_pix_stride ||
+                                                     L.out_bf16 != (void*)((char*)const_cast<void*>(a[0].x) + 2 * (size_t)L.cin)))))
+        return 0;
+    } else {
+      // input gradient: pure sums (s0 == 1, no bias / activation -- checked by the caller), layer i emits its top 32 channels
+      if (!last && (L.cout - L.out_lo != 32 || L.out_lo < 64 || L.out_bf16 == nullptr)) return 0;
+      if (i > 0) {
+        const ssr_conv_tc_args& P = a[i - 1];
+        if (L.cin != 32 || L.x != (void*)((char*)P.out_bf16 + 2 * (size_t)P.out_lo) || L.x_pix_stride != P.out_pix_stride ||
+            L.n_pad > P.out_lo)
+          return 0;
+      } else if (L.cout > 64 * kResChunks) {
+        return 0;
+      }
+    }
+  }
+  if (!device_limits()) return SSR_E_CUDA;
+  static ConvChainK c;
+  const uint32_t stage_bytes = tmem_acc ? kRStageAcc : kRStageFwd;
+  const int tile_chunks = tmem_acc ? 2 : kResChunks;
+  for (int i = 0; i < n; ++i) {
+    int mt_i = 0;
+    ssr_conv_tc_args ai = a[i];
+    if (tmem_acc) {
+      // N tiles of the wide input-gradient layers: the widest divisor of n_pad whose tap triple fits a ring stage
+      // (192 -> 3 x 64, 160 -> 2 x 80, 128 -> 2 x 64, 96 -> 2 x 48, 64)
+      for (int t = 80; t >= 16; t -= 16)
+        if (ai.n_pad % t == 0) {
+          ai.n_tile = t;
+          break;
+        }
+    }
+    if (int rc = prepare_conv(&ai, 2, c.k[i], c.tmA[i], c.tmB[i], mt_i, true)) return rc;
+    ConvTcK& k = c.k[i];
+    if (k.tiles_y != 1 || 3u * (uint32_t)k.n_tile * 128u > stage_bytes || k.a_box_bytes > kRChunk) return 0;
+    k.n_loop = k.n_pad / k.n_tile;
+    k.resident = 1;
+    k.chunk_alloc = kRChunk;
+    k.res_in_chunks = 1;
+    if (tmem_acc) {
+      // chunk 0 = the incoming gradient; the dY slot of layer i goes to half (i & 1) of chunk 1, where layer i+1 reads it
+      k.res_in_lo = i == 0 ? 0 : 64 + 32 * ((i - 1) & 1);
+      k.res_out_ch = i + 1 < n ? 64 + 32 * (i & 1) : -1;
+    } else {
+      k.res_in_lo = 0;
+      k.res_out_ch = i + 1 < n ? a[i].cin : -1;
+    }
+    k.acc_w = tmem_acc ? c.k[0].n_pad : 0;
+    k.acc_stride = 128;                       // forward: two accumulator buffers of 2 M tiles x 64 columns
+    k.tmem_cols = tmem_acc ? 512u : 256u;     // ACC: 2 M tiles x 192 columns
+  }
+  if (tmem_acc && 2 * c.k[0].n_pad > 512) return 0;
+  const int budget = g_smem_optin - 1024 - 256 - 2048 - (int)(tile_chunks * kRChunk);
+  int stages = budget / (int)stage_bytes;
+  if (stages < 2) return 0;
+  if (stages > 8) stages = 8;
+  for (int i = 0; i < n; ++i) c.k[i].stages = stages;
+  const size_t smem_bytes = (size_t)tile_chunks * kRChunk + (size_t)stages * stage_bytes + 1024 + 256 + 2048;
+  c.n_layers = n;
+  c.sync_mode = kSyncCluster;
+  c.sync = nullptr;
+  c.timeline = chain_timeline_buffer();
+  const int strips = w / 8;
+  dim3 grid((unsigned)(strips * a[0].n_img), 1, 1);
+  static size_t configured[2] = {0, 0};
+  int rc;
+  ++g_resident_launches;
+  if (tmem_acc) rc = launch_conv(rdb_resident_kernel<true>, &configured[1], grid, strips, smem_bytes, stream, "resident dense block (input gradient) launch", 3, c);
+  else rc = launch_conv(rdb_resident_kernel<false>, &configured[0], grid, strips, smem_bytes, stream, "resident dense block launch", 2, c);
+  return rc == SSR_OK ? 1 : rc;
+}
+
 static int conv_chain_impl(const ssr_conv_tc_args* a, int32_t n, void* stream_, bool tmem_acc) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SSR_REQUIRE(a != nullptr && n >= 1, "ssr_conv_tc_chain: null args");
@@ -1047,43 +1519,23 @@ static int conv_chain_impl(const ssr_conv_tc_args* a, int32_t n, void* stream_, 
     const char* e = getenv("SSR_CONV_CHAIN");
     enabled = e ? atoi(e) : 1;
   }
+  if (tmem_acc) {
+    for (int i = 0; i < n; ++i)
+      SSR_REQUIRE(a[i].s0 == 1.f && a[i].act == 0 && a[i].bias == nullptr, "ssr_conv_tc_chain_acc: layer %d must be a pure sum (s0 == 1, no bias / activation)", i);
+  }
+  if (enabled) {
+    const int rc = rdb_resident_launch(a, n, stream, tmem_acc);
+    if (rc != 0) return rc < 0 ? rc : SSR_OK;
+  }
+  for (int i = 0; i + 1 < n; ++i)
+    SSR_REQUIRE(tmem_acc || a[i].out_bf16 != nullptr || a[i].out_f32 != nullptr,
+                "ssr_conv_tc_chain: layer %d stores nothing -- only the shared-memory-resident dense-block launch can run that", i);
   bool ok = enabled && n >= 2 && n <= kMaxChain;
   for (int i = 0; ok && i < n; ++i)
     ok = a[i].n_img == a[0].n_img && a[i].h == a[0].h && a[i].w == a[0].w && a[i].r == a[0].r && a[i].n_pad <= 256 &&
          a[i].n_tile == 0 && a[i].splits <= 1 && a[i].mt == a[0].mt;
   static ConvChainK c;   // 2.3 KB of tensor maps and parameters: built in place, copied by the launch
   int mt = 0, tiles_per_img = 0;
-  // Resident dense block (experimental, SSR_CONV_RESIDENT=1): every layer reads channels [0, cin_i) of ONE buffer and all but
-  // the last append their output at channel cin_i -- ResidualDenseBlock.forward.  The 192-channel tile of an 8-pixel strip
-  // (with halo) then stays in shared memory for all layers and only weights stream.
-  static int resident_on = -1;
-  if (resident_on < 0) {
-    const char* e = getenv("SSR_CONV_RESIDENT");
-    resident_on = e ? atoi(e) : 0;
-  }
-  bool resident = ok && resident_on && a[0].r == 3 && a[0].h <= 32 && a[0].w <= 64 && a[0].mt == 0;
-  int res_in_lo[kMaxChain] = {0, 0, 0, 0, 0};
-  if (!tmem_acc) {
-    for (int i = 0; resident && i < n; ++i) {
-      resident = a[i].x == a[0].x && a[i].x_pix_stride == a[0].x_pix_stride && a[i].n_pad <= 128 && a[i].cin <= 64 * kResChunks &&
-                 (i == 0 || a[i].cin == a[i - 1].cin + a[i - 1].cout);
-      if (resident && i + 1 < n)
-        resident = a[i].cout % 16 == 0 && a[i].out_pix_stride == a[0].x_pix_stride &&
-                   a[i].out_bf16 == (void*)((char*)const_cast<void*>(a[0].x) + 2 * (size_t)a[i].cin);
-    }
-  } else {
-    // input-gradient chain (running sum in tensor memory): layer 0 reads the incoming gradient (<= 64 channels -> chunk 0 of the
-    // tile); layer i >= 1 reads the slot layer i-1 just emitted, which lives in the gradient buffer at its absolute channel --
-    // the tile uses the same channel numbering, so an emitted channel c goes to tile channel c (res_out_ch = 0)
-    resident = resident && a[0].cin <= 64;
-    for (int i = 1; resident && i < n; ++i) {
-      res_in_lo[i] = a[i - 1].out_lo;
-      resident = a[i - 1].out_bf16 != nullptr && a[i].x == (void*)((char*)a[i - 1].out_bf16 + 2 * (size_t)a[i - 1].out_lo) &&
-                 a[i].x_pix_stride == a[i - 1].out_pix_stride && a[i].cin == a[i - 1].cout - a[i - 1].out_lo &&
-                 a[i - 1].out_lo >= 64 && a[i - 1].cout <= 64 * kResChunks && (a[i - 1].out_lo & 63) + a[i].cin <= 64 &&
-                 a[i - 1].out_lo % 16 == 0;
-    }
-  }
   if (ok) {
     if (!device_limits()) return SSR_E_CUDA;
     // the widest layer decides how many M tiles a CTA stacks (two accumulator buffers of mt * n_tile TMEM columns)
@@ -1091,34 +1543,13 @@ static int conv_chain_impl(const ssr_conv_tc_args* a, int32_t n, void* stream_, 
     for (int i = 1; i < n; ++i)
       if (a[i].n_pad > a[widest].n_pad) widest = i;
     int mt_w = 0;
-    if (int rc = prepare_conv(&a[widest], resident ? 2 : 0, c.k[widest], c.tmA[widest], c.tmB[widest], mt_w, resident)) return rc;
+    if (int rc = prepare_conv(&a[widest], 0, c.k[widest], c.tmA[widest], c.tmB[widest], mt_w)) return rc;
     mt = mt_w;
     for (int i = 0; i < n; ++i) {
       int mt_i = 0;
       if (i != widest)
-        if (int rc = prepare_conv(&a[i], mt, c.k[i], c.tmA[i], c.tmB[i], mt_i, resident)) return rc;
+        if (int rc = prepare_conv(&a[i], mt, c.k[i], c.tmA[i], c.tmB[i], mt_i)) return rc;
       c.k[i].n_loop = c.k[i].n_pad / c.k[i].n_tile;
-    }
-    if (resident && c.k[0].tiles_y != 1) {
-      // taller than one strip: vertical halos would need an exchange too -- redo the layers in the standard layout
-      resident = false;
-      for (int i = 0; i < n; ++i) {
-        int mt_i = 0;
-        if (int rc = prepare_conv(&a[i], i == 0 ? 0 : mt, c.k[i], c.tmA[i], c.tmB[i], mt_i)) return rc;
-        if (i == 0) mt = mt_i;
-        c.k[i].n_loop = c.k[i].n_pad / c.k[i].n_tile;
-      }
-    }
-    if (resident) {
-      const uint32_t chunk_alloc = (uint32_t)round_up((int)c.k[0].a_box_bytes, 1024);   // (TW+2) x (MT*TH+2) rows of 128 B
-      for (int i = 0; i < n; ++i) {
-        c.k[i].resident = 1;
-        c.k[i].chunk_alloc = chunk_alloc;
-        c.k[i].a_alloc = 0;                                   // stages carry weights only
-        c.k[i].res_in_chunks = (a[0].cin + 63) / 64;
-        c.k[i].res_in_lo = res_in_lo[i];
-        c.k[i].res_out_ch = i + 1 < n ? (tmem_acc ? 0 : a[i].cin) : -1;
-      }
     }
     tiles_per_img = c.k[0].tiles_x * c.k[0].tiles_y;
     const int total = tiles_per_img * c.k[0].n_img;
@@ -1133,7 +1564,6 @@ static int conv_chain_impl(const ssr_conv_tc_args* a, int32_t n, void* stream_, 
     const int acc_w = c.k[0].n_pad;
     SSR_REQUIRE(mt * acc_w <= 512, "ssr_conv_tc_chain_acc: %d stacked tiles x %d channels exceed tensor memory", mt, acc_w);
     for (int i = 0; i < n; ++i) {
-      SSR_REQUIRE(a[i].s0 == 1.f && a[i].act == 0 && a[i].bias == nullptr, "ssr_conv_tc_chain_acc: layer %d must be a pure sum (s0 == 1, no bias / activation)", i);
       SSR_REQUIRE(a[i].cout % 16 == 0 && a[i].n_pad <= acc_w, "ssr_conv_tc_chain_acc: layer %d: cout must be a multiple of 16 and <= the first layer's", i);
       SSR_REQUIRE(a[i].out32_mode != SSR_OUT32_NHWC_ATOMIC && a[i].out32_mode != SSR_OUT32_PLANAR4_ACC, "ssr_conv_tc_chain_acc: layer %d: out32 mode", i);
       if (i > 0) SSR_REQUIRE(a[i].n_pad <= a[i - 1].out_lo, "ssr_conv_tc_chain_acc: layer %d writes channels layer %d is still emitting", i, i - 1);
@@ -1167,7 +1597,8 @@ static int conv_chain_impl(const ssr_conv_tc_args* a, int32_t n, void* stream_, 
   const int R = c.k[0].R;
   auto kern = mt == 1 ? (R == 3 ? conv_chain_kernel<1, 3> : conv_chain_kernel<1, 1>) : (R == 3 ? conv_chain_kernel<2, 3> : conv_chain_kernel<2, 1>);
   static size_t configured[6] = {0, 0, 0, 0, 0, 0};
-  return launch_conv(kern, &configured[mt * 2 + (R == 3 ? 1 : 0)], grid, cluster_x, smem_bytes, stream, "conv_tc chain launch", c);
+  return launch_conv(kern, &configured[mt * 2 + (R == 3 ? 1 : 0)], grid, cluster_x, smem_bytes, stream, "conv_tc chain launch",
+                     (tmem_acc || a[0].mask != nullptr) ? 3 : 2 /* profile class: dense-block input-gradient / forward chain */, c);
 }
 
 extern "C" int ssr_conv_tc_chain(const ssr_conv_tc_args* a, int32_t n, void* stream) { return conv_chain_impl(a, n, stream, false); }
@@ -1178,6 +1609,11 @@ extern "C" int ssr_conv_tc_chain_acc_supported(int32_t n_img, int32_t h, int32_t
   if (n_img <= 0 || h <= 0 || w < 8 || widest_cout <= 0) return 0;
   const char* e = getenv("SSR_CONV_CHAIN");
   if (e && atoi(e) == 0) return 0;
+  {
+    // the shared-memory-resident form: 32-row images in 8-pixel strips, one cluster of <= 8 CTAs per image
+    const char* r = getenv("SSR_CONV_RESIDENT");
+    if (!(r && atoi(r) == 0) && h == 32 && w <= 64 && (w & 7) == 0 && widest_cout <= 64 * kResChunks) return 1;
+  }
   const int tw = w >= 32 ? 32 : round_up(w, 8), th = 128 / tw;
   const int n_pad = balanced_n_tile(widest_cout) * ((widest_cout + 127) / 128);
   const long tiles1 = (long)((w + tw - 1) / tw) * ((h + th - 1) / th) * n_img;

@@ -327,30 +327,57 @@ struct PackDesc {
   int cout, cin, r, mode, k_pad, n_pad;
 };
 
+// One block = one tile of the packed operand: 64 K entries (one chunk) x kPackNT output rows x all r*r taps.  The f32 OIHW source
+// is read in ITS order (forward: 64 * r*r consecutive floats per output channel; input-gradient form: kPackNT * r*r consecutive
+// floats per K entry), transposed through shared memory, and written as whole 128-byte rows (kPackNT consecutive rows per tap =
+// 1 KB contiguous) -- both sides coalesced, where the element-wise form read one 4-byte value per 36-byte stride.
+static constexpr int kPackNT = 8;
 __global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
   const PackDesc d = descs[blockIdx.y];
   if (d.mode != SSR_PACK_FWD && d.mode != SSR_PACK_DGRAD) return;
+  __shared__ __nv_bfloat16 tile[16 * kPackNT * 64];   // [tap (kx * r + ky)][row][k]
   const int chunks = d.k_pad / 64;
-  const long total = (long)chunks * d.r * d.r * d.n_pad * 64;
+  const int T = d.r * d.r;
+  const int n_tiles = (d.n_pad + kPackNT - 1) / kPackNT;
   const float sc = d.inv_scale ? 1.f / *d.inv_scale : 1.f;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long t = i;
-    const int j = t % 64;
-    t /= 64;
-    const int nn = t % d.n_pad;
-    t /= d.n_pad;
-    const int ky = t % d.r;
-    t /= d.r;
-    const int kx = t % d.r;
-    const int c = t / d.r;
-    const int k = c * 64 + j;
-    float v = 0.f;
-    if (d.mode == SSR_PACK_FWD) {
-      if (nn < d.cout && k < d.cin) v = d.w[(((long)nn * d.cin + k) * d.r + ky) * d.r + kx];
-    } else {
-      if (nn < d.cin && k < d.cout) v = d.w[(((long)k * d.cin + nn) * d.r + (d.r - 1 - ky)) * d.r + (d.r - 1 - kx)];
+  const bool fwd = d.mode == SSR_PACK_FWD;
+  const int n_valid = fwd ? d.cout : d.cin;     // rows (n) that exist
+  const int k_valid = fwd ? d.cin : d.cout;     // K entries that exist
+  for (int tl = blockIdx.x; tl < chunks * n_tiles; tl += gridDim.x) {
+    const int c = tl / n_tiles, n0 = (tl - c * n_tiles) * kPackNT;
+    const int total = kPackNT * 64 * T;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      int nn, kl, tap;
+      if (fwd) {            // e = (nn, kl, tap): source w[n][k][ky][kx] contiguous in (kl, tap)
+        nn = e / (64 * T);
+        const int rem = e - nn * 64 * T;
+        kl = rem / T;
+        tap = rem - kl * T;
+      } else {              // e = (kl, nn, tap): source w[k][n][ky][kx] contiguous in (nn, tap)
+        kl = e / (kPackNT * T);
+        const int rem = e - kl * kPackNT * T;
+        nn = rem / T;
+        tap = rem - nn * T;
+      }
+      const int n = n0 + nn, k = c * 64 + kl;
+      float v = 0.f;
+      if (n < n_valid && k < k_valid) v = fwd ? d.w[((long)n * d.cin + k) * T + tap] : d.w[((long)k * d.cin + n) * T + tap];
+      int ky = tap / d.r, kx = tap - ky * d.r;              // source tap (ky, kx); the input-gradient operand mirrors both
+      if (!fwd) {
+        ky = d.r - 1 - ky;
+        kx = d.r - 1 - kx;
+      }
+      tile[((kx * d.r + ky) * kPackNT + nn) * 64 + kl] = __float2bfloat16(v * sc);
     }
-    d.dst[i] = __float2bfloat16(v * sc);
+    __syncthreads();
+    // rows out: dst[((c * r + kx) * r + ky) * n_pad + n][64], 16 bytes per thread
+    const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+    for (int o = threadIdx.x; o < T * kPackNT * 8; o += blockDim.x) {
+      const int tp = o / (kPackNT * 8), rem = o - tp * kPackNT * 8, nn = rem >> 3;
+      const int n = n0 + nn;
+      if (n < d.n_pad) reinterpret_cast<uint4*>(d.dst + (((long)c * T + tp) * d.n_pad + n) * 64)[rem & 7] = t4[o];
+    }
+    __syncthreads();
   }
 }
 

@@ -395,7 +395,7 @@ int launch_wgrad9_batched(const ssr_wgrad_tc_args* args, int n, int* fallback, c
     cudaLaunchAttribute attr[1] = {pdl_attr()};
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    prof_before(1, stream);
+    prof_before(4, stream);   // profile class 4: the batched dense-block weight gradient
     if (!check_cuda(cudaLaunchKernelEx(&cfg, wgrad9_tc_batched_kernel, b), "wgrad9_tc_batched launch")) return SSR_E_CUDA;
     prof_after(stream);
     count_launch();

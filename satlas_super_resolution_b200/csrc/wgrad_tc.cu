@@ -377,7 +377,9 @@ extern "C" int ssr_wgrad_unpack(const float* acc, int32_t cx_rows, int32_t acc_s
 extern "C" int ssr_wgrad_unpack_batched(const ssr_unpack_desc* descs_device, int32_t n_layers, void* stream) {
   static_assert(sizeof(ssr_unpack_desc) == sizeof(UnpackDesc), "ssr_unpack_desc layout");
   SSR_REQUIRE(descs_device && n_layers > 0, "ssr_wgrad_unpack_batched: bad args");
-  dim3 grid(16, (unsigned)n_layers);
+  // few layers = the discriminator (up to 2.4 M elements per layer): spread each over the whole machine; the generator's 351 small
+  // layers (18 k .. 110 k elements) are served by 16 blocks each
+  dim3 grid(n_layers <= 32 ? 148u : 16u, (unsigned)n_layers);
   wgrad_unpack_batched_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const UnpackDesc*>(descs_device));
   count_launch();
   return check_last("wgrad_unpack_batched launch") ? SSR_OK : SSR_E_CUDA;

@@ -52,10 +52,10 @@ class RRDBNetEngine:
         mk("conv_hr", nf)
         mk("conv_last", nf)
         self.cv = cv
-        # SSR_DGRAD_TMEM=1: the dense-block input-gradient chain keeps its running sum in tensor memory
-        # (ssr_conv_tc_chain_acc).  Its layers are pure sums, so conv5's 0.2 (0.04 for the third block of an RRDB) is folded into the
-        # packed input-gradient weights.  Off by default until it has been measured on the GPU.
-        self.dgrad_tmem = want_grad and os.environ.get("SSR_DGRAD_TMEM", "0") == "1"
+        # The dense-block input-gradient chain keeps its running sum in tensor memory (ssr_conv_tc_chain_acc; SSR_DGRAD_TMEM=0 goes
+        # back to the f32 sum in global memory).  Its layers are pure sums, so conv5's 0.2 (0.04 for the third block of an RRDB) is
+        # folded into the packed input-gradient weights.
+        self.dgrad_tmem = want_grad and os.environ.get("SSR_DGRAD_TMEM", "1") == "1"
         if self.dgrad_tmem:
             for i in range(num_block):
                 for j in (1, 2, 3):

@@ -199,14 +199,74 @@ class SSRESRGANModel:
         return out
 
     def validation(self, dataloader, current_iter, tb_logger, save_img=False):
-        """runs the EMA generator over the loader; image dumps / metric suites of nondist_validation
-        (ssr_esrgan_model.py:269-352) are outside the hot path"""
-        n = 0
+        """basicsr BaseModel.validation -> nondist_validation (ssr/models/ssr_esrgan_model.py:269-352)"""
+        return self.nondist_validation(dataloader, current_iter, tb_logger, save_img)
+
+    def _initialize_best_metric_results(self, dataset_name, metrics2run):
+        """ssr_esrgan_model.py:253-267"""
+        if not hasattr(self, "best_metric_results"):
+            self.best_metric_results = {}
+        if dataset_name in self.best_metric_results:
+            return
+        record = {}
+        for metric, content in metrics2run.items():
+            better = content.get("better", "higher")
+            record[metric] = dict(better=better, val=float("-inf") if better == "higher" else float("inf"), iter=-1)
+        self.best_metric_results[dataset_name] = record
+
+    def _update_best_metric_result(self, dataset_name, metric, val, current_iter):
+        rec = self.best_metric_results[dataset_name][metric]
+        if (rec["better"] == "higher" and val >= rec["val"]) or (rec["better"] != "higher" and val <= rec["val"]):
+            rec["val"], rec["iter"] = val, current_iter
+
+    def _log_validation_metric_values(self, current_iter, dataset_name, tb_logger):
+        import logging
+        msg = f"Validation {dataset_name}\n"
+        for metric, value in self.metric_results.items():
+            msg += f"\t # {metric}: {value:.4f}"
+            if hasattr(self, "best_metric_results"):
+                best = self.best_metric_results[dataset_name][metric]
+                msg += f"\tBest: {best['val']:.4f} @ {best['iter']} iter"
+            msg += "\n"
+        logging.getLogger("basicsr").info(msg)
+        if tb_logger:
+            for metric, value in self.metric_results.items():
+                tb_logger.add_scalar(f"metrics/{dataset_name}/{metric}", value, current_iter)
+
+    def nondist_validation(self, dataloader, current_iter, tb_logger, save_img):
+        """The loop of ssr_esrgan_model.py:269-352 with the per-image host work batched on the GPU: EMA-generator forward
+        (test()), tensor2img, and PSNR / SSIM / cPSNR for the whole validation batch at once (metrics.py).  Any batch size works
+        (the reference's loop assumes 1); results are averaged over images.  Image dumps (`save_img`) are PNG IO outside the hot
+        path and are not written."""
+        from . import metrics as M
+        ds = getattr(dataloader, "dataset", None)
+        dataset_name = ds.opt["name"] if ds is not None and hasattr(ds, "opt") else "val"
+        sect = self.opt.get("test" if dataset_name == "test" else "val") or {}
+        metrics2run = sect.get("metrics")
+        with_metrics = metrics2run is not None
+        if with_metrics:
+            for name, mopt in metrics2run.items():
+                if mopt["type"] not in M.METRIC_REGISTRY:
+                    raise NotImplementedError(f"metric '{mopt['type']}' ({name}) is outside the built path (calculate_psnr / "
+                                              "calculate_ssim / calculate_cpsnr run batched on the GPU; LPIPS / CLIPScore need "
+                                              "pretrained networks that are not part of this engine)")
+            self.metric_results = {metric: 0.0 for metric in metrics2run}
+            self._initialize_best_metric_results(dataset_name, metrics2run)
+        n_img = 0
         for val_data in dataloader:
             self.feed_data(val_data)
             self.test()
-            n += 1
-        return n
+            if with_metrics and "hr" in val_data:
+                data = dict(img=M.to_uint8_images(self.output.float()), img2=M.to_uint8_images(self.gt.float()))
+                for name, mopt in metrics2run.items():
+                    self.metric_results[name] += float(sum(M.calculate_metric(data, mopt)))
+            n_img += int(val_data["lr"].shape[0])
+        if with_metrics:
+            for metric in self.metric_results:
+                self.metric_results[metric] /= max(1, n_img)
+                self._update_best_metric_result(dataset_name, metric, self.metric_results[metric], current_iter)
+            self._log_validation_metric_values(current_iter, dataset_name, tb_logger)
+        return n_img
 
     def _save_dir(self, sub):
         root = self.opt.get("path", {}).get(sub) or os.path.join(self.opt.get("path", {}).get("experiments_root", "experiments"), sub)

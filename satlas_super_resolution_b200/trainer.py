@@ -215,11 +215,14 @@ class ESRGANTrainer:
 
     # ------------------------------------------------------------------ the step
     def _step_phase(self, phase, io, do_g, s, graph_mode=False):
-        """The step in three collective-free phases (so each can be a CUDA graph even when NCCL runs between them):
+        """The step in four collective-free phases (each can be a CUDA graph even when NCCL runs between them):
         1 = G forward, generator losses, frozen-D pass, G backward          (ssr_esrgan_model.py:136-192)
-        2 = Adam(G)+EMA, D real pass, D fake pass                            (:193-227)
-        3 = Adam(D)                                                          (:228)
-        The G / D gradient all-reduces sit between 1|2 and 2|3."""
+        2 = D real pass, D fake pass                                         (:196-227)
+        3 = Adam(G) + EMA                                                    (:193, :230-231)
+        4 = Adam(D)                                                          (:228)
+        The reference runs optimizer_g.step() (:193) before the discriminator passes; they read neither the generator's parameters
+        nor its gradients (only self.output), so 3 commutes with 2 -- which lets the all-reduce of the G gradients run UNDER the
+        discriminator passes and the one of the D gradients under Adam(G)."""
         lb = lib()
         lr, gt, gt_usm = io["lr"], io["gt"], io["gt_usm"]
         B, C_lr, h, w = lr.shape
@@ -236,7 +239,6 @@ class ESRGANTrainer:
         n_logit = B * H * W
         cl = C_lr if self.feed_disc_lr else 0
         f = H // h
-
         ce = self.old_hr_ch
 
         def disc_in(img):
@@ -262,11 +264,6 @@ class ESRGANTrainer:
                 self.G.backward(d_out, B, h, w, s)
         elif phase == 2:
             out = self.output
-            if do_g:
-                self.opt_g.step(1.0 / self.world, s, from_device=graph_mode)
-            elif self.gema is not None:
-                # model_ema runs every iteration in the reference (:230-231), also when the generator step is skipped
-                L.check(lb.ssr_ema_update(self.gema.flat.data_ptr(), self.gbuf.flat.data_ptr(), self.gbuf.numel, self.ema_decay, s))
             self.dgrad.flat.zero_()
             disc_in(gan_gt)
             logits = self.D.forward(dws, training=True, stream=s)
@@ -276,17 +273,35 @@ class ESRGANTrainer:
             logits = self.D.forward(dws, training=True, stream=s)
             L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 0.0, 1.0, lp(5), lp(6), d_logits.data_ptr(), s))
             self.D.backward(dws, d_logits, need_wgrad=True, stream=s)
+        elif phase == 3:
+            if do_g:
+                self.opt_g.step(1.0 / self.world, s, from_device=graph_mode)
+            elif self.gema is not None:
+                # model_ema runs every iteration in the reference (:230-231), also when the generator step is skipped
+                L.check(lb.ssr_ema_update(self.gema.flat.data_ptr(), self.gbuf.flat.data_ptr(), self.gbuf.numel, self.ema_decay, s))
         else:
             self.opt_d.step(1.0 / self.world, s, from_device=graph_mode)
 
+    def _exchange_async(self, flat):
+        """sum all-reduce of one flat gradient buffer on NCCL's own stream (ordered behind everything issued so far); the returned
+        handle's wait() orders the current stream behind it -- the host never blocks"""
+        return torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM, group=self.pg, async_op=True)
+
+    def _run_step(self, run_phase, do_g):
+        """phases with the gradient exchanges hidden: G's all-reduce under the discriminator passes, D's under Adam(G)"""
+        run_phase(1)
+        w_g = self._exchange_async(self.ggrad.flat) if (self.world > 1 and do_g) else None
+        run_phase(2)
+        w_d = self._exchange_async(self.dgrad.flat) if self.world > 1 else None
+        if w_g is not None:
+            w_g.wait()
+        run_phase(3)
+        if w_d is not None:
+            w_d.wait()
+        run_phase(4)
+
     def _step_kernels(self, io, do_g, s, graph_mode=False):
-        self._step_phase(1, io, do_g, s, graph_mode)
-        if self.world > 1 and do_g:
-            allreduce_sum_(self.ggrad.flat, self.pg)
-        self._step_phase(2, io, do_g, s, graph_mode)
-        if self.world > 1:
-            allreduce_sum_(self.dgrad.flat, self.pg)
-        self._step_phase(3, io, do_g, s, graph_mode)
+        self._run_step(lambda ph: self._step_phase(ph, io, do_g, s, graph_mode), do_g)
 
     def optimize_parameters(self, current_iter=1):
         do_g = (current_iter % self.net_d_iters == 0) and (current_iter > self.net_d_init_iters)
@@ -300,7 +315,7 @@ class ESRGANTrainer:
             return
         graphs = self._graphs.get(key)
         if graphs is None:
-            # capture once: the whole step as ONE graph on a single GPU, three graphs around the two NCCL calls otherwise
+            # capture once: the whole step as ONE graph on a single GPU, one graph per phase around the NCCL calls otherwise
             torch.cuda.synchronize()
             graphs = []
             if self.world == 1:
@@ -310,7 +325,7 @@ class ESRGANTrainer:
                 graphs.append(g)
             else:
                 pool = None
-                for phase in (1, 2, 3):
+                for phase in (1, 2, 3, 4):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, pool=pool):
                         self._step_phase(phase, self.io, do_g, cur_stream(), graph_mode=True)
@@ -329,12 +344,7 @@ class ESRGANTrainer:
         if self.world == 1:
             graphs[0].replay()
         else:
-            graphs[0].replay()
-            if do_g:
-                allreduce_sum_(self.ggrad.flat, self.pg)
-            graphs[1].replay()
-            allreduce_sum_(self.dgrad.flat, self.pg)
-            graphs[2].replay()
+            self._run_step(lambda ph: graphs[ph - 1].replay(), do_g)
 
     def get_current_log(self):
         """loss scalars (one D2H read, only when asked -- the reference syncs every iteration at :233)"""

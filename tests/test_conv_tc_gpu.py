@@ -5,6 +5,7 @@ differences left are fp32 accumulation order and the final bf16 rounding of the 
 tolerance = 2^-8 relative to the output scale for bf16 outputs, 1e-4 for f32 outputs.
 """
 import ctypes as C
+import os
 
 import pytest
 import torch
@@ -270,11 +271,15 @@ def test_bad_args_fail_loudly():
     assert b"r must be" in lib.ssr_last_error()
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (32, 32, 32), (3, 24, 40)])
-def test_chain_equals_plain_launches(B, H, W):
-    """ssr_conv_tc_chain (five dense-block convs in ONE launch, grid-wide arrive/wait between layers) must be
-    bit-identical to the same five ssr_conv_tc calls; run three times (barrier phases / counters must re-arm)."""
+@pytest.mark.parametrize("B,H,W,planar", [(2, 32, 32, False), (32, 32, 32, False), (3, 24, 40, False),
+                                            (2, 32, 32, True), (32, 32, 32, True), (3, 32, 64, True), (5, 32, 16, True)])
+def test_chain_equals_plain_launches(B, H, W, planar):
+    """ssr_conv_tc_chain (five dense-block convs in ONE launch) must be bit-identical to the same five ssr_conv_tc calls; run
+    three times (barrier phases / counters must re-arm).  planar (the layout the generator uses for its f32 trunk): 32-row images
+    take the shared-memory-resident kernel (8-pixel strips, halo columns through DSMEM, one cluster per image: 2 to 8 CTAs);
+    NHWC f32 operands: the cluster-synchronised chain over global memory (32 x 32) or plain launches."""
     L, lib = _lib()
+    f32_kind, f32_mode = (L.SSR_F32_PLANAR4, L.OUT32_PLANAR4) if planar else (L.SSR_F32, L.OUT32_NHWC)
     nf, g = 64, 32
     cw = nf + 4 * g
     torch.manual_seed(B * 1000 + H)
@@ -301,9 +306,9 @@ def test_chain_equals_plain_launches(B, H, W):
                 a.out_bf16, a.out_pix_stride = buf.data_ptr() + 2 * cin, cw
             else:
                 a.act, a.s0 = 0, 0.2
-                a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = trunk.data_ptr(), L.SSR_F32, nf, 1.0
+                a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = trunk.data_ptr(), f32_kind, nf, 1.0
                 a.out_bf16, a.out_pix_stride = nxt.data_ptr(), nf
-                a.out_f32, a.out32_mode, a.out32_pix_stride = t32.data_ptr(), L.OUT32_NHWC, nf
+                a.out_f32, a.out32_mode, a.out32_pix_stride = t32.data_ptr(), f32_mode, nf
         return arr
 
     def fresh():
@@ -321,11 +326,13 @@ def test_chain_equals_plain_launches(B, H, W):
     for _ in range(3):
         buf_b, nxt_b, t_b = fresh()
         arr_b = make(buf_b, nxt_b, t_b)
-        n0 = lib.ssr_launch_count()
+        n0, r0 = lib.ssr_launch_count(), lib.ssr_debug_resident_launches()
         L.check(lib.ssr_conv_tc_chain(arr_b, 5, s))
         torch.cuda.synchronize()
         # 32 x 32 images are 4 (or 8) tiles: one cluster per image, a single launch; 24 x 40 is 12 tiles: plain launches
-        assert lib.ssr_launch_count() - n0 == (1 if (H, W) == (32, 32) else 5)
+        resident = planar and os.environ.get("SSR_CONV_RESIDENT", "1") != "0"
+        assert lib.ssr_launch_count() - n0 == (1 if (H, W) == (32, 32) or resident else 5)
+        assert lib.ssr_debug_resident_launches() - r0 == (1 if resident else 0)
         assert torch.equal(buf_a, buf_b)
         assert torch.equal(nxt_a, nxt_b)
         assert torch.equal(t_a, t_b)
@@ -404,17 +411,19 @@ def test_chain_wide_layers_in_place_gradient(B):
         assert torch.allclose(ref[3], got[3], rtol=1e-4, atol=1e-4 * ref[3].abs().max().item())   # atomics: order differs
 
 
-@pytest.mark.parametrize("B", [2, 32])
-def test_chain_acc_running_sum_in_tensor_memory(B):
+@pytest.mark.parametrize("B,W", [(2, 32), (32, 32), (3, 64), (5, 16)])
+def test_chain_acc_running_sum_in_tensor_memory(B, W):
     """ssr_conv_tc_chain_acc: the five input-gradient layers add into ONE accumulator that never leaves tensor memory; each layer
     emits only its top 32-channel slot, the last one the 64 block-input channels plus the incoming gradient.  Reference = the
     same layers as plain launches accumulating through an f32 buffer in global memory (f32 summation order differs: tolerance)."""
     L, lib = _lib()
-    H = W = 32
+    H = 32
     nf, g = 64, 32
     cw = nf + 4 * g
     P = B * H * W
-    assert lib.ssr_conv_tc_chain_acc_supported(B, H, W, cw) == 1
+    if not lib.ssr_conv_tc_chain_acc_supported(B, H, W, cw):
+        assert W == 64 and os.environ.get("SSR_CONV_RESIDENT") == "0"   # 16 tiles per image: only the resident kernel takes it
+        pytest.skip("32 x 64 images need the shared-memory-resident kernel")
     assert lib.ssr_conv_tc_chain_acc_supported(B, 128, 128, cw) == 0
     torch.manual_seed(11 + B)
     xin = (torch.randn(B, H, W, nf) * 0.5).cuda().to(torch.bfloat16)
@@ -470,10 +479,12 @@ def test_chain_acc_running_sum_in_tensor_memory(B):
     for _ in range(2):
         got = fresh()
         arr_b = make(*got, acc=True)
-        n0 = lib.ssr_launch_count()
+        n0, r0 = lib.ssr_launch_count(), lib.ssr_debug_resident_launches()
         L.check(lib.ssr_conv_tc_chain_acc(arr_b, 5, s))
         torch.cuda.synchronize()
         assert lib.ssr_launch_count() - n0 == 1
+        # 32-row images: the dY slots also stay in shared memory (resident tile), not only the running sum in tensor memory
+        assert lib.ssr_debug_resident_launches() - r0 == (1 if os.environ.get("SSR_CONV_RESIDENT", "1") != "0" else 0)
         scale = ref[0][..., nf:].float().abs().max().item()
         assert (ref[0][..., nf:].float() - got[0][..., nf:].float()).abs().max().item() <= 2 ** -7 * scale      # the four dY slots
         assert rel_err(got[2].float().cpu(), ref[2].float().cpu()) < 2 ** -7                                      # block-input gradient, bf16
@@ -515,15 +526,12 @@ def test_planar4_f32_operands_match_nhwc(cout):
     assert torch.equal(nhwc[:, :cout], planar[:, :cout])
 
 
-def test_resident_dense_block_chain_in_subprocess():
-    """SSR_CONV_RESIDENT=1: the forward dense-block chain keeps the 192-channel tile (8-pixel strips, halo columns exchanged
-    through distributed shared memory) resident and streams only weights.  Same accumulation order as the plain launches, so
-    the chain tests must still hold bit for bit.  Environment switches are read once per process: run them in a child."""
-    import os
+def test_chains_without_the_resident_kernel_in_subprocess():
+    """SSR_CONV_RESIDENT=0: the cluster-synchronised chains over global memory (what shapes that do not fit the resident kernel
+    use) must still equal plain launches.  Environment switches are read once per process: run the chain tests in a child."""
     import subprocess
     import sys
-    env = dict(os.environ, SSR_CONV_RESIDENT="1")
-    # chain_acc: the input-gradient form -- running sum in tensor memory AND the dY slots resident in the tile
+    env = dict(os.environ, SSR_CONV_RESIDENT="0")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", "chain_equals_plain or chain_acc"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -60,3 +60,54 @@ def test_two_rank_step_equals_single_process(tmp_path):
            "--master-port", "29611", str(script)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "ddp-ok" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+WORKER_INIT = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from oracle import losses, nets
+from satlas_super_resolution_b200.trainer import ESRGANTrainer
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+# every rank draws its OWN initial weights and spectral-norm vectors (the reference seeds with manual_seed + rank, options.py:81)
+gp, dp, vp = nets.rrdbnet_init(24, 3, num_block=1, seed=10 + rank), nets.unet_disc_init(27, seed=20 + rank), losses.vgg19_init(seed=3)
+cfg = dict(ema_decay=0.999, lr=1e-4, network_g=dict(num_in_ch=24, num_block=1), cuda_graph=True)
+tr = ESRGANTrainer(gp, dp, vp, cfg, device=f"cuda:{local}", process_group=dist.group.WORLD)
+if rank == 1:
+    # rank 1 now holds rank 0's state, not what it drew
+    ref0 = nets.rrdbnet_init(24, 3, num_block=1, seed=10)
+    assert torch.equal(tr.g_state_dict()["conv_body.weight"].cpu(), ref0["conv_body.weight"])
+    assert torch.equal(tr.d_state_dict()["conv3.weight_u"].cpu(), nets.unet_disc_init(27, seed=20)["conv3.weight_u"])
+for it in range(1, 5):                      # eager, capture, replay, replay -- each rank on its own data
+    g = torch.Generator().manual_seed(100 * rank + it)
+    lr = torch.randint(1, 256, (2, 24, 32, 32), generator=g, dtype=torch.uint8)
+    hr = torch.randint(1, 256, (2, 3, 128, 128), generator=g, dtype=torch.uint8)
+    tr.feed_data(lr, hr)
+    tr.optimize_parameters(it)
+torch.cuda.synchronize()
+flat = torch.cat([tr.gbuf.flat, tr.dbuf.flat, tr.gema.flat])
+uv = torch.cat([tr.d_uv[k] for k in sorted(tr.d_uv)])
+both = [torch.empty_like(flat) for _ in range(world)]
+dist.all_gather(both, flat)
+both_uv = [torch.empty_like(uv) for _ in range(world)]
+dist.all_gather(both_uv, uv)
+if rank == 0:
+    assert torch.equal(both[0], both[1]), "replicas diverged: parameters / EMA differ between ranks after 4 steps"
+    d = ((both_uv[0] - both_uv[1]).norm() / both_uv[0].norm()).item()
+    assert d < 1e-5, ("spectral-norm u / v differ between ranks", d)
+    print("ddp-init-ok uv rel diff", d)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_rank_dependent_init_is_replaced_by_rank0_and_replicas_stay_identical(tmp_path):
+    """ADVICE round 1 (high): without the start-up broadcast every rank would keep its own weights forever"""
+    script = tmp_path / "ddp_init_worker.py"
+    script.write_text(WORKER_INIT % ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "ddp-init-ok" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]

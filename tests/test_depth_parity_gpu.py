@@ -138,10 +138,13 @@ def test_full_step_23_blocks():
     with open(os.path.join(OUT, "full_step_nb23_b4.json"), "w") as fh:
         json.dump(report, fh, indent=1)
 
-    assert worst < 3e-2, f"pattern-forced generator gradients: worst rel_l2 {worst}"
-    assert report["grad_plain"]["G_cos"]["median"] > 0.95 and report["grad_plain"]["D_cos"]["min"] > 0.9
-    assert min(upd.values()) > 0.8
-    assert ema_e < 1e-4 and uv_e < 5e-3
+    # measured on the B200 (profiles/r02_parity_full_step_nb23_b4.json): pattern-forced max 7.5e-3; plain oracle G max 9.4e-3
+    # (cosine >= 0.99996 on all 702 tensors), D max 2.6e-2; update cosines >= 0.986; EMA 3e-6; u / v 5e-7
+    assert worst < 2e-2, f"pattern-forced generator gradients: worst rel_l2 {worst}"
+    assert report["grad_plain"]["G_rel_l2"]["max"] < 3e-2 and report["grad_plain"]["G_cos"]["min"] > 0.999
+    assert report["grad_plain"]["D_rel_l2"]["max"] < 6e-2 and report["grad_plain"]["D_cos"]["min"] > 0.999
+    assert min(upd.values()) > 0.95
+    assert ema_e < 1e-4 and uv_e < 1e-4
 
 
 def test_trajectory_20_steps():
@@ -196,7 +199,16 @@ def test_trajectory_20_steps():
     with open(os.path.join(OUT, f"trajectory_nb{nb}_b{B}.json"), "w") as fh:
         json.dump(dict(config=dict(num_block=nb, batch=B, steps=steps), curves=curves, worst_rel_dev=worst, ulp_band=band,
                        weight_change_cosine=cos), fh, indent=1)
+    # Measured (profiles/r02_parity_trajectory_nb23_b2.json): the reconstruction losses stay within 1.2 % for all 20 steps and every loss
+    # within 0.3 % for the first 10; after that the discriminator game amplifies ANY perturbation -- the two fp32 oracle runs that
+    # start one ulp apart are 1.5 % apart in l_d_* and 100 % in out_d_* by step 20 (x1.8 per step) -- so the late GAN terms are
+    # only bounded coarsely, next to that band.
+    early = [c for c in curves if c["step"] <= 10]
     for k in keys:
-        tol = 0.25 if k.startswith("out_d") else 0.05    # out_d_* are means of logits around zero: relative to |a| + 1e-3
-        assert worst[k] < tol, (k, worst[k])
-    assert min(cos.values()) > 0.7
+        if k.startswith("out_d"):
+            assert max(abs(c["engine"][k] - c["oracle"][k]) for c in early) < 0.01, k
+            assert max(abs(c["engine"][k] - c["oracle"][k]) for c in curves) < 0.3, k
+        else:
+            assert max(abs(c["engine"][k] - c["oracle"][k]) / abs(c["oracle"][k]) for c in early) < 0.02, k
+            assert worst[k] < (0.03 if k in ("l_g_pix", "l_g_percep") else 0.25), (k, worst[k])
+    assert min(cos.values()) > 0.99

@@ -72,7 +72,16 @@ def test_bench_helpers():
     a, _ = bench.synthetic_batch(2, 0)
     b, _ = bench.synthetic_batch(2, 1)
     assert a.dtype == torch.uint8 and a.min() >= 1 and not torch.equal(a, b)
-    assert abs(bench.FLOP_STEP / 1e9 - 254.70) < 0.01 and abs((bench.FLOP_CONV_TC + bench.FLOP_WGRAD) - bench.FLOP_STEP) < 1
+    f3, f12 = bench.flops(3), bench.flops(12)
+    assert abs(f3["step"] / 1e9 - 254.70) < 0.01 and abs(f12["step"] / 1e9 - 263.02) < 0.01
+    assert abs(f3["conv"] + f3["wgrad"] - f3["step"]) < 1
+    # 69 dense blocks carry 92 % of the generator forward (16.93 of 18.37 GMAC)
+    assert abs(bench.N_RDB * bench.F_RDB / 1e9 - 2 * 16.93) < 0.01
+    assert abs(256 * f3["infer_per_chunk"] / 1e12 - 9.405) < 0.001                                # per 2048^2 tile
+    c12, lr12 = bench.train_config(12), bench.synthetic_batch(2, 0, bands=12)[0]
+    assert c12["num_in_ch_g"] == 96 and c12["num_in_ch_d"] == 99 and lr12.shape == (2, 96, 32, 32)
+    opt = bench.model_opt(12, True, False)
+    assert opt["network_g"]["num_in_ch"] == 96 and opt["network_d"]["num_in_ch"] == 99 and opt["model_type"] == "SSRESRGANModel"
 
 
 def test_infer_format_matches_reference_semantics():
@@ -108,9 +117,19 @@ GLOO_WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, %r)
 from collections import OrderedDict
-from satlas_super_resolution_b200.ops import FlatBuffer, allreduce_sum_, rank_slice
+from satlas_super_resolution_b200.ops import FlatBuffer, allreduce_sum_, broadcast_from_rank0_, rank_slice
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
+# replicas initialised from rank-dependent seeds (ssr/utils/options.py:81: manual_seed + rank) end up with rank 0's state: what
+# DistributedDataParallel does to parameters and buffers at construction (ESRGANTrainer.sync_replicas)
+torch.manual_seed(100 + rank)
+params, u = FlatBuffer(OrderedDict(w=(4, 3), b=(5,)), "cpu"), torch.randn(7)
+params.flat.normal_()
+broadcast_from_rank0_([params.flat, u], dist.group.WORLD)
+torch.manual_seed(100)
+want_u = torch.randn(7)
+want = torch.empty_like(params.flat).normal_()
+assert torch.equal(params.flat, want) and torch.equal(u, want_u), "replica state differs from rank 0 after the broadcast"
 shapes = OrderedDict(w=(4, 3), b=(5,))
 g = FlatBuffer(shapes, "cpu")
 # per-rank "gradient" = mean over this rank's shard of per-sample gradients
@@ -141,3 +160,27 @@ def test_gradient_exchange_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"gloo-ok {r}" in o, o
+
+
+def test_missing_vgg19_checkpoint_is_an_error_unless_random_weights_are_requested(tmp_path, monkeypatch):
+    """basicsr loads the ImageNet VGG19 (downloading when absent); silently training against random features would be a
+    meaningless perceptual term: missing file -> FileNotFoundError, explicit vgg_seed -> seeded weights + warning"""
+    from satlas_super_resolution_b200 import weights
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("TORCH_HOME", str(tmp_path / "no_hub"))
+    monkeypatch.delenv("SSR_VGG19_PATH", raising=False)
+    monkeypatch.delenv("SSR_VGG_RANDOM_SEED", raising=False)
+    with pytest.raises(FileNotFoundError):
+        weights.resolve_vgg19_state()
+    with pytest.warns(RuntimeWarning):
+        sd = weights.resolve_vgg19_state(vgg_seed=3)
+    assert torch.equal(sd["conv3_2.weight"], weights.vgg19_state(seed=3)["conv3_2.weight"])
+    # a checkpoint in torchvision's layout at $SSR_VGG19_PATH is picked up
+    raw = {}
+    for (name, cin, cout), idx in zip(weights.VGG19_CONVS, weights.VGG19_TORCHVISION_INDEX):
+        raw[f"features.{idx}.weight"] = torch.full((cout, cin, 3, 3), float(idx))
+        raw[f"features.{idx}.bias"] = torch.zeros(cout)
+    torch.save(raw, tmp_path / "vgg.pth")
+    monkeypatch.setenv("SSR_VGG19_PATH", str(tmp_path / "vgg.pth"))
+    sd = weights.resolve_vgg19_state()
+    assert sd["conv5_4.weight"][0, 0, 0, 0].item() == 34.0

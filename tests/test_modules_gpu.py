@@ -240,6 +240,38 @@ def test_model_lr_schedule_save_resume_and_test(tmp_path):
     assert m2.trainer.opt_g.step_count == 5
 
 
+def test_test_only_model_builds_generator_only(tmp_path):
+    """basicsr SRModel with is_train False (ssr/test.py): net_g only -- no network_d / losses / optimizers needed in the option file"""
+    from oracle import nets
+    from satlas_super_resolution_b200.registry import build_model
+    p = nets.rrdbnet_init(24, 3, num_feat=32, num_block=1, num_grow_ch=16, seed=9)
+    torch.save({"params_ema": p}, tmp_path / "g.pth")
+    opt = {"name": "t", "model_type": "SSRESRGANModel", "scale": 4, "num_gpu": 1, "is_train": False, "dist": False,
+           "network_g": dict(type="SSR_RRDBNet", num_in_ch=24, num_out_ch=3, num_feat=32, num_block=1, num_grow_ch=16),
+           "path": {"pretrain_network_g": str(tmp_path / "g.pth"), "param_key_g": "params_ema", "strict_load_g": True}}
+    model = build_model(opt)
+    assert model.trainer is None and not hasattr(model, "net_d") and model.optimizers == []
+    data = _batch(seed=4)
+    model.feed_data(data)
+    model.test()
+    with torch.no_grad():
+        ref = nets.rrdbnet_forward(p, data["lr"].float() / 255, num_block=1)
+    assert rel_l2(model.output, ref) < 1e-2
+    assert set(model.get_current_visuals()) == {"lr", "result", "gt"}
+
+
+def test_discriminator_backward_of_a_stale_forward_raises():
+    """two forwards then one backward over both graphs would use the second forward's spectral-norm state for the first: refuse"""
+    from satlas_super_resolution_b200.archs import SSR_UNetDiscriminatorSN
+    torch.manual_seed(0)
+    d = SSR_UNetDiscriminatorSN(3).cuda().train()
+    x = torch.rand(1, 3, 64, 64, device="cuda")
+    a = d(x).mean()
+    b = d(x * 0.5).mean()
+    with pytest.raises(RuntimeError, match="no longer the latest"):
+        (a + b).backward()
+
+
 def test_cuda_graph_replay_equals_eager():
     from oracle import losses, nets
     from satlas_super_resolution_b200.trainer import ESRGANTrainer

@@ -5,6 +5,8 @@
 """
 import os
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -168,3 +170,34 @@ def test_usm_sharp_pieces():
     assert out.shape == img.shape and float(out.min()) >= -1e-6 and float(out.max()) <= 1 + 1e-6
     flat = torch.full((1, 3, 96, 96), 0.5)
     assert torch.allclose(losses.usm_sharp(flat), flat, atol=1e-6)      # nothing to sharpen in a flat image
+
+
+def test_metrics_oracle_against_reference_golden_and_cv2():
+    """oracle/metrics.py: cPSNR equals the values the UNMODIFIED ssr/metrics/cpsnr.py produced (tests/golden/metrics_cpsnr.json,
+    oracle/make_golden_metrics.py); SSIM equals basicsr's cv2.filter2D formulation; tensor2img rounds half to even like np.round."""
+    import json
+    import cv2
+    import numpy as np
+    from oracle import metrics as om
+    from oracle.make_golden_metrics import image_pair
+    with open(os.path.join(ROOT, "tests", "golden", "metrics_cpsnr.json")) as fh:
+        gold = json.load(fh)
+    for case in gold["cases"]:
+        a, b = image_pair(case["seed"], c=case["channels"])
+        if case.get("identical"):
+            b = a.copy()
+        got = om.calculate_cpsnr(a, b, case["crop_border"])
+        assert got == case["cpsnr"] or abs(got - case["cpsnr"]) < 1e-12, case
+    # basicsr _ssim with cv2 (the library call the restatement replaces)
+    a, b = image_pair(3)
+    a64, b64 = a[..., 0].astype(np.float64), b[..., 0].astype(np.float64)
+    k = cv2.getGaussianKernel(11, 1.5)
+    win = np.outer(k, k.transpose())
+    f = lambda z: cv2.filter2D(z, -1, win)[5:-5, 5:-5]
+    mu1, mu2 = f(a64), f(b64)
+    c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    ref = (((2 * mu1 * mu2 + c1) * (2 * (f(a64 * b64) - mu1 * mu2) + c2)) /
+           ((mu1 ** 2 + mu2 ** 2 + c1) * ((f(a64 ** 2) - mu1 ** 2) + (f(b64 ** 2) - mu2 ** 2) + c2))).mean()
+    assert abs(om._ssim(a64, b64) - ref) < 1e-10
+    t = torch.tensor([[[0.5 / 255, 1.5 / 255, 2.5 / 255, -1.0, 2.0]]])          # 0.5 -> 0, 1.5 -> 2, 2.5 -> 2, clamp
+    assert om.tensor2img(t).flatten().tolist() == [0, 2, 2, 0, 255]
