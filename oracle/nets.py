@@ -189,3 +189,39 @@ def unet_disc_init(num_in_ch, num_feat=64, seed=0):
 
 G_PARAM_COUNT_RGB8 = 16_710_083   # SURVEY.md [probe]: num_in_ch=24
 D_PARAM_COUNT_RGB8 = 4_390_721    # num_in_ch=27
+
+
+# --------------------------------------------------------------------------- rounding model of the engine's forward
+def rrdbnet_forward_bf16_model(p, x, scale=4, num_block=23):
+    """The generator forward with bf16 rounding applied at exactly the points the B200 engine rounds:
+    conv OPERANDS (stored activations and weights) are bf16, every accumulation, bias, residual add and the 64-channel trunk are
+    f32.  Evaluated in fp32 on the CPU, so what is left between this model and the engine is f32 summation order plus the
+    occasional bf16 neighbour flip it causes -- a kernel bug is NOT absorbed by this model, bf16 operand noise is.
+    (Test infrastructure: separates "kernel wrong" from "bf16 noise" without a second operand precision in the kernels.)"""
+    bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    w = {k: (bf(v) if k.endswith(".weight") else v) for k, v in p.items()}
+    conv = lambda name, t: F.conv2d(t, w[f"{name}.weight"], w[f"{name}.bias"], padding=1)     # t is already bf16-valued
+    if scale == 2:
+        x = pixel_unshuffle(x, 2)
+    elif scale == 1:
+        x = pixel_unshuffle(x, 4)
+    trunk = conv("conv_first", bf(x))          # f32 trunk; its bf16 copy is the operand of the first dense block
+    trunk0 = trunk
+    for i in range(num_block):
+        rrdb_in = trunk
+        for j in (1, 2, 3):
+            pre = f"body.{i}.rdb{j}"
+            feats = [bf(trunk)]
+            for k in range(1, 5):
+                feats.append(bf(F.leaky_relu(conv(f"{pre}.conv{k}", torch.cat(feats, 1)), 0.2)))
+            x5 = conv(f"{pre}.conv5", torch.cat(feats, 1))
+            if j < 3:
+                trunk = x5 * 0.2 + trunk                          # epilogue: s0 * (acc + bias) + s1 * trunk, all f32
+            else:
+                trunk = x5 * 0.04 + trunk * 0.2 + rrdb_in         # (x5 * 0.2 + x_rdb3) * 0.2 + x_rrdb folded into one epilogue
+    feat = bf(conv("conv_body", bf(trunk)) + trunk0)
+    n_up = {1: 2, 2: 2, 4: 2, 8: 3, 16: 4}[scale]
+    for u in range(1, n_up + 1):
+        feat = bf(F.leaky_relu(conv(f"conv_up{u}", F.interpolate(feat, scale_factor=2, mode="nearest")), 0.2))
+    feat = bf(F.leaky_relu(conv("conv_hr", feat), 0.2))
+    return conv("conv_last", feat)

@@ -33,6 +33,8 @@ struct ConvTcK {
   int resident, res_out_ch, res_in_chunks;
   int res_in_lo;          // channel offset of this layer's INPUT inside the tile (0 forward; the dY slot of an input-gradient layer)
   uint32_t chunk_alloc;   // bytes of one 64-channel chunk of the resident tile ((TW+2) x (MT*TH+2) rows of 128 B, 1 KB aligned)
+  int b_row_bytes;        // resident kernel: bytes of one weight row in shared memory -- 128 (64 K entries, SWIZZLE_128B) or 64 (a
+                          // 32-channel input: only the first half of every packed row is loaded, SWIZZLE_64B)
   int acc_w;              // > 0: chain with ONE f32 accumulator of acc_w channels per pixel that stays in TMEM for all layers
   int n_loop;             // N tiles one CTA walks itself (1 when gridDim.y spreads them; n_pad / n_tile inside a chain)
   int splits;
@@ -67,6 +69,7 @@ struct ConvChainK {
   int sync_mode;       // kSyncGrid: global arrive counter; kSyncCluster: one image per thread-block cluster, mbarriers in DSMEM
   unsigned int* sync;  // kSyncGrid only. [2]: arrive counter, done counter (self-resetting)
   long long* timeline; // diagnostics (SSR_CHAIN_TIMELINE=1): clock64 stamps [cta][layer][8], else NULL
+  int multicast;       // resident kernel: every CTA of the cluster loads 1 / n of the weight taps and multicasts them to all
 };
 
 static constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
@@ -728,7 +731,8 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
       prefetch_tmap(&cc.tmB[0]);
       for (int s = 0; s < stages; ++s) {
         mbar_init(&bar_full[s], 1);
-        mbar_init(&bar_empty[s], 1);
+        // multicast weights: a ring slot may be refilled (in ALL CTAs) once the MMA warp of EVERY CTA has released it
+        mbar_init(&bar_empty[s], cc.multicast ? cluster_nctarank() : 1u);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bar_acc_full[b], 1);
@@ -755,42 +759,64 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   cluster_sync_all();   // no remote store / arrive may reach shared memory that is not initialised yet
-  griddep_wait();       // everything above touched only this CTA's smem / TMEM
+  // everything above touched only this CTA's smem / TMEM.  griddepcontrol.wait (the previous kernel has completed and its memory
+  // is visible) is executed per role: the epilogue warps before their first global access, the producer only in front of the
+  // activation tile -- the first ring-full of WEIGHTS (written by the pack kernel long before the previous launch) streams in
+  // while the previous kernel is still draining.
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (elect_one()) {
-      mbar_expect_tx(bar_x, (uint32_t)p.res_in_chunks * p.a_box_bytes);
-      for (int c = 0; c < p.res_in_chunks; ++c)
-        tma_load_4d(dense + (size_t)c * kRChunk, &cc.tmA[0], bar_x, c * 64, tx * 8 - 1, -1, img);
-    }
-    __syncwarp();
+    auto load_tile = [&]() {
+      griddep_wait();
+      if (elect_one()) {
+        mbar_expect_tx(bar_x, (uint32_t)p.res_in_chunks * p.a_box_bytes);
+        for (int c = 0; c < p.res_in_chunks; ++c)
+          tma_load_4d(dense + (size_t)c * kRChunk, &cc.tmA[0], bar_x, c * 64, tx * 8 - 1, -1, img);
+      }
+      __syncwarp();
+    };
+    bool tile_loaded = false;
     int g = 0;
+    const bool mc = cc.multicast != 0;
+    const uint32_t mc_rank = cluster_ctarank(), mc_n = cluster_nctarank();
+    const uint16_t mc_mask = (uint16_t)((1u << mc_n) - 1u);
     for (int l = 0; l < n_layers; ++l) {
       const ConvTcK q = ps[l];
       const CUtensorMap* tmB = &cc.tmB[l];
       if (l > 0) prefetch_tmap(tmB);
-      const uint32_t tap_bytes = (uint32_t)q.n_tile * 128u;
+      const uint32_t tap_bytes = (uint32_t)(q.n_tile * q.b_row_bytes);
       const int gps = max(1, (int)(kRStage / (3u * tap_bytes)));   // triples per stage
       const int n_tr = 3 * q.chunks;                               // triples of one N tile, order (chunk, kx)
       for (int nb = 0; nb < q.n_loop; ++nb) {
         for (int tr0 = 0; tr0 < n_tr; tr0 += gps, ++g) {
           const int nt = min(gps, n_tr - tr0) * 3;                 // taps in this stage
           const int s = g % stages;
+          if (!tile_loaded && g == stages) {                       // the ring is full of prefetched weights: now the activations
+            load_tile();
+            tile_loaded = true;
+          }
           mbar_wait(&bar_empty[s], ((g / stages) & 1) ^ 1);
           if (elect_one()) {
             uint8_t* dst = ring + (size_t)s * kRStage;
-            mbar_expect_tx(&bar_full[s], (uint32_t)nt * tap_bytes);
-            for (int j = 0; j < nt; ++j)   // packed rows: ((chunk * 3 + kx) * 3 + ky) * n_pad + n
-              tma_load_2d(dst + (size_t)j * tap_bytes, tmB, &bar_full[s], 0, (tr0 * 3 + j) * q.n_pad + nb * q.n_tile);
+            mbar_expect_tx(&bar_full[s], (uint32_t)nt * tap_bytes);   // all taps land here, whoever loads them
+            if (mc) {
+              for (int j = (int)mc_rank; j < nt; j += (int)mc_n)   // this CTA's share, written into every CTA of the cluster
+                tma_load_2d_multicast(dst + (size_t)j * tap_bytes, tmB, &bar_full[s], 0, (tr0 * 3 + j) * q.n_pad + nb * q.n_tile, mc_mask);
+            } else {
+              for (int j = 0; j < nt; ++j)   // packed rows: ((chunk * 3 + kx) * 3 + ky) * n_pad + n
+                tma_load_2d(dst + (size_t)j * tap_bytes, tmB, &bar_full[s], 0, (tr0 * 3 + j) * q.n_pad + nb * q.n_tile);
+            }
           }
           __syncwarp();
         }
       }
     }
+    if (!tile_loaded) load_tile();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     int g = 0;
+    const bool mc = cc.multicast != 0;
+    const uint16_t mc_mask = (uint16_t)((1u << cluster_nctarank()) - 1u);
     const uint32_t acc_cols = p.acc_stride;
     const uint32_t dense_addr = smem_u32(dense);
     const uint32_t ring_addr = smem_u32(ring);
@@ -798,8 +824,9 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
     for (int l = 0; l < n_layers; ++l) {
       const ConvTcK q = ps[l];
       const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)q.n_tile);
-      const uint32_t b_tap = (uint32_t)q.n_tile * 8u;              // one tap's weight tile, descriptor units
-      const int gps = max(1, (int)(kRStage / (3u * (uint32_t)q.n_tile * 128u)));
+      const uint32_t b_tap = (uint32_t)(q.n_tile * q.b_row_bytes) >> 4;   // one tap's weight tile, descriptor units
+      const int gps = max(1, (int)(kRStage / (3u * (uint32_t)(q.n_tile * q.b_row_bytes))));
+      const bool b64 = q.b_row_bytes == 64;
       const int n_tr = 3 * q.chunks;
       const int b = ACC ? 0 : (l & 1);
       const uint32_t m_cols = ACC ? (uint32_t)q.acc_w : (uint32_t)q.n_tile;
@@ -823,7 +850,8 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
           tc_fence_after_sync();
           if (lane == 0 && nb == 0 && tr0 == 0) SSR_STAMP(l, 2);                            // first weights landed
           if (lane == 0 && nb == q.n_loop - 1 && tr0 + gps >= n_tr) SSR_STAMP(l, 3);        // last weights landed
-          const uint64_t db_stage = umma_desc_k128(ring_addr + (uint32_t)s * kRStage);
+          // K-major weight rows: 128 B (SWIZZLE_128B, 8-row groups 1024 B apart) or 64 B (SWIZZLE_64B, groups 512 B apart)
+          const uint64_t db_stage = b64 ? umma_desc(ring_addr + (uint32_t)s * kRStage, 16u, 512u, 4u) : umma_desc_k128(ring_addr + (uint32_t)s * kRStage);
 #pragma unroll 1
           for (int jj = 0; jj < gps; ++jj) {
             const int tr = tr0 + jj;
@@ -842,7 +870,10 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
               const uint32_t first = (tr == 0 && !(ACC && l > 0)) ? 0u : 1u;   // ACC: layer 0 initialises, later layers add
               if (c + 1 < q.chunks || ks_tail == 4) rdb_issue_triple<4>(d_base, m_cols, da, db, b_tap, idesc, first);
               else rdb_issue_triple<2>(d_base, m_cols, da, db, b_tap, idesc, first);
-              if (jj == gps - 1 || tr == n_tr - 1) umma_commit(&bar_empty[s]);
+              if (jj == gps - 1 || tr == n_tr - 1) {
+                if (mc) umma_commit_multicast(&bar_empty[s], mc_mask);
+                else umma_commit(&bar_empty[s]);
+              }
               if (tr == n_tr - 1 && (!ACC || nb == q.n_loop - 1)) umma_commit(&bar_acc_full[b]);
             }
             __syncwarp();
@@ -862,6 +893,7 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
     const long n_pix = (long)p.n_img * p.H * p.W;
     const uint32_t rank = cluster_ctarank();
     const uint32_t n_rank = cluster_nctarank();
+    griddep_wait();   // before the first global access (bias, masks, residuals, stores)
 #pragma unroll 1
     for (int l = 0; l < n_layers; ++l) {
       const ConvTcK p = ps[l];
@@ -914,12 +946,11 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
         }
       };
       // one work item = 32 pixels (this warp's TMEM lanes) x 16 channels of M tile mt; returns the packed bf16 result
-      auto item = [&](int mt, int ci, const uint4* r1, const uint4* r2, const uint4* mk, long pix, uint4& o0, uint4& o1) {
+      auto acc_load = [&](int mt, int ci, uint32_t (&v)[16]) {
+        tmem_ld16(d_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)mt * m_cols + (uint32_t)(ci * 16), v);
+      };
+      auto item = [&](const uint32_t (&v)[16], int ci, const uint4* r1, const uint4* r2, const uint4* mk, long pix, uint4& o0, uint4& o1) {
         const int c0 = ci * 16;
-        uint32_t v[16];
-        __syncwarp();
-        tmem_ld16(d_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)mt * m_cols + (uint32_t)c0, v);
-        tmem_ld_wait();
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
@@ -1015,9 +1046,19 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
         const uint32_t chunk_base = smem_u32(dense + (size_t)(dc >> 6) * kRChunk);
         const uint32_t j0 = (uint32_t)(dc & 63) >> 3;              // 16-byte piece of the 128-byte row
         uint4 keep[2][2];
+        uint32_t va[2][16];
+        __syncwarp();
+        acc_load(0, ci, va[0]);      // both M tiles in flight, one wait
+        acc_load(1, ci, va[1]);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        if (!ACC) {                  // the accumulator buffer is free again as soon as it has been read
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+        }
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-          item(mt, ci, nullptr, nullptr, mk2[mt], pixs[mt], keep[mt][0], keep[mt][1]);
+          item(va[mt], ci, nullptr, nullptr, mk2[mt], pixs[mt], keep[mt][0], keep[mt][1]);
           const uint32_t yl = (uint32_t)(mt * kRTH + tyy);
           const uint32_t row = (yl + 1u) * kRPitch + (uint32_t)txx + 1u;
           st_shared_v4(chunk_base + row * 128u + ((j0 ^ (row & 7u)) << 4), keep[mt][0]);
@@ -1036,13 +1077,11 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
             st_shared_cluster_v4(chunk_base + prow * 128u + (((j0 + 1u) ^ (prow & 7u)) << 4), (uint32_t)peer, keep[mt][1]);
           }
         }
-        tc_fence_before_sync();
+        if (et == 0) SSR_STAMP(l, 1);   // both items computed, tile stores issued
         fence_proxy_async();        // our generic-proxy stores (local and remote) before the tensor core's reads of them
         __syncwarp();
-        if (lane == 0) {
-          if (!ACC) mbar_arrive(&bar_acc_empty[b]);
-          for (uint32_t r = 0; r < n_rank; ++r) mbar_arrive_remote_release(bar_layer, r);
-        }
+        if (et == 0) SSR_STAMP(l, 4);   // fenced
+        if ((uint32_t)lane < n_rank) mbar_arrive_remote_release(bar_layer, (uint32_t)lane);   // lane r -> CTA r of the cluster
         if (et == 0) SSR_STAMP(l, 7);   // arrived
         if (p.out_bf16 != nullptr) {
 #pragma unroll
@@ -1062,7 +1101,11 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
             if (!first) fetch(pixs[mt], ci * 16, o);
             first = false;
             uint4 o0, o1;
-            item(mt, ci, o.r1, o.r2, o.mk, pixs[mt], o0, o1);
+            uint32_t v[16];
+            __syncwarp();
+            acc_load(mt, ci, v);
+            tmem_ld_wait();
+            item(v, ci, o.r1, o.r2, o.mk, pixs[mt], o0, o1);
             if (p.out_bf16 != nullptr && ci * 16 >= p.out_lo) {
               uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pixs[mt] * p.out_stride + ci * 16);
               dst[0] = o0;
@@ -1196,7 +1239,8 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
   p.n_tile = a->n_tile ? a->n_tile : (a->n_pad <= 128 ? a->n_pad : a->n_pad / ((a->n_pad + 127) / 128));
   SSR_REQUIRE(p.n_tile % 16 == 0 && p.n_tile <= 256 && p.n_pad % p.n_tile == 0,
               "ssr_conv_tc: n_tile %d incompatible with n_pad %d", p.n_tile, p.n_pad);
-  SSR_REQUIRE(2 * mt * p.n_tile <= 512, "ssr_conv_tc: two accumulator buffers of mt*n_tile columns exceed TMEM");
+  // (the resident dense-block kernel budgets tensor memory itself: one accumulator of 2 x 192 columns in the input-gradient form)
+  if (!halo_tile) SSR_REQUIRE(2 * mt * p.n_tile <= 512, "ssr_conv_tc: two accumulator buffers of mt*n_tile columns exceed TMEM");
   p.splits = a->splits > 0 ? a->splits : 1;
   if (p.splits > p.chunks) p.splits = p.chunks;
   // make sure no split is empty
@@ -1463,17 +1507,30 @@ static int rdb_resident_launch(const ssr_conv_tc_args* a, int32_t n, cudaStream_
     int mt_i = 0;
     ssr_conv_tc_args ai = a[i];
     if (tmem_acc) {
-      // N tiles of the wide input-gradient layers: the widest divisor of n_pad whose tap triple fits a ring stage
-      // (192 -> 3 x 64, 160 -> 2 x 80, 128 -> 2 x 64, 96 -> 2 x 48, 64)
-      for (int t = 80; t >= 16; t -= 16)
-        if (ai.n_pad % t == 0) {
+      // N tiles of the wide input-gradient layers: the widest divisor of n_pad whose tap triple fits a ring stage -- 64-byte
+      // weight rows for the 32-channel dY slots (160, 128, 96, 64: one tile each), 128-byte rows for the 64-channel first
+      // layer (192 -> 3 x 64)
+      const uint32_t row = ai.cin == 32 ? 64u : 128u;
+      for (int t = ai.n_pad; t >= 16; t -= 16)
+        if (ai.n_pad % t == 0 && t <= 256 && 3u * (uint32_t)t * row <= stage_bytes) {
           ai.n_tile = t;
           break;
         }
     }
     if (int rc = prepare_conv(&ai, 2, c.k[i], c.tmA[i], c.tmB[i], mt_i, true)) return rc;
     ConvTcK& k = c.k[i];
-    if (k.tiles_y != 1 || 3u * (uint32_t)k.n_tile * 128u > stage_bytes || k.a_box_bytes > kRChunk) return 0;
+    k.b_row_bytes = 128;
+    if (a[i].cin == 32) {
+      // a 32-channel input (the dY slots of the input-gradient chain): the upper half of every packed 64-entry weight row is zero
+      // padding -- load only the first 64 bytes of each row (half the L2 -> SM traffic of these layers)
+      uint64_t dims[2] = {64, (uint64_t)k.chunks * 9 * k.n_pad};
+      uint64_t str[1] = {128};
+      uint32_t box[2] = {32, (uint32_t)k.n_tile};
+      if (!encode_tmap_tiled(&c.tmB[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a[i].w_packed, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B))
+        return SSR_E_CUDA;
+      k.b_row_bytes = 64;
+    }
+    if (k.tiles_y != 1 || 3u * (uint32_t)(k.n_tile * k.b_row_bytes) > stage_bytes || k.a_box_bytes > kRChunk) return 0;
     k.n_loop = k.n_pad / k.n_tile;
     k.resident = 1;
     k.chunk_alloc = kRChunk;
@@ -1501,6 +1558,14 @@ static int rdb_resident_launch(const ssr_conv_tc_args* a, int32_t n, cudaStream_
   c.sync_mode = kSyncCluster;
   c.sync = nullptr;
   c.timeline = chain_timeline_buffer();
+  {
+    static int mc = -1;
+    if (mc < 0) {
+      const char* e = getenv("SSR_RDB_MULTICAST");
+      mc = e ? atoi(e) : 0;
+    }
+    c.multicast = mc;
+  }
   const int strips = w / 8;
   dim3 grid((unsigned)(strips * a[0].n_img), 1, 1);
   static size_t configured[2] = {0, 0};

@@ -43,30 +43,31 @@ __global__ void u8_shift_diff_sums_kernel(const uint8_t* __restrict__ a, const u
     const int y = p / cw_, x = p - y * cw_;
     const uint8_t* qa = pa + ((long)(y + cb + ro) * W + (x + cb + co)) * C;
     const uint8_t* qb = pb + ((long)(y + cb + M - ro) * W + (x + cb + M - co)) * C;
-    for (int c = 0; c < C; ++c) {
-      const int d = (int)qa[c] - (int)qb[c];
-      s1[c] += d;
-      s2[c] += d * d;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < C) {
+        const int d = (int)qa[c] - (int)qb[c];
+        s1[c] += d;
+        s2[c] += (long long)(d * d);
+      }
     }
   }
-  __shared__ long long red[8][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int c = 0; c < C; ++c) {
-    long long v1 = s1[c], v2 = s2[c];
-    for (int off = 16; off; off >>= 1) {
-      v1 += __shfl_xor_sync(0xffffffffu, v1, off);
-      v2 += __shfl_xor_sync(0xffffffffu, v2, off);
+  // warp sums -> one 64-bit atomic per warp, channel and moment (the caller zeroes `out`; two's complement makes the unsigned add exact)
+  const int lane = threadIdx.x & 31;
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(out) + (((long)n * (M + 1) * (M + 1) + o) * C) * 2;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c < C) {
+      long long v1 = s1[c], v2 = s2[c];
+      for (int off = 16; off; off >>= 1) {
+        v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, off);
+      }
+      if (lane == 0) {
+        atomicAdd(dst + 2 * c, (unsigned long long)v1);
+        atomicAdd(dst + 2 * c + 1, (unsigned long long)v2);
+      }
     }
-    if (lane == 0) {
-      red[2 * c][warp] = v1;
-      red[2 * c + 1][warp] = v2;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 2 * C) {
-    long long t = 0;
-    for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += red[threadIdx.x][w2];
-    out[(((long)n * (M + 1) * (M + 1) + o) * C + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1)] = t;
   }
 }
 

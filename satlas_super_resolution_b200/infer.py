@@ -70,3 +70,76 @@ def infer_grid(net_g, lr_u8, grid_size=16, batch=256):
     H, W = h * eng.scale, w * eng.scale
     canvas = torch.empty((grid_size * H, grid_size * W, 3), dtype=torch.uint8, device=eng.device)
     return super_resolve(net_g, lr_u8, batch=batch, canvas=canvas, grid_cols=grid_size)
+
+
+class TilePipeline:
+    """Tiles of grid_size^2 chunks streamed through one GPU with the host work off the critical path: the uint8 chunks of tile
+    t+1 are copied from pinned host memory (copy stream) while tile t runs, and the stitched uint8 canvas of tile t-1 drains
+    to pinned host memory -- what `ssr/infer_grid.py:46-85` does with one PNG round trip per 32x32 chunk.  PNG decode / encode
+    stay on host threads of the caller (out of scope: SURVEY.md section 2 rows 8, 12)."""
+
+    def __init__(self, net_g, grid_size=16, chunk_hw=32, in_ch=None, batch=256, depth=2):
+        eng = net_g._get_engine() if hasattr(net_g, "_get_engine") else net_g
+        self.net_g, self.eng, self.grid, self.batch = net_g, eng, grid_size, batch
+        n = grid_size * grid_size
+        cin = in_ch if in_ch is not None else eng.cin
+        side = grid_size * chunk_hw * eng.scale
+        dev = eng.device
+        self.host_in = [torch.empty((n, cin, chunk_hw, chunk_hw), dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.dev_in = [torch.empty((n, cin, chunk_hw, chunk_hw), dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.dev_out = [torch.empty((side, side, 3), dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.host_out = [torch.empty((side, side, 3), dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.copy_in, self.copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_done = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.depth = depth
+
+    @torch.no_grad()
+    def run(self, tiles, consume):
+        """tiles: iterable of uint8 [grid^2, C, h, w] host tensors; consume(index, uint8 [S, S, 3] pinned host canvas) is called
+        once the canvas has arrived (the buffer is reused `depth` tiles later)."""
+        main = torch.cuda.current_stream()
+        pending = []
+        for i, t in enumerate(tiles):
+            k = i % self.depth
+            if i >= self.depth:                       # slot k: its previous canvas must have been consumed
+                self.ev_out[k].synchronize()
+                j = pending.pop(0)
+                consume(j, self.host_out[j % self.depth])
+            self.host_in[k].copy_(t)
+            with torch.cuda.stream(self.copy_in):
+                self.dev_in[k].copy_(self.host_in[k], non_blocking=True)
+                self.ev_in[k].record()
+            main.wait_event(self.ev_in[k])
+            super_resolve(self.net_g, self.dev_in[k], batch=self.batch, canvas=self.dev_out[k], grid_cols=self.grid)
+            self.ev_done[k].record(main)
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(self.ev_done[k])
+                self.host_out[k].copy_(self.dev_out[k], non_blocking=True)
+                self.ev_out[k].record()
+            pending.append(i)
+        for j in pending:
+            self.ev_out[j % self.depth].synchronize()
+            consume(j, self.host_out[j % self.depth])
+
+
+def infer_tiles_sharded(net_g, tiles, rank=0, world=1, consume=None, **kw):
+    """Grid inference over many tiles on `world` GPUs: tiles are independent (ssr/infer_grid.py stitches each directory on its
+    own), so rank r simply takes the contiguous slice ops.rank_slice(len(tiles), r, world) -- replicas, no collective.
+    Returns {tile index: uint8 [S, S, 3] host tensor} for this rank's tiles unless `consume` takes them."""
+    from .ops import rank_slice
+    mine = list(rank_slice(len(tiles), rank, world))
+    out = {}
+
+    def sink(j, canvas):
+        if consume is not None:
+            consume(mine[j], canvas)
+        else:
+            out[mine[j]] = canvas.clone()
+
+    if mine:
+        t0 = tiles[mine[0]]
+        TilePipeline(net_g, grid_size=int(round(t0.shape[0] ** 0.5)), chunk_hw=t0.shape[-1], in_ch=t0.shape[1], **kw).run(
+            (tiles[i] for i in mine), sink)
+    return out

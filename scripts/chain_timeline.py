@@ -158,17 +158,21 @@ def main():
             tl = (C.c_longlong * (n_ctas * 5 * 8))()
             L.check(lib.ssr_debug_chain_timeline(tl, n_ctas))
             t = torch.tensor(list(tl), dtype=torch.float64).view(n_ctas, 5, 8)
-            names = {0: "in-ready", 2: "w0-landed", 3: "wN-landed", 5: "acc-full", 7: "arrived", 6: "stores-out"}
+            names = {0: "in-ready", 2: "w0-landed", 3: "wN-landed", 5: "acc-full", 1: "tile-written", 4: "fenced", 7: "arrived", 6: "stores-out"}
             for cta in (0, 1, 64, 127):
                 t0 = min(t[cta, 0, 0].item(), t[cta, 0, 2].item())
                 print(f"  CTA {cta}: us since the first stamp")
                 for l in range(5):
-                    print(f"    layer {l}: " + "  ".join(f"{names[e]} {(t[cta, l, e].item() - t0) / mhz:6.2f}" for e in (2, 0, 3, 5, 7, 6)))
+                    print(f"    layer {l}: " + "  ".join(f"{names[e]} {(t[cta, l, e].item() - t0) / mhz:6.2f}" for e in (2, 0, 3, 5, 1, 4, 7, 6)))
             d = lambda a, b: ((t[:, :, a] - t[:, :, b]) / mhz).mean(0)
             print("  mean over CTAs per layer [us]:")
             print("    in-ready -> wN-landed (MMAs that waited for the previous layer):", [f"{v:.2f}" for v in d(3, 0).tolist()])
             print("    wN-landed -> acc-full  :", [f"{v:.2f}" for v in d(5, 3).tolist()])
+            print("    acc-full  -> tile-written:", [f"{v:.2f}" for v in d(1, 5)[:4].tolist()])
+            print("    tile-written -> fenced :", [f"{v:.2f}" for v in d(4, 1)[:4].tolist()])
+            print("    fenced    -> arrived   :", [f"{v:.2f}" for v in d(7, 4)[:4].tolist()])
             print("    acc-full  -> arrived   :", [f"{v:.2f}" for v in d(7, 5)[:4].tolist()])
+            print("    arrived (layer l) -> in-ready (layer l+1) at the MMA warp:", [f"{v:.2f}" for v in ((t[:, 1:, 0] - t[:, :-1, 7]) / mhz).mean(0).tolist()])
             print("    acc-full  -> stores-out:", [f"{v:.2f}" for v in d(6, 5).tolist()])
             print("    layer total (acc-full -> next acc-full):", [f"{v:.2f}" for v in ((t[:, 1:, 5] - t[:, :-1, 5]) / mhz).mean(0).tolist()])
             print(f"    first stamp -> last stores-out: {((t[:, 4, 6] - torch.minimum(t[:, 0, 0], t[:, 0, 2])) / mhz).mean().item():.2f}")

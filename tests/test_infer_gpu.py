@@ -31,3 +31,26 @@ def test_super_resolve_and_stitch():
         for j in range(grid):
             tile = canvas[i * 128:(i + 1) * 128, j * 128:(j + 1) * 128]
             assert np.array_equal(tile, got[i * grid + j]), (i, j)
+
+
+def test_tile_pipeline_and_sharding_equal_direct_inference():
+    """TilePipeline (pinned double-buffered H2D / D2H around the batched forward) and infer_tiles_sharded (rank slices, no
+    collective) return exactly the canvases infer_grid produces tile by tile"""
+    from oracle import nets
+    from satlas_super_resolution_b200.archs import SSR_RRDBNet
+    from satlas_super_resolution_b200.infer import infer_grid, infer_tiles_sharded
+    nb, grid, n_tiles = 1, 4, 5
+    net = SSR_RRDBNet(24, 3, num_block=nb)
+    net.load_state_dict(nets.rrdbnet_init(24, 3, num_block=nb, seed=8))
+    net = net.cuda().eval()
+    g = torch.Generator().manual_seed(9)
+    tiles = [torch.randint(0, 256, (grid * grid, 24, 32, 32), generator=g, dtype=torch.uint8) for _ in range(n_tiles)]
+    want = [infer_grid(net, t, grid_size=grid, batch=16).cpu() for t in tiles]
+    got = {}
+    for rank in range(2):                                   # two "ranks" on one device: 3 + 2 tiles
+        part = infer_tiles_sharded(net, tiles, rank=rank, world=2, batch=16)
+        assert set(part) == set(range(3)) if rank == 0 else set(part) == {3, 4}
+        got.update(part)
+    assert sorted(got) == list(range(n_tiles))
+    for i in range(n_tiles):
+        assert torch.equal(got[i], want[i]), i
