@@ -695,6 +695,16 @@ __device__ __forceinline__ void rdb_issue_triple(uint32_t d0, uint32_t m_cols, u
                      (ky == 0 && k == 0) ? first : 1u);
 }
 
+// one tap (layers whose N tile is so wide that a ring stage holds a single tap)
+template <int KS>
+__device__ __forceinline__ void rdb_issue_tap(uint32_t d0, uint32_t m_cols, uint64_t da, uint64_t db, uint32_t idesc, uint32_t first) {
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int k = 0; k < KS; ++k)
+      umma_bf16_ss(d0 + (uint32_t)m * m_cols, da + (uint32_t)(m * kRMt + 2 * k), db + (uint32_t)(2 * k), idesc, k == 0 ? first : 1u);
+}
+
 template <bool ACC>
 __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_constant__ ConvChainK cc) {
   const ConvTcK* ps = cc.k;
@@ -785,11 +795,11 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
       const CUtensorMap* tmB = &cc.tmB[l];
       if (l > 0) prefetch_tmap(tmB);
       const uint32_t tap_bytes = (uint32_t)(q.n_tile * q.b_row_bytes);
-      const int gps = max(1, (int)(kRStage / (3u * tap_bytes)));   // triples per stage
-      const int n_tr = 3 * q.chunks;                               // triples of one N tile, order (chunk, kx)
+      const int tps = 3u * tap_bytes <= kRStage ? 3 * (int)(kRStage / (3u * tap_bytes)) : 1;   // taps per stage: whole triples, or one tap
+      const int n_taps = 9 * q.chunks;                             // taps of one N tile, order (chunk, kx, ky)
       for (int nb = 0; nb < q.n_loop; ++nb) {
-        for (int tr0 = 0; tr0 < n_tr; tr0 += gps, ++g) {
-          const int nt = min(gps, n_tr - tr0) * 3;                 // taps in this stage
+        for (int t0 = 0; t0 < n_taps; t0 += tps, ++g) {
+          const int nt = min(tps, n_taps - t0);                    // taps in this stage
           const int s = g % stages;
           if (!tile_loaded && g == stages) {                       // the ring is full of prefetched weights: now the activations
             load_tile();
@@ -801,10 +811,10 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
             mbar_expect_tx(&bar_full[s], (uint32_t)nt * tap_bytes);   // all taps land here, whoever loads them
             if (mc) {
               for (int j = (int)mc_rank; j < nt; j += (int)mc_n)   // this CTA's share, written into every CTA of the cluster
-                tma_load_2d_multicast(dst + (size_t)j * tap_bytes, tmB, &bar_full[s], 0, (tr0 * 3 + j) * q.n_pad + nb * q.n_tile, mc_mask);
+                tma_load_2d_multicast(dst + (size_t)j * tap_bytes, tmB, &bar_full[s], 0, (t0 + j) * q.n_pad + nb * q.n_tile, mc_mask);
             } else {
               for (int j = 0; j < nt; ++j)   // packed rows: ((chunk * 3 + kx) * 3 + ky) * n_pad + n
-                tma_load_2d(dst + (size_t)j * tap_bytes, tmB, &bar_full[s], 0, (tr0 * 3 + j) * q.n_pad + nb * q.n_tile);
+                tma_load_2d(dst + (size_t)j * tap_bytes, tmB, &bar_full[s], 0, (t0 + j) * q.n_pad + nb * q.n_tile);
             }
           }
           __syncwarp();
@@ -839,6 +849,42 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
       if (!ACC) {
         mbar_wait(&bar_acc_empty[b], (uint32_t)(((l >> 1) & 1) ^ 1));   // layer l-2's epilogue has drained this buffer
         tc_fence_after_sync();
+      }
+      if (3u * (uint32_t)(q.n_tile * q.b_row_bytes) > kRStage) {
+        // ---- one tap per ring stage (an N tile of more than 64 (ACC: 80) channels with 128-byte weight rows)
+#pragma unroll 1
+        for (int nb = 0; nb < q.n_loop; ++nb) {
+          const uint32_t d_base = ACC ? tmem_base + (uint32_t)(nb * q.n_tile) : tmem_base + (uint32_t)b * acc_cols;
+          const int n_taps = 9 * q.chunks, t_dep = 3 * tr_dep;
+#pragma unroll 1
+          for (int t = 0; t < n_taps; ++t, ++g) {
+            const int s = g % stages;
+            mbar_wait(&bar_full[s], (uint32_t)(g / stages) & 1);
+            tc_fence_after_sync();
+            if (lane == 0 && nb == 0 && t == 0) SSR_STAMP(l, 2);
+            if (lane == 0 && nb == q.n_loop - 1 && t == n_taps - 1) SSR_STAMP(l, 3);
+            if (nb == 0 && t == t_dep) {
+              if (l == 0) mbar_wait(bar_x, 0);
+              else mbar_wait_cluster(bar_layer, (uint32_t)(l - 1) & 1);
+              fence_proxy_async();
+              tc_fence_after_sync();
+              if (lane == 0) SSR_STAMP(l, 0);
+            }
+            if (elect_one()) {
+              const int c = t / 9, r9 = t - 9 * c, kx = r9 / 3, ky = r9 - 3 * kx;
+              const uint64_t da = da_layer + (uint32_t)(c * (int)(kRChunk >> 4) + kx * 8 + ky * (int)kRTapRow);
+              const uint64_t db = b64 ? umma_desc(ring_addr + (uint32_t)s * kRStage, 16u, 512u, 4u) : umma_desc_k128(ring_addr + (uint32_t)s * kRStage);
+              const uint32_t first = (t == 0 && !(ACC && l > 0)) ? 0u : 1u;
+              if (c + 1 < q.chunks || ks_tail == 4) rdb_issue_tap<4>(d_base, m_cols, da, db, idesc, first);
+              else rdb_issue_tap<2>(d_base, m_cols, da, db, idesc, first);
+              if (mc) umma_commit_multicast(&bar_empty[s], mc_mask);
+              else umma_commit(&bar_empty[s]);
+              if (t == n_taps - 1 && (!ACC || nb == q.n_loop - 1)) umma_commit(&bar_acc_full[b]);
+            }
+            __syncwarp();
+          }
+        }
+        continue;
       }
 #pragma unroll 1
       for (int nb = 0; nb < q.n_loop; ++nb) {
@@ -1507,12 +1553,12 @@ static int rdb_resident_launch(const ssr_conv_tc_args* a, int32_t n, cudaStream_
     int mt_i = 0;
     ssr_conv_tc_args ai = a[i];
     if (tmem_acc) {
-      // N tiles of the wide input-gradient layers: the widest divisor of n_pad whose tap triple fits a ring stage -- 64-byte
-      // weight rows for the 32-channel dY slots (160, 128, 96, 64: one tile each), 128-byte rows for the 64-channel first
-      // layer (192 -> 3 x 64)
+      // N tiles of the wide input-gradient layers: the widest divisor of n_pad one tap of which fits a ring stage -- every layer
+      // is ONE N tile (192 with 128-byte weight rows: a tap per stage; 160, 128, 96, 64 with the 64-byte rows of the 32-channel
+      // dY slots: one or two tap triples per stage).  128 x 192 x 16 MMAs are tensor-pipe bound, not operand-read bound.
       const uint32_t row = ai.cin == 32 ? 64u : 128u;
       for (int t = ai.n_pad; t >= 16; t -= 16)
-        if (ai.n_pad % t == 0 && t <= 256 && 3u * (uint32_t)t * row <= stage_bytes) {
+        if (ai.n_pad % t == 0 && t <= 256 && (uint32_t)t * row <= stage_bytes) {   // (a stage holds whole tap triples, or one tap)
           ai.n_tile = t;
           break;
         }
@@ -1530,7 +1576,7 @@ static int rdb_resident_launch(const ssr_conv_tc_args* a, int32_t n, cudaStream_
         return SSR_E_CUDA;
       k.b_row_bytes = 64;
     }
-    if (k.tiles_y != 1 || 3u * (uint32_t)(k.n_tile * k.b_row_bytes) > stage_bytes || k.a_box_bytes > kRChunk) return 0;
+    if (k.tiles_y != 1 || (uint32_t)(k.n_tile * k.b_row_bytes) > stage_bytes || k.a_box_bytes > kRChunk) return 0;
     k.n_loop = k.n_pad / k.n_tile;
     k.resident = 1;
     k.chunk_alloc = kRChunk;

@@ -530,11 +530,14 @@ extern "C" int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, 
                                              void* stream) {
   SSR_REQUIRE(descs_device && n_layers > 0, "ssr_pack_conv_weights_batched: bad args");
   static_assert(sizeof(ssr_pack_desc) == sizeof(PackDesc), "ssr_pack_desc layout");
-  dim3 grid(32, (unsigned)n_layers);
+  // blocks per layer: the generator has 702 small operands (4 .. 24 tiles of 4608 elements each) -- more than a few blocks per
+  // layer only adds block-launch overhead (22 k mostly empty blocks cost 0.2 ms); the discriminator has 20 large ones
+  dim3 grid(n_layers > 64 ? 4u : 96u, (unsigned)n_layers);
   pack_batched_kernel<<<grid, 256, 0, STREAM(stream)>>>(reinterpret_cast<const PackDesc*>(descs_device));
   count_launch();
   if (has_gemm_forms) {
-    pack_gemm_kernel<<<grid, 256, 0, STREAM(stream)>>>(reinterpret_cast<const PackDesc*>(descs_device));
+    dim3 grid_g(148, (unsigned)n_layers);
+    pack_gemm_kernel<<<grid_g, 256, 0, STREAM(stream)>>>(reinterpret_cast<const PackDesc*>(descs_device));
     count_launch();
   }
   return check_last("pack_batched launch") ? SSR_OK : SSR_E_CUDA;

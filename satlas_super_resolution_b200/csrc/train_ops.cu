@@ -344,18 +344,35 @@ struct SnDesc {
 
 // phase 1: t = W^T u ; nt2 = |t|^2        (threads walk columns: coalesced rows of W)
 __global__ void sn_phase1(const SnDesc* __restrict__ descs) {
+  // block = 32 columns x 8 row groups: a warp reads 128 contiguous bytes of one row, the eight warps walk the rows interleaved
+  // (the first version gave every thread a whole column: up to 512 dependent loads per thread on 128 blocks)
   const SnDesc d = descs[blockIdx.y];
   float* t = d.scratch;
   float* norms = d.scratch + d.cols + d.rows;
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   float local = 0.f;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.cols; j += gridDim.x * blockDim.x) {
+  for (int j0 = blockIdx.x * 32; j0 < d.cols; j0 += gridDim.x * 32) {
+    const int j = j0 + tx;
     float acc = 0.f;
-    for (int i = 0; i < d.rows; ++i) acc = fmaf(d.w[(long)i * d.cols + j], d.u[i], acc);
-    t[j] = acc;
-    local += acc * acc;
+    if (j < d.cols)
+      for (int i = ty; i < d.rows; i += 8) acc = fmaf(d.w[(long)i * d.cols + j], d.u[i], acc);
+    part[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && j < d.cols) {
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += part[k][tx];
+      t[j] = sum;
+      local += sum * sum;
+    }
+    __syncthreads();
   }
-  local = block_reduce_sum(local);
-  if (threadIdx.x == 0 && local != 0.f) atomicAdd(&norms[0], local);
+  if (ty == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (tx == 0 && local != 0.f) atomicAdd(&norms[0], local);
+  }
 }
 // phase 2: v = t / max(|t|, eps) ; s = W v ; ns2 = |s|^2     (one warp per row)
 __global__ void sn_phase2(const SnDesc* __restrict__ descs, float eps) {
@@ -621,7 +638,7 @@ extern "C" int ssr_spectral_norm(const ssr_sn_desc* descs_device, int32_t n_laye
   SSR_REQUIRE(descs_device && n_layers > 0, "ssr_spectral_norm: bad args");
   const SnDesc* d = reinterpret_cast<const SnDesc*>(descs_device);
   if (power_iteration) {
-    sn_phase1<<<dim3(16, n_layers), 256, 0, STREAM(stream)>>>(d);
+    sn_phase1<<<dim3(144, n_layers), 256, 0, STREAM(stream)>>>(d);   // 144 x 32 columns covers the widest layer (4608) in one pass
     count_launch();
     sn_phase2<<<dim3(32, n_layers), 256, 0, STREAM(stream)>>>(d, eps);
     count_launch();

@@ -9,6 +9,12 @@
 // tile is loaded ONCE for nine taps (the first version reloaded it per kx from three CTAs).  Operands are MN-major (one
 // 128-byte row per pixel = per K index); nine f32 accumulators [128 cx, 32 cy] live in 288 TMEM columns; a CTA walks a range
 // of pixel tiles and reduces its partial sums with vector red.global.add.v4.f32.
+//
+// fuse3 (default): the shift is moved from X to dY -- dW[ky][kx] = sum_q X[q] * dY[q - (ky-1, kx-1)] over the pixels q of the
+// tile, with the dY tile carrying the halo -- so that the three horizontal taps of one ky share ONE MMA: their dY windows are
+// the same 16 pixel rows shifted by one pixel (64 bytes), i.e. three N blocks of an MN-major operand with LBO = 64 B.  One
+// 128 x 96 x 16 MMA (4 KB of X + 3 KB of dY from shared memory) replaces three 128 x 32 x 16 MMAs (3 x 5 KB): the operand
+// reads that bound this kernel drop 2.1x.  Three accumulators [128 cx, 3 x 32 cy] in 288 TMEM columns.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -18,6 +24,7 @@ struct Wg9K {
   int n_img, H, W, TW, TH, tiles_x, tiles_y, total_tiles, kpr;
   int cx, cx_rows, cy, out_stride;
   int stages, splits;
+  int fuse3;   // dY carries the halo, the three kx taps of a ky are one N = 96 MMA
   uint32_t x_chunk_bytes, x_chunk_alloc, y_bytes, stage_bytes;
   float* out;
   float scale;
@@ -84,14 +91,15 @@ __device__ __forceinline__ void wgrad9_body(const CUtensorMap& tmX, const CUtens
       if (elect_one()) {
         uint8_t* xs = smem + (size_t)s * p.stage_bytes;
         mbar_expect_tx(&bar_full[s], nchunks * p.x_chunk_bytes + p.y_bytes);
+        const int hx = p.fuse3 ? 0 : 1, hy = p.fuse3 ? 1 : 0;   // which operand carries the halo
         for (int ch = 0; ch < nchunks; ++ch)
-          tma_load_4d(xs + (size_t)ch * p.x_chunk_alloc, &tmX, &bar_full[s], mtile * 128 + ch * 64, x0 - 1, y0 - 1, n);
-        tma_load_4d(xs + x_bytes, &tmY, &bar_full[s], n0, x0, y0, n);
+          tma_load_4d(xs + (size_t)ch * p.x_chunk_alloc, &tmX, &bar_full[s], mtile * 128 + ch * 64, x0 - hx, y0 - hx, n);
+        tma_load_4d(xs + x_bytes, &tmY, &bar_full[s], n0, x0 - hy, y0 - hy, n);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_bf16(128u, 32u, 1u, 1u);
+    const uint32_t idesc = umma_idesc_bf16(128u, p.fuse3 ? 96u : 32u, 1u, 1u);
     const int pitch = p.TW + 2;
     uint32_t acc = 0;
     for (int it = 0; it < iters; ++it) {
@@ -102,18 +110,33 @@ __device__ __forceinline__ void wgrad9_body(const CUtensorMap& tmX, const CUtens
       if (elect_one()) {
         const uint32_t xs = smem_u32(smem + (size_t)s * p.stage_bytes);
         const uint64_t da0 = umma_desc(xs, p.x_chunk_alloc, 1024u, 2u);               // X: 128-byte rows, SWIZZLE_128B
-        const uint64_t db0 = umma_desc(xs + x_bytes, 0u, 512u, 4u);                    // dY: 64-byte rows, SWIZZLE_64B
+        if (p.fuse3) {
+          // dY with halo, 64-byte rows, SWIZZLE_64B; N blocks (kx = 2, 1, 0) are one pixel row = 64 B apart
+          const uint64_t db0 = umma_desc(xs + x_bytes, 64u, 512u, 4u);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const int ry = ks / p.kpr, hx = ks - ry * p.kpr;
-          const uint32_t row0 = (uint32_t)(ry * pitch + hx * 16);
-          const uint64_t db = db0 + (uint32_t)(ks * 64);                               // 16 pixels * 64 B >> 4
+          for (int ks = 0; ks < 8; ++ks) {
+            const int ry = ks / p.kpr, hx = ks - ry * p.kpr;
+            const uint64_t da = da0 + (uint32_t)(ry * p.TW + hx * 16) * 8u;            // 16 interior pixels of X
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint64_t db = db0 + (uint32_t)((ry + 2 - ky) * pitch + hx * 16) * 4u;   // 64 B >> 4 per pixel row
+              umma_bf16_ss(tmem_base + (uint32_t)(ky * 96), da, db, idesc, ks == 0 ? acc : 1u);
+            }
+          }
+        } else {
+          const uint64_t db0 = umma_desc(xs + x_bytes, 0u, 512u, 4u);                  // dY: 64-byte rows, SWIZZLE_64B
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const uint64_t da = da0 + (row0 + (uint32_t)(ky * pitch + kx)) * 8u;     // 128 B >> 4 per pixel row
-              umma_bf16_ss(tmem_base + (uint32_t)((ky * 3 + kx) * 32), da, db, idesc, ks == 0 ? acc : 1u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const int ry = ks / p.kpr, hx = ks - ry * p.kpr;
+            const uint32_t row0 = (uint32_t)(ry * pitch + hx * 16);
+            const uint64_t db = db0 + (uint32_t)(ks * 64);                             // 16 pixels * 64 B >> 4
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const uint64_t da = da0 + (row0 + (uint32_t)(ky * pitch + kx)) * 8u;   // 128 B >> 4 per pixel row
+                umma_bf16_ss(tmem_base + (uint32_t)((ky * 3 + kx) * 32), da, db, idesc, ks == 0 ? acc : 1u);
+              }
             }
           }
         }
@@ -134,9 +157,11 @@ __device__ __forceinline__ void wgrad9_body(const CUtensorMap& tmX, const CUtens
 #pragma unroll 1
     for (int item = half; item < 18; item += 2) {
       const int tap = item >> 1, cb = (item & 1) * 16;
+      // fuse3: accumulator ky holds the N blocks in the order kx = 2, 1, 0
+      const int col = p.fuse3 ? (tap / 3) * 96 + (2 - tap % 3) * 32 + cb : tap * 32 + cb;
       uint32_t v[16];
       __syncwarp();
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * 32 + cb), v);
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
       tmem_ld_wait();
       if (!valid) continue;
       const int c0 = n0 + cb;
@@ -232,10 +257,23 @@ static int prepare_wgrad9(const ssr_wgrad_tc_args* a, Wg9Prepared* out, int targ
   p.cx = a->cx; p.cx_rows = a->out_cx_rows; p.cy = a->cy; p.out_stride = a->out_stride;
   SSR_REQUIRE(p.cx_rows >= p.cx && p.out_stride >= p.cy && p.out_stride % 4 == 0, "ssr_wgrad_tc: output layout");
   SSR_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "ssr_wgrad_tc: out must be 16-byte aligned");
-  p.x_chunk_bytes = (uint32_t)((TW + 2) * (p.TH + 2)) * 128u;
-  // the last tap of the last K-step reads up to ((TH+1)*(TW+2) + TW + 2) rows: keep it inside the chunk allocation
-  p.x_chunk_alloc = (uint32_t)round_up((int)(((p.TH + 2) * (TW + 2) + 16) * 128), 1024);
-  p.y_bytes = (uint32_t)(TW * p.TH * 64);
+  static int fuse3 = -1;
+  if (fuse3 < 0) {
+    const char* e = getenv("SSR_WGRAD9_FUSE3");
+    fuse3 = e ? atoi(e) : 1;
+  }
+  p.fuse3 = fuse3;
+  if (fuse3) {
+    // X: the 128 interior pixels; dY: the tile with its halo (operand windows end exactly at its last row)
+    p.x_chunk_bytes = (uint32_t)(TW * p.TH) * 128u;
+    p.x_chunk_alloc = p.x_chunk_bytes;
+    p.y_bytes = (uint32_t)((TW + 2) * (p.TH + 2)) * 64u;
+  } else {
+    p.x_chunk_bytes = (uint32_t)((TW + 2) * (p.TH + 2)) * 128u;
+    // the last tap of the last K-step reads up to ((TH+1)*(TW+2) + TW + 2) rows: keep it inside the chunk allocation
+    p.x_chunk_alloc = (uint32_t)round_up((int)(((p.TH + 2) * (TW + 2) + 16) * 128), 1024);
+    p.y_bytes = (uint32_t)(TW * p.TH * 64);
+  }
   p.stage_bytes = (uint32_t)round_up((int)(2 * p.x_chunk_alloc + p.y_bytes), 1024);
   int stages = (g_w9_smem - 1280) / (int)p.stage_bytes;
   if (stages > 4) stages = 4;
@@ -261,13 +299,13 @@ static int prepare_wgrad9(const ssr_wgrad_tc_args* a, Wg9Prepared* out, int targ
   {
     uint64_t dims[4] = {(uint64_t)a->cx, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
     uint64_t str[3] = {(uint64_t)a->x_pix_stride * 2, (uint64_t)a->x_pix_stride * 2 * a->w, (uint64_t)a->x_pix_stride * 2 * a->w * a->h};
-    uint32_t box[4] = {64, (uint32_t)(TW + 2), (uint32_t)(p.TH + 2), 1};
+    uint32_t box[4] = {64, (uint32_t)(TW + (fuse3 ? 0 : 2)), (uint32_t)(p.TH + (fuse3 ? 0 : 2)), 1};
     if (!encode_tmap_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return SSR_E_CUDA;
   }
   {
     uint64_t dims[4] = {(uint64_t)a->cy, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
     uint64_t str[3] = {(uint64_t)a->dy_pix_stride * 2, (uint64_t)a->dy_pix_stride * 2 * a->w, (uint64_t)a->dy_pix_stride * 2 * a->w * a->h};
-    uint32_t box[4] = {32, (uint32_t)TW, (uint32_t)p.TH, 1};
+    uint32_t box[4] = {32, (uint32_t)(TW + (fuse3 ? 2 : 0)), (uint32_t)(p.TH + (fuse3 ? 2 : 0)), 1};
     if (!encode_tmap_tiled(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->dy, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return SSR_E_CUDA;
   }
   out->p = p;
