@@ -53,6 +53,10 @@ extern "C" {
 #define SSR_PACK_DGRAD 1 /* B[n=cin][k=cout], taps flipped (conv^T)   */
 #define SSR_PACK_FWD_GEMM 2   /* 1x1 form over im2col columns: B[n=cout][k'=(ky*R+kx)*cin+ci]          */
 #define SSR_PACK_DGRAD_GEMM 3 /* 1x1 form producing dcol:      B[n=k'][k=cout]                           */
+/* input gradient of a 4 x 4 stride-2 conv as four 2 x 2 convs over dY, one per output parity (oy, ox):
+ * dst[class = oy*2 + ox][cout chunk][b][a][n = cin][64], tap (a, b) of class (oy, ox) = w[k][n][ky][kx] with
+ * ky = oy ? 2 - 2a : 3 - 2a, kx = ox ? 2 - 2b : 3 - 2b (dx[2u+oy] collects dy[u - pad + a], pad = 1 - oy) */
+#define SSR_PACK_DGRAD_S2 4
 
 const char* ssr_last_error(void);
 int ssr_abi_version(void);
@@ -123,6 +127,14 @@ typedef struct ssr_conv_tc_args {
   float* bias_grad;  /* bias_grad[c - out_lo] += bias_grad_scale * sum_p (the value out_bf16 receives), or NULL: the bf16 output
                       * of an input-gradient conv is the dY of the conv below it, its pixel sum that conv's bias gradient */
   float bias_grad_scale;
+  /* r == 4: the 4 x 4 stride-2 pad-1 convolution (conv1..conv3 of ssr/archs/discriminator_arch.py:30-32) as an implicit GEMM --
+   * stride must be 2, (h, w) is the INPUT size, the output is (h/2, w/2); weights packed with r = 4.
+   * r == 2: one parity class of its transposed convolution (the input gradient): a 2 x 2 stride-1 conv over dY of size (h, w) whose
+   * box origin is shifted by (pad_y, pad_x) in {0, 1} and whose output pixel (y, x) is stored at (2y + out_oy, 2x + out_ox) of
+   * the (2h, 2w) image out_bf16 / mask / residuals describe; weights: class out_oy * 2 + out_ox of an SSR_PACK_DGRAD_S2 operand. */
+  int32_t stride;
+  int32_t pad_y, pad_x;
+  int32_t out_oy, out_ox;
 } ssr_conv_tc_args;
 
 int ssr_conv_tc(const ssr_conv_tc_args* args, void* stream);

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libssr_b200.so")
 
 SSR_NONE, SSR_BF16, SSR_F32, SSR_F32_PLANAR4 = 0, 1, 2, 3
 OUT32_NONE, OUT32_NHWC, OUT32_NHWC_ATOMIC, OUT32_NCHW, OUT32_PLANAR4, OUT32_PLANAR4_ACC = 0, 1, 2, 3, 4, 5
-PACK_FWD, PACK_DGRAD, PACK_FWD_GEMM, PACK_DGRAD_GEMM = 0, 1, 2, 3
+PACK_FWD, PACK_DGRAD, PACK_FWD_GEMM, PACK_DGRAD_GEMM, PACK_DGRAD_S2 = 0, 1, 2, 3, 4
 
 
 class ConvTcArgs(C.Structure):
@@ -33,6 +33,7 @@ class ConvTcArgs(C.Structure):
         ("out_f32", C.c_void_p), ("out32_mode", C.c_int32), ("out32_pix_stride", C.c_int32),
         ("n_tile", C.c_int32), ("mt", C.c_int32), ("splits", C.c_int32), ("res1_cmax", C.c_int32),
         ("out_lo", C.c_int32), ("bias_grad", C.c_void_p), ("bias_grad_scale", C.c_float),
+        ("stride", C.c_int32), ("pad_y", C.c_int32), ("pad_x", C.c_int32), ("out_oy", C.c_int32), ("out_ox", C.c_int32),
     ]
 
 

@@ -50,7 +50,7 @@ static EncodeTiledFn get_encode_fn() {
 
 bool encode_tmap_tiled(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, const void* gaddr,
                        const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                       CUtensorMapSwizzle swizzle) {
+                       CUtensorMapSwizzle swizzle, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver / GPU)");
@@ -63,7 +63,7 @@ bool encode_tmap_tiled(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t ran
   for (uint32_t i = 0; i < rank; ++i) {
     gdims[i] = dims[i];
     gbox[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   CUresult r = fn(out, dtype, rank, const_cast<void*>(gaddr), gdims, gstr, gbox, estr,

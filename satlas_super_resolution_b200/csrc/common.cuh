@@ -20,10 +20,12 @@ void prof_after(cudaStream_t s);
 bool check_cuda(cudaError_t e, const char* what);
 bool check_last(const char* what);
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
+// elem_strides (optional, rank entries): traversal stride per dimension -- with stride s only every s-th element inside the
+// bounding box `box` is copied (box[i] / s elements land in shared memory): how a stride-2 convolution gathers its taps.
 bool encode_tmap_tiled(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, const void* gaddr,
                        const uint64_t* dims, const uint64_t* strides_bytes /* rank-1 */,
-                       const uint32_t* box, CUtensorMapSwizzle swizzle);
+                       const uint32_t* box, CUtensorMapSwizzle swizzle, const uint32_t* elem_strides = nullptr);
 
 // true unless SSR_PDL=0: tensor-core kernels are launched with programmatic stream serialization
 bool pdl_enabled();

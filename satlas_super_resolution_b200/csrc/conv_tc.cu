@@ -19,7 +19,9 @@
 namespace ssr {
 
 struct ConvTcK {
-  int n_img, H, W, R, pad;
+  int n_img, H, W, R, pad;      // H, W: the OUTPUT grid the tiles walk (= input size except for the stride-2 conv)
+  int pad_x, pad_y;             // box origin shift (= pad; per launch for the 2 x 2 parity convs of a transposed stride-2 conv)
+  int out_oy, out_ox;           // R == 2: the output pixel (y, x) is stored at (2y + out_oy, 2x + out_ox)
   int TW, TH, tiles_x, tiles_y;
   int pitch;   // shared-memory rows per tile row: TW, or TW + 2 for the halo tile of the resident dense block
   int chunks, cin;
@@ -121,6 +123,13 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
                                              const int sync_mode, unsigned int* gsync, long long* timeline = nullptr) {
 #define SSR_STAMP(layer, slot) \
   do { if (timeline) timeline[((long)blockIdx.x * kMaxChain + (layer)) * 8 + (slot)] = clock64(); } while (0)
+  // R = 1, 3: stride-1 conv, one stage per (chunk, kx), R vertical taps per stage.
+  // R = 4: the 4 x 4 stride-2 pad-1 conv (discriminator_arch.py:30-32): the TMA box gathers every second pixel (element strides
+  //        2, 2), one stage per (chunk, kx, parity of ky) holding the two taps ky = parity, parity + 2 as consecutive box rows.
+  // R = 2: one parity class of the TRANSPOSED 4 x 4 stride-2 conv (its input gradient): a 2 x 2 stride-1 conv over dY with
+  //        per-launch pads (0 | 1), whose output pixel (y, x) is stored at (2y + oy, 2x + ox).
+  constexpr int NH = R == 4 ? 8 : R;   // stages per 64-channel chunk
+  constexpr int NV = R == 4 ? 2 : R;   // vertical taps per stage
   const ConvTcK& p = ps[0];   // geometry, tiling and the shared-memory ring are identical for every layer of a chain
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -183,7 +192,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       const CUtensorMap* tmB = &tmBs[l];
       const int per = (q.chunks + q.splits - 1) / q.splits;
       const int c_begin = blockIdx.z * per;
-      const int iters = (min(q.chunks, c_begin + per) - c_begin) * R;
+      const int iters = (min(q.chunks, c_begin + per) - c_begin) * NH;
       if (l > 0) {
         // layer l-1 has been stored (generic proxy) by every CTA we can depend on: acquire that, then order our TMA
         // (async proxy) loads behind it
@@ -211,8 +220,10 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
         for (int nb = 0; nb < q.n_loop; ++nb) {
         const int n0 = ((int)blockIdx.y * q.n_loop + nb) * q.n_tile;
         for (int it = 0; it < iters; ++it, ++g) {
-          const int c = c_begin + it / R;
-          const int kx = it - (it / R) * R;
+          const int c = c_begin + it / NH;
+          const int hs = it - (it / NH) * NH;
+          const int kx = R == 4 ? (hs >> 1) : hs;
+          const int par = R == 4 ? (hs & 1) : 0;
           const int s = g % q.stages;
           const uint32_t ph = (g / q.stages) & 1;
           mbar_wait(&bar_empty[s], ph ^ 1);
@@ -220,10 +231,13 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
             uint8_t* a_dst = smem + (size_t)s * stage_bytes;
             uint8_t* b_dst = a_dst + q.a_alloc;
             mbar_expect_tx(&bar_full[s], q.a_box_bytes + q.b_bytes);
-            tma_load_4d(a_dst, tmA, &bar_full[s], c * 64, x0 + kx - q.pad, y0 - q.pad, n);
+            if (R == 4) tma_load_4d(a_dst, tmA, &bar_full[s], c * 64, 2 * x0 + kx - 1, 2 * y0 + par - 1, n);   // input coordinates
+            else tma_load_4d(a_dst, tmA, &bar_full[s], c * 64, x0 + kx - q.pad_x, y0 - q.pad_y, n);
 #pragma unroll
-            for (int ky = 0; ky < R; ++ky)
-              tma_load_2d(b_dst + (size_t)ky * q.n_tile * 128, tmB, &bar_full[s], 0, ((c * R + kx) * R + ky) * q.n_pad + n0);
+            for (int v = 0; v < NV; ++v) {
+              const int ky = R == 4 ? par + 2 * v : v;
+              tma_load_2d(b_dst + (size_t)v * q.n_tile * 128, tmB, &bar_full[s], 0, ((c * R + kx) * R + ky) * q.n_pad + n0);
+            }
           }
           __syncwarp();
         }
@@ -243,7 +257,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       const uint32_t b_tap = (uint32_t)(q.n_tile * 128) >> 4;    // next vertical tap's weight tile
       const int per = (q.chunks + q.splits - 1) / q.splits;
       const int c_begin = blockIdx.z * per;
-      const int iters = (min(q.chunks, c_begin + per) - c_begin) * R;
+      const int iters = (min(q.chunks, c_begin + per) - c_begin) * NH;
       const int items = my_tiles * q.n_loop;  // (pixel tile, N tile) work items of this layer
       // TMEM-resident accumulator (acc_w > 0): channel c of M tile m is column m * acc_w + c in EVERY layer; layer 0 initialises,
       // later layers add; nothing is handed back by the epilogue (a layer only writes columns below the slot being drained)
@@ -255,7 +269,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
         const uint32_t d_base = q.acc_w ? tmem_base + (uint32_t)((lt % q.n_loop) * q.n_tile) : tmem_base + (uint32_t)b * acc_cols;
         uint32_t acc = (q.acc_w && l > 0) ? 1u : 0u;
         for (int it = 0; it < iters; ++it, ++g) {
-          const int c = c_begin + it / R;
+          const int c = c_begin + it / NH;
           const int s = g % q.stages;
           const uint32_t ph = (g / q.stages) & 1;
           mbar_wait(&bar_full[s], ph);
@@ -271,7 +285,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
 #pragma unroll
-                for (int ky = 0; ky < R; ++ky) {
+                for (int ky = 0; ky < NV; ++ky) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
                     umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
@@ -281,7 +295,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
             } else {
 #pragma unroll
               for (int m = 0; m < MT; ++m)
-                for (int ky = 0; ky < R; ++ky)
+                for (int ky = 0; ky < NV; ++ky)
                   for (int k = 0; k < ks; ++k)
                     umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
                                  idesc, (ky == 0 && k == 0) ? acc : 1u);
@@ -403,7 +417,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         ys[mt] = y0 + mt * p.TH + tyy;
-        pixs[mt] = ((long)n * p.H + ys[mt]) * p.W + x;
+        // where the pixel lives in the output / residual / mask buffers: itself, or (2y + oy, 2x + ox) of the twice as large image
+        // a transposed stride-2 conv writes (one parity class per launch)
+        pixs[mt] = R == 2 ? ((long)n * (2 * p.H) + (2 * ys[mt] + p.out_oy)) * (2 * p.W) + (2 * x + p.out_ox) : ((long)n * p.H + ys[mt]) * p.W + x;
         oks[mt] = (tyy < p.TH) && (ys[mt] < p.H) && (x < p.W);
       }
 #pragma unroll 1
@@ -1228,8 +1244,14 @@ extern "C" int64_t ssr_packed_weight_bytes(int32_t cin, int32_t cout, int32_t r,
 static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUtensorMap& tmA, CUtensorMap& tmB, int& mt_out,
                         bool halo_tile = false) {
   SSR_REQUIRE(a != nullptr, "ssr_conv_tc: null args");
-  SSR_REQUIRE(a->r == 1 || a->r == 3, "ssr_conv_tc: r must be 1 or 3 (got %d)", a->r);
+  SSR_REQUIRE(a->r >= 1 && a->r <= 4, "ssr_conv_tc: r must be 1, 3 (stride 1), 4 (stride 2) or 2 (transposed parity class) (got %d)", a->r);
   SSR_REQUIRE(a->n_img > 0 && a->h > 0 && a->w > 0, "ssr_conv_tc: bad geometry");
+  if (a->r == 4) SSR_REQUIRE(a->stride == 2 && a->h % 2 == 0 && a->w % 2 == 0, "ssr_conv_tc: r == 4 is the stride-2 pad-1 conv over an even-sized image");
+  else SSR_REQUIRE(a->stride <= 1, "ssr_conv_tc: stride 2 needs r == 4");
+  if (a->r == 2)
+    SSR_REQUIRE((a->pad_y | a->pad_x | a->out_oy | a->out_ox) >= 0 && a->pad_y <= 1 && a->pad_x <= 1 && a->out_oy <= 1 && a->out_ox <= 1,
+                "ssr_conv_tc: r == 2 (parity class of a transposed stride-2 conv): pads and output offsets are 0 or 1");
+  SSR_REQUIRE(a->r == 1 || a->r == 3 || (!halo_tile && a->splits <= 1 && a->out32_mode != SSR_OUT32_NCHW), "ssr_conv_tc: r == 2 / 4: no split-K, no NCHW output");
   SSR_REQUIRE(a->cin > 0 && a->cin % 16 == 0, "ssr_conv_tc: cin must be a positive multiple of 16 (got %d)", a->cin);
   SSR_REQUIRE(a->x_pix_stride % 8 == 0 && a->x_pix_stride >= a->cin, "ssr_conv_tc: x_pix_stride %d", a->x_pix_stride);
   SSR_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0, "ssr_conv_tc: x must be 16-byte aligned");
@@ -1239,11 +1261,17 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
   if (!device_limits()) return SSR_E_CUDA;
 
   p = ConvTcK{};
+  const int out_h = a->r == 4 ? a->h / 2 : a->h, out_w = a->r == 4 ? a->w / 2 : a->w;   // the grid the tiles walk
+  const int nv = a->r == 4 ? 2 : a->r;                                                   // vertical taps per pipeline stage
   p.n_img = a->n_img;
-  p.H = a->h;
-  p.W = a->w;
+  p.H = out_h;
+  p.W = out_w;
   p.R = a->r;
-  p.pad = (a->r - 1) / 2;
+  p.pad = a->r == 3 ? 1 : 0;
+  p.pad_x = a->r == 2 ? a->pad_x : p.pad;
+  p.pad_y = a->r == 2 ? a->pad_y : p.pad;
+  p.out_oy = a->out_oy;
+  p.out_ox = a->out_ox;
   // tile width: narrower tiles have less vertical-halo overhead per pixel (box rows = MT*TH + 2), and every pixel is its own
   // 128-byte TMA segment anyway, so wide images are cut into 32-column tiles (SSR_CONV_TW overrides for experiments)
   {
@@ -1253,7 +1281,7 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
       tw_max = e ? atoi(e) : 32;
       if (tw_max != 8 && tw_max != 16 && tw_max != 32 && tw_max != 64 && tw_max != 128) tw_max = 32;
     }
-    p.TW = a->w >= tw_max && a->r == 3 ? tw_max : (a->w >= 128 ? 128 : round_up(a->w, 8));
+    p.TW = out_w >= tw_max && a->r != 1 ? tw_max : (out_w >= 128 ? 128 : round_up(out_w, 8));
     if (halo_tile) p.TW = 8;   // resident dense block: 8-pixel strips, the tile keeps its halo columns in shared memory
   }
   p.TH = 128 / p.TW;
@@ -1270,14 +1298,14 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
       forced = e ? atoi(e) : 0;
     }
     const int nt_guess = a->n_tile ? a->n_tile : (a->n_pad <= 128 ? a->n_pad : a->n_pad / ((a->n_pad + 127) / 128));
-    const long tiles1 = (long)((a->w + p.TW - 1) / p.TW) * ((a->h + p.TH - 1) / p.TH) * a->n_img;
+    const long tiles1 = (long)((out_w + p.TW - 1) / p.TW) * ((out_h + p.TH - 1) / p.TH) * a->n_img;
     mt = 1;
     if (forced == 1 || forced == 2) mt = forced;
-    else if (a->h >= 2 * p.TH && tiles1 >= 200 && 2 * nt_guess <= 512) mt = 2;
+    else if (out_h >= 2 * p.TH && tiles1 >= 200 && 2 * nt_guess <= 512) mt = 2;
   }
   SSR_REQUIRE(mt == 1 || mt == 2, "ssr_conv_tc: mt must be 1 or 2");
-  p.tiles_x = (a->w + p.TW - 1) / p.TW;
-  p.tiles_y = (a->h + mt * p.TH - 1) / (mt * p.TH);
+  p.tiles_x = (out_w + p.TW - 1) / p.TW;
+  p.tiles_y = (out_h + mt * p.TH - 1) / (mt * p.TH);
   p.chunks = (a->cin + 63) / 64;
   p.cin = a->cin;
   p.n_pad = a->n_pad;
@@ -1299,12 +1327,12 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
                     a->res1_kind == SSR_NONE && a->res2_kind == SSR_NONE && a->mask == nullptr,
                 "ssr_conv_tc: split-K needs a pure atomic f32 epilogue");
 
-  const int rows = mt * p.TH + p.R - 1;
+  const int rows = mt * p.TH + nv - 1;
   p.a_box_bytes = (uint32_t)p.pitch * rows * 128u;
   // the M=128 operand window of the last tap may run past the box when TW*TH < 128: keep it inside the stage
-  uint32_t need = (uint32_t)(((mt - 1) * p.TH + p.R - 1) * p.pitch) * 128u + (p.pitch == p.TW ? 16384u : (uint32_t)(15 * p.pitch + 8) * 128u);
+  uint32_t need = (uint32_t)(((mt - 1) * p.TH + nv - 1) * p.pitch) * 128u + (p.pitch == p.TW ? 16384u : (uint32_t)(15 * p.pitch + 8) * 128u);
   p.a_alloc = (uint32_t)round_up((int)max(p.a_box_bytes, need), 1024);
-  p.b_bytes = (uint32_t)(p.R * p.n_tile * 128);
+  p.b_bytes = (uint32_t)(nv * p.n_tile * 128);
   p.n_loop = 1;
   p.acc_w = 0;
   p.resident = 0;
@@ -1365,8 +1393,14 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
     uint64_t str[3] = {(uint64_t)a->x_pix_stride * 2, (uint64_t)a->x_pix_stride * 2 * a->w,
                        (uint64_t)a->x_pix_stride * 2 * a->w * a->h};
     uint32_t box[4] = {64, (uint32_t)p.pitch, (uint32_t)rows, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (a->r == 4) {   // every second pixel in x and y: the bounding box is twice the tile, TW x rows pixels land in shared memory
+      box[1] *= 2;
+      box[2] *= 2;
+      es[1] = es[2] = 2;
+    }
     if (!encode_tmap_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x, dims, str, box,
-                           CU_TENSOR_MAP_SWIZZLE_128B))
+                           CU_TENSOR_MAP_SWIZZLE_128B, es))
       return SSR_E_CUDA;
   }
   {
@@ -1388,7 +1422,7 @@ static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
   for (int i = 0; i < n; ++i) {
     stage_bytes = max(stage_bytes, ps[i].a_alloc + ps[i].b_bytes);
     n_tile_max = max(n_tile_max, ps[i].n_tile);
-    iters += ((ps[i].chunks + ps[i].splits - 1) / ps[i].splits) * ps[i].R;
+    iters += ((ps[i].chunks + ps[i].splits - 1) / ps[i].splits) * (ps[i].R == 4 ? 8 : ps[i].R);
   }
   const int budget = g_smem_optin - 1024 - 256 - 2048;
   int stages = budget / (int)stage_bytes;
@@ -1469,9 +1503,24 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   const size_t smem_bytes = finalize_ring(&p, 1, mt);
   if (!smem_bytes) return SSR_E_ARG;
   dim3 grid((unsigned)persistent_ctas(p), (unsigned)(p.n_pad / p.n_tile), (unsigned)p.splits);
-  auto kern = mt == 1 ? (p.R == 3 ? conv_tc_kernel<1, 3> : conv_tc_kernel<1, 1>) : (p.R == 3 ? conv_tc_kernel<2, 3> : conv_tc_kernel<2, 1>);
-  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
-  return launch_conv(kern, &configured[mt * 2 + (p.R == 3 ? 1 : 0)], grid, 1, smem_bytes, stream, "conv_tc launch", 0, tmA, tmB, p);
+  static size_t configured[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  size_t* cfgd = &configured[(mt - 1) * 5 + p.R];
+#define SSR_LAUNCH_CONV(MT_, R_) launch_conv(conv_tc_kernel<MT_, R_>, cfgd, grid, 1, smem_bytes, stream, "conv_tc launch", 0, tmA, tmB, p)
+  if (mt == 1) {
+    switch (p.R) {
+      case 1: return SSR_LAUNCH_CONV(1, 1);
+      case 2: return SSR_LAUNCH_CONV(1, 2);
+      case 3: return SSR_LAUNCH_CONV(1, 3);
+      default: return SSR_LAUNCH_CONV(1, 4);
+    }
+  }
+  switch (p.R) {
+    case 1: return SSR_LAUNCH_CONV(2, 1);
+    case 2: return SSR_LAUNCH_CONV(2, 2);
+    case 3: return SSR_LAUNCH_CONV(2, 3);
+    default: return SSR_LAUNCH_CONV(2, 4);
+  }
+#undef SSR_LAUNCH_CONV
 }
 
 // diagnostics: with SSR_CHAIN_TIMELINE=1 every chained launch overwrites a [512 CTAs][kMaxChain][8] table of clock64 stamps

@@ -334,8 +334,9 @@ struct PackDesc {
 static constexpr int kPackNT = 8;
 __global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
   const PackDesc d = descs[blockIdx.y];
-  if (d.mode != SSR_PACK_FWD && d.mode != SSR_PACK_DGRAD) return;
+  if (d.mode != SSR_PACK_FWD && d.mode != SSR_PACK_DGRAD && d.mode != SSR_PACK_DGRAD_S2) return;
   __shared__ __nv_bfloat16 tile[16 * kPackNT * 64];   // [tap (kx * r + ky)][row][k]
+  const bool s2 = d.mode == SSR_PACK_DGRAD_S2;        // r == 4: sixteen taps -> four parity classes of a 2 x 2 kernel
   const int chunks = d.k_pad / 64;
   const int T = d.r * d.r;
   const int n_tiles = (d.n_pad + kPackNT - 1) / kPackNT;
@@ -363,11 +364,19 @@ __global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
       float v = 0.f;
       if (n < n_valid && k < k_valid) v = fwd ? d.w[((long)n * d.cin + k) * T + tap] : d.w[((long)k * d.cin + n) * T + tap];
       int ky = tap / d.r, kx = tap - ky * d.r;              // source tap (ky, kx); the input-gradient operand mirrors both
-      if (!fwd) {
-        ky = d.r - 1 - ky;
-        kx = d.r - 1 - kx;
+      int slot;
+      if (s2) {
+        // dx[2u + oy] collects w[ky] * dy[u - (1 - oy) + a] with ky = oy ? 2 - 2a : 3 - 2a  <=>  oy = 1 - (ky & 1), a = 1 - (ky >> 1)
+        const int oy = 1 - (ky & 1), a = 1 - (ky >> 1), ox = 1 - (kx & 1), b = 1 - (kx >> 1);
+        slot = (oy * 2 + ox) * 4 + b * 2 + a;
+      } else {
+        if (!fwd) {
+          ky = d.r - 1 - ky;
+          kx = d.r - 1 - kx;
+        }
+        slot = kx * d.r + ky;
       }
-      tile[((kx * d.r + ky) * kPackNT + nn) * 64 + kl] = __float2bfloat16(v * sc);
+      tile[(slot * kPackNT + nn) * 64 + kl] = __float2bfloat16(v * sc);
     }
     __syncthreads();
     // rows out: dst[((c * r + kx) * r + ky) * n_pad + n][64], 16 bytes per thread
@@ -375,7 +384,9 @@ __global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
     for (int o = threadIdx.x; o < T * kPackNT * 8; o += blockDim.x) {
       const int tp = o / (kPackNT * 8), rem = o - tp * kPackNT * 8, nn = rem >> 3;
       const int n = n0 + nn;
-      if (n < d.n_pad) reinterpret_cast<uint4*>(d.dst + (((long)c * T + tp) * d.n_pad + n) * 64)[rem & 7] = t4[o];
+      // plain: [chunk][tap][n][64]; parity classes: [class][chunk][2 x 2 tap][n][64]
+      const long row = s2 ? (((long)(tp >> 2) * chunks + c) * 4 + (tp & 3)) * d.n_pad + n : ((long)c * T + tp) * d.n_pad + n;
+      if (n < d.n_pad) reinterpret_cast<uint4*>(d.dst + row * 64)[rem & 7] = t4[o];
     }
     __syncthreads();
   }

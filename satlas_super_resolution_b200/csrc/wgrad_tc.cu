@@ -42,10 +42,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint64_t* bar_tmem = bar_empty + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tmem + 1);
 
+  // R = 1, 3: stride-1 conv, a CTA owns (128-channel block, kx) and keeps the R vertical taps in R accumulators.
+  // R = 4: the 4 x 4 stride-2 conv of the discriminator -- X is gathered with element strides (2, 2); a CTA owns
+  //        (128-channel block, kx, parity of ky) and keeps the two taps ky = parity, parity + 2 (consecutive box rows).
+  constexpr int NH = R == 4 ? 8 : R;
+  constexpr int NV = R == 4 ? 2 : R;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int mtile = blockIdx.y / R;
-  const int kx = blockIdx.y % R;
+  const int mtile = blockIdx.y / NH;
+  const int hs = blockIdx.y % NH;
+  const int kx = R == 4 ? (hs >> 1) : hs;
+  const int par = R == 4 ? (hs & 1) : 0;
   const int n0 = blockIdx.z * p.n_tile;
   const int per = (p.total_tiles + p.splits - 1) / p.splits;
   const int t_begin = blockIdx.x * per;
@@ -93,8 +100,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         uint8_t* xs = smem + (size_t)s * p.stage_bytes;
         uint8_t* ys = xs + x_bytes;
         mbar_expect_tx(&bar_full[s], nchunks * p.x_chunk_bytes + p.y_blocks * p.y_blk_bytes);
-        for (int ch = 0; ch < nchunks; ++ch)
-          tma_load_4d(xs + (size_t)ch * p.x_chunk_bytes, &tmX, &bar_full[s], mtile * 128 + ch * 64, x0 + kx - p.pad, y0 - p.pad, n);
+        for (int ch = 0; ch < nchunks; ++ch) {
+          if (R == 4) tma_load_4d(xs + (size_t)ch * p.x_chunk_bytes, &tmX, &bar_full[s], mtile * 128 + ch * 64, 2 * x0 + kx - 1, 2 * y0 + par - 1, n);
+          else tma_load_4d(xs + (size_t)ch * p.x_chunk_bytes, &tmX, &bar_full[s], mtile * 128 + ch * 64, x0 + kx - p.pad, y0 - p.pad, n);
+        }
         for (int yb = 0; yb < p.y_blocks; ++yb)
           tma_load_4d(ys + (size_t)yb * p.y_blk_bytes, &tmY, &bar_full[s], n0 + yb * 64, x0, y0, n);
       }
@@ -119,14 +128,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint64_t db0 = umma_desc(xs + x_bytes, p.y_blk_bytes, 8u * (uint32_t)p.y_rowbytes, y_layout);
         if (p.ksteps == 8) {
 #pragma unroll
-          for (int ky = 0; ky < R; ++ky) {
+          for (int ky = 0; ky < NV; ++ky) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
               umma_bf16_ss(tmem_base + (uint32_t)(ky * p.n_tile), da0 + (ky * a_tap + ks * a_k), db0 + ks * b_k, idesc,
                            ks == 0 ? acc : 1u);
           }
         } else {
-          for (int ky = 0; ky < R; ++ky)
+          for (int ky = 0; ky < NV; ++ky)
             for (int ks = 0; ks < p.ksteps; ++ks)
               umma_bf16_ss(tmem_base + (uint32_t)(ky * p.n_tile), da0 + (ky * a_tap + ks * a_k), db0 + ks * b_k, idesc,
                            ks == 0 ? acc : 1u);
@@ -147,13 +156,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // accumulator layout [cy / 4][R*R taps * cx_rows][4]: 32 consecutive cx rows of one channel quad are 512 contiguous bytes
     const long plane = (long)R * R * p.cx_rows * 4;
 #pragma unroll 1
-    for (int ky = 0; ky < R; ++ky) {
+    for (int vt = 0; vt < NV; ++vt) {
+      const int ky = R == 4 ? par + 2 * vt : vt;
       float* dst = p.out + ((long)(ky * R + kx) * p.cx_rows + cxi) * 4;
 #pragma unroll 1
       for (int cb = 0; cb < p.n_tile; cb += 16) {
         uint32_t v[16];
         __syncwarp();
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ky * p.n_tile + cb), v);
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(vt * p.n_tile + cb), v);
         tmem_ld_wait();
         if (!valid) continue;
 #pragma unroll
@@ -264,12 +274,14 @@ using namespace ssr;
 extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SSR_REQUIRE(a && a->x && a->dy && a->out, "ssr_wgrad_tc: null pointer");
-  SSR_REQUIRE(a->r == 1 || a->r == 3, "ssr_wgrad_tc: r must be 1 or 3");
+  SSR_REQUIRE(a->r == 1 || a->r == 3 || a->r == 4, "ssr_wgrad_tc: r must be 1, 3 or 4 (the 4 x 4 stride-2 conv)");
+  const bool s2 = a->r == 4;
+  if (s2) SSR_REQUIRE(a->h % 2 == 0 && a->w % 2 == 0 && a->w >= 16, "ssr_wgrad_tc: r == 4: (h, w) is the even INPUT size of the stride-2 conv");
   SSR_REQUIRE(a->w >= 8 && a->h > 0 && a->n_img > 0, "ssr_wgrad_tc: geometry");
   SSR_REQUIRE(a->cx > 0 && a->cy > 0, "ssr_wgrad_tc: channels");
   SSR_REQUIRE(a->x_pix_stride % 8 == 0 && a->dy_pix_stride % 8 == 0, "ssr_wgrad_tc: strides must be multiples of 8");
   SSR_REQUIRE(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->dy)) & 15) == 0, "ssr_wgrad_tc: alignment");
-  {
+  if (!s2) {
     // fast path: all nine taps from one halo tile per CTA (cy <= 64, power-of-two tile widths)
     const int rc = launch_wgrad9(a, stream);
     if (rc <= 0) return rc;
@@ -283,16 +295,20 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
       return SSR_E_CUDA;
     if (!check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v), "cudaFuncSetAttribute(wgrad)"))
       return SSR_E_CUDA;
+    if (!check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v), "cudaFuncSetAttribute(wgrad)"))
+      return SSR_E_CUDA;
   }
   WgradK p{};
-  p.n_img = a->n_img; p.H = a->h; p.W = a->w; p.R = a->r; p.pad = (a->r - 1) / 2;
-  p.TW = a->w >= 128 ? 128 : round_up(a->w, 8);
+  const int oh = s2 ? a->h / 2 : a->h, ow = s2 ? a->w / 2 : a->w;   // the dY grid the pixel tiles walk
+  const int nh = s2 ? 8 : a->r, nv = s2 ? 2 : a->r;
+  p.n_img = a->n_img; p.H = oh; p.W = ow; p.R = a->r; p.pad = a->r == 3 ? 1 : 0;
+  p.TW = ow >= 128 ? 128 : round_up(ow, 8);
   p.TH = 128 / p.TW;
   while (p.TH > 1 && (p.TW * p.TH) % 16) --p.TH;
   SSR_REQUIRE((p.TW * p.TH) % 16 == 0, "ssr_wgrad_tc: tile %dx%d not a multiple of 16 pixels", p.TW, p.TH);
   p.ksteps = p.TW * p.TH / 16;
-  p.tiles_x = (a->w + p.TW - 1) / p.TW;
-  p.tiles_y = (a->h + p.TH - 1) / p.TH;
+  p.tiles_x = (ow + p.TW - 1) / p.TW;
+  p.tiles_y = (oh + p.TH - 1) / p.TH;
   p.total_tiles = p.tiles_x * p.tiles_y * a->n_img;
   p.cx = a->cx; p.cx_rows = a->out_cx_rows; p.cy = a->cy; p.out_stride = a->out_stride;
   SSR_REQUIRE(p.cx_rows >= p.cx && p.out_stride >= p.cy && p.out_stride % 4 == 0, "ssr_wgrad_tc: output too small / cy stride not a multiple of 4");
@@ -302,13 +318,13 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
   else { p.n_tile = 128; p.y_blocks = 2; p.y_rowbytes = 128; }
   const int n_tiles = (a->cy + p.n_tile - 1) / p.n_tile;
   const int mtiles = (a->cx + 127) / 128;
-  p.x_chunk_bytes = (uint32_t)(p.TW * (p.TH + p.R - 1)) * 128u;
+  p.x_chunk_bytes = (uint32_t)(p.TW * (p.TH + nv - 1)) * 128u;
   p.y_blk_bytes = (uint32_t)(p.TW * p.TH * p.y_rowbytes);
   p.stage_bytes = (uint32_t)round_up((int)(2 * p.x_chunk_bytes + p.y_blocks * p.y_blk_bytes), 1024);
   int stages = (g_w_smem_optin - 1280) / (int)p.stage_bytes;
   SSR_REQUIRE(stages >= 1, "ssr_wgrad_tc: stage does not fit shared memory");
   if (stages > 4) stages = 4;
-  int units = mtiles * p.R * n_tiles;
+  int units = mtiles * nh * n_tiles;
   static int target_ctas = -1;
   if (target_ctas < 0) {
     const char* e = getenv("SSR_WGRAD_CTAS");
@@ -321,7 +337,7 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
   { int per = (p.total_tiles + splits - 1) / splits; if (stages > per) stages = per; }
   p.stages = stages;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(p.R * p.n_tile)) cols <<= 1;
+  while (cols < (uint32_t)(nv * p.n_tile)) cols <<= 1;
   p.tmem_cols = cols;
   p.out = a->out;
   p.scale = a->scale;
@@ -330,18 +346,24 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
   {
     uint64_t dims[4] = {(uint64_t)a->cx, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
     uint64_t str[3] = {(uint64_t)a->x_pix_stride * 2, (uint64_t)a->x_pix_stride * 2 * a->w, (uint64_t)a->x_pix_stride * 2 * a->w * a->h};
-    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)(p.TH + p.R - 1), 1};
-    if (!encode_tmap_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return SSR_E_CUDA;
+    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)(p.TH + nv - 1), 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (s2) {   // every second pixel of X: bounding box twice the tile
+      box[1] *= 2;
+      box[2] *= 2;
+      es[1] = es[2] = 2;
+    }
+    if (!encode_tmap_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, es)) return SSR_E_CUDA;
   }
   {
-    uint64_t dims[4] = {(uint64_t)a->cy, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
-    uint64_t str[3] = {(uint64_t)a->dy_pix_stride * 2, (uint64_t)a->dy_pix_stride * 2 * a->w, (uint64_t)a->dy_pix_stride * 2 * a->w * a->h};
+    uint64_t dims[4] = {(uint64_t)a->cy, (uint64_t)ow, (uint64_t)oh, (uint64_t)a->n_img};
+    uint64_t str[3] = {(uint64_t)a->dy_pix_stride * 2, (uint64_t)a->dy_pix_stride * 2 * ow, (uint64_t)a->dy_pix_stride * 2 * ow * oh};
     uint32_t box[4] = {(uint32_t)(p.y_rowbytes / 2), (uint32_t)p.TW, (uint32_t)p.TH, 1};
     if (!encode_tmap_tiled(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->dy, dims, str, box,
                            p.y_rowbytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return SSR_E_CUDA;
   }
   const size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024 + 256;
-  dim3 grid((unsigned)splits, (unsigned)(mtiles * p.R), (unsigned)n_tiles);
+  dim3 grid((unsigned)splits, (unsigned)(mtiles * nh), (unsigned)n_tiles);
   prof_before(1, stream);
   {
     cudaLaunchConfig_t cfg{};
@@ -354,7 +376,9 @@ extern "C" int ssr_wgrad_tc(const ssr_wgrad_tc_args* a, void* stream_) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    cudaError_t e = p.R == 3 ? cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<3>, tmX, tmY, p) : cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<1>, tmX, tmY, p);
+    cudaError_t e = p.R == 3 ? cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<3>, tmX, tmY, p)
+                    : p.R == 4 ? cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<4>, tmX, tmY, p)
+                               : cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<1>, tmX, tmY, p);
     if (!check_cuda(e, "wgrad_tc launch")) return SSR_E_CUDA;
   }
   prof_after(stream);

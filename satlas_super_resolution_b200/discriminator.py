@@ -1,7 +1,8 @@
 """U-Net spectral-norm discriminator engine (forward, input gradient, weight gradients) over the C ABI.
 
 Mirrors /root/reference/ssr/archs/discriminator_arch.py:42-71:
-  conv0 (3x3, bias) -> conv1..3 (4x4 stride 2, spectral norm; im2col + tcgen05 GEMM) -> bilinear x2 -> conv4 (+x2)
+  conv0 (3x3, bias) -> conv1..3 (4x4 stride 2, spectral norm; implicit GEMM: the TMA box gathers every second pixel per tap,
+  no im2col columns; input gradient = four 2x2 parity-class convs over dY scattered to (2y+oy, 2x+ox)) -> bilinear x2 -> conv4 (+x2)
   -> bilinear x2 -> conv5 (+x1) -> bilinear x2 -> conv6 (+x0) -> conv7, conv8 -> conv9 (bias) -> logits.
 The three `x = x + skip` adds are folded into the consumer (the bilinear kernel's second source / one axpby), so the
 LeakyReLU outputs stay available unmodified as the masks of the backward pass.
@@ -14,7 +15,7 @@ import torch
 
 from . import _lib as L
 from ._protos import SnDesc
-from .ops import (Act, GemmConv, PackedConv, Packer, Plan, WgradSet, conv_args, cur_stream, lib, plan_wgrad, round_up)
+from .ops import (Act, PackedConv, Packer, Plan, WgradSet, conv_args, cur_stream, dgrad_s2_class_ptr, lib, plan_wgrad, round_up)
 
 SN_LAYERS = ["conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv8"]
 
@@ -34,7 +35,8 @@ class UNetDiscEngine:
         cv = {}
         cv["conv0"] = PackedConv(params["conv0.weight"], params["conv0.bias"], self.cin_pad, True, dev)
         for i, name in enumerate(("conv1", "conv2", "conv3")):
-            cv[name] = GemmConv(params[f"{name}.weight_orig"], True, dev, inv_scale=sg(i))
+            w = params[f"{name}.weight_orig"]
+            cv[name] = PackedConv(w, None, w.shape[1], True, dev, inv_scale=sg(i))
         for i, name in enumerate(("conv4", "conv5", "conv6", "conv7", "conv8")):
             w = params[f"{name}.weight_orig"]
             cv[name] = PackedConv(w, None, w.shape[1], True, dev, inv_scale=sg(3 + i))
@@ -65,7 +67,6 @@ class UNetDiscEngine:
             self.wg = WgradSet(dev)
             self.wg.add("conv0", cv["conv0"], self.cin_pad)
             for name in ("conv1", "conv2", "conv3"):
-                # GEMM form: rows = (ky, kx, ci) = taps x cin, exactly the [taps][cin] layout the unpack expects
                 self.wg.add(name, cv[name], cv[name].cin)
             for name in ("conv4", "conv5", "conv6", "conv7", "conv8", "conv9"):
                 self.wg.add(name, cv[name], cv[name].cin)
@@ -136,11 +137,8 @@ class _DWorkspace:
         A = lambda hh, ww, c: Act(B, hh, ww, c, dev)
         self.x_in = Act(B, H, W, eng.cin_pad, dev, zero=True)
         self.x0 = A(H, W, nf)
-        self.col1 = torch.empty((B * (H // 2) * (W // 2), 16 * nf), dtype=torch.bfloat16, device=dev)
         self.x1 = A(H // 2, W // 2, nf * 2)
-        self.col2 = torch.empty((B * (H // 4) * (W // 4), 16 * nf * 2), dtype=torch.bfloat16, device=dev)
         self.x2 = A(H // 4, W // 4, nf * 4)
-        self.col3 = torch.empty((B * (H // 8) * (W // 8), 16 * nf * 4), dtype=torch.bfloat16, device=dev)
         self.x3 = A(H // 8, W // 8, nf * 8)
         self.x3u = A(H // 4, W // 4, nf * 8)
         self.a4 = A(H // 4, W // 4, nf * 4)
@@ -164,16 +162,15 @@ class _DWorkspace:
         plan.conv(conv_args(self.x_in.ptr(), B, H, W, self.x_in.stride, eng.cin_pad, c.packed.data_ptr(), 3, c.cout, c.n_pad,
                             bias=c.bias.data_ptr(), act=1, out=self.x0.ptr(), out_stride=nf))
 
-        def strided(name, src, col, dst, hh, ww, cin):
+        def strided(name, src, dst, hh, ww, cin):
+            """4 x 4 stride-2 pad-1 conv + LeakyReLU (discriminator_arch.py:45-47) straight from the NHWC input: (hh, ww) = input size"""
             c = cv[name]
-            plan.add(lb.ssr_im2col, src.ptr(), src.stride, col.data_ptr(), B, hh, ww, cin, 4, 2, 1)
-            m = B * (hh // 2) * (ww // 2)
-            plan.conv(conv_args(col.data_ptr(), 1, 1, m, 16 * cin, 16 * cin, c.packed.data_ptr(), 1, c.cout, c.n_pad, act=1,
-                                out=dst.ptr(), out_stride=dst.stride))
+            plan.conv(conv_args(src.ptr(), B, hh, ww, src.stride, cin, c.packed.data_ptr(), 4, c.cout, c.n_pad, act=1,
+                                out=dst.ptr(), out_stride=dst.stride, stride=2))
 
-        strided("conv1", self.x0, self.col1, self.x1, H, W, nf)
-        strided("conv2", self.x1, self.col2, self.x2, H // 2, W // 2, nf * 2)
-        strided("conv3", self.x2, self.col3, self.x3, H // 4, W // 4, nf * 4)
+        strided("conv1", self.x0, self.x1, H, W, nf)
+        strided("conv2", self.x1, self.x2, H // 2, W // 2, nf * 2)
+        strided("conv3", self.x2, self.x3, H // 4, W // 4, nf * 4)
 
         def conv3(name, src, dst, hh, ww):
             c = cv[name]
@@ -214,14 +211,11 @@ class _DWorkspace:
         gs4, g4 = A(H // 4, W // 4, nf * 4), A(H // 4, W // 4, nf * 4)
         gx3u = A(H // 4, W // 4, nf * 8)
         gx3, g3 = A(H // 8, W // 8, nf * 8), A(H // 8, W // 8, nf * 8)
-        dcol3 = torch.empty_like(self.col3)
         g2 = A(H // 4, W // 4, nf * 4)
-        dcol2 = torch.empty_like(self.col2)
         g1 = A(H // 2, W // 2, nf * 2)
-        dcol1 = torch.empty_like(self.col1)
         g0 = A(H, W, nf)
         self.d_in = A(H, W, eng.cin_pad)
-        self._keep = [g8, g7, gx6, g6, gx5u, gs5, g5, gx4u, gs4, g4, gx3u, gx3, g3, dcol3, g2, dcol2, g1, dcol1, g0]
+        self._keep = [g8, g7, gx6, g6, gx5u, gs5, g5, gx4u, gs4, g4, gx3u, gx3, g3, g2, g1, g0]
         sk = eng.skip
         grads = eng.grads
 
@@ -269,21 +263,25 @@ class _DWorkspace:
             plan.add(lb.ssr_axpby, gx3.ptr(), nf * 8, 1.0, None, 0, 0.0, self.x3.ptr(), nf * 8, 0, g3.ptr(), nf * 8,
                      B * (H // 8) * (W // 8), nf * 8)
 
-            def strided_bwd(name, gy, cy, col, dcol, dst, hh, ww, cin, skip_grad, act_in):
-                """gy: dY of the strided conv [M][cy]; hh, ww = INPUT size of the conv; dst = dY of the producer."""
+            def strided_bwd(name, gy, cy, src, dst, hh, ww, cin, skip_grad, act_in):
+                """gy: dY of the strided conv [B, hh/2, ww/2, cy]; (hh, ww) = INPUT size of the conv; src = its input activation;
+                dst = dY of the producer = (conv^T(gy) + skip gradient) * LeakyReLU'(act_in).  The transposed conv runs as four
+                2 x 2 convs over gy, one per parity (oy, ox) of the output pixel: dx[2u+oy, 2v+ox] reads gy rows u - (1-oy) + {0, 1}."""
                 c = cv[name]
-                m = B * (hh // 2) * (ww // 2)
-                kk = 16 * cin
-                plan.conv(conv_args(gy.ptr(), 1, 1, m, cy, cy, c.packed_dg.data_ptr(), 1, kk, c.n_pad_dg,
-                                    out=dcol.data_ptr(), out_stride=kk))
-                wgrad(name, col.data_ptr(), kk, kk, gy.ptr(), cy, cy, 1, 1, m, r=1)
-                plan.add(lb.ssr_col2im, dcol.data_ptr(), dst.ptr(), dst.stride, B, hh, ww, cin, 4, 2, 1,
-                         skip_grad.ptr() if (skip_grad is not None and sk) else None,
-                         skip_grad.stride if skip_grad is not None else 0, act_in.ptr(), act_in.stride)
+                res = {}
+                if skip_grad is not None and sk:
+                    res = dict(res1=skip_grad.ptr(), res1_kind=L.SSR_BF16, res1_stride=skip_grad.stride, s1=1.0)
+                for cls in range(4):
+                    oy, ox = divmod(cls, 2)
+                    plan.conv(conv_args(gy.ptr(), B, hh // 2, ww // 2, gy.stride, cy, dgrad_s2_class_ptr(c, cls), 2, cin, c.n_pad_dg,
+                                        pad_y=1 - oy, pad_x=1 - ox, out_oy=oy, out_ox=ox,
+                                        mask=act_in.ptr(), mask_stride=act_in.stride, mask_lo=0,
+                                        out=dst.ptr(), out_stride=dst.stride, **res))
+                wgrad(name, src.ptr(), src.stride, cin, gy.ptr(), gy.stride, cy, B, hh, ww, r=4)
 
-            strided_bwd("conv3", g3, nf * 8, self.col3, dcol3, g2, H // 4, W // 4, nf * 4, gs4, self.x2)
-            strided_bwd("conv2", g2, nf * 4, self.col2, dcol2, g1, H // 2, W // 2, nf * 2, gs5, self.x1)
-            strided_bwd("conv1", g1, nf * 2, self.col1, dcol1, g0, H, W, nf, gx6, self.x0)
+            strided_bwd("conv3", g3, nf * 8, self.x2, g2, H // 4, W // 4, nf * 4, gs4, self.x2)
+            strided_bwd("conv2", g2, nf * 4, self.x1, g1, H // 2, W // 2, nf * 2, gs5, self.x1)
+            strided_bwd("conv1", g1, nf * 2, self.x0, g0, H, W, nf, gx6, self.x0)
             wgrad("conv0", self.x_in.ptr(), self.x_in.stride, eng.cin_pad, g0.ptr(), nf, nf, B, H, W)
             if with_wgrad:
                 plan.add(lb.ssr_bias_grad, g0.ptr(), nf, B * H * W, nf, grads["conv0.bias"].data_ptr(), 1.0)

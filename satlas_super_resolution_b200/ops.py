@@ -119,10 +119,18 @@ class PackedConv:
             # dg_inv_scale: the input-gradient operand may carry a constant factor (1 / dg_inv_scale) of its own
             dg_inv = getattr(self, "dg_inv_scale", None)
             d.inv_scale = dg_inv.data_ptr() if dg_inv is not None else (self.inv_scale.data_ptr() if self.inv_scale is not None else None)
-            d.cout, d.cin, d.r, d.mode, d.k_pad, d.n_pad = (self.cout, self.cin, self.r, L.PACK_DGRAD, self.k_pad_dg,
-                                                            self.n_pad_dg)
+            # a 4 x 4 kernel is the stride-2 conv: its input gradient runs as four 2 x 2 parity-class convs (SSR_PACK_DGRAD_S2)
+            d.cout, d.cin, d.r, d.mode, d.k_pad, d.n_pad = (self.cout, self.cin, self.r, L.PACK_DGRAD_S2 if self.r == 4 else L.PACK_DGRAD,
+                                                            self.k_pad_dg, self.n_pad_dg)
             out.append(d)
         return out
+
+
+def dgrad_s2_class_ptr(conv, cls):
+    """device pointer of parity class `cls` (= oy * 2 + ox) inside the SSR_PACK_DGRAD_S2 operand of a 4 x 4 stride-2 conv:
+    [class][cout chunk][2 x 2 tap][n_pad][64] bf16"""
+    per_class = (conv.k_pad_dg // 64) * 4 * conv.n_pad_dg * 64 * 2
+    return conv.packed_dg.data_ptr() + cls * per_class
 
 
 class Packer:
@@ -148,7 +156,8 @@ def conv_args(x_ptr, B, H, W, x_stride, cin, w_ptr, r, cout, n_pad, bias=None, a
               res2=None, res2_kind=L.SSR_BF16, res2_stride=0, s2=0.0,
               mask=None, mask_stride=0, mask_lo=0, mask_relu=0,
               out=None, out_stride=0, out32=None, out32_mode=L.OUT32_NONE, out32_stride=0,
-              n_tile=0, mt=0, splits=0, res1_cmax=0, out_lo=0, bias_grad=None, bias_grad_scale=1.0):
+              n_tile=0, mt=0, splits=0, res1_cmax=0, out_lo=0, bias_grad=None, bias_grad_scale=1.0,
+              stride=0, pad_y=0, pad_x=0, out_oy=0, out_ox=0):
     a = L.ConvTcArgs()
     a.x, a.n_img, a.h, a.w, a.x_pix_stride, a.cin = x_ptr, B, H, W, x_stride, cin
     a.w_packed, a.r, a.cout, a.n_pad = w_ptr, r, cout, n_pad
@@ -168,6 +177,7 @@ def conv_args(x_ptr, B, H, W, x_stride, cin, w_ptr, r, cout, n_pad, bias=None, a
     a.out_lo = out_lo
     if bias_grad is not None:
         a.bias_grad, a.bias_grad_scale = bias_grad, bias_grad_scale
+    a.stride, a.pad_y, a.pad_x, a.out_oy, a.out_ox = stride, pad_y, pad_x, out_oy, out_ox
     return a
 
 

@@ -536,3 +536,39 @@ def test_chains_without_the_resident_kernel_in_subprocess():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", "chain_equals_plain or chain_acc"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("B,cin,cout,H,W", [(2, 64, 128, 32, 32), (1, 128, 256, 64, 64), (3, 256, 512, 16, 32), (32, 64, 128, 128, 128)])
+def test_strided_4x4_conv_forward_and_transposed_parity_classes(B, cin, cout, H, W):
+    """discriminator conv1..3 (discriminator_arch.py:30-32, 45-47): the 4 x 4 stride-2 pad-1 conv as an implicit GEMM (TMA element
+    strides gather every second pixel per tap; no im2col columns), and its input gradient as four 2 x 2 parity-class convs over dY
+    that scatter to (2y + oy, 2x + ox) with the skip-gradient add and the LeakyReLU mask of the producer fused in."""
+    from satlas_super_resolution_b200.ops import PackedConv, Packer, conv_args, dgrad_s2_class_ptr
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(cin + H)
+    x = bf16_round(torch.randn(B, cin, H, W, generator=g))
+    w = bf16_round(torch.randn(cout, cin, 4, 4, generator=g) / (cin * 16) ** 0.5)
+    wd = w.cuda().contiguous()
+    cv = PackedConv(wd, None, cin, True, "cuda")
+    Packer([cv], "cuda").run(None)
+    xb = nhwc_buffer(x)
+    out = torch.full((B, H // 2, W // 2, cout), 7.0, dtype=torch.bfloat16, device="cuda")
+    a = conv_args(xb.data_ptr(), B, H, W, cin, cin, cv.packed.data_ptr(), 4, cout, cv.n_pad, act=1, out=out.data_ptr(), out_stride=cout, stride=2)
+    L.check(lib.ssr_conv_tc(C.byref(a), None))
+    torch.cuda.synchronize()
+    ref = F.leaky_relu(F.conv2d(x, w, stride=2, padding=1), 0.2)
+    assert rel_err(out.float().cpu().permute(0, 3, 1, 2), ref) < 2 ** -7
+    # ---- transposed: dX = (conv_transpose(dY) + skip) * LeakyReLU'(x)
+    dy = bf16_round(torch.randn(B, cout, H // 2, W // 2, generator=g))
+    skip = bf16_round(torch.randn(B, cin, H, W, generator=g))
+    dyb, skb = nhwc_buffer(dy), nhwc_buffer(skip)
+    dx = torch.full((B, H, W, cin), 7.0, dtype=torch.bfloat16, device="cuda")
+    for cls in range(4):
+        oy, ox = divmod(cls, 2)
+        a = conv_args(dyb.data_ptr(), B, H // 2, W // 2, cout, cout, dgrad_s2_class_ptr(cv, cls), 2, cin, cv.n_pad_dg,
+                      pad_y=1 - oy, pad_x=1 - ox, out_oy=oy, out_ox=ox, mask=xb.data_ptr(), mask_stride=cin, mask_lo=0,
+                      res1=skb.data_ptr(), res1_kind=L.SSR_BF16, res1_stride=cin, s1=1.0, out=dx.data_ptr(), out_stride=cin)
+        L.check(lib.ssr_conv_tc(C.byref(a), None))
+    torch.cuda.synchronize()
+    ref_dx = (F.conv_transpose2d(dy, w, stride=2, padding=1) + skip) * torch.where(x > 0, 1.0, 0.2)
+    assert rel_err(dx.float().cpu().permute(0, 3, 1, 2), ref_dx) < 2 ** -7

@@ -72,3 +72,27 @@ def test_wgrad_slices_and_scale():
     ref, rb = ref_wgrad(x, dy, 3, scale=0.2)
     assert rel_err(got, ref) < 1e-4
     assert rel_err(gb, rb) < 1e-4
+
+
+@pytest.mark.parametrize("B,cx,cy,H,W", [(2, 64, 128, 32, 32), (1, 128, 256, 64, 64), (2, 256, 512, 16, 32), (4, 64, 128, 128, 128)])
+def test_wgrad_strided_4x4(B, cx, cy, H, W):
+    """weight gradient of the 4 x 4 stride-2 pad-1 conv straight from the NHWC input (element-strided TMA gather per tap)"""
+    from satlas_super_resolution_b200 import _lib as L
+    from satlas_super_resolution_b200._protos import WgradArgs
+    lib = L.load()
+    g = torch.Generator().manual_seed(cx + H)
+    x = bf16_round(torch.randn(B, cx, H, W, generator=g))
+    dy = bf16_round(torch.randn(B, cy, H // 2, W // 2, generator=g))
+    xb, db = nhwc_buffer(x), nhwc_buffer(dy)
+    acc = torch.zeros((16, cx, cy), dtype=torch.float32, device="cuda")
+    a = WgradArgs()
+    a.x, a.n_img, a.h, a.w, a.x_pix_stride, a.cx = xb.data_ptr(), B, H, W, cx, cx
+    a.dy, a.dy_pix_stride, a.cy, a.r = db.data_ptr(), cy, cy, 4
+    a.out, a.out_cx_rows, a.out_stride, a.scale, a.splits = acc.data_ptr(), cx, cy, 1.0, 0
+    L.check(lib.ssr_wgrad_tc(C.byref(a), None))
+    grad = torch.zeros((cy, cx, 4, 4), dtype=torch.float32, device="cuda")
+    L.check(lib.ssr_wgrad_unpack(acc.data_ptr(), cx, cy, grad.data_ptr(), cy, cx, 4, 1.0, 0, None))
+    torch.cuda.synchronize()
+    w = torch.zeros(cy, cx, 4, 4, requires_grad=True)
+    F.conv2d(x, w, stride=2, padding=1).backward(dy)
+    assert rel_err(grad.cpu(), w.grad) < 1e-4
