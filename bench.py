@@ -13,7 +13,7 @@ build_model(opt) -> MODEL_REGISTRY['SSRESRGANModel'].
   value : pairs/s, whole job, inputs already resident in HBM, device-timed (CUDA events, max over ranks)
   e2e   : the plugin call sequence model.feed_data({'lr','hr'} HOST pinned uint8) / model.optimize_parameters(it) /
           model.get_current_log(): H2D copy inside the timed region, loss scalars read back (D2H) every step
-  roofline          : the dominant kernel, conv_chain_kernel (a ResidualDenseBlock's five convs / five input-gradient convs per
+  roofline          : the dominant kernel, rdb_resident_kernel (a ResidualDenseBlock's five convs / five input-gradient convs per
                       launch), algorithmic FLOPs / summed device time (per-launch CUDA events in one extra eager step)
   roofline_kernels  : the same for the single-launch conv kernel and the two weight-gradient kernels
   cpu_baseline      : the CPU restatement of the reference step (oracle/step.py, torch fp32) on this box's host cores
@@ -340,12 +340,12 @@ def train_rooflines(m, bands, peak, peak_src):
     ms, cnt = m["ms_cls"], m["cnt_cls"]
     chain_flop = N_RDB * F_RDB * B
     traffic = ncu_traffic()
-    t_chain = dict(traffic.get("conv_chain_kernel") or {})
-    main = roofline_entry("ssr::conv_chain_kernel (one ResidualDenseBlock per launch: its five forward convs, or its five input-gradient "
-                          "convs; tcgen05 implicit GEMM)", 2 * chain_flop, ms[2] + ms[3], cnt[2] + cnt[3], peak, peak_src,
+    t_chain = dict(traffic.get("rdb_resident_kernel") or traffic.get("conv_chain_kernel") or {})
+    main = roofline_entry("ssr::rdb_resident_kernel (one ResidualDenseBlock per launch: its five forward convs, or its five input-gradient "
+                          "convs; tcgen05 implicit GEMM over a shared-memory-resident 192-channel tile, one 4-CTA cluster per image)", 2 * chain_flop, ms[2] + ms[3], cnt[2] + cnt[3], peak, peak_src,
                           dict(traffic=t_chain.get("dram_bytes_per_launch"), traffic_note=t_chain.get("note"),
-                               forward=roofline_entry("conv_chain_kernel, forward", chain_flop, ms[2], cnt[2], peak, peak_src),
-                               input_gradient=roofline_entry("conv_chain_kernel, input gradient", chain_flop, ms[3], cnt[3], peak, peak_src)))
+                               forward=roofline_entry("rdb_resident_kernel<false>, forward", chain_flop, ms[2], cnt[2], peak, peak_src),
+                               input_gradient=roofline_entry("rdb_resident_kernel<true>, input gradient", chain_flop, ms[3], cnt[3], peak, peak_src)))
     others = {
         "conv_tc_kernel": roofline_entry("ssr::conv_tc_kernel (single-launch convs: G head / tail, D, VGG19; forward + input gradient)",
                                          f["conv"] * B - 2 * chain_flop, ms[0], cnt[0], peak, peak_src),

@@ -773,18 +773,30 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
     tmem_relinquish();
   }
   {
-    // the chunks the block input does not fill start as zeros: image borders stay zero, interior halo columns are written by
-    // the neighbour CTAs layer by layer.  Generic-proxy stores that the tensor core reads later: proxy fence.
-    uint4* z = reinterpret_cast<uint4*>(dense + (size_t)p.res_in_chunks * kRChunk);
-    const int n16 = (int)(((size_t)(kTileChunks - p.res_in_chunks) * kRChunk) >> 4);
-    for (int i = (int)threadIdx.x; i < n16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    // Only the halo pixels on the IMAGE border must be zero in the chunks the block input does not fill (chunk 0 is zero-filled
+    // by TMA): the top and bottom tile rows (a strip spans the whole image height) and the outer column of the first / last
+    // strip.  Interior halo columns are written by the neighbour CTAs layer by layer before anything reads them, interior
+    // pixels by this CTA's own epilogues.  Generic-proxy stores that the tensor core reads later: proxy fence.
+    const uint32_t rank0 = cluster_ctarank(), nr0 = cluster_nctarank();
+    constexpr int kRows = 2 * kRPitch + 2 * 32;   // 10 + 10 pixels of the two border rows, 32 + 32 of the two border columns
+    for (int i = (int)threadIdx.x; i < (kTileChunks - p.res_in_chunks) * kRows * 8; i += kThreads) {
+      const int piece = i & 7, r = (i >> 3) % kRows, c = p.res_in_chunks + (i >> 3) / kRows;
+      int row;
+      if (r < kRPitch) row = r;                                            // top halo row
+      else if (r < 2 * kRPitch) row = 33 * kRPitch + (r - kRPitch);        // bottom halo row
+      else if (r < 2 * kRPitch + 32) row = rank0 == 0 ? (r - 2 * kRPitch + 1) * kRPitch : -1;                    // left image border
+      else row = rank0 + 1 == nr0 ? (r - 2 * kRPitch - 32 + 1) * kRPitch + (kRPitch - 1) : -1;                   // right image border
+      if (row >= 0) *reinterpret_cast<uint4*>(dense + (size_t)c * kRChunk + (size_t)row * 128 + piece * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
     fence_proxy_async();
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  cluster_sync_all();   // no remote store / arrive may reach shared memory that is not initialised yet
+  // no remote store / arrive may reach shared memory that is not initialised yet: cluster barrier, split -- every thread arrives
+  // now and waits only in front of its first access to a peer CTA (by then the peers have long arrived: no start-up stall)
+  cluster_arrive();
   // everything above touched only this CTA's smem / TMEM.  griddepcontrol.wait (the previous kernel has completed and its memory
   // is visible) is executed per role: the epilogue warps before their first global access, the producer only in front of the
   // activation tile -- the first ring-full of WEIGHTS (written by the pack kernel long before the previous launch) streams in
@@ -838,6 +850,7 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
       }
     }
     if (!tile_loaded) load_tile();
+    cluster_wait();   // (the producer touches peers only with multicast weight loads)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     int g = 0;
@@ -846,6 +859,8 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
     const uint32_t acc_cols = p.acc_stride;
     const uint32_t dense_addr = smem_u32(dense);
     const uint32_t ring_addr = smem_u32(ring);
+    if (mc) cluster_wait();   // multicast commits arrive on the peers' barriers
+    bool cl_waited = mc;
 #pragma unroll 1
     for (int l = 0; l < n_layers; ++l) {
       const ConvTcK q = ps[l];
@@ -956,6 +971,7 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
     const uint32_t rank = cluster_ctarank();
     const uint32_t n_rank = cluster_nctarank();
     griddep_wait();   // before the first global access (bias, masks, residuals, stores)
+    bool cl_waited = false;
 #pragma unroll 1
     for (int l = 0; l < n_layers; ++l) {
       const ConvTcK p = ps[l];
@@ -1109,6 +1125,10 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
         const uint32_t j0 = (uint32_t)(dc & 63) >> 3;              // 16-byte piece of the 128-byte row
         uint4 keep[2][2];
         uint32_t va[2][16];
+        if (!cl_waited) {            // first access to the neighbours' shared memory
+          cluster_wait();
+          cl_waited = true;
+        }
         __syncwarp();
         acc_load(0, ci, va[0]);      // both M tiles in flight, one wait
         acc_load(1, ci, va[1]);
@@ -1188,6 +1208,7 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
       }
     }
   }
+  if (warp == 1 && !cc.multicast) cluster_wait();           // (the MMA warp itself never touches a peer)
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();   // no CTA may exit while a peer can still push halo columns into its shared memory
@@ -1301,7 +1322,10 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
     const long tiles1 = (long)((out_w + p.TW - 1) / p.TW) * ((out_h + p.TH - 1) / p.TH) * a->n_img;
     mt = 1;
     if (forced == 1 || forced == 2) mt = forced;
-    else if (out_h >= 2 * p.TH && tiles1 >= 200 && 2 * nt_guess <= 512) mt = 2;
+    // measured (scripts/bench_conv.py, B = 32, warm): stacking pays for the 32-wide dense-block layers (conv4: 11.1 vs 12.0 us),
+    // where the weight tile is small next to the activation tile; 64-wide and wider layers run 8 - 15 % FASTER with one M tile per
+    // CTA (64 -> 64 @ 128^2: 66 vs 71 us, @ 64^2: 19.4 vs 22.9 us): twice as many tiles balance better over the 148 SMs
+    else if (out_h >= 2 * p.TH && tiles1 >= 200 && nt_guess <= 32) mt = 2;
   }
   SSR_REQUIRE(mt == 1 || mt == 2, "ssr_conv_tc: mt must be 1 or 2");
   p.tiles_x = (out_w + p.TW - 1) / p.TW;

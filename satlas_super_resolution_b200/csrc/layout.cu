@@ -347,36 +347,50 @@ __global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
   for (int tl = blockIdx.x; tl < chunks * n_tiles; tl += gridDim.x) {
     const int c = tl / n_tiles, n0 = (tl - c * n_tiles) * kPackNT;
     const int total = kPackNT * 64 * T;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-      int nn, kl, tap;
-      if (fwd) {            // e = (nn, kl, tap): source w[n][k][ky][kx] contiguous in (kl, tap)
-        nn = e / (64 * T);
-        const int rem = e - nn * 64 * T;
-        kl = rem / T;
-        tap = rem - kl * T;
-      } else {              // e = (kl, nn, tap): source w[k][n][ky][kx] contiguous in (nn, tap)
-        kl = e / (kPackNT * T);
-        const int rem = e - kl * kPackNT * T;
-        nn = rem / T;
-        tap = rem - nn * T;
-      }
-      const int n = n0 + nn, k = c * 64 + kl;
-      float v = 0.f;
-      if (n < n_valid && k < k_valid) v = fwd ? d.w[((long)n * d.cin + k) * T + tap] : d.w[((long)k * d.cin + n) * T + tap];
-      int ky = tap / d.r, kx = tap - ky * d.r;              // source tap (ky, kx); the input-gradient operand mirrors both
-      int slot;
-      if (s2) {
-        // dx[2u + oy] collects w[ky] * dy[u - (1 - oy) + a] with ky = oy ? 2 - 2a : 3 - 2a  <=>  oy = 1 - (ky & 1), a = 1 - (ky >> 1)
-        const int oy = 1 - (ky & 1), a = 1 - (ky >> 1), ox = 1 - (kx & 1), b = 1 - (kx >> 1);
-        slot = (oy * 2 + ox) * 4 + b * 2 + a;
-      } else {
-        if (!fwd) {
-          ky = d.r - 1 - ky;
-          kx = d.r - 1 - kx;
+    // six source elements per thread in flight (one dependent load -> shared-memory store per iteration made this kernel
+    // latency bound: 17 us per 4608-element tile)
+    constexpr int U = 6;
+    for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * U) {
+      float vals[U];
+      int slots[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * (int)blockDim.x;
+        vals[u] = 0.f;
+        slots[u] = -1;
+        if (e >= total) continue;
+        int nn, kl, tap;
+        if (fwd) {            // e = (nn, kl, tap): source w[n][k][ky][kx] contiguous in (kl, tap)
+          nn = e / (64 * T);
+          const int rem = e - nn * 64 * T;
+          kl = rem / T;
+          tap = rem - kl * T;
+        } else {              // e = (kl, nn, tap): source w[k][n][ky][kx] contiguous in (nn, tap)
+          kl = e / (kPackNT * T);
+          const int rem = e - kl * kPackNT * T;
+          nn = rem / T;
+          tap = rem - nn * T;
         }
-        slot = kx * d.r + ky;
+        const int n = n0 + nn, k = c * 64 + kl;
+        if (n < n_valid && k < k_valid) vals[u] = fwd ? __ldg(d.w + ((long)n * d.cin + k) * T + tap) : __ldg(d.w + ((long)k * d.cin + n) * T + tap);
+        int ky = tap / d.r, kx = tap - ky * d.r;              // source tap (ky, kx); the input-gradient operand mirrors both
+        int slot;
+        if (s2) {
+          // dx[2u + oy] collects w[ky] * dy[u - (1 - oy) + a] with ky = oy ? 2 - 2a : 3 - 2a  <=>  oy = 1 - (ky & 1), a = 1 - (ky >> 1)
+          const int oy = 1 - (ky & 1), a = 1 - (ky >> 1), ox = 1 - (kx & 1), b = 1 - (kx >> 1);
+          slot = (oy * 2 + ox) * 4 + b * 2 + a;
+        } else {
+          if (!fwd) {
+            ky = d.r - 1 - ky;
+            kx = d.r - 1 - kx;
+          }
+          slot = kx * d.r + ky;
+        }
+        slots[u] = (slot * kPackNT + nn) * 64 + kl;
       }
-      tile[(slot * kPackNT + nn) * 64 + kl] = __float2bfloat16(v * sc);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (slots[u] >= 0) tile[slots[u]] = __float2bfloat16(vals[u] * sc);
     }
     __syncthreads();
     // rows out: dst[((c * r + kx) * r + ky) * n_pad + n][64], 16 bytes per thread
@@ -543,7 +557,7 @@ extern "C" int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, 
   static_assert(sizeof(ssr_pack_desc) == sizeof(PackDesc), "ssr_pack_desc layout");
   // blocks per layer: the generator has 702 small operands (4 .. 24 tiles of 4608 elements each) -- more than a few blocks per
   // layer only adds block-launch overhead (22 k mostly empty blocks cost 0.2 ms); the discriminator has 20 large ones
-  dim3 grid(n_layers > 64 ? 4u : 96u, (unsigned)n_layers);
+  dim3 grid(n_layers > 64 ? 8u : 96u, (unsigned)n_layers);
   pack_batched_kernel<<<grid, 256, 0, STREAM(stream)>>>(reinterpret_cast<const PackDesc*>(descs_device));
   count_launch();
   if (has_gemm_forms) {

@@ -71,6 +71,10 @@ __device__ __forceinline__ void st_shared_cluster_v4(uint32_t local_addr, uint32
       "r"(cta_rank), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
       : "memory");
 }
+// split-phase form: arrive early (e.g. right after this CTA's barriers are initialised), wait only in front of the first
+// access to a peer's shared memory
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }

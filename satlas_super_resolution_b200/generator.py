@@ -194,7 +194,15 @@ class _Workspace:
                                     res2=t_blk.data_ptr(), res2_kind=L.SSR_F32_PLANAR4, res2_stride=nf, s2=1.0,
                                     out=nxt.ptr(0), out_stride=nxt.stride,
                                     out32=t_nxt.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf))
-            plan.chain(block)
+            # Training batches (one cluster of 4 CTAs per image, <= one wave of the 148 SMs) run the block as ONE shared-memory-
+            # resident launch: latency-bound, but launch + prologue are paid once per block.  Large inference batches are the
+            # opposite regime -- many waves of CTAs: there the persistent per-layer kernel (tiles streamed back to back through
+            # double-buffered TMEM) keeps the tensor pipe busier than a chain that serialises five layers per CTA.
+            if self.train or B * max(1, (h * w) // 256) <= 2 * 148:
+                plan.chain(block)
+            else:
+                for a in block:
+                    plan.conv(a)
         c = eng.cv["conv_body"]
         plan.conv(conv_args(self.body_out.ptr(), B, h, w, nf, nf, c.packed.data_ptr(), 3, c.cout, c.n_pad, bias=bptr(c),
                             res1=self.trunk_of(0).data_ptr(), res1_kind=L.SSR_F32_PLANAR4, res1_stride=nf, s1=1.0,
