@@ -35,6 +35,8 @@ struct ConvTcK {
   int resident, res_out_ch, res_in_chunks;
   int res_in_lo;          // channel offset of this layer's INPUT inside the tile (0 forward; the dY slot of an input-gradient layer)
   uint32_t chunk_alloc;   // bytes of one 64-channel chunk of the resident tile ((TW+2) x (MT*TH+2) rows of 128 B, 1 KB aligned)
+  uint32_t w_bytes;       // > 0: weights-stationary single-layer launch (one 64-channel chunk): all R*R taps of this CTA's N tile are
+                          // loaded ONCE into a region of w_bytes behind the stage ring; the stages carry activations only
   int b_row_bytes;        // resident kernel: bytes of one weight row in shared memory -- 128 (64 K entries, SWIZZLE_128B) or 64 (a
                           // 32-channel input: only the first half of every packed row is loaded, SWIZZLE_64B)
   int acc_w;              // > 0: chain with ONE f32 accumulator of acc_w channels per pixel that stays in TMEM for all layers
@@ -58,6 +60,9 @@ struct ConvTcK {
   int out_lo;          // the bf16 output (and its bias-gradient sum) only covers channels >= out_lo
   float* bgrad;        // bgrad[c - out_lo] += bgrad_scale * sum over pixels of the bf16-path value, or NULL
   float bgrad_scale;
+  int lean;            // 1: the epilogue is bias / activation / scale / bf16 residual / mask -> bf16 store (+ bias gradient) only:
+                       // the short code path (profiles/r02_conv64_ncu.md: the general one was instruction-bound, 360 warp
+                       // instructions per 16-channel chunk)
 };
 
 static constexpr int kSyncNone = 0, kSyncGrid = 1, kSyncCluster = 2;
@@ -105,6 +110,31 @@ __device__ __forceinline__ void load16_f32(const float* p, float (&f)[16]) {
   }
 }
 
+// per-channel sum over the warp's 32 pixels of a 16-channel chunk: a transposing butterfly (16 values -> 1 per lane in 16
+// shuffles), then one shared-memory atomic per channel; the CTA adds its partial sums to global memory once per layer
+__device__ __forceinline__ void bias_grad_butterfly(const float (&f)[16], int lane, float* s_dst /* [16] of this chunk */) {
+  float g8[8], g4[4], g2[2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float keep = (lane & 16) ? f[j + 8] : f[j], send = (lane & 16) ? f[j] : f[j + 8];
+    g8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float keep = (lane & 8) ? g8[j + 4] : g8[j], send = (lane & 8) ? g8[j] : g8[j + 4];
+    g4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float keep = (lane & 4) ? g4[j + 2] : g4[j], send = (lane & 4) ? g4[j] : g4[j + 2];
+    g2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  float g1 = ((lane & 2) ? g2[1] : g2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 2) ? g2[0] : g2[1], 2);
+  g1 += __shfl_xor_sync(0xffffffffu, g1, 1);
+  const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  if ((lane & 1) == 0) atomicAdd(&s_dst[ch], g1);
+}
+
 // Persistent, warp-specialised kernel.  CTA c owns M-tile groups c, c + gridDim.x, ...; its three roles run as
 // independent loops coupled only by mbarriers:
 //   warp 0     TMA producer   : streams (chunk, kx) stages for tile after tile (runs ahead across tile boundaries)
@@ -136,13 +166,15 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
   const uint32_t stage_bytes = p.stage_stride;
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* const w_region = smem + (size_t)p.stages * stage_bytes;   // weights-stationary launches: all taps of this CTA's N tile
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(w_region + p.w_bytes);
   uint64_t* bar_empty = bar_full + p.stages;
   uint64_t* bar_acc_full = bar_empty + p.stages;   // [2] accumulator buffer b complete (MMA -> epilogue)
   uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2] accumulator buffer b drained  (epilogue -> MMA), 8 warp arrivals
-  uint64_t* bar_layer = bar_acc_empty + 2;         // kSyncCluster: every epilogue warp of the cluster arrives once per layer
+  uint64_t* bar_layer = bar_acc_empty + 2;         // kSyncCluster: every epilogue warp of the cluster arrives once per layer; else:
+                                                   // the stationary weights have landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_layer + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [256] bias of the layer's output channels
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [256] bias of the layer's output channels
   float* s_bg = s_bias + 256;                                // [256] per-CTA bias-gradient partial sums
 
   const int warp = threadIdx.x >> 5;
@@ -170,6 +202,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
         mbar_init(&bar_acc_empty[b], 8);
       }
       if (sync_mode == kSyncCluster) mbar_init(bar_layer, 8 * cluster_nctarank());
+      else mbar_init(bar_layer, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -210,6 +243,14 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
         prefetch_tmap(tmB);
       }
       if (lane == 0) SSR_STAMP(l, 0);   // producer: inputs of this layer are ready
+      if (q.w_bytes && elect_one()) {
+        // one 64-channel chunk: the R*R weight tiles of this CTA's N tile stay in shared memory for all its pixel tiles
+        const int n0w = (int)blockIdx.y * q.n_tile;
+        mbar_expect_tx(bar_layer, q.w_bytes);
+        for (int t = 0; t < R * R; ++t)   // t = kx * R + ky, the packed order
+          tma_load_2d(w_region + (size_t)t * q.n_tile * 128, tmB, bar_layer, 0, t * q.n_pad + n0w);
+      }
+      __syncwarp();
       for (int lt = 0; lt < my_tiles; ++lt) {
         int t = (int)blockIdx.x + lt * (int)gridDim.x;
         const int tx = t % q.tiles_x;
@@ -230,13 +271,15 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
           if (elect_one()) {
             uint8_t* a_dst = smem + (size_t)s * stage_bytes;
             uint8_t* b_dst = a_dst + q.a_alloc;
-            mbar_expect_tx(&bar_full[s], q.a_box_bytes + q.b_bytes);
+            mbar_expect_tx(&bar_full[s], q.a_box_bytes + (q.w_bytes ? 0u : q.b_bytes));
             if (R == 4) tma_load_4d(a_dst, tmA, &bar_full[s], c * 64, 2 * x0 + kx - 1, 2 * y0 + par - 1, n);   // input coordinates
             else tma_load_4d(a_dst, tmA, &bar_full[s], c * 64, x0 + kx - q.pad_x, y0 - q.pad_y, n);
+            if (!q.w_bytes) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              const int ky = R == 4 ? par + 2 * v : v;
-              tma_load_2d(b_dst + (size_t)v * q.n_tile * 128, tmB, &bar_full[s], 0, ((c * R + kx) * R + ky) * q.n_pad + n0);
+              for (int v = 0; v < NV; ++v) {
+                const int ky = R == 4 ? par + 2 * v : v;
+                tma_load_2d(b_dst + (size_t)v * q.n_tile * 128, tmB, &bar_full[s], 0, ((c * R + kx) * R + ky) * q.n_pad + n0);
+              }
             }
           }
           __syncwarp();
@@ -259,6 +302,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       const int c_begin = blockIdx.z * per;
       const int iters = (min(q.chunks, c_begin + per) - c_begin) * NH;
       const int items = my_tiles * q.n_loop;  // (pixel tile, N tile) work items of this layer
+      if (q.w_bytes) {
+        mbar_wait(bar_layer, 0);
+        tc_fence_after_sync();
+      }
+      const uint32_t w_addr = smem_u32(w_region);
       // TMEM-resident accumulator (acc_w > 0): channel c of M tile m is column m * acc_w + c in EVERY layer; layer 0 initialises,
       // later layers add; nothing is handed back by the epilogue (a layer only writes columns below the slot being drained)
       const uint32_t m_cols = q.acc_w ? (uint32_t)q.acc_w : (uint32_t)q.n_tile;
@@ -279,7 +327,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
           if (elect_one()) {
             const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
             const uint64_t da0 = umma_desc_k128(a_base);
-            const uint64_t db0 = umma_desc_k128(a_base + q.a_alloc);
+            // weights: behind the activation box of this stage, or (stationary) tap row kx of the resident region
+            const uint64_t db0 = q.w_bytes ? umma_desc_k128(w_addr + (uint32_t)((it % NH) * NV * q.n_tile * 128)) : umma_desc_k128(a_base + q.a_alloc);
             const int ks = min(4, (q.cin - c * 64) >> 4);
             if (ks == 4) {
 #pragma unroll
@@ -402,6 +451,150 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       }
     };
 
+    if (p.lean) {
+      // ---- short path (plain launches: no f32 output, no second residual, whole 16-channel chunks) ----
+      // A warp owns chunks half, half + 2, ... of its lane quarter and walks them in PAIRS: both TMEM loads are issued, the
+      // operands of the NEXT pair are requested, then one wait -- the accumulator-independent loads hide behind the TMEM reads.
+      const bool has_mk = use_mk, has_bg = p.bgrad != nullptr;
+      const bool has_r1 = use_r1;                                  // bf16, all channels (checked on the host)
+      const int npairs = nchunks > half ? (nchunks - half + 3) >> 2 : 0;
+      const int total = MT * npairs;
+      struct LeanOps {
+        uint4 r1[2][2], mk[2][2];
+      };
+      auto lean_fetch = [&](long pix, int ci, LeanOps& o) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int c0 = n_base + (ci + 2 * h2) * 16;
+          if (ci + 2 * h2 < nchunks && c0 + 16 <= p.cout) {
+            if (has_r1) {
+              const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res1) + pix * p.res1_stride + c0);
+              o.r1[h2][0] = s4[0];
+              o.r1[h2][1] = s4[1];
+            }
+            if (has_mk && c0 >= p.mask_lo) {
+              const uint4* s4 = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_stride + c0);
+              o.mk[h2][0] = s4[0];
+              o.mk[h2][1] = s4[1];
+            }
+          }
+        }
+      };
+      auto lean_chunk = [&](const uint32_t (&v)[16], int ci, long pix, bool in_img, const uint4 (&r1)[2], const uint4 (&mk)[2]) {
+        const int c0 = n_base + ci * 16;
+        const bool live = in_img && (c0 + 16 <= p.cout);
+        if (!live && !has_bg) return;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = live ? __uint_as_float(v[j]) : 0.f;
+        if (live) {
+          if (add_bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + ci * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 bv = b4[j];
+              f[4 * j] += bv.x;
+              f[4 * j + 1] += bv.y;
+              f[4 * j + 2] += bv.z;
+              f[4 * j + 3] += bv.w;
+            }
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.2f * f[j]);   // LeakyReLU(0.2)
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.s0 != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] *= p.s0;
+          }
+          if (has_r1) {
+            const uint32_t u[8] = {r1[0].x, r1[0].y, r1[0].z, r1[0].w, r1[1].x, r1[1].y, r1[1].z, r1[1].w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[2 * j] = fmaf(p.s1, bf16_lo(u[j]), f[2 * j]);
+              f[2 * j + 1] = fmaf(p.s1, bf16_hi(u[j]), f[2 * j + 1]);
+            }
+          }
+          if (has_mk && c0 >= p.mask_lo) {
+            const float neg = p.mask_relu ? 0.f : 0.2f;
+            const uint32_t u[8] = {mk[0].x, mk[0].y, mk[0].z, mk[0].w, mk[1].x, mk[1].y, mk[1].z, mk[1].w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[2 * j] *= (bf16_lo(u[j]) > 0.f ? 1.f : neg);
+              f[2 * j + 1] *= (bf16_hi(u[j]) > 0.f ? 1.f : neg);
+            }
+          }
+          uint4 o0, o1;
+          o0.x = pack_bf16(f[0], f[1]);
+          o0.y = pack_bf16(f[2], f[3]);
+          o0.z = pack_bf16(f[4], f[5]);
+          o0.w = pack_bf16(f[6], f[7]);
+          o1.x = pack_bf16(f[8], f[9]);
+          o1.y = pack_bf16(f[10], f[11]);
+          o1.z = pack_bf16(f[12], f[13]);
+          o1.w = pack_bf16(f[14], f[15]);
+          uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.out_stride + c0);
+          dst[0] = o0;
+          dst[1] = o1;
+        }
+        if (has_bg) bias_grad_butterfly(f, lane, &s_bg[ci * 16]);
+      };
+      LeanOps cur = {}, nxt = {};
+#pragma unroll 1
+      for (int lt = 0; lt < my_tiles; ++lt, ++gt) {
+        int t = (int)blockIdx.x + lt * (int)gridDim.x;
+        const int tx = t % p.tiles_x;
+        t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int n = t / p.tiles_y;
+        const int x = tx * p.TW + txx;
+        const int y0 = ty * (MT * p.TH);
+        long pixs[MT];
+        bool oks[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int y = y0 + mt * p.TH + tyy;
+          pixs[mt] = R == 2 ? ((long)n * (2 * p.H) + (2 * y + p.out_oy)) * (2 * p.W) + (2 * x + p.out_ox) : ((long)n * p.H + y) * p.W + x;
+          oks[mt] = (tyy < p.TH) && (y < p.H) && (x < p.W);
+        }
+        const int b = gt & 1;
+        const uint32_t d_base = tmem_base + (uint32_t)b * acc_cols + ((uint32_t)(q * 32) << 16);
+        if (total > 0 && oks[0]) lean_fetch(pixs[0], half, cur);   // overlaps the MMAs
+        mbar_wait(&bar_acc_full[b], (uint32_t)((gt >> 1) & 1));
+        tc_fence_after_sync();
+        if (et == 0 && lt == 0) SSR_STAMP(l, 4);
+        if (et == 0 && lt == my_tiles - 1) SSR_STAMP(l, 5);
+#pragma unroll 1
+        for (int it = 0; it < total; ++it) {
+          const int mt = (MT == 2 && it >= npairs) ? 1 : 0;
+          const int ci = half + 4 * (it - mt * npairs);
+          const bool two = ci + 2 < nchunks;
+          const long pix = (MT == 2 && mt) ? pixs[MT - 1] : pixs[0];
+          const bool ok = (MT == 2 && mt) ? oks[MT - 1] : oks[0];
+          uint32_t va[16], vb[16];
+          __syncwarp();
+          const uint32_t taddr = d_base + (uint32_t)mt * m_cols + (uint32_t)(ci * 16);
+          tmem_ld16(taddr, va);
+          if (two) tmem_ld16(taddr + 32u, vb);
+          if (it + 1 < total) {
+            const int mt2 = (MT == 2 && it + 1 >= npairs) ? 1 : 0;
+            const bool ok2 = (MT == 2 && mt2) ? oks[MT - 1] : oks[0];
+            if (ok2) lean_fetch((MT == 2 && mt2) ? pixs[MT - 1] : pixs[0], half + 4 * (it + 1 - mt2 * npairs), nxt);
+          }
+          tmem_ld_wait();
+          lean_chunk(va, ci, pix, ok, cur.r1[0], cur.mk[0]);
+          if (two) lean_chunk(vb, ci + 2, pix, ok, cur.r1[1], cur.mk[1]);
+          cur = nxt;
+        }
+        // this warp has finished reading accumulator buffer b: hand it back to the MMA issuer
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+      }
+    } else {
 #pragma unroll 1
     for (int lt = 0; lt < my_tiles; ++lt) {
       int t = (int)blockIdx.x + lt * (int)gridDim.x;
@@ -565,32 +758,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
             }
           }
           if (sum_bg) {
-            // per-channel sum over the warp's 32 pixels: a transposing butterfly (16 values -> 1 per lane in 16 shuffles),
-            // then one shared-memory atomic per channel; the CTA adds its partial sums to global memory once per layer
             if (!live) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] = 0.f;
             }
-            float g8[8], g4[4], g2[2];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float keep = (lane & 16) ? f[j + 8] : f[j], send = (lane & 16) ? f[j] : f[j + 8];
-              g8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float keep = (lane & 8) ? g8[j + 4] : g8[j], send = (lane & 8) ? g8[j] : g8[j + 4];
-              g4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const float keep = (lane & 4) ? g4[j + 2] : g4[j], send = (lane & 4) ? g4[j] : g4[j + 2];
-              g2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-            float g1 = ((lane & 2) ? g2[1] : g2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 2) ? g2[0] : g2[1], 2);
-            g1 += __shfl_xor_sync(0xffffffffu, g1, 1);
-            const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            if ((lane & 1) == 0) atomicAdd(&s_bg[c0 - n_base + ch], g1);
+            bias_grad_butterfly(f, lane, &s_bg[c0 - n_base]);
           }
         }
       }
@@ -600,6 +772,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       if (lane == 0 && !p.acc_w) mbar_arrive(&bar_acc_empty[b]);
       }  // N tiles
     }
+    }   // general epilogue
     if (p.bgrad != nullptr) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int i = et; i < p.n_loop * p.n_tile; i += kThreads - 64) {
@@ -1443,19 +1616,20 @@ static int prepare_conv(const ssr_conv_tc_args* a, int mt_force, ConvTcK& p, CUt
 static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
   uint32_t stage_bytes = 0;
   int n_tile_max = 0, iters = 0;
+  const uint32_t w_bytes = n == 1 ? ps[0].w_bytes : 0u;
   for (int i = 0; i < n; ++i) {
-    stage_bytes = max(stage_bytes, ps[i].a_alloc + ps[i].b_bytes);
+    stage_bytes = max(stage_bytes, ps[i].a_alloc + (w_bytes ? 0u : ps[i].b_bytes));
     n_tile_max = max(n_tile_max, ps[i].n_tile);
     iters += ((ps[i].chunks + ps[i].splits - 1) / ps[i].splits) * (ps[i].R == 4 ? 8 : ps[i].R);
   }
-  const int budget = g_smem_optin - 1024 - 256 - 2048;
+  const int budget = g_smem_optin - 1024 - 256 - 2048 - (int)w_bytes;
   int stages = budget / (int)stage_bytes;
   if (stages < 1) {
     set_error("ssr_conv_tc: stage of %u bytes does not fit shared memory", stage_bytes);
     return 0;
   }
   // prefer two co-resident CTAs per SM when that still leaves a >= 3 deep pipeline
-  int stages_half = (budget / 2 - 1024) / (int)stage_bytes;
+  int stages_half = ((g_smem_optin - 1024 - 256 - 2048) / 2 - 1024 - (int)w_bytes) / (int)stage_bytes;
   if (stages_half >= 3 && n == 1) stages = stages_half;
   if (stages > 8) stages = 8;
   if (stages > iters) stages = iters;
@@ -1469,7 +1643,7 @@ static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
     ps[i].acc_stride = (uint32_t)(mt * n_tile_max);
     ps[i].tmem_cols = cols;
   }
-  return (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias, bias-gradient sums*/;
+  return (size_t)stages * stage_bytes + w_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias, bias-gradient sums*/;
 }
 
 static int persistent_ctas(const ConvTcK& p) {
@@ -1524,6 +1698,29 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   CUtensorMap tmA, tmB;
   int mt = 0;
   if (int rc = prepare_conv(a, 0, p, tmA, tmB, mt)) return rc;
+  {
+    // Weights-stationary form: with a single 64-channel chunk the whole weight operand of an N tile (9 taps x n_tile x 128 B:
+    // 72 KB at 64 output channels) fits beside the activation ring, and a persistent CTA re-uses it for all its pixel tiles --
+    // the per-tile L2 -> SM traffic halves (measured 64 -> 64 @ 128^2: load-bound at 583 TFLOP/s before).
+    static int ws = -1;
+    if (ws < 0) {
+      const char* e = getenv("SSR_CONV_WSTAT");
+      ws = e ? atoi(e) : 1;
+    }
+    const long tiles = (long)p.tiles_x * p.tiles_y * p.n_img;
+    const uint32_t wb = (uint32_t)(p.R * p.R * p.n_tile * 128);
+    if (ws && p.R == 3 && p.chunks == 1 && p.splits == 1 && tiles >= 2L * persistent_ctas(p) && wb + 3u * p.a_alloc <= (uint32_t)(g_smem_optin - 4096))
+      p.w_bytes = wb;
+  }
+  {
+    static int lean = -1;
+    if (lean < 0) {
+      const char* e = getenv("SSR_CONV_LEAN");
+      lean = e ? atoi(e) : 1;
+    }
+    p.lean = lean && a->cout % 16 == 0 && p.splits == 1 && p.out32_mode == SSR_OUT32_NONE && p.res2_kind == SSR_NONE &&
+             (p.res1_kind == SSR_NONE || (p.res1_kind == SSR_BF16 && p.res1_cmax == 0)) && p.out_lo == 0 && p.out_bf16 != nullptr;
+  }
   const size_t smem_bytes = finalize_ring(&p, 1, mt);
   if (!smem_bytes) return SSR_E_ARG;
   dim3 grid((unsigned)persistent_ctas(p), (unsigned)(p.n_pad / p.n_tile), (unsigned)p.splits);

@@ -263,14 +263,16 @@ class _DWorkspace:
             plan.add(lb.ssr_axpby, gx3.ptr(), nf * 8, 1.0, None, 0, 0.0, self.x3.ptr(), nf * 8, 0, g3.ptr(), nf * 8,
                      B * (H // 8) * (W // 8), nf * 8)
 
-            def strided_bwd(name, gy, cy, src, dst, hh, ww, cin, skip_grad, act_in):
+            def strided_bwd(name, gy, cy, src, dst, hh, ww, cin, skip_grad, act_in, bias_grad=None):
                 """gy: dY of the strided conv [B, hh/2, ww/2, cy]; (hh, ww) = INPUT size of the conv; src = its input activation;
                 dst = dY of the producer = (conv^T(gy) + skip gradient) * LeakyReLU'(act_in).  The transposed conv runs as four
                 2 x 2 convs over gy, one per parity (oy, ox) of the output pixel: dx[2u+oy, 2v+ox] reads gy rows u - (1-oy) + {0, 1}."""
                 c = cv[name]
                 res = {}
+                if bias_grad is not None:     # dst = dY of the producing conv: its bias gradient is the pixel sum, taken in the epilogues
+                    res = dict(bias_grad=bias_grad.data_ptr(), bias_grad_scale=1.0)
                 if skip_grad is not None and sk:
-                    res = dict(res1=skip_grad.ptr(), res1_kind=L.SSR_BF16, res1_stride=skip_grad.stride, s1=1.0)
+                    res.update(res1=skip_grad.ptr(), res1_kind=L.SSR_BF16, res1_stride=skip_grad.stride, s1=1.0)
                 for cls in range(4):
                     oy, ox = divmod(cls, 2)
                     plan.conv(conv_args(gy.ptr(), B, hh // 2, ww // 2, gy.stride, cy, dgrad_s2_class_ptr(c, cls), 2, cin, c.n_pad_dg,
@@ -281,10 +283,9 @@ class _DWorkspace:
 
             strided_bwd("conv3", g3, nf * 8, self.x2, g2, H // 4, W // 4, nf * 4, gs4, self.x2)
             strided_bwd("conv2", g2, nf * 4, self.x1, g1, H // 2, W // 2, nf * 2, gs5, self.x1)
-            strided_bwd("conv1", g1, nf * 2, self.x0, g0, H, W, nf, gx6, self.x0)
+            strided_bwd("conv1", g1, nf * 2, self.x0, g0, H, W, nf, gx6, self.x0,
+                        bias_grad=grads["conv0.bias"] if with_wgrad else None)
             wgrad("conv0", self.x_in.ptr(), self.x_in.stride, eng.cin_pad, g0.ptr(), nf, nf, B, H, W)
-            if with_wgrad:
-                plan.add(lb.ssr_bias_grad, g0.ptr(), nf, B * H * W, nf, grads["conv0.bias"].data_ptr(), 1.0)
             return plan
 
         self.bwd = build(False)

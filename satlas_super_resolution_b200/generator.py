@@ -269,13 +269,15 @@ class _Workspace:
         # ---- tail: conv_last <- conv_hr <- conv_up_n ... conv_up1
         c = eng.cv["conv_last"]
         plan.conv(conv_args(self.d_last.ptr(), B, H, W, 16, 16, c.packed_dg.data_ptr(), 3, nf, c.n_pad_dg,
-                            mask=self.hr.ptr(), mask_stride=nf, mask_lo=0, out=gA.ptr(), out_stride=nf))
+                            mask=self.hr.ptr(), mask_stride=nf, mask_lo=0, out=gA.ptr(), out_stride=nf,
+                            bias_grad=grads["conv_hr.bias"].data_ptr(), bias_grad_scale=1.0))   # gA = dY of conv_hr
         wgrad("conv_last", self.hr.ptr(), nf, nf, self.d_last.ptr(), 16, eng.cout, B, H, W)
         c = eng.cv["conv_hr"]
         top = self.up_out[-1]
         plan.conv(conv_args(gA.ptr(), B, H, W, nf, nf, c.packed_dg.data_ptr(), 3, nf, c.n_pad_dg,
-                            mask=top.ptr(), mask_stride=nf, mask_lo=0, out=gB.ptr(), out_stride=nf))
-        wgrad("conv_hr", top.ptr(), nf, nf, gA.ptr(), nf, nf, B, H, W)
+                            mask=top.ptr(), mask_stride=nf, mask_lo=0, out=gB.ptr(), out_stride=nf,
+                            bias_grad=grads[f"conv_up{eng.n_up}.bias"].data_ptr(), bias_grad_scale=1.0))   # gB = dY of the last conv_up
+        wgrad("conv_hr", top.ptr(), nf, nf, gA.ptr(), nf, nf, B, H, W, bias=False)
         dy = gB            # dY of conv_up{n}
         hh, ww = H, W
         spare = gA
@@ -286,7 +288,7 @@ class _Workspace:
             self._bwd_keep.append(d_ui)
             plan.conv(conv_args(dy.ptr(), B, hh, ww, nf, nf, c.packed_dg.data_ptr(), 3, nf, c.n_pad_dg,
                                 out=d_ui.ptr(), out_stride=nf))
-            wgrad(f"conv_up{u + 1}", ui.ptr(), nf, nf, dy.ptr(), nf, nf, B, hh, ww)
+            wgrad(f"conv_up{u + 1}", ui.ptr(), nf, nf, dy.ptr(), nf, nf, B, hh, ww, bias=(u != eng.n_up - 1))
             hh, ww = hh // 2, ww // 2
             if u > 0:
                 nxt = Act(B, hh, ww, nf, dev)

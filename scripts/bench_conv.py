@@ -9,6 +9,7 @@ from satlas_super_resolution_b200.ops import conv_args, cur_stream
 
 lib = L.load()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+ONLY = sys.argv[2] if len(sys.argv) > 2 else ""   # substring filter on the case name (for ncu captures)
 
 
 def time_graph(fn, reps=50):
@@ -61,10 +62,14 @@ print(f"B={B}")
 for name, cin, cout, hw in (("rdb conv1", 64, 32, 32), ("rdb conv2", 96, 32, 32), ("rdb conv3", 128, 32, 32), ("rdb conv4", 160, 32, 32),
                             ("rdb conv5", 192, 64, 32), ("dgrad5", 64, 192, 32), ("dgrad4", 32, 160, 32), ("dgrad3", 32, 128, 32),
                             ("dgrad2", 32, 96, 32), ("dgrad1", 32, 64, 32), ("hr 128^2", 64, 64, 128), ("up1 64^2", 64, 64, 64)):
+    if ONLY not in name:
+        continue
     for mt in (1, 2):
         us, tf = conv_case(cin, cout, hw, hw, mt)
         print(f"conv  {name:10s} {cin:3d}->{cout:3d} {hw:3d}^2 mt={mt}: {us:7.1f} us  {tf:7.1f} TFLOP/s")
 for name, cx, cy, hw in (("rdb conv1", 64, 32, 32), ("rdb conv3", 128, 32, 32), ("rdb conv4", 160, 32, 32), ("rdb conv5", 192, 64, 32),
                          ("hr 128^2", 64, 64, 128)):
+    if ONLY not in name:
+        continue
     us, tf = wgrad_case(cx, cy, hw, hw)
     print(f"wgrad {name:10s} {cx:3d}x{cy:3d} {hw:3d}^2: {us:7.1f} us  {tf:7.1f} TFLOP/s")
