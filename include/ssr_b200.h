@@ -165,6 +165,9 @@ int ssr_conv_tc_chain_acc_supported(int32_t n_img, int32_t h, int32_t w, int32_t
 /* diagnostics: how many chains ran as the shared-memory-resident dense-block kernel (32-row images, 8 | w <= 64, the channel pattern
  * of ResidualDenseBlock; SSR_CONV_RESIDENT=0 disables it) */
 int64_t ssr_debug_resident_launches(void);
+/* diagnostics: how many ssr_conv_tc launches took path `which`: 0 = halo tile + stationary weights (3 x 3, cin % 64 == 0, enough
+ * tiles; SSR_CONV_HALO=0 disables), 1 = the short epilogue (SSR_CONV_LEAN=0 disables), 2 = stationary weights in the streamed form */
+int64_t ssr_debug_conv_path_count(int32_t which);
 /* diagnostics: with SSR_CHAIN_TIMELINE=1 in the environment every chained launch records clock64 stamps
  * [cta][layer (5)][8 events]; copies the first n_ctas (<= 512) rows of the LAST launch to host memory (synchronises). */
 int ssr_debug_chain_timeline(long long* host_out, int32_t n_ctas);

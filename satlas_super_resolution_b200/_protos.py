@@ -56,6 +56,7 @@ PROTOS = {
     "ssr_adam_ema": (C.c_int, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, f32, vp, vp]),
     "ssr_debug_chain_timeline": (C.c_int, [vp, i32]),
     "ssr_debug_resident_launches": (C.c_int64, []),
+    "ssr_debug_conv_path_count": (C.c_int64, [i32]),
     "ssr_wgrad_tc": (C.c_int, [C.POINTER(WgradArgs), vp]),
     "ssr_wgrad_tc_batched": (C.c_int, [C.POINTER(WgradArgs), i32, vp]),
     "ssr_wgrad_unpack": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, f32, i32, vp]),

@@ -60,6 +60,7 @@ struct ConvTcK {
   int out_lo;          // the bf16 output (and its bias-gradient sum) only covers channels >= out_lo
   float* bgrad;        // bgrad[c - out_lo] += bgrad_scale * sum over pixels of the bf16-path value, or NULL
   float bgrad_scale;
+  int halo;            // 1: conv_tc_kernel<MT, 5> -- halo tile + stationary weights (host-side bookkeeping only)
   int lean;            // 1: the epilogue is bias / activation / scale / bf16 residual / mask -> bf16 store (+ bias gradient) only:
                        // the short code path (profiles/r02_conv64_ncu.md: the general one was instruction-bound, 360 warp
                        // instructions per 16-channel chunk)
@@ -80,6 +81,10 @@ struct ConvChainK {
 };
 
 static constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// halo tile (resident dense block, and the 3 x 3 convs with stationary weights): 8-pixel strips with one halo pixel each side
+static constexpr int kRPitch = 10, kRTH = 16;                  // tile row = 8 pixels + 2 halo pixels; rows per M tile
+static constexpr uint32_t kRTapRow = kRPitch * 128 / 16;       // descriptor units (16 B): one tile row down
+static constexpr uint32_t kRMt = kRTH * kRPitch * 128 / 16;    // ... the second M tile
 
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
@@ -158,8 +163,13 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
   //        2, 2), one stage per (chunk, kx, parity of ky) holding the two taps ky = parity, parity + 2 as consecutive box rows.
   // R = 2: one parity class of the TRANSPOSED 4 x 4 stride-2 conv (its input gradient): a 2 x 2 stride-1 conv over dY with
   //        per-launch pads (0 | 1), whose output pixel (y, x) is stored at (2y + oy, 2x + ox).
-  constexpr int NH = R == 4 ? 8 : R;   // stages per 64-channel chunk
-  constexpr int NV = R == 4 ? 2 : R;   // vertical taps per stage
+  // R = 5: the 3 x 3 stride-1 conv again, in the HALO form: 8-pixel strips whose tile keeps one halo pixel on every side
+  //        (rows of 10 pixels, SBO = 1280 B), ONE stage per 64-channel chunk feeding all 9 taps through descriptor offsets, all
+  //        weights of the CTA's N tile stationary in shared memory.  The activation tile is read once instead of three times and
+  //        the MMA issuer spends 36 instructions-with-constant-offsets per stage instead of 3 x (wait, 12 MMAs, commit).
+  constexpr int NH = R == 4 ? 8 : (R == 5 ? 1 : R);   // stages per 64-channel chunk
+  constexpr int NV = R == 4 ? 2 : (R == 5 ? 3 : R);   // vertical taps per stage
+  constexpr int TAPS = R == 5 ? 9 : R * R;
   const ConvTcK& p = ps[0];   // geometry, tiling and the shared-memory ring are identical for every layer of a chain
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -218,7 +228,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
-    int g = 0;  // running stage counter across tiles and layers
+    int ps_s = 0;          // ring stage and its phase, running across tiles and layers
+    uint32_t ps_ph = 0;
     for (int l = 0; l < n_layers; ++l) {
       const ConvTcK q = ps[l];   // by value: registers, not parameter-space loads repeated after every asm memory clobber
       const CUtensorMap* tmA = &tmAs[l];
@@ -247,7 +258,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
         // one 64-channel chunk: the R*R weight tiles of this CTA's N tile stay in shared memory for all its pixel tiles
         const int n0w = (int)blockIdx.y * q.n_tile;
         mbar_expect_tx(bar_layer, q.w_bytes);
-        for (int t = 0; t < R * R; ++t)   // t = kx * R + ky, the packed order
+        for (int t = 0; t < q.chunks * TAPS; ++t)   // t = (chunk * R + kx) * R + ky, the packed order
           tma_load_2d(w_region + (size_t)t * q.n_tile * 128, tmB, bar_layer, 0, t * q.n_pad + n0w);
       }
       __syncwarp();
@@ -260,13 +271,17 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
         const int x0 = tx * q.TW, y0 = ty * (MT * q.TH);
         for (int nb = 0; nb < q.n_loop; ++nb) {
         const int n0 = ((int)blockIdx.y * q.n_loop + nb) * q.n_tile;
-        for (int it = 0; it < iters; ++it, ++g) {
+        for (int it = 0; it < iters; ++it) {
           const int c = c_begin + it / NH;
           const int hs = it - (it / NH) * NH;
           const int kx = R == 4 ? (hs >> 1) : hs;
           const int par = R == 4 ? (hs & 1) : 0;
-          const int s = g % q.stages;
-          const uint32_t ph = (g / q.stages) & 1;
+          const int s = ps_s;
+          const uint32_t ph = ps_ph;
+          if (++ps_s == q.stages) {
+            ps_s = 0;
+            ps_ph ^= 1u;
+          }
           mbar_wait(&bar_empty[s], ph ^ 1);
           if (elect_one()) {
             uint8_t* a_dst = smem + (size_t)s * stage_bytes;
@@ -291,9 +306,10 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     // Descriptors differ only in their 14-bit start-address field: build one per stage, then add constant offsets.
-    const uint32_t a_tap = (uint32_t)(p.TW * 128) >> 4;        // one tile row down  (descriptor address units of 16 B)
-    const uint32_t a_mt = (uint32_t)(p.TH * p.TW * 128) >> 4;  // next stacked M tile
-    int g = 0, gt = 0;  // running stage / tile counters across layers
+    int gt = 0;            // running tile counter across layers
+    int ms_s = 0;          // ring stage and its phase, running across tiles and layers
+    uint32_t ms_ph = 0;
+    const uint32_t smem_addr0 = smem_u32(smem);
     for (int l = 0; l < n_layers; ++l) {
       const ConvTcK q = ps[l];
       const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)q.n_tile);
@@ -310,44 +326,78 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
       // TMEM-resident accumulator (acc_w > 0): channel c of M tile m is column m * acc_w + c in EVERY layer; layer 0 initialises,
       // later layers add; nothing is handed back by the epilogue (a layer only writes columns below the slot being drained)
       const uint32_t m_cols = q.acc_w ? (uint32_t)q.acc_w : (uint32_t)q.n_tile;
+      const int ks_last = min(4, (q.cin - (q.chunks - 1) * 64) >> 4);   // K steps of the (possibly short) last chunk
       for (int lt = 0; lt < items; ++lt, ++gt) {
         const int b = q.acc_w ? 0 : (gt & 1);
         if (!q.acc_w) mbar_wait(&bar_acc_empty[b], ((gt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator buffer
         tc_fence_after_sync();
         const uint32_t d_base = q.acc_w ? tmem_base + (uint32_t)((lt % q.n_loop) * q.n_tile) : tmem_base + (uint32_t)b * acc_cols;
         uint32_t acc = (q.acc_w && l > 0) ? 1u : 0u;
-        for (int it = 0; it < iters; ++it, ++g) {
+        for (int it = 0; it < iters; ++it) {
           const int c = c_begin + it / NH;
-          const int s = g % q.stages;
-          const uint32_t ph = (g / q.stages) & 1;
+          const int s = ms_s;
+          const uint32_t ph = ms_ph;
+          if (++ms_s == q.stages) {
+            ms_s = 0;
+            ms_ph ^= 1u;
+          }
           mbar_wait(&bar_full[s], ph);
           tc_fence_after_sync();
           if (lane == 0 && lt == 0 && it == 0) SSR_STAMP(l, 2);                     // MMA: first stage landed
           if (lane == 0 && lt == items - 1 && it == iters - 1) SSR_STAMP(l, 3);     // MMA: last stage landed
           if (elect_one()) {
-            const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-            const uint64_t da0 = umma_desc_k128(a_base);
-            // weights: behind the activation box of this stage, or (stationary) tap row kx of the resident region
-            const uint64_t db0 = q.w_bytes ? umma_desc_k128(w_addr + (uint32_t)((it % NH) * NV * q.n_tile * 128)) : umma_desc_k128(a_base + q.a_alloc);
-            const int ks = min(4, (q.cin - c * 64) >> 4);
-            if (ks == 4) {
+            const uint32_t a_base = smem_addr0 + (uint32_t)s * stage_bytes;
+            const int ks = (c == q.chunks - 1) ? ks_last : 4;
+            if (R == 5) {
+              // halo tile: tap (ky, kx) of M tile m is the window that starts (m * 16 + ky) tile rows down and kx pixels right
+              const uint64_t da0 = umma_desc(a_base, 16u, kRPitch * 128u, 2u);
+              const uint64_t db0 = umma_desc_k128(w_addr + (uint32_t)(c * 9) * (uint32_t)(q.n_tile * 128));
+              if (ks == 4) {
 #pragma unroll
-              for (int m = 0; m < MT; ++m) {
+                for (int m = 0; m < MT; ++m) {
 #pragma unroll
-                for (int ky = 0; ky < NV; ++ky) {
+                  for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
-                                 idesc, (ky == 0 && k == 0) ? acc : 1u);
+                    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                      for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (uint32_t)(m * kRMt + ky * kRTapRow + kx * 8 + 2 * k),
+                                     db0 + ((uint32_t)(kx * 3 + ky) * b_tap + 2 * k), idesc, (kx == 0 && ky == 0 && k == 0) ? acc : 1u);
+                    }
+                  }
                 }
+              } else {
+                for (int m = 0; m < MT; ++m)
+                  for (int t = 0; t < 9; ++t)
+                    for (int k = 0; k < ks; ++k)
+                      umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (uint32_t)(m * kRMt + (t % 3) * kRTapRow + (t / 3) * 8 + 2 * k),
+                                   db0 + ((uint32_t)t * b_tap + 2 * k), idesc, (t == 0 && k == 0) ? acc : 1u);
               }
             } else {
+              const uint32_t a_tap = (uint32_t)(q.TW * 128) >> 4;        // one tile row down  (descriptor address units of 16 B)
+              const uint32_t a_mt = (uint32_t)(q.TH * q.TW * 128) >> 4;  // next stacked M tile
+              const uint64_t da0 = umma_desc_k128(a_base);
+              // weights: behind the activation box of this stage, or (stationary) tap row kx of the resident region
+              const uint64_t db0 = q.w_bytes ? umma_desc_k128(w_addr + (uint32_t)((it % NH) * NV) * (uint32_t)(q.n_tile * 128)) : umma_desc_k128(a_base + q.a_alloc);
+              if (ks == 4) {
 #pragma unroll
-              for (int m = 0; m < MT; ++m)
-                for (int ky = 0; ky < NV; ++ky)
-                  for (int k = 0; k < ks; ++k)
-                    umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
-                                 idesc, (ky == 0 && k == 0) ? acc : 1u);
+                for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                  for (int ky = 0; ky < NV; ++ky) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
+                                   idesc, (ky == 0 && k == 0) ? acc : 1u);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                  for (int ky = 0; ky < NV; ++ky)
+                    for (int k = 0; k < ks; ++k)
+                      umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (m * a_mt + ky * a_tap + 2 * k), db0 + (ky * b_tap + 2 * k),
+                                   idesc, (ky == 0 && k == 0) ? acc : 1u);
+              }
             }
             umma_commit(&bar_empty[s]);                              // frees this smem stage once the MMAs above have read it
             // accumulators of this tile complete (TMEM-resident form: once per layer, after its last N tile)
@@ -863,12 +913,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_chain_kernel(const __grid_co
 // Roles as in conv_tc_body: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue.  The unit of the weight stream is a
 // "triple": the three vertical taps of one (64-channel chunk, kx) -- 24 (12 for a 32-channel tail) MMAs with constant
 // descriptor offsets, issued by one elected lane; a ring stage holds as many consecutive triples of the current N tile as fit.
-static constexpr int kRPitch = 10, kRTH = 16;                  // tile row = 8 pixels + 2 halo pixels; rows per M tile
 static constexpr uint32_t kRChunk = 44032;                     // 10 x 34 rows of 128 B = 43520, rounded up to 1 KB
 static constexpr uint32_t kRStageFwd = 24576;                  // one triple of a 64-wide layer, two of a 32-wide one
 static constexpr uint32_t kRStageAcc = 32768;                  // one triple of an N tile of up to 80 channels
-static constexpr uint32_t kRTapRow = kRPitch * 128 / 16;       // descriptor units (16 B): one tile row down
-static constexpr uint32_t kRMt = kRTH * kRPitch * 128 / 16;    // ... the second M tile
 
 // the 3 vertical taps of one (chunk, kx) for both stacked M tiles: accumulation order (ky, k) per M tile, as conv_tc_body
 template <int KS>
@@ -1620,7 +1667,7 @@ static size_t finalize_ring(ConvTcK* ps, int n, int mt) {
   for (int i = 0; i < n; ++i) {
     stage_bytes = max(stage_bytes, ps[i].a_alloc + (w_bytes ? 0u : ps[i].b_bytes));
     n_tile_max = max(n_tile_max, ps[i].n_tile);
-    iters += ((ps[i].chunks + ps[i].splits - 1) / ps[i].splits) * (ps[i].R == 4 ? 8 : ps[i].R);
+    iters += ((ps[i].chunks + ps[i].splits - 1) / ps[i].splits) * (ps[i].halo ? 1 : (ps[i].R == 4 ? 8 : ps[i].R));
   }
   const int budget = g_smem_optin - 1024 - 256 - 2048 - (int)w_bytes;
   int stages = budget / (int)stage_bytes;
@@ -1692,21 +1739,44 @@ static int launch_conv(Kern kern, size_t* configured, dim3 grid, int cluster_x, 
   return SSR_OK;
 }
 
+static int64_t g_conv_paths[3] = {0, 0, 0};
+extern "C" int64_t ssr_debug_conv_path_count(int32_t which) { return which >= 0 && which < 3 ? g_conv_paths[which] : -1; }
+
 extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ConvTcK p;
   CUtensorMap tmA, tmB;
   int mt = 0;
-  if (int rc = prepare_conv(a, 0, p, tmA, tmB, mt)) return rc;
-  {
-    // Weights-stationary form: with a single 64-channel chunk the whole weight operand of an N tile (9 taps x n_tile x 128 B:
-    // 72 KB at 64 output channels) fits beside the activation ring, and a persistent CTA re-uses it for all its pixel tiles --
-    // the per-tile L2 -> SM traffic halves (measured 64 -> 64 @ 128^2: load-bound at 583 TFLOP/s before).
-    static int ws = -1;
-    if (ws < 0) {
-      const char* e = getenv("SSR_CONV_WSTAT");
-      ws = e ? atoi(e) : 1;
+  static int ws = -1, halo_on = -1;
+  if (ws < 0) {
+    const char* e = getenv("SSR_CONV_WSTAT");
+    ws = e ? atoi(e) : 1;
+    e = getenv("SSR_CONV_HALO");
+    halo_on = e ? atoi(e) : 1;
+  }
+  bool halo = false;
+  if (halo_on && a && a->r == 3 && a->cin > 0 && a->cin % 64 == 0 && a->splits <= 1 && a->n_img > 0 && a->h > 0 && a->w >= 8 && device_limits()) {
+    // Halo form (conv_tc_body, R = 5): 8-pixel strips with the halo in shared memory, all 9 taps of a 64-channel chunk from ONE
+    // activation stage, the weights of the N tile stationary.  Needs chunks * 9 * n_tile * 128 B of weights beside >= 2 stages.
+    const int budget = g_smem_optin - 1024 - 256 - 2048;
+    const long strips = (long)((a->w + 7) / 8) * a->n_img;
+    for (int m = (a->mt ? a->mt : 2); m >= 1 && !halo; m = (a->mt ? 0 : m - 1)) {
+      if (int rc = prepare_conv(a, m, p, tmA, tmB, mt, true)) return rc;
+      const long tiles = strips * ((a->h + 16 * m - 1) / (16 * m));
+      const long wb = (long)p.chunks * 9 * p.n_tile * 128;
+      const bool fits = wb + 2L * p.a_alloc <= budget && 2 * m * p.n_tile <= 512;
+      const bool enough = a->mt ? tiles >= 2L * g_num_sms : tiles >= (m == 2 ? 6L : 2L) * g_num_sms;
+      if (fits && enough) {
+        p.w_bytes = (uint32_t)wb;
+        p.halo = 1;
+        halo = true;
+      }
     }
+  }
+  if (!halo) {
+    if (int rc = prepare_conv(a, 0, p, tmA, tmB, mt)) return rc;
+    // Weights-stationary form: with a single 64-channel chunk the whole weight operand of an N tile (9 taps x n_tile x 128 B:
+    // 72 KB at 64 output channels) fits beside the activation ring, and a persistent CTA re-uses it for all its pixel tiles
     const long tiles = (long)p.tiles_x * p.tiles_y * p.n_img;
     const uint32_t wb = (uint32_t)(p.R * p.R * p.n_tile * 128);
     if (ws && p.R == 3 && p.chunks == 1 && p.splits == 1 && tiles >= 2L * persistent_ctas(p) && wb + 3u * p.a_alloc <= (uint32_t)(g_smem_optin - 4096))
@@ -1723,10 +1793,14 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
   }
   const size_t smem_bytes = finalize_ring(&p, 1, mt);
   if (!smem_bytes) return SSR_E_ARG;
+  g_conv_paths[0] += p.halo;
+  g_conv_paths[1] += p.lean;
+  g_conv_paths[2] += (p.w_bytes && !p.halo) ? 1 : 0;
   dim3 grid((unsigned)persistent_ctas(p), (unsigned)(p.n_pad / p.n_tile), (unsigned)p.splits);
-  static size_t configured[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  size_t* cfgd = &configured[(mt - 1) * 5 + p.R];
+  static size_t configured[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  size_t* cfgd = &configured[(mt - 1) * 6 + (p.halo ? 5 : p.R)];
 #define SSR_LAUNCH_CONV(MT_, R_) launch_conv(conv_tc_kernel<MT_, R_>, cfgd, grid, 1, smem_bytes, stream, "conv_tc launch", 0, tmA, tmB, p)
+  if (p.halo) return mt == 1 ? SSR_LAUNCH_CONV(1, 5) : SSR_LAUNCH_CONV(2, 5);
   if (mt == 1) {
     switch (p.R) {
       case 1: return SSR_LAUNCH_CONV(1, 1);

@@ -25,7 +25,12 @@ def time_graph(fn, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""   # substring filter on the case name (for ncu captures)
+
+
 def case(name, B, cin, cout, H, W, r=3):
+    if ONLY not in name:
+        return
     x = torch.randn(B, H, W, cin, device="cuda").to(torch.bfloat16)
     n_pad = C.c_int32(0)
     nbytes = lib.ssr_packed_weight_bytes((cin + 63) // 64 * 64, cout, r, C.byref(n_pad))
@@ -46,6 +51,11 @@ case("D conv1 gemm", 1, 1024, 128, 1, 131072, r=1)
 case("D conv2 gemm", 1, 2048, 256, 1, 32768, r=1)
 case("D conv3 gemm", 1, 4096, 512, 1, 8192, r=1)
 case("D conv1 dcol gemm", 1, 128, 1024, 1, 131072, r=1)
+case("G tail / D conv7-8", 32, 64, 64, 128, 128)
+case("G conv_up1", 32, 64, 64, 64, 64)
+case("D conv6 dgrad", 32, 64, 128, 128, 128)
+case("VGG conv2_1", 64, 64, 128, 64, 64)
+case("VGG conv2_1 dgrad", 32, 128, 64, 64, 64)
 case("VGG conv1_2", 64, 64, 64, 128, 128)
 case("VGG conv2_2", 64, 128, 128, 64, 64)
 case("VGG conv3_x", 64, 256, 256, 32, 32)

@@ -166,6 +166,37 @@ def test_conv3x3_plain(B, Cin, Cout, H, W):
     assert rel_err(got, ref) < 1e-4
 
 
+@pytest.mark.parametrize("B,Cin,Cout,H,W,mt", [
+    (16, 64, 64, 64, 64, 0),     # one chunk, one M tile per CTA (512 tiles)
+    (20, 64, 64, 64, 64, 2),     # two stacked M tiles
+    (32, 64, 64, 128, 64, 0),    # enough tiles for the automatic two-M-tile choice
+    (16, 128, 64, 64, 44, 0),    # two chunks; ragged last strip (44 = 5 * 8 + 4)
+    (20, 64, 96, 48, 64, 2),     # 96 output channels; 48 rows: the second M tile of the last tile row is half outside
+    (20, 192, 32, 40, 40, 0),    # three chunks, narrow N
+])
+def test_conv3x3_halo_tile_stationary_weights(B, Cin, Cout, H, W, mt):
+    """the 8-pixel-strip form (halo in shared memory, 9 taps per stage, stationary weights) against torch, through the short
+    epilogue (bias + LeakyReLU -> bf16; mask + bf16 residual) and the general one (f32 output)"""
+    L, lib = _lib()
+    x, w = make(B, Cin, Cout, H, W, seed=Cin + Cout + W)
+    g = torch.Generator().manual_seed(3)
+    b = torch.randn(Cout, generator=g)
+    n_halo, n_lean = lib.ssr_debug_conv_path_count(0), lib.ssr_debug_conv_path_count(1)
+    ref = F.conv2d(x, w, b, padding=1)
+    got, _ = run_conv(x, w, bias=b, act=1, mt=mt)
+    assert rel_err(got, F.leaky_relu(ref, 0.2)) < 2 ** -8
+    act = bf16_round(torch.randn(B, Cout, H, W, generator=g))
+    r1 = bf16_round(torch.randn(B, Cout, H, W, generator=g))
+    got, _ = run_conv(x, w, bias=b, s0=0.5, res1=r1, s1=2.0, mask=act, mt=mt)
+    assert rel_err(got, (ref * 0.5 + 2.0 * r1) * torch.where(act > 0, 1.0, 0.2)) < 2 ** -7
+    got, _ = run_conv(x, w, bias=b, out_kind="f32", mt=mt)
+    assert rel_err(got, ref) < 1e-4
+    if os.environ.get("SSR_CONV_HALO", "1") != "0":
+        assert lib.ssr_debug_conv_path_count(0) - n_halo == 3
+    if os.environ.get("SSR_CONV_LEAN", "1") != "0":
+        assert lib.ssr_debug_conv_path_count(1) - n_lean == 2
+
+
 def test_conv3x3_bf16_out_bias_lrelu():
     x, w = make(2, 128, 32, 32, 32, seed=5)
     b = torch.randn(32)
