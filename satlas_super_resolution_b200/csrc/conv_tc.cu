@@ -115,6 +115,30 @@ __device__ __forceinline__ void load16_f32(const float* p, float (&f)[16]) {
   }
 }
 
+// the 9 taps of one 64-channel chunk (KS K-steps of 16 channels) of a halo tile, for MT stacked M tiles: tap (ky, kx) of M tile m
+// is the operand window that starts (m * 16 + ky) tile rows down and kx pixels right; weights in the packed order (kx, ky)
+// BT > 0: the weight-tap stride (n_tile * 128 / 16 descriptor units) as a compile-time constant, so that every B descriptor is
+// base + immediate (one uniform add); BT == 0: run-time stride
+template <int MT, int KS, int BT>
+__device__ __forceinline__ void halo_issue(uint32_t d_base, uint32_t m_cols, uint64_t da0, uint64_t db0, uint32_t b_tap_rt, uint32_t idesc,
+                                           uint32_t acc) {
+  const uint32_t b_tap = BT > 0 ? (uint32_t)BT : b_tap_rt;
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const uint64_t db = db0 + ((uint32_t)(kx * 3 + ky) * b_tap + 2 * k);
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+          umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (uint32_t)(m * kRMt + ky * kRTapRow + kx * 8 + 2 * k), db, idesc,
+                       (kx == 0 && ky == 0 && k == 0) ? acc : 1u);
+      }
+    }
+  }
+}
+
 // per-channel sum over the warp's 32 pixels of a 16-channel chunk: a transposing butterfly (16 values -> 1 per lane in 16
 // shuffles), then one shared-memory atomic per channel; the CTA adds its partial sums to global memory once per layer
 __device__ __forceinline__ void bias_grad_butterfly(const float (&f)[16], int lane, float* s_dst /* [16] of this chunk */) {
@@ -350,28 +374,21 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
             const int ks = (c == q.chunks - 1) ? ks_last : 4;
             if (R == 5) {
               // halo tile: tap (ky, kx) of M tile m is the window that starts (m * 16 + ky) tile rows down and kx pixels right
-              const uint64_t da0 = umma_desc(a_base, 16u, kRPitch * 128u, 2u);
-              const uint64_t db0 = umma_desc_k128(w_addr + (uint32_t)(c * 9) * (uint32_t)(q.n_tile * 128));
+              // opaque(): the compiler otherwise folds the descriptor's constant high word into every tap offset and rebuilds
+              // each of the 144 descriptors from two 32-bit constants (7 instructions per MMA on the single issuing thread;
+              // profiles/r02_conv64_ncu.md); an opaque 64-bit base leaves one add-immediate per descriptor
+              const uint64_t da0 = opaque64(umma_desc(a_base, 16u, kRPitch * 128u, 2u));
+              const uint64_t db0 = opaque64(umma_desc_k128(w_addr + (uint32_t)(c * 9) * (uint32_t)(q.n_tile * 128)));
               if (ks == 4) {
-#pragma unroll
-                for (int m = 0; m < MT; ++m) {
-#pragma unroll
-                  for (int kx = 0; kx < 3; ++kx) {
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-                      for (int k = 0; k < 4; ++k)
-                        umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (uint32_t)(m * kRMt + ky * kRTapRow + kx * 8 + 2 * k),
-                                     db0 + ((uint32_t)(kx * 3 + ky) * b_tap + 2 * k), idesc, (kx == 0 && ky == 0 && k == 0) ? acc : 1u);
-                    }
-                  }
-                }
+                if (b_tap == 512u) halo_issue<MT, 4, 512>(d_base, m_cols, da0, db0, b_tap, idesc, acc);          // n_tile 64
+                else if (b_tap == 1024u) halo_issue<MT, 4, 1024>(d_base, m_cols, da0, db0, b_tap, idesc, acc);   // n_tile 128
+                else halo_issue<MT, 4, 0>(d_base, m_cols, da0, db0, b_tap, idesc, acc);
+              } else if (ks == 2) {
+                halo_issue<MT, 2, 0>(d_base, m_cols, da0, db0, b_tap, idesc, acc);
+              } else if (ks == 1) {
+                halo_issue<MT, 1, 0>(d_base, m_cols, da0, db0, b_tap, idesc, acc);
               } else {
-                for (int m = 0; m < MT; ++m)
-                  for (int t = 0; t < 9; ++t)
-                    for (int k = 0; k < ks; ++k)
-                      umma_bf16_ss(d_base + (uint32_t)m * m_cols, da0 + (uint32_t)(m * kRMt + (t % 3) * kRTapRow + (t / 3) * 8 + 2 * k),
-                                   db0 + ((uint32_t)t * b_tap + 2 * k), idesc, (t == 0 && k == 0) ? acc : 1u);
+                halo_issue<MT, 3, 0>(d_base, m_cols, da0, db0, b_tap, idesc, acc);
               }
             } else {
               const uint32_t a_tap = (uint32_t)(q.TW * 128) >> 4;        // one tile row down  (descriptor address units of 16 B)
@@ -504,141 +521,184 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap* tmAs, const CUte
     if (p.lean) {
       // ---- short path (plain launches: no f32 output, no second residual, whole 16-channel chunks) ----
       // A warp owns chunks half, half + 2, ... of its lane quarter and walks them in PAIRS: both TMEM loads are issued, the
-      // operands of the NEXT pair are requested, then one wait -- the accumulator-independent loads hide behind the TMEM reads.
+      // operands (residual, mask) of the NEXT pair are requested into the other of two register buffers, then one wait -- the
+      // accumulator-independent loads hide behind the TMEM reads.  Written for instruction count (the general path below was
+      // issue-bound, profiles/r02_conv64_ncu.md): no divisions in the tile walk, 32-bit pixel indices, no register copies.
       const bool has_mk = use_mk, has_bg = p.bgrad != nullptr;
       const bool has_r1 = use_r1;                                  // bf16, all channels (checked on the host)
+      const bool has_ops = has_mk || has_r1;
       const int npairs = nchunks > half ? (nchunks - half + 3) >> 2 : 0;
       const int total = MT * npairs;
       struct LeanOps {
         uint4 r1[2][2], mk[2][2];
       };
-      auto lean_fetch = [&](long pix, int ci, LeanOps& o) {
+      auto lean_fetch = [&](int pix, int ci, LeanOps& o) {
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           const int c0 = n_base + (ci + 2 * h2) * 16;
           if (ci + 2 * h2 < nchunks && c0 + 16 <= p.cout) {
             if (has_r1) {
-              const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res1) + pix * p.res1_stride + c0);
+              const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res1) + (long)pix * p.res1_stride + c0);
               o.r1[h2][0] = s4[0];
               o.r1[h2][1] = s4[1];
             }
             if (has_mk && c0 >= p.mask_lo) {
-              const uint4* s4 = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_stride + c0);
+              const uint4* s4 = reinterpret_cast<const uint4*>(p.mask + (long)pix * p.mask_stride + c0);
               o.mk[h2][0] = s4[0];
               o.mk[h2][1] = s4[1];
             }
           }
         }
       };
-      auto lean_chunk = [&](const uint32_t (&v)[16], int ci, long pix, bool in_img, const uint4 (&r1)[2], const uint4 (&mk)[2]) {
+      // one 16-channel chunk of 32 pixels: accumulator -> bias, activation, scale, residual, mask -> bf16 store
+      auto lean_values = [&](const uint32_t (&v)[16], float (&f)[16], int ci, int c0, const uint4 (&r1)[2], const uint4 (&mk)[2]) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (add_bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + ci * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 bv = b4[j];
+            f[4 * j] += bv.x;
+            f[4 * j + 1] += bv.y;
+            f[4 * j + 2] += bv.z;
+            f[4 * j + 3] += bv.w;
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.2f * f[j]);   // LeakyReLU(0.2)
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (p.s0 != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] *= p.s0;
+        }
+        if (has_r1) {
+          const uint32_t u[8] = {r1[0].x, r1[0].y, r1[0].z, r1[0].w, r1[1].x, r1[1].y, r1[1].z, r1[1].w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            f[2 * j] = fmaf(p.s1, bf16_lo(u[j]), f[2 * j]);
+            f[2 * j + 1] = fmaf(p.s1, bf16_hi(u[j]), f[2 * j + 1]);
+          }
+        }
+        if (has_mk && c0 >= p.mask_lo) {
+          const float neg = p.mask_relu ? 0.f : 0.2f;
+          const uint32_t u[8] = {mk[0].x, mk[0].y, mk[0].z, mk[0].w, mk[1].x, mk[1].y, mk[1].z, mk[1].w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            f[2 * j] *= (bf16_lo(u[j]) > 0.f ? 1.f : neg);
+            f[2 * j + 1] *= (bf16_hi(u[j]) > 0.f ? 1.f : neg);
+          }
+        }
+      };
+      auto lean_store = [&](const float (&f)[16], int pix, int c0) {
+        uint4 o0, o1;
+        o0.x = pack_bf16(f[0], f[1]);
+        o0.y = pack_bf16(f[2], f[3]);
+        o0.z = pack_bf16(f[4], f[5]);
+        o0.w = pack_bf16(f[6], f[7]);
+        o1.x = pack_bf16(f[8], f[9]);
+        o1.y = pack_bf16(f[10], f[11]);
+        o1.z = pack_bf16(f[12], f[13]);
+        o1.w = pack_bf16(f[14], f[15]);
+        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + (long)pix * p.out_stride + c0);
+        dst[0] = o0;
+        dst[1] = o1;
+      };
+      auto lean_chunk = [&](const uint32_t (&v)[16], int ci, int pix, bool in_img, const uint4 (&r1)[2], const uint4 (&mk)[2]) {
         const int c0 = n_base + ci * 16;
         const bool live = in_img && (c0 + 16 <= p.cout);
-        if (!live && !has_bg) return;
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = live ? __uint_as_float(v[j]) : 0.f;
-        if (live) {
-          if (add_bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(s_bias + ci * 16);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 bv = b4[j];
-              f[4 * j] += bv.x;
-              f[4 * j + 1] += bv.y;
-              f[4 * j + 2] += bv.z;
-              f[4 * j + 3] += bv.w;
-            }
+        if (!has_bg) {
+          if (live) {
+            float f[16];
+            lean_values(v, f, ci, c0, r1, mk);
+            lean_store(f, pix, c0);
           }
-          if (p.act == 1) {
+        } else {
+          float f[16];
+          if (live) {
+            lean_values(v, f, ci, c0, r1, mk);
+            lean_store(f, pix, c0);
+          } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.2f * f[j]);   // LeakyReLU(0.2)
-          } else if (p.act == 2) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            for (int j = 0; j < 16; ++j) f[j] = 0.f;
           }
-          if (p.s0 != 1.f) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] *= p.s0;
-          }
-          if (has_r1) {
-            const uint32_t u[8] = {r1[0].x, r1[0].y, r1[0].z, r1[0].w, r1[1].x, r1[1].y, r1[1].z, r1[1].w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              f[2 * j] = fmaf(p.s1, bf16_lo(u[j]), f[2 * j]);
-              f[2 * j + 1] = fmaf(p.s1, bf16_hi(u[j]), f[2 * j + 1]);
-            }
-          }
-          if (has_mk && c0 >= p.mask_lo) {
-            const float neg = p.mask_relu ? 0.f : 0.2f;
-            const uint32_t u[8] = {mk[0].x, mk[0].y, mk[0].z, mk[0].w, mk[1].x, mk[1].y, mk[1].z, mk[1].w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              f[2 * j] *= (bf16_lo(u[j]) > 0.f ? 1.f : neg);
-              f[2 * j + 1] *= (bf16_hi(u[j]) > 0.f ? 1.f : neg);
-            }
-          }
-          uint4 o0, o1;
-          o0.x = pack_bf16(f[0], f[1]);
-          o0.y = pack_bf16(f[2], f[3]);
-          o0.z = pack_bf16(f[4], f[5]);
-          o0.w = pack_bf16(f[6], f[7]);
-          o1.x = pack_bf16(f[8], f[9]);
-          o1.y = pack_bf16(f[10], f[11]);
-          o1.z = pack_bf16(f[12], f[13]);
-          o1.w = pack_bf16(f[14], f[15]);
-          uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.out_stride + c0);
-          dst[0] = o0;
-          dst[1] = o1;
+          bias_grad_butterfly(f, lane, &s_bg[ci * 16]);
         }
-        if (has_bg) bias_grad_butterfly(f, lane, &s_bg[ci * 16]);
       };
-      LeanOps cur = {}, nxt = {};
+      // tile walk without divisions: this CTA's tiles are blockIdx.x + k * gridDim.x; the stride decomposes once into
+      // (images, tile rows, tile columns) and every step is an add with two carries
+      const int tpi = p.tiles_x * p.tiles_y;
+      int tn = (int)blockIdx.x / tpi;
+      int trem = (int)blockIdx.x - tn * tpi;
+      int tty = trem / p.tiles_x;
+      int ttx = trem - tty * p.tiles_x;
+      const int dn = (int)gridDim.x / tpi;
+      const int drem = (int)gridDim.x - dn * tpi;
+      const int dty = drem / p.tiles_x;
+      const int dtx = drem - dty * p.tiles_x;
+      LeanOps opsA = {}, opsB = {};
 #pragma unroll 1
       for (int lt = 0; lt < my_tiles; ++lt, ++gt) {
-        int t = (int)blockIdx.x + lt * (int)gridDim.x;
-        const int tx = t % p.tiles_x;
-        t /= p.tiles_x;
-        const int ty = t % p.tiles_y;
-        const int n = t / p.tiles_y;
-        const int x = tx * p.TW + txx;
-        const int y0 = ty * (MT * p.TH);
-        long pixs[MT];
-        bool oks[MT];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const int y = y0 + mt * p.TH + tyy;
-          pixs[mt] = R == 2 ? ((long)n * (2 * p.H) + (2 * y + p.out_oy)) * (2 * p.W) + (2 * x + p.out_ox) : ((long)n * p.H + y) * p.W + x;
-          oks[mt] = (tyy < p.TH) && (y < p.H) && (x < p.W);
+        const int x = ttx * p.TW + txx;
+        const int y_a = tty * (MT * p.TH) + tyy;
+        const int y_b = y_a + p.TH;   // second stacked M tile (MT == 2)
+        const bool okx = (tyy < p.TH) && (x < p.W);
+        const bool ok_a = okx && (y_a < p.H), ok_b = okx && (y_b < p.H);
+        int pix_a, pix_b;
+        if (R == 2) {   // one parity class of a transposed stride-2 conv: pixel (y, x) is stored at (2y + oy, 2x + ox)
+          pix_a = (tn * (2 * p.H) + (2 * y_a + p.out_oy)) * (2 * p.W) + (2 * x + p.out_ox);
+          pix_b = pix_a + 2 * p.TH * (2 * p.W);
+        } else {
+          pix_a = (tn * p.H + y_a) * p.W + x;
+          pix_b = pix_a + p.TH * p.W;
+        }
+        ttx += dtx;
+        tty += dty;
+        tn += dn;
+        if (ttx >= p.tiles_x) {
+          ttx -= p.tiles_x;
+          ++tty;
+        }
+        if (tty >= p.tiles_y) {
+          tty -= p.tiles_y;
+          ++tn;
         }
         const int b = gt & 1;
         const uint32_t d_base = tmem_base + (uint32_t)b * acc_cols + ((uint32_t)(q * 32) << 16);
-        if (total > 0 && oks[0]) lean_fetch(pixs[0], half, cur);   // overlaps the MMAs
+        if (has_ops && total > 0 && ok_a) lean_fetch(pix_a, half, opsA);   // overlaps the MMAs
         mbar_wait(&bar_acc_full[b], (uint32_t)((gt >> 1) & 1));
         tc_fence_after_sync();
         if (et == 0 && lt == 0) SSR_STAMP(l, 4);
         if (et == 0 && lt == my_tiles - 1) SSR_STAMP(l, 5);
-#pragma unroll 1
-        for (int it = 0; it < total; ++it) {
-          const int mt = (MT == 2 && it >= npairs) ? 1 : 0;
-          const int ci = half + 4 * (it - mt * npairs);
+        auto item = [&](int it, LeanOps& cur, LeanOps& nxt) {
+          const bool second = MT == 2 && it >= npairs;
+          const int ci = half + 4 * (it - (second ? npairs : 0));
           const bool two = ci + 2 < nchunks;
-          const long pix = (MT == 2 && mt) ? pixs[MT - 1] : pixs[0];
-          const bool ok = (MT == 2 && mt) ? oks[MT - 1] : oks[0];
+          const int pix = second ? pix_b : pix_a;
+          const bool ok = second ? ok_b : ok_a;
           uint32_t va[16], vb[16];
           __syncwarp();
-          const uint32_t taddr = d_base + (uint32_t)mt * m_cols + (uint32_t)(ci * 16);
+          const uint32_t taddr = d_base + (second ? m_cols : 0u) + (uint32_t)(ci * 16);
           tmem_ld16(taddr, va);
           if (two) tmem_ld16(taddr + 32u, vb);
-          if (it + 1 < total) {
-            const int mt2 = (MT == 2 && it + 1 >= npairs) ? 1 : 0;
-            const bool ok2 = (MT == 2 && mt2) ? oks[MT - 1] : oks[0];
-            if (ok2) lean_fetch((MT == 2 && mt2) ? pixs[MT - 1] : pixs[0], half + 4 * (it + 1 - mt2 * npairs), nxt);
+          if (has_ops && it + 1 < total) {
+            const bool second2 = MT == 2 && it + 1 >= npairs;
+            if (second2 ? ok_b : ok_a) lean_fetch(second2 ? pix_b : pix_a, half + 4 * (it + 1 - (second2 ? npairs : 0)), nxt);
           }
           tmem_ld_wait();
           lean_chunk(va, ci, pix, ok, cur.r1[0], cur.mk[0]);
           if (two) lean_chunk(vb, ci + 2, pix, ok, cur.r1[1], cur.mk[1]);
-          cur = nxt;
+        };
+#pragma unroll 1
+        for (int it = 0; it < total; it += 2) {
+          item(it, opsA, opsB);
+          if (it + 1 < total) item(it + 1, opsB, opsA);
         }
+        // (an odd item count leaves the next tile's first operands expected in opsA: they are fetched into opsA above)
         // this warp has finished reading accumulator buffer b: hand it back to the MMA issuer
         tc_fence_before_sync();
         __syncwarp();
@@ -1755,7 +1815,7 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
     halo_on = e ? atoi(e) : 1;
   }
   bool halo = false;
-  if (halo_on && a && a->r == 3 && a->cin > 0 && a->cin % 64 == 0 && a->splits <= 1 && a->n_img > 0 && a->h > 0 && a->w >= 8 && device_limits()) {
+  if (halo_on && a && a->r == 3 && a->cin > 0 && a->cin % 16 == 0 && a->splits <= 1 && a->n_img > 0 && a->h > 0 && a->w >= 8 && device_limits()) {
     // Halo form (conv_tc_body, R = 5): 8-pixel strips with the halo in shared memory, all 9 taps of a 64-channel chunk from ONE
     // activation stage, the weights of the N tile stationary.  Needs chunks * 9 * n_tile * 128 B of weights beside >= 2 stages.
     const int budget = g_smem_optin - 1024 - 256 - 2048;
@@ -1789,7 +1849,8 @@ extern "C" int ssr_conv_tc(const ssr_conv_tc_args* a, void* stream_) {
       lean = e ? atoi(e) : 1;
     }
     p.lean = lean && a->cout % 16 == 0 && p.splits == 1 && p.out32_mode == SSR_OUT32_NONE && p.res2_kind == SSR_NONE &&
-             (p.res1_kind == SSR_NONE || (p.res1_kind == SSR_BF16 && p.res1_cmax == 0)) && p.out_lo == 0 && p.out_bf16 != nullptr;
+             (p.res1_kind == SSR_NONE || (p.res1_kind == SSR_BF16 && p.res1_cmax == 0)) && p.out_lo == 0 && p.out_bf16 != nullptr &&
+             (long)p.n_img * p.H * p.W * (p.R == 2 ? 4 : 1) < (1L << 31);
   }
   const size_t smem_bytes = finalize_ring(&p, 1, mt);
   if (!smem_bytes) return SSR_E_ARG;

@@ -256,6 +256,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
+// identity the optimiser cannot see through (keeps a computed 64-bit descriptor as ONE value that offsets are added to)
+__device__ __forceinline__ uint64_t opaque64(uint64_t v) {
+  uint64_t r;
+  asm volatile("mov.b64 %0, %1;" : "=l"(r) : "l"(v));
+  return r;
+}
+
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn_major,
                                                        uint32_t b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) |

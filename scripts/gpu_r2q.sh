@@ -1,0 +1,7 @@
+# GPU call Q: halo MMA issue with immediate descriptor offsets
+set -x
+O=gpurun_out/r2q; mkdir -p $O
+timeout 900 python -m pytest tests/test_conv_tc_gpu.py -x -q > $O/conv_tests.log 2>&1; tail -n 3 $O/conv_tests.log
+timeout 300 python scripts/bench_conv_big.py > $O/bench_conv_big.log 2>&1; cat $O/bench_conv_big.log
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras > $O/bench.json 2> $O/bench.err; cut -c1-200 $O/bench.json
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras > $O/bench2.json 2> $O/bench2.err; cut -c1-200 $O/bench2.json

@@ -173,6 +173,9 @@ def test_conv3x3_plain(B, Cin, Cout, H, W):
     (16, 128, 64, 64, 44, 0),    # two chunks; ragged last strip (44 = 5 * 8 + 4)
     (20, 64, 96, 48, 64, 2),     # 96 output channels; 48 rows: the second M tile of the last tile row is half outside
     (20, 192, 32, 40, 40, 0),    # three chunks, narrow N
+    (20, 16, 64, 64, 64, 0),     # a 16-channel input (conv9^T, VGG conv1_1): one K step per tap
+    (20, 32, 64, 64, 64, 2),     # the discriminator's conv0 (27 -> 32 padded channels)
+    (16, 96, 32, 64, 64, 0),     # short second chunk (two K steps)
 ])
 def test_conv3x3_halo_tile_stationary_weights(B, Cin, Cout, H, W, mt):
     """the 8-pixel-strip form (halo in shared memory, 9 taps per stage, stationary weights) against torch, through the short
