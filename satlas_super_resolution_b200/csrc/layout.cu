@@ -224,50 +224,91 @@ __device__ __forceinline__ uint4 add_bf16x8(const uint4& a, const uint4& b) {
 
 // src2 (optional) is added to src before interpolating: the U-Net skip `x4 = x4 + x2` of discriminator_arch.py:53-64
 // (the sum is rounded to bf16 once, like a materialised tensor would be).
+// One thread = one INPUT pixel x 8 channels: it loads the 3 x 3 neighbourhood once (18 independent 16-byte loads with the skip)
+// and writes the 2 x 2 output pixels it owns -- 2.25 loads per output instead of 4 (8 with the skip) and a quarter of the index
+// arithmetic of the one-thread-per-output form (which ran at 24 % of the HBM roofline, profiles/r02_hbm_table.md).
+__device__ __forceinline__ uint4 bilin_mix(const uint4& v00, const uint4& v01, const uint4& v10, const uint4& v11, float wx, float wy) {
+  const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, b[4] = {v01.x, v01.y, v01.z, v01.w};
+  const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
+  // same operation order as ATen's upsample_bilinear2d: w0y*(w0x*a + w1x*b) + w1y*(w0x*c + w1x*d)
+  const float w0x = 1.f - wx, w0y = 1.f - wy;
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float lo = w0y * (w0x * __uint_as_float(a[j] << 16) + wx * __uint_as_float(b[j] << 16)) +
+               wy * (w0x * __uint_as_float(c[j] << 16) + wx * __uint_as_float(d[j] << 16));
+    float hi = w0y * (w0x * __uint_as_float(a[j] & 0xFFFF0000u) + wx * __uint_as_float(b[j] & 0xFFFF0000u)) +
+               wy * (w0x * __uint_as_float(c[j] & 0xFFFF0000u) + wx * __uint_as_float(d[j] & 0xFFFF0000u));
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    o[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 __global__ void upsample_bilinear2x_kernel(const __nv_bfloat16* __restrict__ src, int src_stride,
                                            const __nv_bfloat16* __restrict__ src2, int src2_stride,
                                            __nv_bfloat16* __restrict__ dst, int dst_stride, int B, int H, int W, int C) {
   const int groups = C / 8;
-  const int OH = H * 2, OW = W * 2;
-  const long total = (long)B * OH * OW * groups;
+  const int OW = W * 2;
+  const long total = (long)B * H * W * groups;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int g = (int)(i % groups);
     long p = i / groups;
-    const int ox = (int)(p % OW);
-    p /= OW;
-    const int oy = (int)(p % OH);
-    const long n = p / OH;
-    int y0, y1, x0, x1;
-    float wy, wx;
-    bilin_src(oy, H, y0, y1, wy);
-    bilin_src(ox, W, x0, x1, wx);
+    const int x = (int)(p % W);
+    p /= W;
+    const int y = (int)(p % H);
+    const long n = p / H;
+    // rows / columns of the neighbourhood: index 0 = max(. - 1, 0), 1 = itself, 2 = min(. + 1, size - 1)
+    const int ys[3] = {max(y - 1, 0), y, min(y + 1, H - 1)};
+    const int xs[3] = {max(x - 1, 0), x, min(x + 1, W - 1)};
+    uint4 v[3][3];
     const __nv_bfloat16* base = src + n * H * W * (long)src_stride + g * 8;
-    uint4 v00 = *reinterpret_cast<const uint4*>(base + ((long)y0 * W + x0) * src_stride);
-    uint4 v01 = *reinterpret_cast<const uint4*>(base + ((long)y0 * W + x1) * src_stride);
-    uint4 v10 = *reinterpret_cast<const uint4*>(base + ((long)y1 * W + x0) * src_stride);
-    uint4 v11 = *reinterpret_cast<const uint4*>(base + ((long)y1 * W + x1) * src_stride);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[r][c] = *reinterpret_cast<const uint4*>(base + ((long)ys[r] * W + xs[c]) * src_stride);
     if (src2) {
       const __nv_bfloat16* b2 = src2 + n * H * W * (long)src2_stride + g * 8;
-      v00 = add_bf16x8(v00, *reinterpret_cast<const uint4*>(b2 + ((long)y0 * W + x0) * src2_stride));
-      v01 = add_bf16x8(v01, *reinterpret_cast<const uint4*>(b2 + ((long)y0 * W + x1) * src2_stride));
-      v10 = add_bf16x8(v10, *reinterpret_cast<const uint4*>(b2 + ((long)y1 * W + x0) * src2_stride));
-      v11 = add_bf16x8(v11, *reinterpret_cast<const uint4*>(b2 + ((long)y1 * W + x1) * src2_stride));
-    }
-    const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, b[4] = {v01.x, v01.y, v01.z, v01.w};
-    const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
-    // same operation order as ATen's upsample_bilinear2d: w0y*(w0x*a + w1x*b) + w1y*(w0x*c + w1x*d)
-    const float w0x = 1.f - wx, w0y = 1.f - wy;
-    uint32_t o[4];
+      uint4 u[3][3];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float lo = w0y * (w0x * __uint_as_float(a[j] << 16) + wx * __uint_as_float(b[j] << 16)) +
-                 wy * (w0x * __uint_as_float(c[j] << 16) + wx * __uint_as_float(d[j] << 16));
-      float hi = w0y * (w0x * __uint_as_float(a[j] & 0xFFFF0000u) + wx * __uint_as_float(b[j] & 0xFFFF0000u)) +
-                 wy * (w0x * __uint_as_float(c[j] & 0xFFFF0000u) + wx * __uint_as_float(d[j] & 0xFFFF0000u));
-      __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-      o[j] = *reinterpret_cast<uint32_t*>(&h);
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) u[r][c] = *reinterpret_cast<const uint4*>(b2 + ((long)ys[r] * W + xs[c]) * src2_stride);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[r][c] = add_bf16x8(v[r][c], u[r][c]);
     }
-    *reinterpret_cast<uint4*>(dst + ((n * OH + oy) * OW + ox) * (long)dst_stride + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    // output row 2y reads rows (y - 1, y) with weight 0.75 on the second -- at y = 0 the clamped source is row 0 itself with
+    // weight 0 on row min(1, H - 1); output row 2y + 1 reads rows (y, y + 1) with weight 0.25 (bilin_src gives exactly these)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      int y0, y1;
+      float wy;
+      bilin_src(2 * y + dy, H, y0, y1, wy);
+      const bool top = (dy == 0) && (y > 0);   // taps are neighbourhood rows (0, 1); otherwise rows (1, 2)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        int x0, x1;
+        float wx;
+        bilin_src(2 * x + dx, W, x0, x1, wx);
+        const bool left = (dx == 0) && (x > 0);
+        uint4 a00, a01, a10, a11;
+        if (top) {
+          a00 = left ? v[0][0] : v[0][1];
+          a01 = left ? v[0][1] : v[0][2];
+          a10 = left ? v[1][0] : v[1][1];
+          a11 = left ? v[1][1] : v[1][2];
+        } else {
+          a00 = left ? v[1][0] : v[1][1];
+          a01 = left ? v[1][1] : v[1][2];
+          a10 = left ? v[2][0] : v[2][1];
+          a11 = left ? v[2][1] : v[2][2];
+        }
+        *reinterpret_cast<uint4*>(dst + ((n * (2 * H) + 2 * y + dy) * OW + 2 * x + dx) * (long)dst_stride + g * 8) =
+            bilin_mix(a00, a01, a10, a11, wx, wy);
+      }
+    }
   }
 }
 
@@ -532,7 +573,7 @@ extern "C" int ssr_upsample_bilinear2x(const void* src, int32_t src_pix_stride, 
                                        void* dst, int32_t dst_pix_stride, int32_t b, int32_t h, int32_t w, int32_t c,
                                        void* stream) {
   if (int rc = check_vec(src, src_pix_stride, dst, dst_pix_stride, c, "ssr_upsample_bilinear2x")) return rc;
-  const long total = (long)b * h * 2 * w * 2 * (c / 8);
+  const long total = (long)b * h * w * (c / 8);   // one thread per input pixel and 8 channels
   upsample_bilinear2x_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(src), src_pix_stride, reinterpret_cast<const __nv_bfloat16*>(src2),
       src2_pix_stride, reinterpret_cast<__nv_bfloat16*>(dst), dst_pix_stride, b, h, w, c);
