@@ -978,9 +978,11 @@ static constexpr uint32_t kRStageFwd = 24576;                  // one triple of 
 static constexpr uint32_t kRStageAcc = 32768;                  // one triple of an N tile of up to 80 channels
 
 // the 3 vertical taps of one (chunk, kx) for both stacked M tiles: accumulation order (ky, k) per M tile, as conv_tc_body
-template <int KS>
-__device__ __forceinline__ void rdb_issue_triple(uint32_t d0, uint32_t m_cols, uint64_t da, uint64_t db, uint32_t b_tap, uint32_t idesc,
+// BT > 0: the weight-tap stride in descriptor units as a compile-time constant (every B descriptor = base + immediate)
+template <int KS, int BT>
+__device__ __forceinline__ void rdb_issue_triple(uint32_t d0, uint32_t m_cols, uint64_t da, uint64_t db, uint32_t b_tap_rt, uint32_t idesc,
                                                  uint32_t first) {
+  const uint32_t b_tap = BT > 0 ? (uint32_t)BT : b_tap_rt;
 #pragma unroll
   for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -990,8 +992,6 @@ __device__ __forceinline__ void rdb_issue_triple(uint32_t d0, uint32_t m_cols, u
         umma_bf16_ss(d0 + (uint32_t)m * m_cols, da + (uint32_t)(m * kRMt + ky * kRTapRow + 2 * k), db + (uint32_t)(ky * b_tap + 2 * k), idesc,
                      (ky == 0 && k == 0) ? first : 1u);
 }
-
-// one tap (layers whose N tile is so wide that a ring stage holds a single tap)
 template <int KS>
 __device__ __forceinline__ void rdb_issue_tap(uint32_t d0, uint32_t m_cols, uint64_t da, uint64_t db, uint32_t idesc, uint32_t first) {
 #pragma unroll
@@ -1094,7 +1094,8 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
       __syncwarp();
     };
     bool tile_loaded = false;
-    int g = 0;
+    int g = 0, ring_s = 0;      // stages issued so far; ring slot and its phase (no division in the loop)
+    uint32_t ring_ph = 0;
     const bool mc = cc.multicast != 0;
     const uint32_t mc_rank = cluster_ctarank(), mc_n = cluster_nctarank();
     const uint16_t mc_mask = (uint16_t)((1u << mc_n) - 1u);
@@ -1108,12 +1109,17 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
       for (int nb = 0; nb < q.n_loop; ++nb) {
         for (int t0 = 0; t0 < n_taps; t0 += tps, ++g) {
           const int nt = min(tps, n_taps - t0);                    // taps in this stage
-          const int s = g % stages;
+          const int s = ring_s;
+          const uint32_t ph = ring_ph;
+          if (++ring_s == stages) {
+            ring_s = 0;
+            ring_ph ^= 1u;
+          }
           if (!tile_loaded && g == stages) {                       // the ring is full of prefetched weights: now the activations
             load_tile();
             tile_loaded = true;
           }
-          mbar_wait(&bar_empty[s], ((g / stages) & 1) ^ 1);
+          mbar_wait(&bar_empty[s], ph ^ 1u);
           if (elect_one()) {
             uint8_t* dst = ring + (size_t)s * kRStage;
             mbar_expect_tx(&bar_full[s], (uint32_t)nt * tap_bytes);   // all taps land here, whoever loads them
@@ -1133,7 +1139,8 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
     cluster_wait();   // (the producer touches peers only with multicast weight loads)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    int g = 0;
+    int ring_s = 0;            // ring slot and its phase (no division in the loop)
+    uint32_t ring_ph = 0;
     const bool mc = cc.multicast != 0;
     const uint16_t mc_mask = (uint16_t)((1u << cluster_nctarank()) - 1u);
     const uint32_t acc_cols = p.acc_stride;
@@ -1168,9 +1175,14 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
           const uint32_t d_base = ACC ? tmem_base + (uint32_t)(nb * q.n_tile) : tmem_base + (uint32_t)b * acc_cols;
           const int n_taps = 9 * q.chunks, t_dep = 3 * tr_dep;
 #pragma unroll 1
-          for (int t = 0; t < n_taps; ++t, ++g) {
-            const int s = g % stages;
-            mbar_wait(&bar_full[s], (uint32_t)(g / stages) & 1);
+          for (int t = 0; t < n_taps; ++t) {
+            const int s = ring_s;
+            const uint32_t ph = ring_ph;
+            if (++ring_s == stages) {
+              ring_s = 0;
+              ring_ph ^= 1u;
+            }
+            mbar_wait(&bar_full[s], ph);
             tc_fence_after_sync();
             if (lane == 0 && nb == 0 && t == 0) SSR_STAMP(l, 2);
             if (lane == 0 && nb == q.n_loop - 1 && t == n_taps - 1) SSR_STAMP(l, 3);
@@ -1201,9 +1213,14 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
       for (int nb = 0; nb < q.n_loop; ++nb) {
         const uint32_t d_base = ACC ? tmem_base + (uint32_t)(nb * q.n_tile) : tmem_base + (uint32_t)b * acc_cols;
 #pragma unroll 1
-        for (int tr0 = 0; tr0 < n_tr; tr0 += gps, ++g) {
-          const int s = g % stages;
-          mbar_wait(&bar_full[s], (uint32_t)(g / stages) & 1);
+        for (int tr0 = 0; tr0 < n_tr; tr0 += gps) {
+          const int s = ring_s;
+          const uint32_t ph = ring_ph;
+          if (++ring_s == stages) {
+            ring_s = 0;
+            ring_ph ^= 1u;
+          }
+          mbar_wait(&bar_full[s], ph);
           tc_fence_after_sync();
           if (lane == 0 && nb == 0 && tr0 == 0) SSR_STAMP(l, 2);                            // first weights landed
           if (lane == 0 && nb == q.n_loop - 1 && tr0 + gps >= n_tr) SSR_STAMP(l, 3);        // last weights landed
@@ -1225,8 +1242,14 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
               const uint64_t da = da_layer + (uint32_t)(c * (int)(kRChunk >> 4) + kx * 8);
               const uint64_t db = db_stage + (uint32_t)(jj * 3) * b_tap;
               const uint32_t first = (tr == 0 && !(ACC && l > 0)) ? 0u : 1u;   // ACC: layer 0 initialises, later layers add
-              if (c + 1 < q.chunks || ks_tail == 4) rdb_issue_triple<4>(d_base, m_cols, da, db, b_tap, idesc, first);
-              else rdb_issue_triple<2>(d_base, m_cols, da, db, b_tap, idesc, first);
+              if (c + 1 < q.chunks || ks_tail == 4) {
+                if (b_tap == 256u) rdb_issue_triple<4, 256>(d_base, m_cols, da, db, b_tap, idesc, first);        // 32 output channels
+                else if (b_tap == 512u) rdb_issue_triple<4, 512>(d_base, m_cols, da, db, b_tap, idesc, first);   // 64
+                else rdb_issue_triple<4, 0>(d_base, m_cols, da, db, b_tap, idesc, first);
+              } else {
+                if (b_tap == 256u) rdb_issue_triple<2, 256>(d_base, m_cols, da, db, b_tap, idesc, first);
+                else rdb_issue_triple<2, 0>(d_base, m_cols, da, db, b_tap, idesc, first);
+              }
               if (jj == gps - 1 || tr == n_tr - 1) {
                 if (mc) umma_commit_multicast(&bar_empty[s], mc_mask);
                 else umma_commit(&bar_empty[s]);
