@@ -330,8 +330,40 @@ def measure_train(args, bands, rank, world, local, lib, L, harness, steps, warmu
     cnt_cls = (ctypes.c_int64 * PROFILE_CLASSES)()
     L.check(lib.ssr_profile_stop(ms_cls, cnt_cls, PROFILE_CLASSES))
     tr.use_graph = not args.no_graph
+    # ---- the dense-block launches as they run inside the step's graph: back to back with programmatic dependent launch (the
+    # per-launch events above sit BETWEEN the launches and forbid that overlap: +6 .. 8 us per launch).  The 69 forward launches
+    # of the generator's own forward plan / the 69 input-gradient launches of its backward plan, same buffers, one graph each.
+    graph_us = {}
+    try:
+        from satlas_super_resolution_b200.ops import Plan
+        h, w = lr_h.shape[-2] // tr.G.unshuffle, lr_h.shape[-1] // tr.G.unshuffle
+        ws = tr.G.workspace(B, h, w, True)
+        for key, plan, fn in (("forward", ws.fwd, lib.ssr_conv_tc_chain), ("input_gradient", ws.bwd, lib.ssr_conv_tc_chain_acc)):
+            calls = [c for c in (plan.calls if plan is not None else []) if c[0] is fn or getattr(c[0], "__name__", "") == fn.__name__]
+            if not calls:
+                continue
+            sub = Plan()
+            sub.calls = calls
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                sub.run(cur_stream())
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    sub.run(cur_stream())
+                for _ in range(2):
+                    g.replay()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+            graph_us[key] = {"launches": len(calls), "us_per_launch": e0.elapsed_time(e1) * 1e3 / (5 * len(calls))}
+    except Exception as exc:   # diagnostics only: the per-launch numbers above stand on their own
+        log(f"back-to-back dense-block timing skipped: {exc!r}")
     return dict(B=B, ms_step=ms_total / steps, ms_e2e=ms_e2e / steps, launches=int(launches), ms_cls=list(ms_cls), cnt_cls=list(cnt_cls),
-                h2d=int(lr_h.numel() + hr_h.numel()), model=model)
+                h2d=int(lr_h.numel() + hr_h.numel()), model=model, graph_us=graph_us)
 
 
 def train_rooflines(m, bands, peak, peak_src):
@@ -346,6 +378,21 @@ def train_rooflines(m, bands, peak, peak_src):
                           dict(traffic=t_chain.get("dram_bytes_per_launch"), traffic_note=t_chain.get("note"),
                                forward=roofline_entry("rdb_resident_kernel<false>, forward", chain_flop, ms[2], cnt[2], peak, peak_src),
                                input_gradient=roofline_entry("rdb_resident_kernel<true>, input gradient", chain_flop, ms[3], cnt[3], peak, peak_src)))
+    # in-graph figure: the same launches back to back in a CUDA graph (what the step replays); operand ceiling: an SS-form
+    # tcgen05.mma M = 128, N, K = 16 reads (4096 + 32 N) B of shared memory at 128 B / clk = 32 + N / 4 cycles for N / 2 cycles of math
+    gu = m.get("graph_us") or {}
+    if gu:
+        per_launch_flop = chain_flop / N_RDB
+        for key, ent in gu.items():
+            ach = per_launch_flop / (ent["us_per_launch"] * 1e-6) / 1e12
+            main[key]["in_graph"] = {"us_per_launch": ent["us_per_launch"], "achieved": ach, "frac": ach / peak, "launches": ent["launches"],
+                                     "how": "the generator's own dense-block launches of one pass, captured back to back in one CUDA graph (programmatic dependent launch active), CUDA events around 5 replays"}
+        if "forward" in gu and "input_gradient" in gu:
+            us = 0.5 * (gu["forward"]["us_per_launch"] + gu["input_gradient"]["us_per_launch"])
+            ach = per_launch_flop / (us * 1e-6) / 1e12
+            main["in_graph"] = {"us_per_launch": us, "achieved": ach, "frac": ach / peak}
+    main["operand_ceiling"] = {"forward_frac_of_peak": (504 * 16 + 216 * 32) / (504 * 40 + 216 * 48),
+                               "note": "shared-memory operand bandwidth of SS-form MMAs: the forward block issues 504 MMAs with N = 32 (16 cycles of math, 40 of operand reads) and 216 with N = 64 (32 / 48); profiles/r02_conv64_ncu.md"}
     others = {
         "conv_tc_kernel": roofline_entry("ssr::conv_tc_kernel (single-launch convs: G head / tail, D, VGG19; forward + input gradient)",
                                          f["conv"] * B - 2 * chain_flop, ms[0], cnt[0], peak, peak_src),
