@@ -256,6 +256,14 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
+// one 32-byte store per thread (sm_100: STG.256): a lane's 16 bf16 channels are ONE full L2 sector instead of two half-sector
+// writes (partial sectors cost a fill from DRAM under ECC).  The address must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // identity the optimiser cannot see through (keeps a computed 64-bit descriptor as ONE value that offsets are added to)
 __device__ __forceinline__ uint64_t opaque64(uint64_t v) {
   uint64_t r;
