@@ -294,6 +294,11 @@ int ssr_feat_grad(const void* x, const void* dpool, void* dx, int32_t b, int32_t
 int ssr_feat_l1(const void* x, int64_t n_half, float scale, float* loss, void* stream);
 /* basicsr L1Loss(mean)*weight (ssr_esrgan_model.py:148): loss += ..., grad (=|+=) weight*sign(a-b)/n */
 int ssr_l1_loss(const float* a, const float* b, int64_t n, float weight, float* loss, float* grad, int32_t accumulate, void* stream);
+/* SSIMLoss (ssr/losses/basic_loss.py:50-60, call site ssr_esrgan_model.py:163-164) = kornia.losses.ssim_loss(x, gt, window_size=5):
+   loss += weight * mean(clamp((1 - ssim) / 2, 0, 1)) over `planes` f32 planes [h, w]; grad (=|+=) dLoss/dx (y is a constant).
+   scratch: 3 * planes * h * w floats, needed only with grad. */
+int ssr_ssim_loss(const float* x, const float* y, int32_t planes, int32_t h, int32_t w, float weight, float* loss, float* grad,
+                  int32_t accumulate, float* scratch, void* stream);
 /* basicsr GANLoss('vanilla') = BCEWithLogitsLoss against a constant target (ssr_esrgan_model.py:182,218,224) */
 int ssr_bce_logits(const float* x, int64_t n, float target, float weight, float* loss, float* mean_logit, float* grad, void* stream);
 /* torch.cat((img, F.interpolate(lr, scale_factor=factor)), 1) -> NHWC bf16 (ssr_esrgan_model.py:133,176,208-210) */

@@ -66,8 +66,8 @@ def vgg19_features(p, x, layer_names, use_input_norm=True, range_norm=False, rel
     if range_norm:
         x = (x + 1) / 2
     if use_input_norm:
-        mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
-        std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+        mean = torch.tensor(IMAGENET_MEAN, device=x.device).view(1, 3, 1, 1)
+        std = torch.tensor(IMAGENET_STD, device=x.device).view(1, 3, 1, 1)
         x = (x - mean) / std
     out = {}
     remaining = set(layer_names)
@@ -122,10 +122,29 @@ def usm_sharp(img, radius=50, sigma=0, weight=0.5, threshold=10):
     if radius % 2 == 0:
         radius += 1
     k1 = gaussian_kernel_1d(radius, sigma)
-    kernel = torch.outer(k1, k1).to(torch.float32)
+    kernel = torch.outer(k1, k1).to(torch.float32).to(img.device)
     blur = filter2d(img, kernel)
     residual = img - blur
     mask = (residual.abs() * 255 > threshold).float()
     soft_mask = filter2d(mask, kernel)
     sharp = torch.clip(img + weight * residual, 0, 1)
     return soft_mask * sharp + (1 - soft_mask) * img
+
+
+def ssim_loss(x, gt, loss_weight=1.0, window_size=5, sigma=1.5, max_val=1.0, eps=1e-12):
+    """SSIMLoss -- /root/reference/ssr/losses/basic_loss.py:50-60 (call site ssr_esrgan_model.py:163-164):
+    `kornia.losses.ssim_loss(x, gt, window_size=5, reduction="none")`, mean over (C, H, W), mean over the batch, times loss_weight.
+    kornia is a requirements.txt:7 dependency (no version pinned) that is not installed here -- "parity unpinned"; restated from
+    kornia.metrics.ssim / kornia.losses.ssim_loss: Gaussian window get_gaussian_kernel1d(5, 1.5), filter2d with reflect padding
+    ('same'), C1 = (0.01 max_val)^2, C2 = (0.03 max_val)^2, ssim = num / (den + eps), loss map = clamp((1 - ssim) / 2, 0, 1)."""
+    k1 = gaussian_kernel_1d(window_size, sigma).to(torch.float32)
+    kernel = torch.outer(k1, k1).to(x.device)
+    c1, c2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
+    mu1, mu2 = filter2d(x, kernel), filter2d(gt, kernel)
+    s11 = filter2d(x * x, kernel) - mu1 * mu1
+    s22 = filter2d(gt * gt, kernel) - mu2 * mu2
+    s12 = filter2d(x * gt, kernel) - mu1 * mu2
+    num = (2.0 * mu1 * mu2 + c1) * (2.0 * s12 + c2)
+    den = (mu1 * mu1 + mu2 * mu2 + c1) * (s11 + s22 + c2)
+    loss_map = torch.clamp((1.0 - num / (den + eps)) / 2, min=0, max=1)
+    return torch.mean(loss_map.mean(dim=(-1, -2, -3))) * loss_weight

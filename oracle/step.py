@@ -36,6 +36,7 @@ class OracleESRGAN:
         self.feed_disc_lr = opt.get("feed_disc_lr", True)
         self.pixel_weight = opt.get("pixel_weight", 1.0)
         self.gan_weight = opt.get("gan_weight", 0.1)
+        self.ssim_weight = opt.get("ssim_weight", 0.0)                                       # train.ssim_opt, :87-90
         self.percep = opt.get("perceptual", True)
         self.layer_weights = opt.get("layer_weights", losses.DEFAULT_LAYER_WEIGHTS)
 
@@ -86,6 +87,10 @@ class OracleESRGAN:
                 l_g_percep = losses.perceptual_loss(self.vgg, self.output, percep_gt, self.layer_weights)   # :154
                 l_g_total = l_g_total + l_g_percep
                 log["l_g_percep"] = l_g_percep
+            if self.ssim_weight:
+                l_g_ssim = losses.ssim_loss(self.output, percep_gt, self.ssim_weight)        # :163-166
+                l_g_total = l_g_total + l_g_ssim
+                log["l_g_ssim"] = l_g_ssim
             disc_input = self._disc_input(self.output, lr_resized)                           # :171-178
             fake_g_pred = self.net_d(disc_input)                                             # :181
             l_g_gan = losses.gan_loss_vanilla(fake_g_pred, True, is_disc=False, loss_weight=self.gan_weight)   # :182

@@ -290,6 +290,110 @@ __global__ void bce_logits_kernel(const float* __restrict__ x, long n, float tar
   }
 }
 
+// ------------------------------------------------------------------ SSIMLoss (ssr/losses/basic_loss.py:50-60)
+// kornia.losses.ssim_loss(x, gt, window_size=5, reduction="none"): 5x5 Gaussian window (sigma 1.5), reflect-padded 'same' filtering,
+//   mu = F(img), sigma = F(img * img') - mu mu', ssim = (2 mu_x mu_y + C1)(2 sigma_xy + C2) / ((mu_x^2 + mu_y^2 + C1)(sigma_xx + sigma_yy + C2) + eps),
+//   loss map = clamp((1 - ssim) / 2, 0, 1); the module takes the mean over (C, H, W) and then over the batch = the mean over everything.
+// Planes are [n, h, w] f32 (n = batch x channels).  Forward: one thread per pixel reads its 5 x 5 window of x and y (reflected at the
+// border), adds weight * mean(loss map) into *loss and -- when the gradient is wanted -- stores dLoss/d(mu_x), dLoss/d(E[x^2]),
+// dLoss/d(E[xy]) of its window into `part` ([3][n*h*w]).  Backward: the adjoint of the reflect-padded filter applied to those
+// three maps, gathered per pixel (no atomics: deterministic).
+struct SsimWin {
+  float k[5];
+};
+__device__ __forceinline__ int reflect_idx(int i, int n) {   // torch 'reflect' padding (also used by the USM blur below)
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+__global__ void ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int n, int h, int w, SsimWin win, float weight,
+                                float* __restrict__ loss, float* __restrict__ part) {
+  const long total = (long)n * h * w;
+  const float gs = weight / (float)total;
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f, eps = 1e-12f;
+  float acc = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % w), py = (int)((i / w) % h);
+    const float* xp = x + (i - (long)py * w - px);
+    const float* yp = y + (i - (long)py * w - px);
+    float mx = 0.f, my = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) {
+      const int ry = reflect_idx(py + dy - 2, h) * w;
+#pragma unroll
+      for (int dx = 0; dx < 5; ++dx) {
+        const int rx = reflect_idx(px + dx - 2, w);
+        const float kw = win.k[dy] * win.k[dx];
+        const float a = xp[ry + rx], b = yp[ry + rx];
+        mx = fmaf(kw, a, mx);
+        my = fmaf(kw, b, my);
+        exx = fmaf(kw, a * a, exx);
+        eyy = fmaf(kw, b * b, eyy);
+        exy = fmaf(kw, a * b, exy);
+      }
+    }
+    const float sxx = exx - mx * mx, syy = eyy - my * my, sxy = exy - mx * my;
+    const float A1 = 2.f * mx * my + C1, A2 = 2.f * sxy + C2, B1 = mx * mx + my * my + C1, B2 = sxx + syy + C2;
+    const float D = B1 * B2 + eps;
+    const float s = A1 * A2 / D;
+    const float l = 0.5f * (1.f - s);
+    acc += fminf(fmaxf(l, 0.f), 1.f);
+    if (part) {
+      const float gl = (l > 0.f && l < 1.f) ? -0.5f * gs : 0.f;   // d(clamped loss)/d(ssim), times weight / N
+      const float sd = s / D;
+      part[i] = gl * (2.f * my * (A2 - A1) / D - sd * 2.f * mx * (B2 - B1));   // via mu_x (directly and through sigma_xy, sigma_xx)
+      part[total + i] = gl * (-sd * B1);                                       // via E[x^2]
+      part[2 * total + i] = gl * (2.f * A1 / D);                               // via E[xy]
+    }
+  }
+  acc = block_reduce_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(loss, acc * gs);
+}
+
+// grad[p] (+)= F^T(g_mu)[p] + 2 x[p] F^T(g_xx)[p] + y[p] F^T(g_xy)[p];  F^T(g)[p] = sum over (q, d) with reflect(q + d) == p of k[d] g[q]
+__global__ void ssim_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ part, int n, int h, int w,
+                                SsimWin win, float* __restrict__ grad, int accumulate) {
+  const long total = (long)n * h * w;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % w), py = (int)((i / w) % h);
+    const long base = i - (long)py * w - px;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int dy = 0; dy < 5; ++dy) {
+      // the (up to three) rows q with reflect(q + dy - 2) == py: the direct one and the mirror images about either border
+      int qy[3];
+      qy[0] = py - (dy - 2);
+      qy[1] = py >= 1 ? -py - (dy - 2) : -1;
+      qy[2] = py <= h - 2 ? 2 * (h - 1) - py - (dy - 2) : -1;
+      for (int cy = 0; cy < 3; ++cy) {
+        const int ry = qy[cy];
+        if (ry < 0 || ry >= h) continue;
+        const int ly = ry + dy - 2;   // the unreflected coordinate: direct inside the image, mirrors strictly outside
+        if (cy == 0 ? (ly < 0 || ly >= h) : (cy == 1 ? ly >= 0 : ly <= h - 1)) continue;
+        for (int dx = 0; dx < 5; ++dx) {
+          int qx[3];
+          qx[0] = px - (dx - 2);
+          qx[1] = px >= 1 ? -px - (dx - 2) : -1;
+          qx[2] = px <= w - 2 ? 2 * (w - 1) - px - (dx - 2) : -1;
+          const float kw = win.k[dy] * win.k[dx];
+          for (int cx = 0; cx < 3; ++cx) {
+            const int rx = qx[cx];
+            if (rx < 0 || rx >= w) continue;
+            const int lx = rx + dx - 2;
+            if (cx == 0 ? (lx < 0 || lx >= w) : (cx == 1 ? lx >= 0 : lx <= w - 1)) continue;
+            const long q = base + (long)ry * w + rx;
+            t0 = fmaf(kw, part[q], t0);
+            t1 = fmaf(kw, part[total + q], t1);
+            t2 = fmaf(kw, part[2 * total + q], t2);
+          }
+        }
+      }
+    }
+    const float g = t0 + 2.f * x[i] * t1 + y[i] * t2;
+    if (accumulate) grad[i] += g; else grad[i] = g;
+  }
+}
+
 // ------------------------------------------------------------------ discriminator input assembly
 // out[n, y, x, :] = [ img[n, 0:ci, y, x] (planar f32) | lr[n, y/f, x/f, 0:cl] (NHWC bf16, nearest x f) | extra[n, 0:ce, y, x] (planar f32) | 0 ... ]
 // = torch.cat((output | gt, F.interpolate(lr, scale_factor=4), old_hr), 1) of ssr_esrgan_model.py:133,171-176,202-210.
@@ -453,11 +557,6 @@ __global__ void sn_bwd_reset(const SnDesc* __restrict__ descs) {
 
 // ------------------------------------------------------------------ USM sharpening (basicsr USMSharp, radius 51, sigma 8)
 __constant__ float c_gauss[64];
-__device__ __forceinline__ int reflect_idx(int i, int n) {
-  if (i < 0) i = -i;
-  if (i >= n) i = 2 * n - 2 - i;
-  return i;
-}
 // horizontal (dir=0) or vertical (dir=1) 1-D blur with reflect padding, planes of H x W
 __global__ void blur1d_kernel(const float* __restrict__ src, float* __restrict__ dst, long planes, int H, int W, int taps, int dir) {
   const long total = planes * H * W;
@@ -606,6 +705,24 @@ extern "C" int ssr_l1_loss(const float* a, const float* b, int64_t n, float weig
   SSR_REQUIRE(a && b && loss && n > 0, "ssr_l1_loss: bad args");
   l1_loss_kernel<<<grid_for2(n, 256), 256, 0, STREAM(stream)>>>(a, b, n, weight, loss, grad, accumulate);
   return LAUNCH_OK("l1_loss");
+}
+
+extern "C" int ssr_ssim_loss(const float* x, const float* y, int32_t planes, int32_t h, int32_t w, float weight, float* loss, float* grad,
+                             int32_t accumulate, float* scratch, void* stream) {
+  SSR_REQUIRE(x && y && loss && planes > 0 && h >= 3 && w >= 3, "ssr_ssim_loss: bad args (planes of at least 3 x 3)");
+  SSR_REQUIRE(grad == nullptr || scratch != nullptr, "ssr_ssim_loss: the gradient needs 3 * planes * h * w floats of scratch");
+  SsimWin win;
+  double g[5], sum = 0.0;
+  for (int i = 0; i < 5; ++i) sum += (g[i] = exp(-(double)((i - 2) * (i - 2)) / (2.0 * 1.5 * 1.5)));   // kornia get_gaussian_kernel1d(5, 1.5)
+  for (int i = 0; i < 5; ++i) win.k[i] = (float)(g[i] / sum);
+  const long total = (long)planes * h * w;
+  ssim_fwd_kernel<<<grid_for2(total, 256), 256, 0, STREAM(stream)>>>(x, y, planes, h, w, win, weight, loss, grad ? scratch : nullptr);
+  if (grad) {
+    count_launch();
+    if (!check_last("ssim_fwd")) return SSR_E_CUDA;
+    ssim_bwd_kernel<<<grid_for2(total, 256), 256, 0, STREAM(stream)>>>(x, y, scratch, planes, h, w, win, grad, accumulate);
+  }
+  return LAUNCH_OK("ssim_loss");
 }
 
 extern "C" int ssr_bce_logits(const float* x, int64_t n, float target, float weight, float* loss, float* mean_logit, float* grad,

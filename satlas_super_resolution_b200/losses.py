@@ -4,6 +4,7 @@
     cri_pix(pred, target) -> scalar
     cri_perceptual(x, gt) -> (percep | None, style | None)
     cri_gan(pred, target_is_real: bool, is_disc: bool = False) -> scalar
+    ssim_loss(x, gt) -> scalar                      (ssr/losses/basic_loss.py:50-60, call site ssr_esrgan_model.py:163-164)
 
 Each is an autograd Function over kernels of libssr_b200 (loss value + gradient in one pass); CUDA tensors only.
 """
@@ -47,6 +48,40 @@ class L1Loss(nn.Module):
         if weight is not None:
             raise NotImplementedError("L1Loss: element-wise weights are not built")
         return _L1Fn.apply(pred, target.detach(), float(self.loss_weight))
+
+
+class _SsimFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gt, weight):
+        need = ctx.needs_input_grad[0]
+        ctx.in_dtype = x.dtype
+        x, gt = x.contiguous().float(), gt.contiguous().float()
+        if x.dim() != 4 or x.shape != gt.shape:
+            raise ValueError(f"SSIMLoss: expected two [B, C, H, W] tensors of one shape, got {tuple(x.shape)} / {tuple(gt.shape)}")
+        B, C, H, W = x.shape
+        loss = torch.zeros(1, dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x) if need else None
+        scratch = torch.empty((3,) + tuple(x.shape), dtype=torch.float32, device=x.device) if need else None
+        L.check(lib().ssr_ssim_loss(x.data_ptr(), gt.data_ptr(), B * C, H, W, weight, loss.data_ptr(),
+                                    grad.data_ptr() if need else None, 0, scratch.data_ptr() if need else None, cur_stream()))
+        ctx.grad = grad
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return ((ctx.grad * g).to(ctx.in_dtype) if ctx.grad is not None else None), None, None
+
+
+class SSIMLoss(nn.Module):
+    """ssr/losses/basic_loss.py:50-60: kornia.losses.ssim_loss(x, gt, window_size=5, reduction='none'), mean over (C, H, W), mean
+    over the batch, times loss_weight -- one forward and one adjoint-filter kernel of libssr_b200 (ssr_ssim_loss)."""
+
+    def __init__(self, loss_weight=1.0):
+        super().__init__()
+        self.loss_weight = loss_weight
+
+    def forward(self, x, gt):
+        return _SsimFn.apply(x, gt.detach(), float(self.loss_weight))
 
 
 class _BceFn(torch.autograd.Function):
@@ -125,5 +160,5 @@ class PerceptualLoss(nn.Module):
         return _PercepFn.apply(x, gt.detach(), self), None
 
 
-for _c in (L1Loss, GANLoss, PerceptualLoss):
+for _c in (L1Loss, GANLoss, PerceptualLoss, SSIMLoss):
     _register(LOSS_REGISTRY, _c)

@@ -71,10 +71,13 @@ class SSRESRGANModel:
             raise ValueError("SSRESRGANModel (is_train): the option file has no network_d")
         self.net_d = build_network(opt["network_d"])
         self._load_if_given(self.net_d, "pretrain_network_d", "param_key_d", "strict_load_d", "params")
-        for unsupported in ("ldl_opt", "ssim_opt", "clip_opt"):
+        for unsupported in ("ldl_opt", "clip_opt"):
             if train_opt.get(unsupported):
                 raise NotImplementedError(f"train.{unsupported}: this loss is outside the built hot path (SURVEY.md section 2 rows 5, 13)")
         pix, per, gan = train_opt.get("pixel_opt") or {}, train_opt.get("perceptual_opt") or {}, train_opt.get("gan_opt") or {}
+        ssim = train_opt.get("ssim_opt") or {}                       # ssr_esrgan_model.py:87-90
+        if ssim and ssim.get("type", "SSIMLoss") != "SSIMLoss":
+            raise NotImplementedError(f"train.ssim_opt.type '{ssim.get('type')}' is not built (ssr/losses/basic_loss.py:50 SSIMLoss is)")
         if gan and gan.get("gan_type", "vanilla") != "vanilla":
             raise NotImplementedError("only gan_type 'vanilla' is built")
         optim_g = dict(train_opt.get("optim_g", {"type": "Adam", "lr": 1e-4, "betas": [0.9, 0.99]}))
@@ -94,6 +97,7 @@ class SSRESRGANModel:
                    lr_d=optim_d.get("lr", 1e-4), betas_d=tuple(optim_d.get("betas", (0.9, 0.99))),
                    weight_decay_d=optim_d.get("weight_decay", 0.0),
                    pixel_weight=pix.get("loss_weight", 1.0) if pix else 0.0, gan_weight=gan.get("loss_weight", 0.1),
+                   ssim_weight=ssim.get("loss_weight", 1.0) if ssim else 0.0,
                    perceptual=bool(per), layer_weights=per.get("layer_weights"), perceptual_weight=per.get("perceptual_weight", 1.0),
                    use_input_norm=per.get("use_input_norm", True), range_norm=per.get("range_norm", False),
                    feed_disc_lr=bool(opt.get("feed_disc_lr")), l1_gt_usm=opt.get("l1_gt_usm", True) is not False,

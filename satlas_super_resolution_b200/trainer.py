@@ -16,7 +16,8 @@ from .generator import RRDBNetEngine
 from .ops import FlatBuffer, allreduce_sum_, cur_stream, lib
 from .vgg import PerceptualEngine
 
-LOSS_KEYS = ["l_g_pix", "l_g_percep", "l_g_gan", "l_d_real", "out_d_real", "l_d_fake", "out_d_fake"]
+LOSS_KEYS = ["l_g_pix", "l_g_percep", "l_g_gan", "l_d_real", "out_d_real", "l_d_fake", "out_d_fake", "l_g_ssim"]   # slots of loss_dev
+LOG_ORDER = ["l_g_pix", "l_g_percep", "l_g_ssim", "l_g_gan", "l_d_real", "out_d_real", "l_d_fake", "out_d_fake"]     # ssr_esrgan_model.py:149-226
 
 
 def gaussian_taps(ksize=51, sigma=0.0):
@@ -110,6 +111,7 @@ class ESRGANTrainer:
         # ---- losses
         self.pixel_weight = cfg.get("pixel_weight", 1.0)
         self.gan_weight = cfg.get("gan_weight", 0.1)
+        self.ssim_weight = cfg.get("ssim_weight", 0.0)   # train.ssim_opt (ssr_esrgan_model.py:87-90, 163-166); 0 = no SSIM term
         self.P = None
         if vgg_state is not None and cfg.get("perceptual", True):
             vp = {k: v.to(dev, torch.float32).contiguous() for k, v in vgg_state.items()}
@@ -171,6 +173,7 @@ class ESRGANTrainer:
                       old_hr=torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
                       usm_scratch=torch.empty((3, B, 3, H, W), dtype=torch.float32, device=dev),
                       d_out=torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
+                      ssim_scratch=(torch.empty((3, B, 3, H, W), dtype=torch.float32, device=dev) if self.ssim_weight else None),
                       d_logits=torch.empty((B, 1, H, W), dtype=torch.float32, device=dev))
             self._io[key] = io
         return io
@@ -256,6 +259,10 @@ class ESRGANTrainer:
                 L.check(lb.ssr_l1_loss(out.data_ptr(), l1_gt.data_ptr(), n_img, self.pixel_weight, lp(0), d_out.data_ptr(), 0, s))
                 if self.P is not None:
                     self.P.loss_and_grad(out, percep_gt, loss[1:2], d_out, s)
+                if self.ssim_weight:
+                    # l_g_ssim = ssim_loss(self.output, percep_gt) -- ssr_esrgan_model.py:163-166
+                    L.check(lb.ssr_ssim_loss(out.data_ptr(), percep_gt.data_ptr(), B * 3, H, W, self.ssim_weight, lp(7),
+                                             d_out.data_ptr(), 1, io["ssim_scratch"].data_ptr(), s))
                 disc_in(out)
                 logits = self.D.forward(dws, training=True, stream=s)
                 L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 1.0, self.gan_weight, lp(2), None, d_logits.data_ptr(), s))
@@ -350,8 +357,9 @@ class ESRGANTrainer:
         """loss scalars (one D2H read, only when asked -- the reference syncs every iteration at :233)"""
         vals = self.loss_dev.tolist()
         log = OrderedDict()
-        for i, k in enumerate(LOSS_KEYS):
-            if k == "l_g_percep" and self.P is None:
+        for k in LOG_ORDER:
+            i = LOSS_KEYS.index(k)
+            if (k == "l_g_percep" and self.P is None) or (k == "l_g_ssim" and not self.ssim_weight):
                 continue
             if k.startswith("l_g_") and not getattr(self, "_last_do_g", True):
                 continue      # no generator step this iteration (net_d_iters / net_d_init_iters): the reference logs no l_g_*

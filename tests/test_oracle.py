@@ -201,3 +201,33 @@ def test_metrics_oracle_against_reference_golden_and_cv2():
     assert abs(om._ssim(a64, b64) - ref) < 1e-10
     t = torch.tensor([[[0.5 / 255, 1.5 / 255, 2.5 / 255, -1.0, 2.0]]])          # 0.5 -> 0, 1.5 -> 2, 2.5 -> 2, clamp
     assert om.tensor2img(t).flatten().tolist() == [0, 2, 2, 0, 255]
+
+
+def test_ssim_loss_restatement_properties_and_naive_evaluation():
+    """oracle.losses.ssim_loss (kornia.losses.ssim_loss restated; kornia is absent offline -> "parity unpinned"): checked against a
+    direct float64 evaluation of the definition (explicit reflect indexing, no conv) on a tiny image, plus ssim(x, x) = 1."""
+    import math
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(1, 2, 6, 7, generator=g)
+    y = torch.rand(1, 2, 6, 7, generator=g)
+    assert abs(losses.ssim_loss(x, x).item()) < 1e-6
+    k = [math.exp(-((i - 2) ** 2) / (2 * 1.5 ** 2)) for i in range(5)]
+    k = [v / sum(k) for v in k]
+    refl = lambda i, n: -i if i < 0 else (2 * (n - 1) - i if i >= n else i)
+    tot = 0.0
+    for c in range(2):
+        for py in range(6):
+            for px in range(7):
+                m = [0.0] * 5
+                for dy in range(5):
+                    for dx in range(5):
+                        a = x[0, c, refl(py + dy - 2, 6), refl(px + dx - 2, 7)].item()
+                        b = y[0, c, refl(py + dy - 2, 6), refl(px + dx - 2, 7)].item()
+                        w = k[dy] * k[dx]
+                        for j, v in enumerate((a, b, a * a, b * b, a * b)):
+                            m[j] += w * v
+                mx, my, exx, eyy, exy = m
+                num = (2 * mx * my + 1e-4) * (2 * (exy - mx * my) + 9e-4)
+                den = (mx * mx + my * my + 1e-4) * ((exx - mx * mx) + (eyy - my * my) + 9e-4)
+                tot += min(max((1 - num / (den + 1e-12)) / 2, 0.0), 1.0)
+    assert abs(losses.ssim_loss(x, y, 0.7).item() - 0.7 * tot / (2 * 6 * 7)) < 1e-6

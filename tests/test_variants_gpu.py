@@ -129,3 +129,35 @@ def test_pixel_unshuffle_front_end(scale):
     # d_out = 1 / numel is not a bf16 number: the back-propagated constant carries its 0.2 % rounding
     assert rel_l2(net.conv_last.bias.grad, po["conv_last.bias"].grad) < 5e-3
     assert rel_l2(net.conv_first.weight.grad, po["conv_first.weight"].grad) < 0.3
+
+
+def test_ssim_loss_kernel_vs_oracle():
+    """SSIMLoss (ssr/losses/basic_loss.py:50-60): loss value and dLoss/dx of ssr_ssim_loss against autograd of the oracle's torch
+    restatement of kornia.losses.ssim_loss -- odd sizes, so every reflected border row / column of the adjoint filter is hit"""
+    from oracle import losses
+    from satlas_super_resolution_b200.losses import SSIMLoss
+    g = torch.Generator().manual_seed(11)
+    for shape, w in (((2, 3, 128, 128), 1.0), ((3, 2, 17, 9), 0.37), ((1, 1, 3, 5), 2.0)):
+        x = torch.rand(shape, generator=g)
+        y = (x + 0.2 * torch.randn(shape, generator=g)).clamp(0, 1)
+        xo = x.clone().requires_grad_(True)
+        ref = losses.ssim_loss(xo, y, w)
+        ref.backward()
+        xe = x.cuda().requires_grad_(True)
+        out = SSIMLoss(loss_weight=w)(xe, y.cuda())
+        out.backward()
+        torch.cuda.synchronize()
+        assert abs(out.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item())), (shape, out.item(), ref.item())
+        assert rel_l2(xe.grad, xo.grad) < 1e-4, (shape, rel_l2(xe.grad, xo.grad))
+    # identical images: ssim == 1 everywhere, loss 0, zero gradient
+    xe = x.cuda().requires_grad_(True)
+    out = SSIMLoss()(xe, x.cuda())
+    out.backward()
+    assert abs(out.item()) < 1e-6 and xe.grad.abs().max().item() < 1e-6
+
+
+def test_step_with_ssim_opt():
+    """train.ssim_opt (ssr_esrgan_model.py:87-90, 163-166): l_g_ssim joins the generator loss and the log"""
+    tr, orc = _step(24, 32, 2, extra_opt=dict(ssim_weight=0.5))
+    assert "l_g_ssim" in tr.get_current_log()
+    assert list(tr.get_current_log())[:4] == ["l_g_pix", "l_g_percep", "l_g_ssim", "l_g_gan"]
