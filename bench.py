@@ -373,8 +373,8 @@ def train_rooflines(m, bands, peak, peak_src):
     chain_flop = N_RDB * F_RDB * B
     traffic = ncu_traffic()
     t_chain = dict(traffic.get("rdb_resident_kernel") or traffic.get("conv_chain_kernel") or {})
-    main = roofline_entry("ssr::rdb_resident_kernel (one ResidualDenseBlock per launch: its five forward convs, or its five input-gradient "
-                          "convs; tcgen05 implicit GEMM over a shared-memory-resident 192-channel tile, one 4-CTA cluster per image)", 2 * chain_flop, ms[2] + ms[3], cnt[2] + cnt[3], peak, peak_src,
+    main = roofline_entry("ssr::rdb_resident_kernel (ResidualDenseBlocks -- up to three, an RRDB, per launch: their five forward convs each, or their five "
+                          "input-gradient convs; tcgen05 implicit GEMM over a shared-memory-resident 192-channel tile, one 4-CTA cluster per image)", 2 * chain_flop, ms[2] + ms[3], cnt[2] + cnt[3], peak, peak_src,
                           dict(traffic=t_chain.get("dram_bytes_per_launch"), traffic_note=t_chain.get("note"),
                                forward=roofline_entry("rdb_resident_kernel<false>, forward", chain_flop, ms[2], cnt[2], peak, peak_src),
                                input_gradient=roofline_entry("rdb_resident_kernel<true>, input gradient", chain_flop, ms[3], cnt[3], peak, peak_src)))
@@ -382,15 +382,19 @@ def train_rooflines(m, bands, peak, peak_src):
     # tcgen05.mma M = 128, N, K = 16 reads (4096 + 32 N) B of shared memory at 128 B / clk = 32 + N / 4 cycles for N / 2 cycles of math
     gu = m.get("graph_us") or {}
     if gu:
-        per_launch_flop = chain_flop / N_RDB
+        per_block_flop = chain_flop / N_RDB
         for key, ent in gu.items():
-            ach = per_launch_flop / (ent["us_per_launch"] * 1e-6) / 1e12
-            main[key]["in_graph"] = {"us_per_launch": ent["us_per_launch"], "achieved": ach, "frac": ach / peak, "launches": ent["launches"],
+            # one launch takes ssr_rdb_resident_max_blocks consecutive blocks (an RRDB): report per launch AND per dense block
+            us_block = ent["us_per_launch"] * ent["launches"] / N_RDB
+            ent["us_per_block"] = us_block
+            ach = per_block_flop / (us_block * 1e-6) / 1e12
+            main[key]["in_graph"] = {"us_per_launch": ent["us_per_launch"], "us_per_block": us_block, "blocks_per_launch": N_RDB / ent["launches"],
+                                     "achieved": ach, "frac": ach / peak, "launches": ent["launches"],
                                      "how": "the generator's own dense-block launches of one pass, captured back to back in one CUDA graph (programmatic dependent launch active), CUDA events around 5 replays"}
         if "forward" in gu and "input_gradient" in gu:
-            us = 0.5 * (gu["forward"]["us_per_launch"] + gu["input_gradient"]["us_per_launch"])
-            ach = per_launch_flop / (us * 1e-6) / 1e12
-            main["in_graph"] = {"us_per_launch": us, "achieved": ach, "frac": ach / peak}
+            us = 0.5 * (gu["forward"]["us_per_block"] + gu["input_gradient"]["us_per_block"])
+            ach = per_block_flop / (us * 1e-6) / 1e12
+            main["in_graph"] = {"us_per_block": us, "achieved": ach, "frac": ach / peak}
     main["operand_ceiling"] = {"forward_frac_of_peak": (504 * 16 + 216 * 32) / (504 * 40 + 216 * 48),
                                "note": "shared-memory operand bandwidth of SS-form MMAs: the forward block issues 504 MMAs with N = 32 (16 cycles of math, 40 of operand reads) and 216 with N = 64 (32 / 48); profiles/r02_conv64_ncu.md"}
     others = {

@@ -57,6 +57,10 @@ extern "C" {
  * dst[class = oy*2 + ox][cout chunk][b][a][n = cin][64], tap (a, b) of class (oy, ox) = w[k][n][ky][kx] with
  * ky = oy ? 2 - 2a : 3 - 2a, kx = ox ? 2 - 2b : 3 - 2b (dx[2u+oy] collects dy[u - pad + a], pad = 1 - oy) */
 #define SSR_PACK_DGRAD_S2 4
+/* OR-ed into SSR_PACK_FWD / SSR_PACK_DGRAD (ssr_pack_conv_weight only): pack the ROUNDING RESIDUAL w - bf16(w) instead of bf16(w) --
+ * the low half of the split-bf16 operand pair of the tight-parity forward (a = a_hi + a_lo, w = w_hi + w_lo,
+ * a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo: three bf16 launches summed in f32, relative error ~2^-16 instead of 2^-8) */
+#define SSR_PACK_LO 16
 
 const char* ssr_last_error(void);
 int ssr_abi_version(void);
@@ -162,6 +166,10 @@ int ssr_conv_tc_chain(const ssr_conv_tc_args* args, int32_t n, void* stream);
 int ssr_conv_tc_chain_acc(const ssr_conv_tc_args* args, int32_t n, void* stream);
 /* 1 if ssr_conv_tc_chain_acc can run this geometry (host arithmetic only, no device needed), else 0 */
 int ssr_conv_tc_chain_acc_supported(int32_t n_img, int32_t h, int32_t w, int32_t widest_cout);
+/* How many consecutive ResidualDenseBlocks (rrdbnet_arch.py:37-44, 63-68) ONE resident launch may take for this geometry: the caller
+   concatenates that many blocks' five layers in one ssr_conv_tc_chain / ssr_conv_tc_chain_acc call (each block's last layer must store
+   its bf16 output exactly where the next block's first layer reads its input).  1 = one block per call ($SSR_RDB_FUSE overrides). */
+int ssr_rdb_resident_max_blocks(int32_t n_img, int32_t h, int32_t w);
 /* diagnostics: how many chains ran as the shared-memory-resident dense-block kernel (32-row images, 8 | w <= 64, the channel pattern
  * of ResidualDenseBlock; SSR_CONV_RESIDENT=0 disables it) */
 int64_t ssr_debug_resident_launches(void);
@@ -288,6 +296,12 @@ int ssr_col2im(const void* dcol, void* dx, int32_t dx_pix_stride, int32_t b, int
 /* y = a*x1 + b*x2 (x2 may be NULL), times the LeakyReLU(0.2) (mask_relu=0) or ReLU (1) derivative from `mask` (may be NULL) */
 int ssr_axpby(const void* x1, int32_t s1, float a, const void* x2, int32_t s2, float b, const void* mask, int32_t sm,
               int32_t mask_relu, void* y, int32_t sy, int64_t npix, int32_t c, void* stream);
+/* Tight-parity (split-bf16) forward, the epilogue as its own kernel: v = act(s1 + s2 + s3 + bias) * s0 + w1 * r1 + w2 * r2 over NHWC f32
+ * [npix, c] (s2, s3, bias, r1, r2 may be NULL; act: 0 none, 1 LeakyReLU(0.2)), then out_f32[pix * c + ch] = v (may be NULL),
+ * hi[pix * out_stride + ch] = bf16(v), lo[...] = bf16(v - hi) for ch < c and zeros for c <= ch < c_pad (hi / lo may be NULL). */
+int ssr_split_finish(const float* s1, const float* s2, const float* s3, int32_t sum_stride, int64_t npix, int32_t c, const float* bias,
+                     int32_t act, float s0, const float* r1, float w1, const float* r2, float w2, float* out_f32, void* hi, void* lo,
+                     int32_t out_stride, int32_t c_pad, void* stream);
 /* VGG19 feature extractor pieces of basicsr PerceptualLoss (ssr_esrgan_model.py:154): x holds 2b images (generated | gt) */
 int ssr_maxpool_relu(const void* x, void* y, int32_t b, int32_t h, int32_t w, int32_t c, void* stream);
 int ssr_feat_grad(const void* x, const void* dpool, void* dx, int32_t b, int32_t h, int32_t w, int32_t c, float l1_scale, void* stream);

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libssr_b200.so")
 SSR_NONE, SSR_BF16, SSR_F32, SSR_F32_PLANAR4 = 0, 1, 2, 3
 OUT32_NONE, OUT32_NHWC, OUT32_NHWC_ATOMIC, OUT32_NCHW, OUT32_PLANAR4, OUT32_PLANAR4_ACC = 0, 1, 2, 3, 4, 5
 PACK_FWD, PACK_DGRAD, PACK_FWD_GEMM, PACK_DGRAD_GEMM, PACK_DGRAD_S2 = 0, 1, 2, 3, 4
+PACK_LO = 16   # | PACK_FWD / PACK_DGRAD: the rounding residual w - bf16(w) (split-bf16 tight-parity forward)
 
 
 class ConvTcArgs(C.Structure):
@@ -66,6 +67,8 @@ def load(build_if_missing=True):
     lib.ssr_conv_tc_chain_acc.restype = C.c_int
     lib.ssr_conv_tc_chain_acc_supported.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     lib.ssr_conv_tc_chain_acc_supported.restype = C.c_int
+    lib.ssr_rdb_resident_max_blocks.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.ssr_rdb_resident_max_blocks.restype = C.c_int
     lib.ssr_packed_weight_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     lib.ssr_packed_weight_bytes.restype = C.c_int64
     lib.ssr_pack_conv_weight.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

@@ -6,6 +6,7 @@ Same registry names, constructor signatures, forward contract (f32 NCHW in / out
 runs the tcgen05 engines of this package through the C ABI, not torch.nn.functional.  There is no CPU path:
 calling forward on CPU tensors raises.
 """
+import os
 import weakref
 from collections import OrderedDict
 
@@ -191,9 +192,21 @@ class SSR_RRDBNet(_FlatModule):
         pool.append((ws, [weakref.ref(token)]))
         return ws, token
 
+    def forward_split_bf16(self, x):
+        """The tight-parity forward (tight.SplitBf16RRDBNet): operands as (hi, lo) bf16 pairs, ~2^-16 per layer -- a validation mode
+        that agrees with the fp32 reference to ~1e-5; no autograd.  The production forward is `forward`."""
+        if not x.is_cuda:
+            raise RuntimeError("SSR_RRDBNet: the B200 engine has no CPU path (input must be a CUDA tensor)")
+        from .tight import SplitBf16RRDBNet
+        net = SplitBf16RRDBNet({k: v.detach() for k, v in self.state_dict().items()}, self.num_in_ch, self.num_out_ch, scale=self.scale,
+                               num_feat=self.num_feat, num_block=self.num_block, num_grow_ch=self.num_grow_ch, device=x.device)
+        return net.forward(x.float())
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("SSR_RRDBNet: the B200 engine has no CPU path (input must be a CUDA tensor)")
+        if os.environ.get("SSR_PRECISION") == "split_bf16" and not torch.is_grad_enabled():
+            return self.forward_split_bf16(x)      # ssr/infer.py / infer_grid.py under torch.no_grad(): tight-parity evaluation
         if x.requires_grad and torch.is_grad_enabled():
             raise NotImplementedError("SSR_RRDBNet: the gradient w.r.t. the low-res input is never needed on the path and is not built")
         anchor = self._anchor if any(p.requires_grad for p in self.parameters()) else self._anchor.detach()

@@ -34,6 +34,10 @@ struct ConvTcK {
   // only weights stream.  res_out_ch = channel offset of this layer's output inside the tile (-1: not written back)
   int resident, res_out_ch, res_in_chunks;
   int res_in_lo;          // channel offset of this layer's INPUT inside the tile (0 forward; the dY slot of an input-gradient layer)
+  int blk_first, blk_last; // resident kernel, several dense blocks per launch: this layer is the first / last conv of its block.  A first
+                          // layer depends on ALL of its input (the TMA-loaded tile, or the previous block's last layer) and restarts the
+                          // tensor-memory sum of the input-gradient form; a last layer with res_out_ch >= 0 also writes its 64 output
+                          // channels into the tile, where the next block reads them (its global stores are unchanged)
   uint32_t chunk_alloc;   // bytes of one 64-channel chunk of the resident tile ((TW+2) x (MT*TH+2) rows of 128 B, 1 KB aligned)
   uint32_t w_bytes;       // > 0: weights-stationary single-layer launch (one 64-channel chunk): all R*R taps of this CTA's N tile are
                           // loaded ONCE into a region of w_bytes behind the stage ring; the stages carry activations only
@@ -82,6 +86,18 @@ struct ConvChainK {
   unsigned int* sync;  // kSyncGrid only. [2]: arrive counter, done counter (self-resetting)
   long long* timeline; // diagnostics (SSR_CHAIN_TIMELINE=1): clock64 stamps [cta][layer][8], else NULL
   int multicast;       // resident kernel: every CTA of the cluster loads 1 / n of the weight taps and multicasts them to all
+};
+
+// the resident dense-block kernel takes up to kMaxRdbBlocks consecutive blocks (one RRDB) per launch: the activation tile stays in
+// shared memory across block boundaries, and launch / prologue / drain (8 us of a 41 us block) are paid once per group
+static constexpr int kMaxRdbBlocks = 3, kMaxRdb = kMaxChain * kMaxRdbBlocks;
+struct RdbChainK {
+  CUtensorMap tmA;             // the first block's input (later blocks read the tile)
+  CUtensorMap tmB[kMaxRdb];
+  ConvTcK k[kMaxRdb];
+  int n_layers;
+  long long* timeline;         // SSR_CHAIN_TIMELINE=1 and n_layers <= kMaxChain, else NULL
+  int multicast;
 };
 
 static constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
@@ -1130,7 +1146,7 @@ __device__ __forceinline__ void rdb_issue_tap(uint32_t d0, uint32_t m_cols, uint
 }
 
 template <bool ACC>
-__global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_constant__ ConvChainK cc) {
+__global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_constant__ RdbChainK cc) {
   const ConvTcK* ps = cc.k;
   const int n_layers = cc.n_layers;
   long long* timeline = cc.timeline;
@@ -1149,7 +1165,8 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
   uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2], 8 warp arrivals
   uint64_t* bar_layer = bar_acc_empty + 2;         // every epilogue warp of the cluster arrives once per layer
   uint64_t* bar_x = bar_layer + 1;                 // the block input has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_x + 1);
+  uint64_t* bar_free = bar_x + 1;                  // forward, block boundary inside a launch: every CTA's MMAs of the block's last layer are done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_free + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [256]
   float* s_bg = s_bias + 256;                                // [256]
 
@@ -1161,7 +1178,7 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
-      prefetch_tmap(&cc.tmA[0]);
+      prefetch_tmap(&cc.tmA);
       prefetch_tmap(&cc.tmB[0]);
       for (int s = 0; s < stages; ++s) {
         mbar_init(&bar_full[s], 1);
@@ -1174,6 +1191,7 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
       }
       mbar_init(bar_layer, 8 * cluster_nctarank());
       mbar_init(bar_x, 1);
+      mbar_init(bar_free, 8 * cluster_nctarank());
       fence_barrier_init();
     }
     __syncwarp();
@@ -1217,7 +1235,7 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
       if (elect_one()) {
         mbar_expect_tx(bar_x, (uint32_t)p.res_in_chunks * p.a_box_bytes);
         for (int c = 0; c < p.res_in_chunks; ++c)
-          tma_load_4d(dense + (size_t)c * kRChunk, &cc.tmA[0], bar_x, c * 64, tx * 8 - 1, -1, img);
+          tma_load_4d(dense + (size_t)c * kRChunk, &cc.tmA, bar_x, c * 64, tx * 8 - 1, -1, img);
       }
       __syncwarp();
     };
@@ -1287,7 +1305,7 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
       const int b = ACC ? 0 : (l & 1);
       const uint32_t m_cols = ACC ? (uint32_t)q.acc_w : (uint32_t)q.n_tile;
       // the first triple that reads what layer l-1 wrote: the whole input (ACC: the dY slot), or the last 64-channel chunk
-      const int tr_dep = (ACC || l == 0) ? 0 : 3 * (q.chunks - 1);
+      const int tr_dep = (ACC || q.blk_first) ? 0 : 3 * (q.chunks - 1);
       // operand window of (chunk 0, kx 0, ky 0): chunk res_in_lo / 64 of the tile, K steps from (res_in_lo % 64) / 16
       const uint64_t da_layer = umma_desc(dense_addr + (uint32_t)(q.res_in_lo >> 6) * kRChunk, 16u, kRPitch * 128u, 2u) +
                                 (uint32_t)((q.res_in_lo & 63) >> 4) * 2u;
@@ -1325,7 +1343,7 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
               const int c = t / 9, r9 = t - 9 * c, kx = r9 / 3, ky = r9 - 3 * kx;
               const uint64_t da = da_layer + (uint32_t)(c * (int)(kRChunk >> 4) + kx * 8 + ky * (int)kRTapRow);
               const uint64_t db = b64 ? umma_desc(ring_addr + (uint32_t)s * kRStage, 16u, 512u, 4u) : umma_desc_k128(ring_addr + (uint32_t)s * kRStage);
-              const uint32_t first = (t == 0 && !(ACC && l > 0)) ? 0u : 1u;
+              const uint32_t first = (t == 0 && !(ACC && !q.blk_first)) ? 0u : 1u;
               if (c + 1 < q.chunks || ks_tail == 4) rdb_issue_tap<4>(d_base, m_cols, da, db, idesc, first);
               else rdb_issue_tap<2>(d_base, m_cols, da, db, idesc, first);
               if (mc) umma_commit_multicast(&bar_empty[s], mc_mask);
@@ -1369,7 +1387,7 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
               const int c = tr / 3, kx = tr - 3 * c;
               const uint64_t da = da_layer + (uint32_t)(c * (int)(kRChunk >> 4) + kx * 8);
               const uint64_t db = db_stage + (uint32_t)(jj * 3) * b_tap;
-              const uint32_t first = (tr == 0 && !(ACC && l > 0)) ? 0u : 1u;   // ACC: layer 0 initialises, later layers add
+              const uint32_t first = (tr == 0 && !(ACC && !q.blk_first)) ? 0u : 1u;   // ACC: a block's first layer initialises, later layers add
               if (c + 1 < q.chunks || ks_tail == 4) {
                 if (b_tap == 256u) rdb_issue_triple<4, 256>(d_base, m_cols, da, db, b_tap, idesc, first);        // 32 output channels
                 else if (b_tap == 512u) rdb_issue_triple<4, 512>(d_base, m_cols, da, db, b_tap, idesc, first);   // 64
@@ -1403,6 +1421,7 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
     const uint32_t n_rank = cluster_nctarank();
     griddep_wait();   // before the first global access (bias, masks, residuals, stores)
     bool cl_waited = false;
+    uint32_t free_ph = 0;   // phase of bar_free: one use per block boundary inside the launch (forward only)
 #pragma unroll 1
     for (int l = 0; l < n_layers; ++l) {
       const ConvTcK p = ps[l];
@@ -1419,7 +1438,10 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
       const uint32_t m_cols = ACC ? (uint32_t)p.acc_w : (uint32_t)p.n_tile;
       const uint32_t d_base = ACC ? tmem_base : tmem_base + (uint32_t)b * p.acc_stride;
       const bool use_r1 = p.res1_kind != SSR_NONE, use_r2 = p.res2_kind != SSR_NONE, use_mk = p.mask != nullptr;
-      const bool to_tile = p.res_out_ch >= 0;
+      const bool to_tile = p.res_out_ch >= 0 && !p.blk_last;
+      // the last layer of a block that is not the last of the launch: its 64 output channels are the NEXT block's input -- besides the
+      // global stores they go into chunk res_out_ch / 64 of the tile (and the neighbours' halo columns), followed by the layer barrier
+      const bool fuse_out = p.res_out_ch >= 0 && p.blk_last;
       const float neg_act = p.act == 2 ? 0.f : 0.2f;
 
       struct Ops {
@@ -1605,7 +1627,23 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
           }
         }
       } else {
-        // ---- the last layer: everything goes to global memory (f32 trunk / running gradient, bf16 copy for the next block)
+        // ---- the last layer of a block: everything goes to global memory (f32 trunk / running gradient, bf16 copy for the next block)
+        bool free_ok = true;
+        if (fuse_out) {
+          if (!cl_waited) {            // first access to the neighbours' shared memory
+            cluster_wait();
+            cl_waited = true;
+          }
+          if (!ACC) {
+            // Forward: the tile chunk this layer overwrites (the block input x) is an operand of THIS layer in every CTA, and the
+            // neighbours' MMAs read the halo columns we are about to push.  Every warp tells every CTA of the cluster that its own
+            // CTA's MMAs are complete (it has just seen bar_acc_full); nobody touches the tile before all have said so.  (Input
+            // gradient: the chunk was read by the block's FIRST layer only, four layer barriers ago.)
+            __syncwarp();
+            if ((uint32_t)lane < n_rank) mbar_arrive_remote_release(bar_free, (uint32_t)lane);
+            free_ok = false;
+          }
+        }
         bool first = true;
 #pragma unroll 1
         for (int mt = 0; mt < 2; ++mt) {
@@ -1619,6 +1657,33 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
             acc_load(mt, ci, v);
             tmem_ld_wait();
             item(v, ci, o.r1, o.r2, o.mk, pixs[mt], o0, o1);
+            if (fuse_out) {
+              if (!free_ok) {
+                mbar_wait_cluster(bar_free, free_ph);
+                free_ph ^= 1u;
+                free_ok = true;
+              }
+              const int dc = p.res_out_ch + ci * 16;
+              const uint32_t chunk_base = smem_u32(dense + (size_t)(dc >> 6) * kRChunk);
+              const uint32_t j0 = (uint32_t)(dc & 63) >> 3;
+              const uint32_t yl = (uint32_t)(mt * kRTH + tyy);
+              const uint32_t row = (yl + 1u) * kRPitch + (uint32_t)txx + 1u;
+              st_shared_v4(chunk_base + row * 128u + ((j0 ^ (row & 7u)) << 4), o0);
+              st_shared_v4(chunk_base + row * 128u + (((j0 + 1u) ^ (row & 7u)) << 4), o1);
+              int peer = -1;
+              uint32_t prow = 0;
+              if (txx == 0 && rank > 0) {
+                peer = (int)rank - 1;
+                prow = (yl + 1u) * kRPitch + 9u;
+              } else if (txx == 7 && rank + 1 < n_rank) {
+                peer = (int)rank + 1;
+                prow = (yl + 1u) * kRPitch;
+              }
+              if (peer >= 0) {
+                st_shared_cluster_v4(chunk_base + prow * 128u + ((j0 ^ (prow & 7u)) << 4), (uint32_t)peer, o0);
+                st_shared_cluster_v4(chunk_base + prow * 128u + (((j0 + 1u) ^ (prow & 7u)) << 4), (uint32_t)peer, o1);
+              }
+            }
             if (p.out_bf16 != nullptr && ci * 16 >= p.out_lo) {
               uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pixs[mt] * p.out_stride + ci * 16);
               dst[0] = o0;
@@ -1627,6 +1692,11 @@ __global__ void __launch_bounds__(kThreads, 1) rdb_resident_kernel(const __grid_
           }
         }
         tc_fence_before_sync();
+        if (fuse_out) {
+          fence_proxy_async();        // our generic-proxy stores (local and remote) before the tensor core's reads of them
+          __syncwarp();
+          if ((uint32_t)lane < n_rank) mbar_arrive_remote_release(bar_layer, (uint32_t)lane);   // lane r -> CTA r of the cluster
+        }
         __syncwarp();
         if (lane == 0 && !ACC) mbar_arrive(&bar_acc_empty[b]);
       }
@@ -2075,18 +2145,43 @@ extern "C" int64_t ssr_debug_resident_launches(void) { return g_resident_launche
 // channels [0, cin_i) of ONE buffer, all but the last append 32 channels at cin_i) or of its input-gradient chain with the
 // running sum in tensor memory (layer i+1 reads the 32-channel dY slot layer i emitted)?  32-row images cut into 8-pixel
 // strips, one cluster per image.  Returns 1 when launched, 0 when the shape does not qualify, < 0 on error.
-static int rdb_resident_launch(const ssr_conv_tc_args* a, int32_t n, cudaStream_t stream, bool tmem_acc) {
+static bool rdb_resident_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("SSR_CONV_RESIDENT");
     on = e ? atoi(e) : 1;
+    const char* c = getenv("SSR_CONV_CHAIN");
+    if (c && atoi(c) == 0) on = 0;
   }
-  if (!on || n < 2 || n > kMaxChain) return 0;
+  return on != 0;
+}
+
+// How many consecutive dense blocks one resident launch may take for this geometry (1 = the resident kernel does not apply, or
+// SSR_RDB_FUSE=1): the caller concatenates that many blocks' layers in one ssr_conv_tc_chain / ssr_conv_tc_chain_acc call.
+extern "C" int ssr_rdb_resident_max_blocks(int32_t n_img, int32_t h, int32_t w) {
+  if (!rdb_resident_enabled() || n_img <= 0 || h != 32 || w < 8 || w > 64 || (w & 7)) return 1;
+  static int fuse = -1;
+  if (fuse < 0) {
+    const char* e = getenv("SSR_RDB_FUSE");
+    fuse = e ? atoi(e) : kMaxRdbBlocks;
+    if (fuse < 1) fuse = 1;
+    if (fuse > kMaxRdbBlocks) fuse = kMaxRdbBlocks;
+  }
+  return fuse;
+}
+
+static int rdb_resident_launch(const ssr_conv_tc_args* a, int32_t n, cudaStream_t stream, bool tmem_acc) {
+  if (!rdb_resident_enabled() || n < 2 || n > kMaxRdb) return 0;
+  // n <= 5: one block of n layers; more: whole blocks of five layers, each block's last layer feeding the next block's first
+  const int bl = n <= kMaxChain ? n : kMaxChain;
+  if (n % bl) return 0;
   const int h = a[0].h, w = a[0].w;
   if (a[0].r != 3 || h != 32 || w < 8 || w > 64 || (w & 7) || a[0].cin != 64) return 0;
   for (int i = 0; i < n; ++i) {
     const ssr_conv_tc_args& L = a[i];
-    const bool last = i + 1 == n;
+    const int li = i % bl;
+    const ssr_conv_tc_args& base = a[i - li];        // the block's first layer
+    const bool last = li + 1 == bl;
     if (L.n_img != a[0].n_img || L.h != h || L.w != w || L.r != 3 || L.n_tile != 0 || L.splits > 1 || L.mt != 0) return 0;
     if (L.cout % 16 || L.out32_mode == SSR_OUT32_NHWC || L.out32_mode == SSR_OUT32_NHWC_ATOMIC || L.out32_mode == SSR_OUT32_NCHW ||
         L.out32_mode == SSR_OUT32_PLANAR4_ACC)
@@ -2094,30 +2189,38 @@ static int rdb_resident_launch(const ssr_conv_tc_args* a, int32_t n, cudaStream_
     if ((L.res1 && L.res1_kind != SSR_F32_PLANAR4) || (L.res2 && L.res2_kind != SSR_F32_PLANAR4) || L.mask_relu) return 0;
     if (!last && (L.res1 || L.res2 || L.out_f32)) return 0;
     if (last && (L.cout != 64 || L.out_lo != 0)) return 0;
+    if (li == 0 && i > 0) {
+      // block boundary: this block's 64 input channels are exactly what the previous block's last layer stores as bf16
+      const ssr_conv_tc_args& P = a[i - 1];
+      if (L.cin != 64 || P.out_bf16 == nullptr || L.x != (const void*)P.out_bf16 || L.x_pix_stride != P.out_pix_stride) return 0;
+    }
     if (!tmem_acc) {
-      // forward: layer i reads [0, 64 + 32 i) of the dense buffer and appends its 32 channels there (or nowhere: inference)
-      if (L.x != a[0].x || L.x_pix_stride != a[0].x_pix_stride || L.cin != 64 + 32 * i || L.mask || L.bias_grad || L.out_lo) return 0;
+      // forward: layer li reads [0, 64 + 32 li) of the block's dense buffer and appends its 32 channels there (or nowhere: inference)
+      if (L.x != base.x || L.x_pix_stride != base.x_pix_stride || L.cin != 64 + 32 * li || L.mask || L.bias_grad || L.out_lo) return 0;
       if (!last && (L.cout != 32 || (L.out_bf16 && (L.out_pix_stride != L.x_pix_stride ||
-                                                     L.out_bf16 != (void*)((char*)const_cast<void*>(a[0].x) + 2 * (size_t)L.cin)))))
+                                                     L.out_bf16 != (void*)((char*)const_cast<void*>(base.x) + 2 * (size_t)L.cin)))))
         return 0;
     } else {
-      // input gradient: pure sums (s0 == 1, no bias / activation -- checked by the caller), layer i emits its top 32 channels
+      // input gradient: pure sums (s0 == 1, no bias / activation -- checked by the caller), layer li emits its top 32 channels
       if (!last && (L.cout - L.out_lo != 32 || L.out_lo < 64 || L.out_bf16 == nullptr)) return 0;
-      if (i > 0) {
+      if (li > 0) {
         const ssr_conv_tc_args& P = a[i - 1];
         if (L.cin != 32 || L.x != (void*)((char*)P.out_bf16 + 2 * (size_t)P.out_lo) || L.x_pix_stride != P.out_pix_stride ||
             L.n_pad > P.out_lo)
           return 0;
-      } else if (L.cout > 64 * kResChunks) {
+      } else if (L.cout > 64 * kResChunks || L.n_pad != a[0].n_pad) {
         return 0;
       }
     }
   }
   if (!device_limits()) return SSR_E_CUDA;
-  static ConvChainK c;
+  static RdbChainK c;
+  static CUtensorMap tm_unused;   // later layers read the shared-memory tile: their activation maps are never used
   const uint32_t stage_bytes = tmem_acc ? kRStageAcc : kRStageFwd;
   const int tile_chunks = tmem_acc ? 2 : kResChunks;
   for (int i = 0; i < n; ++i) {
+    const int li = i % bl;
+    const bool last = li + 1 == bl;
     int mt_i = 0;
     ssr_conv_tc_args ai = a[i];
     if (tmem_acc) {
@@ -2131,7 +2234,7 @@ static int rdb_resident_launch(const ssr_conv_tc_args* a, int32_t n, cudaStream_
           break;
         }
     }
-    if (int rc = prepare_conv(&ai, 2, c.k[i], c.tmA[i], c.tmB[i], mt_i, true)) return rc;
+    if (int rc = prepare_conv(&ai, 2, c.k[i], i == 0 ? c.tmA : tm_unused, c.tmB[i], mt_i, true)) return rc;
     ConvTcK& k = c.k[i];
     k.b_row_bytes = 128;
     if (a[i].cin == 32) {
@@ -2149,13 +2252,17 @@ static int rdb_resident_launch(const ssr_conv_tc_args* a, int32_t n, cudaStream_
     k.resident = 1;
     k.chunk_alloc = kRChunk;
     k.res_in_chunks = 1;
+    k.blk_first = li == 0;
+    k.blk_last = last;
+    // a block's last layer hands its 64 channels to the next block of the launch through chunk 0 of the tile
+    const int handover = i + 1 < n ? 0 : -1;
     if (tmem_acc) {
-      // chunk 0 = the incoming gradient; the dY slot of layer i goes to half (i & 1) of chunk 1, where layer i+1 reads it
-      k.res_in_lo = i == 0 ? 0 : 64 + 32 * ((i - 1) & 1);
-      k.res_out_ch = i + 1 < n ? 64 + 32 * (i & 1) : -1;
+      // chunk 0 = the incoming gradient; the dY slot of layer li goes to half (li & 1) of chunk 1, where layer li+1 reads it
+      k.res_in_lo = li == 0 ? 0 : 64 + 32 * ((li - 1) & 1);
+      k.res_out_ch = !last ? 64 + 32 * (li & 1) : handover;
     } else {
       k.res_in_lo = 0;
-      k.res_out_ch = i + 1 < n ? a[i].cin : -1;
+      k.res_out_ch = !last ? a[i].cin : handover;
     }
     k.acc_w = tmem_acc ? c.k[0].n_pad : 0;
     k.acc_stride = 128;                       // forward: two accumulator buffers of 2 M tiles x 64 columns
@@ -2169,9 +2276,7 @@ static int rdb_resident_launch(const ssr_conv_tc_args* a, int32_t n, cudaStream_
   for (int i = 0; i < n; ++i) c.k[i].stages = stages;
   const size_t smem_bytes = (size_t)tile_chunks * kRChunk + (size_t)stages * stage_bytes + 1024 + 256 + 2048;
   c.n_layers = n;
-  c.sync_mode = kSyncCluster;
-  c.sync = nullptr;
-  c.timeline = chain_timeline_buffer();
+  c.timeline = n <= kMaxChain ? chain_timeline_buffer() : nullptr;   // the stamp table holds kMaxChain layers per CTA
   {
     static int mc = -1;
     if (mc < 0) {
@@ -2309,6 +2414,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
   // out[c][kx][ky][n][j]
   const long total = (long)chunks * r * r * n_pad * 64;
   const float sc = inv_scale ? 1.f / *inv_scale : 1.f;
+  const bool lo = (mode & SSR_PACK_LO) != 0;   // the rounding residual w - bf16(w): second term of the split-bf16 (tight parity) form
+  mode &= ~SSR_PACK_LO;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long t = i;
     const int j = t % 64;
@@ -2327,7 +2434,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
       // dgrad: n indexes the conv's input channel, k its output channel, taps mirrored
       if (nn < cin && k < cout) v = w[(((long)k * cin + nn) * r + (r - 1 - ky)) * r + (r - 1 - kx)];
     }
-    out[i] = __float2bfloat16(v * sc);
+    v *= sc;
+    if (lo) v -= __bfloat162float(__float2bfloat16(v));
+    out[i] = __float2bfloat16(v);
   }
 }
 }  // namespace ssr
@@ -2338,8 +2447,9 @@ extern "C" int ssr_pack_conv_weight(const float* w_oihw, int32_t cout, int32_t c
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SSR_REQUIRE(w_oihw && packed, "ssr_pack_conv_weight: null pointer");
   SSR_REQUIRE(k_pad > 0 && k_pad % 64 == 0 && n_pad % 16 == 0, "ssr_pack_conv_weight: k_pad must be a multiple of 64, n_pad of 16");
-  const int red = mode == SSR_PACK_FWD ? cin : cout;
-  const int outc = mode == SSR_PACK_FWD ? cout : cin;
+  SSR_REQUIRE((mode & ~SSR_PACK_LO) == SSR_PACK_FWD || (mode & ~SSR_PACK_LO) == SSR_PACK_DGRAD, "ssr_pack_conv_weight: mode %d", mode);
+  const int red = (mode & ~SSR_PACK_LO) == SSR_PACK_FWD ? cin : cout;
+  const int outc = (mode & ~SSR_PACK_LO) == SSR_PACK_FWD ? cout : cin;
   SSR_REQUIRE(k_pad >= red && n_pad >= outc, "ssr_pack_conv_weight: padded sizes too small");
   const int chunks = k_pad / 64;
   const long total = (long)chunks * r * r * n_pad * 64;

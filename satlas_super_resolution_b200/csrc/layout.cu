@@ -476,6 +476,34 @@ __global__ void pack_gemm_kernel(const PackDesc* __restrict__ descs) {
   }
 }
 
+// ------------------------------------------------------------------ split-bf16 (tight parity) forward: the conv epilogue as a kernel
+// v = act(s1 + s2 + s3 + bias) * s0 + w1 * r1 + w2 * r2; f32 copy, and the bf16 pair (hi, lo) with hi + lo = v to ~2^-17
+__global__ void split_finish_kernel(const float* __restrict__ s1, const float* __restrict__ s2, const float* __restrict__ s3, int sum_stride,
+                                    long npix, int c, const float* __restrict__ bias, int act, float s0, const float* __restrict__ r1, float w1,
+                                    const float* __restrict__ r2, float w2, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int out_stride, int c_pad) {
+  const long total = npix * c_pad;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / c_pad;
+    const int ch = (int)(i - pix * c_pad);
+    float v = 0.f;
+    if (ch < c) {
+      v = s1[pix * sum_stride + ch];
+      if (s2) v += s2[pix * sum_stride + ch];
+      if (s3) v += s3[pix * sum_stride + ch];
+      if (bias) v += bias[ch];
+      if (act) v = v > 0.f ? v : 0.2f * v;
+      v *= s0;
+      if (r1) v = fmaf(w1, r1[pix * c + ch], v);
+      if (r2) v = fmaf(w2, r2[pix * c + ch], v);
+      if (out_f32) out_f32[pix * c + ch] = v;
+    }
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    if (hi) hi[pix * out_stride + ch] = h;
+    if (lo) lo[pix * out_stride + ch] = __float2bfloat16(v - __bfloat162float(h));
+  }
+}
+
 }  // namespace ssr
 
 using namespace ssr;
@@ -607,4 +635,18 @@ extern "C" int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, 
     count_launch();
   }
   return check_last("pack_batched launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_split_finish(const float* s1, const float* s2, const float* s3, int32_t sum_stride, int64_t npix, int32_t c,
+                                const float* bias, int32_t act, float s0, const float* r1, float w1, const float* r2, float w2,
+                                float* out_f32, void* hi, void* lo, int32_t out_stride, int32_t c_pad, void* stream) {
+  SSR_REQUIRE(s1 && npix > 0 && c > 0 && c_pad >= c && sum_stride >= c, "ssr_split_finish: bad args");
+  SSR_REQUIRE((hi == nullptr && lo == nullptr) || out_stride >= c_pad, "ssr_split_finish: out_stride %d < c_pad %d", out_stride, c_pad);
+  const long total = (long)npix * c_pad;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 16 * 148) blocks = 16 * 148;
+  split_finish_kernel<<<blocks, 256, 0, STREAM(stream)>>>(s1, s2, s3, sum_stride, npix, c, bias, act, s0, r1, w1, r2, w2, out_f32,
+                                                        reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), out_stride, c_pad);
+  count_launch();
+  return check_last("split_finish") ? SSR_OK : SSR_E_CUDA;
 }

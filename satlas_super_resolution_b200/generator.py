@@ -169,6 +169,15 @@ class _Workspace:
                             bias=bptr(c), out=b0.ptr(0), out_stride=b0.stride,
                             out32=self.trunk_of(0).data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf))
         n_rdb = 3 * nb
+        # Training batches (one cluster of 4 CTAs per image, <= one wave of the 148 SMs) run dense blocks as shared-memory-
+        # resident launches: latency-bound, but launch + prologue + drain are paid once per launch -- and one launch takes up to
+        # `fuse` consecutive blocks (ssr_rdb_resident_max_blocks: an RRDB), the tile staying in shared memory across the block
+        # boundaries.  Large inference batches are the opposite regime -- many waves of CTAs: there the persistent per-layer
+        # kernel (tiles streamed back to back through double-buffered TMEM) keeps the tensor pipe busier than a chain that
+        # serialises five layers per CTA.
+        resident = self.train or B * max(1, (h * w) // 256) <= 2 * 148
+        fuse = lib().ssr_rdb_resident_max_blocks(B, h, w) if resident else 1
+        group, in_group = [], 0
         for i in range(n_rdb):
             blk, j = divmod(i, 3)
             cur = self.rdb_buf(i)
@@ -194,12 +203,12 @@ class _Workspace:
                                     res2=t_blk.data_ptr(), res2_kind=L.SSR_F32_PLANAR4, res2_stride=nf, s2=1.0,
                                     out=nxt.ptr(0), out_stride=nxt.stride,
                                     out32=t_nxt.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf))
-            # Training batches (one cluster of 4 CTAs per image, <= one wave of the 148 SMs) run the block as ONE shared-memory-
-            # resident launch: latency-bound, but launch + prologue are paid once per block.  Large inference batches are the
-            # opposite regime -- many waves of CTAs: there the persistent per-layer kernel (tiles streamed back to back through
-            # double-buffered TMEM) keeps the tensor pipe busier than a chain that serialises five layers per CTA.
-            if self.train or B * max(1, (h * w) // 256) <= 2 * 148:
-                plan.chain(block)
+            if resident:
+                group.extend(block)
+                in_group += 1
+                if in_group == fuse or i + 1 == n_rdb:
+                    plan.chain(group)
+                    group, in_group = [], 0
             else:
                 for a in block:
                     plan.conv(a)
@@ -248,10 +257,18 @@ class _Workspace:
         d_feat = Act(B, h, w, nf, dev)
         G32 = torch.empty((B, h, w, cw), dtype=torch.float32, device=dev)
         GO32 = torch.empty((B, h, w, nf), dtype=torch.float32, device=dev)
-        Dg = Act(B, h, w, cw, dev)
-        gR_pp, gO_b = [Act(B, h, w, nf, dev), Act(B, h, w, nf, dev)], Act(B, h, w, nf, dev)
+        # One resident launch takes the input-gradient chains of up to `fuse` consecutive blocks; their weight gradients follow the
+        # launch, so everything those read must survive it: one dY buffer per block of a group, fuse + 1 rotating block-gradient
+        # buffers (block i reads gR[(i+1) % m], writes gR[i % m]), and the RRDB-level gradient ping-pongs between two buffers
+        # (RRDB b reads gO[(b+1) & 1], writes gO[b & 1]).
+        tmem_chain = bool(eng.dgrad_tmem and lib().ssr_conv_tc_chain_acc_supported(B, h, w, cw))
+        fuse = lib().ssr_rdb_resident_max_blocks(B, h, w) if tmem_chain else 1
+        Dgs = [Act(B, h, w, cw, dev) for _ in range(fuse)]
+        m_r = fuse + 1
+        gR = [Act(B, h, w, nf, dev) for _ in range(m_r)]
+        gO = [Act(B, h, w, nf, dev), Act(B, h, w, nf, dev)]
         d_first = Act(B, h, w, nf, dev)
-        self._bwd_keep = [gA, gB, d_feat, G32, GO32, Dg, gR_pp, gO_b, d_first]
+        self._bwd_keep = [gA, gB, d_feat, G32, GO32, Dgs, gR, gO, d_first]
 
         def bias_grad(name, dy_ptr, dy_stride, npix, cy, scale=1.0):
             plan.add(lib().ssr_bias_grad, dy_ptr, dy_stride, npix, cy, grads[f"{name}.bias"].data_ptr(), scale)
@@ -304,21 +321,23 @@ class _Workspace:
         # ---- conv_body
         c = eng.cv["conv_body"]
         plan.conv(conv_args(d_feat.ptr(), B, h, w, nf, nf, c.packed_dg.data_ptr(), 3, nf, c.n_pad_dg,
-                            out=gO_b.ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf,
+                            out=gO[nb & 1].ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf,
                             bias_grad=bgrad_ptr(3 * nb - 1, 5), bias_grad_scale=0.04))
         wgrad("conv_body", self.body_out.ptr(), nf, nf, d_feat.ptr(), nf, nf, B, h, w)
         # ---- the trunk, last block first
-        tmem_chain = bool(eng.dgrad_tmem and lib().ssr_conv_tc_chain_acc_supported(B, h, w, cw))
+        pend_chain, pend_batches = [], []
         for i in range(3 * nb - 1, -1, -1):
             blk, j = divmod(i, 3)
             cur = self.bufs[i]
             pre = f"body.{blk}.rdb{j + 1}"
             c5 = eng.cv[f"{pre}.conv5"]
-            # the block reads its incoming gradient from gR_in (written by block i+1) and hands its result on in gR_out:
-            # ping-pong, because this block's weight-gradient launch (deferred to the end of the block) still reads gR_in
-            gR_in, gR_out = gR_pp[(i + 1) & 1], gR_pp[i & 1]
+            # the block reads its incoming gradient from gR_in (written by block i+1) and hands its result on in gR_out: rotating,
+            # because the weight-gradient launches (deferred to the end of the block / group) still read gR_in
+            gR_in, gR_out = gR[(i + 1) % m_r], gR[i % m_r]
+            gO_in, gO_b = gO[(blk + 1) & 1], gO[blk & 1]   # RRDB-level gradient: read by the third block, written by the first
+            Dg = Dgs[len(pend_batches)]
             if j == 2:
-                xin, s0, r1, r1s, s1 = gO_b, 0.04, GO32.data_ptr(), nf, 0.2
+                xin, s0, r1, r1s, s1 = gO_in, 0.04, GO32.data_ptr(), nf, 0.2
             else:
                 xin, s0, r1, r1s, s1 = gR_in, 0.2, G32.data_ptr(), cw, 1.0
             if tmem_chain:
@@ -348,8 +367,13 @@ class _Workspace:
                                                 out32_stride=nf, bias_grad=bgrad_ptr(i - 1, 5) if i > 0 else None,
                                                 bias_grad_scale=0.04 if j == 0 else 0.2, **res))
                     batch.append(wg.args(f"{pre}.conv{k}", cur.ptr(), cw, nk, dyk, cw, g, B, h, w, 3, 1.0))
-                plan.chain_acc(achain)
-                plan_wgrad_batch(plan, batch)
+                pend_chain.extend(achain)
+                pend_batches.append(batch)
+                if len(pend_batches) == fuse or i == 0:
+                    plan.chain_acc(pend_chain)       # ONE launch: the input-gradient chains of the group's blocks
+                    for bt in pend_batches:          # then each block's five weight gradients in one launch
+                        plan_wgrad_batch(plan, bt)
+                    pend_chain, pend_batches = [], []
                 continue
             if eng.dgrad_tmem:
                 s0 = 1.0   # the factor lives in the packed weights (see RRDBNetEngine.__init__); the wgrad scale below keeps it
@@ -392,6 +416,6 @@ class _Workspace:
             # all five weight gradients of the block in ONE launch (they only need the block's finished dY slots)
             plan_wgrad_batch(plan, batch)
         # ---- conv_first: dY = trunk gradient + the long skip (feat = conv_first + conv_body(...))
-        plan.add(lib().ssr_axpby, gO_b.ptr(), nf, 1.0, d_feat.ptr(), nf, 1.0, None, 0, 0, d_first.ptr(), nf, B * h * w, nf)
+        plan.add(lib().ssr_axpby, gO[0].ptr(), nf, 1.0, d_feat.ptr(), nf, 1.0, None, 0, 0, d_first.ptr(), nf, B * h * w, nf)
         wgrad("conv_first", self.in0.ptr(), self.in0.stride, eng.cin_pad, d_first.ptr(), nf, nf, B, h, w)
         return plan

@@ -143,3 +143,89 @@ def infer_tiles_sharded(net_g, tiles, rank=0, world=1, consume=None, **kw):
         TilePipeline(net_g, grid_size=int(round(t0.shape[0] ** 0.5)), chunk_hw=t0.shape[-1], in_ch=t0.shape[1], **kw).run(
             (tiles[i] for i in mine), sink)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ directory workflow
+def _read_png_rgb(path):
+    import cv2
+    im = cv2.imread(path, cv2.IMREAD_COLOR)
+    if im is None:
+        raise FileNotFoundError(f"cannot decode {path}")
+    return cv2.cvtColor(im, cv2.COLOR_BGR2RGB)
+
+
+def _write_png_rgb(path, rgb):
+    import cv2
+    if not cv2.imwrite(path, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR)):
+        raise OSError(f"cannot write {path}")
+
+
+def load_tile_dir(tile_dir, n_s2_images, grid_size=16, pool=None, rng=None, out=None):
+    """One tile directory of `ssr/infer_grid.py` ({tile}/{i}_{j}.png, each [T*32, 32, 3] uint8) -> (uint8 [grid^2, n*3, 32, 32]
+    chunk stack in i_j row-major order, uint8 [grid*32, grid*32, 3] stitched first frames = the reference's `stitched_s2.png`).
+    Frame choice per chunk = infer_utils.format_s2naip_data (clean frames first, `random.sample`); decode runs on `pool` threads
+    (cv2 releases the GIL); `out` may be a pinned buffer to decode into."""
+    rng = rng or random
+    names = [f"{i}_{j}.png" for i in range(grid_size) for j in range(grid_size)]
+    paths = [f"{tile_dir}/{n}" for n in names]
+    ims = list(pool.map(_read_png_rgb, paths)) if pool is not None else [_read_png_rgb(p) for p in paths]
+    n = grid_size * grid_size
+    stack = out if out is not None else torch.empty((n, n_s2_images * 3, 32, 32), dtype=torch.uint8)
+    s2 = np.zeros((grid_size * 32, grid_size * 32, 3), dtype=np.uint8)
+    dst = stack.numpy()
+    for k, im in enumerate(ims):
+        chunks = np.reshape(im, (-1, 32, 32, 3))
+        goods, bads = [], []
+        for t, ts in enumerate(chunks):
+            (bads if [0, 0, 0] in ts else goods).append(t)          # same membership test as the reference (infer_utils.py:16-20)
+        idx = rng.sample(goods, n_s2_images) if len(goods) >= n_s2_images else goods + rng.sample(bads, n_s2_images - len(goods))
+        dst[k] = np.concatenate([chunks[t].transpose(2, 0, 1) for t in idx], 0)   # channel index = frame * 3 + rgb
+        i, j = divmod(k, grid_size)
+        s2[i * 32:(i + 1) * 32, j * 32:(j + 1) * 32] = chunks[0]
+    return stack, s2
+
+
+def infer_grid_dir(net_g, data_dir, save_path, n_s2_images=8, grid_size=16, threads=8, batch=256, rank=0, world=1, rng=None,
+                   write_chunks=False):
+    """`ssr/infer_grid.py:46-85` for a directory tree {data_dir}/{tile}/{i}_{j}.png: every complete tile (grid_size^2 chunks) is
+    decoded on a thread pool into pinned memory, super-resolved as one batched pass with the stitching done on the GPU
+    (TilePipeline: H2D of tile t+1 and D2H of tile t-1 overlap tile t), and written as {save_path}/{tile}/stitched_sr.png next to
+    stitched_s2.png -- the two files the reference produces -- by the same pool (PNG encode of tile t-1 overlaps tile t).  With
+    write_chunks the grid_size^2 per-chunk PNGs {i}_{j}.png are written too (the reference always writes them; they are only the
+    input of its own stitch step).  Tiles are independent: rank r of `world` takes ops.rank_slice of the sorted tile list."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    from .ops import rank_slice
+    need = grid_size * grid_size
+    tiles = sorted(t for t in os.listdir(data_dir) if os.path.isdir(os.path.join(data_dir, t)))
+    complete = [t for t in tiles if len([f for f in os.listdir(os.path.join(data_dir, t)) if f.endswith(".png")]) >= need]
+    skipped = [t for t in tiles if t not in complete]       # "contains less than 256 chunks, cannot stitch" (infer_grid.py:72-74)
+    mine = [complete[i] for i in rank_slice(len(complete), rank, world)]
+    if not mine:
+        return dict(tiles=[], skipped=skipped)
+    eng = net_g._get_engine() if hasattr(net_g, "_get_engine") else net_g
+    side = 32 * eng.scale
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        pending = []
+
+        def source():
+            for t in mine:
+                stack, s2 = load_tile_dir(os.path.join(data_dir, t), n_s2_images, grid_size, pool, rng)
+                os.makedirs(os.path.join(save_path, t), exist_ok=True)
+                pending.append(pool.submit(_write_png_rgb, os.path.join(save_path, t, "stitched_s2.png"), s2))
+                yield stack
+
+        def sink(j, canvas):
+            img = canvas.numpy().copy()                       # the pinned buffer is reused two tiles later
+            out_dir = os.path.join(save_path, mine[j])
+            pending.append(pool.submit(_write_png_rgb, os.path.join(out_dir, "stitched_sr.png"), img))
+            if write_chunks:
+                for k in range(need):
+                    i, jj = divmod(k, grid_size)
+                    pending.append(pool.submit(_write_png_rgb, os.path.join(out_dir, f"{i}_{jj}.png"),
+                                               img[i * side:(i + 1) * side, jj * side:(jj + 1) * side]))
+
+        TilePipeline(net_g, grid_size=grid_size, chunk_hw=32, in_ch=n_s2_images * 3, batch=batch).run(source(), sink)
+        for f in pending:
+            f.result()
+    return dict(tiles=mine, skipped=skipped)

@@ -529,6 +529,155 @@ def test_chain_acc_running_sum_in_tensor_memory(B, W):
         assert torch.allclose(ref[3], got[3], rtol=1e-3, atol=1e-3 * ref[3].abs().max().item())                    # bias gradients
 
 
+@pytest.mark.parametrize("B,W,nblk", [(2, 32, 3), (32, 32, 3), (3, 64, 2), (5, 16, 3)])
+def test_several_dense_blocks_in_one_resident_launch(B, W, nblk):
+    """ssr_conv_tc_chain with 5 * nblk layers: consecutive ResidualDenseBlocks (an RRDB: the third block also adds the RRDB-level
+    residual) in ONE shared-memory-resident launch -- each block's conv5 hands its 64 channels to the next block through the tile.
+    Must be bit-identical to one resident launch per block (the global stores are the same; only where the next block READS
+    its input differs).  Run three times: barrier phases re-arm."""
+    L, lib = _lib()
+    if lib.ssr_rdb_resident_max_blocks(B, 32, W) < nblk:
+        pytest.skip("resident multi-block launches are switched off (SSR_CONV_RESIDENT=0 / SSR_RDB_FUSE)")
+    H, nf, g = 32, 64, 32
+    cw = nf + 4 * g
+    P = B * H * W
+    torch.manual_seed(B * 100 + W)
+    x0 = torch.randn(B, H, W, nf) * 0.5
+    trunk0 = (torch.randn(nf // 4, P, 4) * 0.5).cuda()
+    packs, biases = [], []
+    for b in range(nblk):
+        for k in range(5):
+            cin, cout = nf + k * g, (g if k < 4 else nf)
+            wk = torch.randn(cout, cin, 3, 3) * (1.0 / (3.0 * cin ** 0.5))
+            packed, n_pad = pack_weight(L, lib, wk, L.PACK_FWD, k_pad=(cin + 63) // 64 * 64)
+            packs.append((packed, n_pad, cin, cout))
+            biases.append((torch.randn(cout) * 0.1).cuda())
+
+    def make(bufs, out, trunks):
+        arr = (L.ConvTcArgs * (5 * nblk))()
+        for b in range(nblk):
+            buf = bufs[b]
+            for k in range(5):
+                packed, n_pad, cin, cout = packs[5 * b + k]
+                a = arr[5 * b + k]
+                a.x, a.n_img, a.h, a.w, a.x_pix_stride, a.cin = buf.data_ptr(), B, H, W, cw, cin
+                a.w_packed, a.r, a.cout, a.n_pad = packed.data_ptr(), 3, cout, n_pad
+                a.bias = biases[5 * b + k].data_ptr()
+                if k < 4:
+                    a.act, a.s0 = 1, 1.0
+                    a.out_bf16, a.out_pix_stride = buf.data_ptr() + 2 * cin, cw
+                else:
+                    last = b + 1 == nblk
+                    a.act, a.s0 = 0, (0.04 if last else 0.2)
+                    a.res1, a.res1_kind, a.res1_pix_stride, a.s1 = trunks[b].data_ptr(), L.SSR_F32_PLANAR4, nf, (0.2 if last else 1.0)
+                    if last:   # (x5*0.2 + x_rdb)*0.2 + x_rrdb -- rrdbnet_arch.py:68
+                        a.res2, a.res2_kind, a.res2_pix_stride, a.s2 = trunks[0].data_ptr(), L.SSR_F32_PLANAR4, nf, 1.0
+                    nxt, stride = (out, nf) if last else (bufs[b + 1], cw)
+                    a.out_bf16, a.out_pix_stride = nxt.data_ptr(), stride
+                    a.out_f32, a.out32_mode, a.out32_pix_stride = trunks[b + 1].data_ptr(), L.OUT32_PLANAR4, nf
+        return arr
+
+    def fresh():
+        bufs = [torch.zeros(B, H, W, cw, dtype=torch.bfloat16, device="cuda") for _ in range(nblk)]
+        bufs[0][..., :nf] = x0.cuda().to(torch.bfloat16)
+        trunks = [trunk0.clone()] + [torch.zeros(nf // 4, P, 4, device="cuda") for _ in range(nblk)]
+        return bufs, torch.zeros(B, H, W, nf, dtype=torch.bfloat16, device="cuda"), trunks
+
+    s = torch.cuda.current_stream().cuda_stream
+    ref = fresh()
+    arr = make(*ref)
+    for b in range(nblk):      # one resident launch per block
+        one = (L.ConvTcArgs * 5)(*[arr[5 * b + k] for k in range(5)])
+        L.check(lib.ssr_conv_tc_chain(one, 5, s))
+    torch.cuda.synchronize()
+    assert ref[1].float().abs().max() > 0
+    for _ in range(3):
+        got = fresh()
+        arr_b = make(*got)
+        n0, r0 = lib.ssr_launch_count(), lib.ssr_debug_resident_launches()
+        L.check(lib.ssr_conv_tc_chain(arr_b, 5 * nblk, s))
+        torch.cuda.synchronize()
+        assert lib.ssr_launch_count() - n0 == 1 and lib.ssr_debug_resident_launches() - r0 == 1
+        for b in range(nblk):
+            assert torch.equal(ref[0][b], got[0][b]), b
+            assert torch.equal(ref[2][b + 1], got[2][b + 1]), b
+        assert torch.equal(ref[1], got[1])
+
+
+@pytest.mark.parametrize("B,W,nblk", [(2, 32, 3), (32, 32, 3), (3, 64, 2), (5, 16, 3)])
+def test_several_input_gradient_chains_in_one_resident_launch(B, W, nblk):
+    """ssr_conv_tc_chain_acc with 5 * nblk layers: the input-gradient chains of consecutive dense blocks in ONE launch; a block's
+    64-channel result (sum in tensor memory + incoming f32 gradient) is the next block's incoming bf16 gradient, handed over through
+    the tile.  Bit-identical to one launch per block (bias gradients: atomics, tolerance)."""
+    L, lib = _lib()
+    if lib.ssr_rdb_resident_max_blocks(B, 32, W) < nblk:
+        pytest.skip("resident multi-block launches are switched off (SSR_CONV_RESIDENT=0 / SSR_RDB_FUSE)")
+    H, nf, g = 32, 64, 32
+    cw = nf + 4 * g
+    P = B * H * W
+    torch.manual_seed(B * 10 + W)
+    xin = (torch.randn(B, H, W, nf) * 0.5).cuda().to(torch.bfloat16)
+    curs = [torch.randn(B, H, W, cw).cuda().to(torch.bfloat16) for _ in range(nblk)]
+    g32_0 = (torch.randn(nf // 4, P, 4) * 0.3).cuda()
+    layers = []
+    for b in range(nblk):
+        for k in range(5, 0, -1):
+            nk = nf + (k - 1) * g
+            cin = nf if k == 5 else g
+            wk = torch.randn(nk, cin, 3, 3) * (1.0 / (3.0 * cin ** 0.5))
+            packed, n_pad = pack_weight(L, lib, wk, L.PACK_FWD, k_pad=64)
+            layers.append((k, nk, cin, packed, n_pad))
+
+    def make(dgs, G32, gouts, bg):
+        arr = (L.ConvTcArgs * (5 * nblk))()
+        for b in range(nblk):
+            dg = dgs[b]
+            for i in range(5):
+                k, nk, cin, packed, n_pad = layers[5 * b + i]
+                a = arr[5 * b + i]
+                if k == 5:
+                    a.x, a.x_pix_stride = (xin if b == 0 else gouts[b - 1]).data_ptr(), nf
+                else:
+                    a.x, a.x_pix_stride = dg.data_ptr() + 2 * nk, cw
+                a.n_img, a.h, a.w, a.cin = B, H, W, cin
+                a.w_packed, a.r, a.cout, a.n_pad, a.s0 = packed.data_ptr(), 3, nk, n_pad, 1.0
+                a.bias_grad, a.bias_grad_scale = bg.data_ptr() + 4 * 64 * (5 * b + i), 0.5
+                if k > 1:
+                    a.mask, a.mask_pix_stride, a.mask_lo, a.out_lo = curs[b].data_ptr(), cw, nk - g, nk - g
+                    a.out_bf16, a.out_pix_stride = dg.data_ptr(), cw
+                else:
+                    a.out_bf16, a.out_pix_stride = gouts[b].data_ptr(), nf
+                    a.res1, a.res1_kind, a.s1 = G32.data_ptr(), L.SSR_F32_PLANAR4, 1.0     # running f32 gradient, in place
+                    a.out_f32, a.out32_mode = G32.data_ptr(), L.OUT32_PLANAR4
+        return arr
+
+    def fresh():
+        return ([torch.zeros(B, H, W, cw, dtype=torch.bfloat16, device="cuda") for _ in range(nblk)], g32_0.clone(),
+                [torch.zeros(B, H, W, nf, dtype=torch.bfloat16, device="cuda") for _ in range(nblk)],
+                torch.zeros(5 * nblk, 64, device="cuda"))
+
+    s = torch.cuda.current_stream().cuda_stream
+    ref = fresh()
+    arr = make(*ref)
+    for b in range(nblk):
+        one = (L.ConvTcArgs * 5)(*[arr[5 * b + i] for i in range(5)])
+        L.check(lib.ssr_conv_tc_chain_acc(one, 5, s))
+    torch.cuda.synchronize()
+    assert ref[2][-1].float().abs().max() > 0
+    for _ in range(3):
+        got = fresh()
+        arr_b = make(*got)
+        n0, r0 = lib.ssr_launch_count(), lib.ssr_debug_resident_launches()
+        L.check(lib.ssr_conv_tc_chain_acc(arr_b, 5 * nblk, s))
+        torch.cuda.synchronize()
+        assert lib.ssr_launch_count() - n0 == 1 and lib.ssr_debug_resident_launches() - r0 == 1
+        for b in range(nblk):
+            assert torch.equal(ref[0][b], got[0][b]), b
+            assert torch.equal(ref[2][b], got[2][b]), b
+        assert torch.equal(ref[1], got[1])
+        assert torch.allclose(ref[3], got[3], rtol=1e-3, atol=1e-3 * ref[3].abs().max().item())
+
+
 @pytest.mark.parametrize("cout", [64, 20])
 def test_planar4_f32_operands_match_nhwc(cout):
     """SSR_F32_PLANAR4 residual + SSR_OUT32_PLANAR4 output hold exactly the values of the NHWC f32 forms (layout only)"""

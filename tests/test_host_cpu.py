@@ -26,7 +26,7 @@ def test_library_builds_loads_and_exports_the_header():
     for n in names:
         assert hasattr(lib, n), f"libssr_b200.so does not export {n}"
     bound = set(_protos.PROTOS) | {"ssr_last_error", "ssr_abi_version", "ssr_launch_count", "ssr_conv_tc", "ssr_conv_tc_chain", "ssr_conv_tc_chain_acc",
-                                   "ssr_conv_tc_chain_acc_supported",
+                                   "ssr_conv_tc_chain_acc_supported", "ssr_rdb_resident_max_blocks",
                                    "ssr_packed_weight_bytes", "ssr_pack_conv_weight"}
     assert set(names) <= bound, f"no ctypes prototype for {set(names) - bound}"
     assert lib.ssr_abi_version() == 1
@@ -184,3 +184,37 @@ def test_missing_vgg19_checkpoint_is_an_error_unless_random_weights_are_requeste
     monkeypatch.setenv("SSR_VGG19_PATH", str(tmp_path / "vgg.pth"))
     sd = weights.resolve_vgg19_state()
     assert sd["conv5_4.weight"][0, 0, 0, 0].item() == 34.0
+
+
+def test_load_tile_dir_matches_the_reference_frame_choice(tmp_path):
+    """infer.load_tile_dir (threaded PNG decode of one {tile}/{i}_{j}.png directory): the chunk stack equals what the reference's
+    format_s2naip_data (ssr/utils/infer_utils.py:6-39, restated in infer.format_s2naip_data) yields chunk by chunk under the same
+    seeded `random`, and the stitched first frames equal stitch(..., sentinel2=True) (infer_utils.py:41-60)."""
+    import random
+    from concurrent.futures import ThreadPoolExecutor
+    import cv2
+    import numpy as np
+    from satlas_super_resolution_b200.infer import format_s2naip_data, load_tile_dir
+    rs = np.random.RandomState(0)
+    grid, T, n = 3, 6, 4
+    d = tmp_path / "tile_a"
+    d.mkdir()
+    ims = {}
+    for i in range(grid):
+        for j in range(grid):
+            im = rs.randint(1, 256, (T * 32, 32, 3)).astype(np.uint8)
+            if (i + j) % 2:                       # some frames with black pixels: used only when clean ones run out
+                im[0:32][5, 7] = 0
+                im[64:96][0, 0] = 0
+                im[96:128][1, 1] = 0
+            ims[(i, j)] = im
+            cv2.imwrite(str(d / f"{i}_{j}.png"), cv2.cvtColor(im, cv2.COLOR_RGB2BGR))
+    with ThreadPoolExecutor(4) as pool:
+        stack, s2 = load_tile_dir(str(d), n, grid_size=grid, pool=pool, rng=random.Random(7))
+    rng = random.Random(7)
+    for k in range(grid * grid):
+        i, j = divmod(k, grid)
+        want, first = format_s2naip_data(ims[(i, j)], n, rng=rng)
+        assert torch.equal(stack[k].float() / 255, want[0])
+        assert np.array_equal(s2[i * 32:(i + 1) * 32, j * 32:(j + 1) * 32], first)
+    assert stack.shape == (grid * grid, n * 3, 32, 32) and stack.dtype == torch.uint8

@@ -54,3 +54,38 @@ def test_tile_pipeline_and_sharding_equal_direct_inference():
     assert sorted(got) == list(range(n_tiles))
     for i in range(n_tiles):
         assert torch.equal(got[i], want[i]), i
+
+
+def test_infer_grid_dir_writes_the_reference_files(tmp_path):
+    """infer_grid_dir: the directory workflow of ssr/infer_grid.py:46-85 -- PNG chunks in, stitched_sr.png / stitched_s2.png out
+    (threaded decode / encode around the batched GPU pass); incomplete tiles are skipped as the reference does"""
+    import random
+    import cv2
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from satlas_super_resolution_b200.archs import SSR_RRDBNet
+    from satlas_super_resolution_b200.infer import infer_grid, infer_grid_dir, load_tile_dir
+    torch.manual_seed(0)
+    net = SSR_RRDBNet(num_in_ch=6, num_out_ch=3, num_block=1).cuda().eval()
+    rs = np.random.RandomState(1)
+    grid, T, n = 2, 3, 2
+    data = tmp_path / "in"
+    for tile, count in (("t0", grid * grid), ("t1", grid * grid), ("short", 1)):
+        (data / tile).mkdir(parents=True)
+        for k in range(count):
+            i, j = divmod(k, grid)
+            im = rs.randint(1, 256, (T * 32, 32, 3)).astype(np.uint8)
+            cv2.imwrite(str(data / tile / f"{i}_{j}.png"), cv2.cvtColor(im, cv2.COLOR_RGB2BGR))
+    out = tmp_path / "out"
+    res = infer_grid_dir(net, str(data), str(out), n_s2_images=n, grid_size=grid, threads=4, batch=4, rng=random.Random(3), write_chunks=True)
+    assert res["tiles"] == ["t0", "t1"] and res["skipped"] == ["short"]
+    rng = random.Random(3)
+    with ThreadPoolExecutor(2) as pool:
+        for tile in ("t0", "t1"):
+            stack, s2 = load_tile_dir(str(data / tile), n, grid, pool, rng)
+            want = infer_grid(net, stack.cuda(), grid_size=grid, batch=4).cpu().numpy()
+            got = cv2.cvtColor(cv2.imread(str(out / tile / "stitched_sr.png")), cv2.COLOR_BGR2RGB)
+            assert np.array_equal(got, want)
+            assert np.array_equal(cv2.cvtColor(cv2.imread(str(out / tile / "stitched_s2.png")), cv2.COLOR_BGR2RGB), s2)
+            chunk = cv2.cvtColor(cv2.imread(str(out / tile / "1_0.png")), cv2.COLOR_BGR2RGB)
+            assert np.array_equal(chunk, want[128:256, 0:128])
