@@ -202,47 +202,19 @@ __global__ void upsample_nearest_bwd_kernel(const __nv_bfloat16* __restrict__ dy
 // ---------------------------------------------------------------- bilinear x2, align_corners=False
 // F.interpolate(scale_factor=2, mode='bilinear', align_corners=False), discriminator_arch.py:50,55,60.
 // Source coordinate (o + 0.5)/2 - 0.5 clamped at 0: taps (0.25, 0.75) in the interior, replicate at edges.
-__device__ __forceinline__ void bilin_src(int o, int n_in, int& i0, int& i1, float& w1) {
-  float s = (o + 0.5f) * 0.5f - 0.5f;
-  if (s < 0.f) s = 0.f;
-  i0 = (int)s;
-  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
-  w1 = s - (float)i0;
-}
-
-__device__ __forceinline__ uint4 add_bf16x8(const uint4& a, const uint4& b) {
-  const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
-  uint32_t o[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(ua[j] << 16) + __uint_as_float(ub[j] << 16),
-                                             __uint_as_float(ua[j] & 0xFFFF0000u) + __uint_as_float(ub[j] & 0xFFFF0000u));
-    o[j] = *reinterpret_cast<uint32_t*>(&h);
-  }
-  return make_uint4(o[0], o[1], o[2], o[3]);
-}
-
-// src2 (optional) is added to src before interpolating: the U-Net skip `x4 = x4 + x2` of discriminator_arch.py:53-64
-// (the sum is rounded to bf16 once, like a materialised tensor would be).
+// src2 (optional) is added to src before interpolating: the U-Net skip `x4 = x4 + x2` of discriminator_arch.py:53-64 (summed in
+// f32; only the interpolated result is rounded to bf16).
 // One thread = one INPUT pixel x 8 channels: it loads the 3 x 3 neighbourhood once (18 independent 16-byte loads with the skip)
-// and writes the 2 x 2 output pixels it owns -- 2.25 loads per output instead of 4 (8 with the skip) and a quarter of the index
-// arithmetic of the one-thread-per-output form (which ran at 24 % of the HBM roofline, profiles/r02_hbm_table.md).
-__device__ __forceinline__ uint4 bilin_mix(const uint4& v00, const uint4& v01, const uint4& v10, const uint4& v11, float wx, float wy) {
-  const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, b[4] = {v01.x, v01.y, v01.z, v01.w};
-  const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
-  // same operation order as ATen's upsample_bilinear2d: w0y*(w0x*a + w1x*b) + w1y*(w0x*c + w1x*d)
-  const float w0x = 1.f - wx, w0y = 1.f - wy;
-  uint32_t o[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float lo = w0y * (w0x * __uint_as_float(a[j] << 16) + wx * __uint_as_float(b[j] << 16)) +
-               wy * (w0x * __uint_as_float(c[j] << 16) + wx * __uint_as_float(d[j] << 16));
-    float hi = w0y * (w0x * __uint_as_float(a[j] & 0xFFFF0000u) + wx * __uint_as_float(b[j] & 0xFFFF0000u)) +
-               wy * (w0x * __uint_as_float(c[j] & 0xFFFF0000u) + wx * __uint_as_float(d[j] & 0xFFFF0000u));
-    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-    o[j] = *reinterpret_cast<uint32_t*>(&h);
-  }
-  return make_uint4(o[0], o[1], o[2], o[3]);
+// and writes the 2 x 2 output pixels it owns.  ncu (profiles/r02b_bilinear_ncu.md) showed the previous form issue-bound (43 % of
+// the stalls "selected / not selected", the bf16 -> f32 shifts on top of the SASS list): every output re-expanded its four
+// inputs and re-derived its taps.  Now every input word is expanded ONCE, the taps are constants and the interpolation is
+// separable: with the clamped neighbourhood (index 0 = max(. - 1, 0), 2 = min(. + 1, size - 1)) output 2i reads (0, 1) with
+// weights (0.25, 0.75) and output 2i + 1 reads (1, 2) with (0.75, 0.25) -- at an image edge both taps are the same pixel and
+// fma(0.75, a, 0.25 a) = a exactly, which is what ATen's clamped source index gives.  Same operation order as ATen's
+// upsample_bilinear2d (horizontal inside vertical): 62 instead of 92 instructions per 2 channels x 4 outputs.
+__device__ __forceinline__ void bf16x2_to_f32(uint32_t u, float& lo, float& hi) {
+  lo = __uint_as_float(u << 16);
+  hi = __uint_as_float(u & 0xFFFF0000u);
 }
 
 __global__ void upsample_bilinear2x_kernel(const __nv_bfloat16* __restrict__ src, int src_stride,
@@ -261,58 +233,74 @@ __global__ void upsample_bilinear2x_kernel(const __nv_bfloat16* __restrict__ src
     // rows / columns of the neighbourhood: index 0 = max(. - 1, 0), 1 = itself, 2 = min(. + 1, size - 1)
     const int ys[3] = {max(y - 1, 0), y, min(y + 1, H - 1)};
     const int xs[3] = {max(x - 1, 0), x, min(x + 1, W - 1)};
-    uint4 v[3][3];
+    uint32_t v[3][3][4];
     const __nv_bfloat16* base = src + n * H * W * (long)src_stride + g * 8;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[r][c] = *reinterpret_cast<const uint4*>(base + ((long)ys[r] * W + xs[c]) * src_stride);
+      for (int c = 0; c < 3; ++c) {
+        const uint4 t = *reinterpret_cast<const uint4*>(base + ((long)ys[r] * W + xs[c]) * src_stride);
+        v[r][c][0] = t.x, v[r][c][1] = t.y, v[r][c][2] = t.z, v[r][c][3] = t.w;
+      }
+    uint32_t u[3][3][4];
     if (src2) {
       const __nv_bfloat16* b2 = src2 + n * H * W * (long)src2_stride + g * 8;
-      uint4 u[3][3];
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) u[r][c] = *reinterpret_cast<const uint4*>(b2 + ((long)ys[r] * W + xs[c]) * src2_stride);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[r][c] = add_bf16x8(v[r][c], u[r][c]);
+        for (int c = 0; c < 3; ++c) {
+          const uint4 t = *reinterpret_cast<const uint4*>(b2 + ((long)ys[r] * W + xs[c]) * src2_stride);
+          u[r][c][0] = t.x, u[r][c][1] = t.y, u[r][c][2] = t.z, u[r][c][3] = t.w;
+        }
     }
-    // output row 2y reads rows (y - 1, y) with weight 0.75 on the second -- at y = 0 the clamped source is row 0 itself with
-    // weight 0 on row min(1, H - 1); output row 2y + 1 reads rows (y, y + 1) with weight 0.25 (bilin_src gives exactly these)
+    uint32_t o[2][2][4];
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      int y0, y1;
-      float wy;
-      bilin_src(2 * y + dy, H, y0, y1, wy);
-      const bool top = (dy == 0) && (y > 0);   // taps are neighbourhood rows (0, 1); otherwise rows (1, 2)
+    for (int j = 0; j < 4; ++j) {          // two channels at a time
+      float f[3][3][2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          bf16x2_to_f32(v[r][c][j], f[r][c][0], f[r][c][1]);
+          if (src2) {
+            float a0, a1;
+            bf16x2_to_f32(u[r][c][j], a0, a1);
+            f[r][c][0] += a0;
+            f[r][c][1] += a1;
+          }
+        }
+      float hx[3][2][2];                   // [row][output column parity][channel]
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          hx[r][0][k] = fmaf(0.75f, f[r][1][k], 0.25f * f[r][0][k]);
+          hx[r][1][k] = fmaf(0.25f, f[r][2][k], 0.75f * f[r][1][k]);
+        }
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
-        int x0, x1;
-        float wx;
-        bilin_src(2 * x + dx, W, x0, x1, wx);
-        const bool left = (dx == 0) && (x > 0);
-        uint4 a00, a01, a10, a11;
-        if (top) {
-          a00 = left ? v[0][0] : v[0][1];
-          a01 = left ? v[0][1] : v[0][2];
-          a10 = left ? v[1][0] : v[1][1];
-          a11 = left ? v[1][1] : v[1][2];
-        } else {
-          a00 = left ? v[1][0] : v[1][1];
-          a01 = left ? v[1][1] : v[1][2];
-          a10 = left ? v[2][0] : v[2][1];
-          a11 = left ? v[2][1] : v[2][2];
-        }
-        *reinterpret_cast<uint4*>(dst + ((n * (2 * H) + 2 * y + dy) * OW + 2 * x + dx) * (long)dst_stride + g * 8) =
-            bilin_mix(a00, a01, a10, a11, wx, wy);
+        const float t0 = fmaf(0.75f, hx[1][dx][0], 0.25f * hx[0][dx][0]), t1 = fmaf(0.75f, hx[1][dx][1], 0.25f * hx[0][dx][1]);
+        const float b0 = fmaf(0.25f, hx[2][dx][0], 0.75f * hx[1][dx][0]), b1 = fmaf(0.25f, hx[2][dx][1], 0.75f * hx[1][dx][1]);
+        __nv_bfloat162 h = __floats2bfloat162_rn(t0, t1);
+        o[0][dx][j] = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(b0, b1);
+        o[1][dx][j] = *reinterpret_cast<uint32_t*>(&h);
       }
     }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx)
+        *reinterpret_cast<uint4*>(dst + ((n * (2 * H) + 2 * y + dy) * OW + 2 * x + dx) * (long)dst_stride + g * 8) =
+            make_uint4(o[dy][dx][0], o[dy][dx][1], o[dy][dx][2], o[dy][dx][3]);
   }
 }
 
-// backward (gather form): each input pixel (y, x) collects from the <= 3x3 output pixels whose taps touch it.
+// backward (gather form): input pixel (y, x) collects from the 4 x 4 output pixels (2y - 1 .. 2y + 2) x (2x - 1 .. 2x + 2) whose
+// taps touch it.  The weights are constants -- rows 2y - 1, 2y, 2y + 1, 2y + 2 contribute 0.25, 0.75, 0.75, 0.25; at the image
+// edge the clamped source index of the forward folds the missing neighbour's weight onto the edge pixel: row 2y counts 1.0 at
+// y = 0 and row 2y + 1 counts 1.0 at y = H - 1, rows outside the image count 0 -- and the sum is separable: horizontal inside
+// vertical, 16 loads, every word expanded once (the loop over bilin_src() of round 1 spent 46 instructions per tap).
 __global__ void upsample_bilinear2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
                                                __nv_bfloat16* __restrict__ dx, int dx_stride, int B, int H, int W,
                                                int C) {
@@ -326,29 +314,32 @@ __global__ void upsample_bilinear2x_bwd_kernel(const __nv_bfloat16* __restrict__
     p /= W;
     const int y = (int)(p % H);
     const long n = p / H;
+    const float cy[4] = {y > 0 ? 0.25f : 0.f, y == 0 ? 1.f : 0.75f, y == H - 1 ? 1.f : 0.75f, y < H - 1 ? 0.25f : 0.f};
+    const float cx[4] = {x > 0 ? 0.25f : 0.f, x == 0 ? 1.f : 0.75f, x == W - 1 ? 1.f : 0.75f, x < W - 1 ? 0.25f : 0.f};
+    // rows / columns with weight 0 lie outside the image: read a valid address instead
+    const int oys[4] = {max(2 * y - 1, 0), 2 * y, 2 * y + 1, min(2 * y + 2, OH - 1)};
+    const int oxs[4] = {max(2 * x - 1, 0), 2 * x, 2 * x + 1, min(2 * x + 2, OW - 1)};
+    const __nv_bfloat16* base = dy + n * OH * OW * (long)dy_stride + g * 8;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    // output rows whose (y0, y1) can include y: oy in [2y-1, 2y+2]
-    for (int oy = max(0, 2 * y - 1); oy <= min(OH - 1, 2 * y + 2); ++oy) {
-      int y0, y1;
-      float wy;
-      bilin_src(oy, H, y0, y1, wy);
-      float cy = (y0 == y ? 1.f - wy : 0.f) + (y1 == y ? wy : 0.f);
-      if (cy == 0.f) continue;
-      for (int ox = max(0, 2 * x - 1); ox <= min(OW - 1, 2 * x + 2); ++ox) {
-        int x0, x1;
-        float wx;
-        bilin_src(ox, W, x0, x1, wx);
-        float cx = (x0 == x ? 1.f - wx : 0.f) + (x1 == x ? wx : 0.f);
-        if (cx == 0.f) continue;
-        const float cw = cy * cx;
-        const uint4 v = *reinterpret_cast<const uint4*>(dy + ((n * OH + oy) * OW + ox) * (long)dy_stride + g * 8);
-        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      uint4 v[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v[b] = *reinterpret_cast<const uint4*>(base + ((long)oys[a] * OW + oxs[b]) * dy_stride);
+      float row[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t w4[4] = {v[b].x, v[b].y, v[b].z, v[b].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          acc[2 * j] += cw * __uint_as_float(u[j] << 16);
-          acc[2 * j + 1] += cw * __uint_as_float(u[j] & 0xFFFF0000u);
+          float lo, hi;
+          bf16x2_to_f32(w4[j], lo, hi);
+          row[2 * j] = fmaf(cx[b], lo, row[2 * j]);
+          row[2 * j + 1] = fmaf(cx[b], hi, row[2 * j + 1]);
         }
       }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(cy[a], row[k], acc[k]);
     }
     uint4 o;
     __nv_bfloat162 h;
@@ -373,13 +364,15 @@ struct PackDesc {
 // floats per K entry), transposed through shared memory, and written as whole 128-byte rows (kPackNT consecutive rows per tap =
 // 1 KB contiguous) -- both sides coalesced, where the element-wise form read one 4-byte value per 36-byte stride.
 static constexpr int kPackNT = 8;
-__global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
-  const PackDesc d = descs[blockIdx.y];
-  if (d.mode != SSR_PACK_FWD && d.mode != SSR_PACK_DGRAD && d.mode != SSR_PACK_DGRAD_S2) return;
-  __shared__ __nv_bfloat16 tile[16 * kPackNT * 64];   // [tap (kx * r + ky)][row][k]
+// RT > 0: the filter size as a compile-time constant -- the index arithmetic below divides by r and r * r per element, and ncu
+// (profiles/r02b_pack_ncu.md: 246 us for the generator's 702 operands at 5 % of the DRAM roofline, the stalls "math / not selected")
+// showed the run-time divisions, not memory, bounding the kernel
+template <int RT>
+__device__ __forceinline__ void pack_tiles(const PackDesc& d, __nv_bfloat16* tile) {
+  const int r = RT > 0 ? RT : d.r;
   const bool s2 = d.mode == SSR_PACK_DGRAD_S2;        // r == 4: sixteen taps -> four parity classes of a 2 x 2 kernel
   const int chunks = d.k_pad / 64;
-  const int T = d.r * d.r;
+  const int T = r * r;
   const int n_tiles = (d.n_pad + kPackNT - 1) / kPackNT;
   const float sc = d.inv_scale ? 1.f / *d.inv_scale : 1.f;
   const bool fwd = d.mode == SSR_PACK_FWD;
@@ -414,7 +407,7 @@ __global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
         }
         const int n = n0 + nn, k = c * 64 + kl;
         if (n < n_valid && k < k_valid) vals[u] = fwd ? __ldg(d.w + ((long)n * d.cin + k) * T + tap) : __ldg(d.w + ((long)k * d.cin + n) * T + tap);
-        int ky = tap / d.r, kx = tap - ky * d.r;              // source tap (ky, kx); the input-gradient operand mirrors both
+        int ky = tap / r, kx = tap - ky * r;              // source tap (ky, kx); the input-gradient operand mirrors both
         int slot;
         if (s2) {
           // dx[2u + oy] collects w[ky] * dy[u - (1 - oy) + a] with ky = oy ? 2 - 2a : 3 - 2a  <=>  oy = 1 - (ky & 1), a = 1 - (ky >> 1)
@@ -422,10 +415,10 @@ __global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
           slot = (oy * 2 + ox) * 4 + b * 2 + a;
         } else {
           if (!fwd) {
-            ky = d.r - 1 - ky;
-            kx = d.r - 1 - kx;
+            ky = r - 1 - ky;
+            kx = r - 1 - kx;
           }
-          slot = kx * d.r + ky;
+          slot = kx * r + ky;
         }
         slots[u] = (slot * kPackNT + nn) * 64 + kl;
       }
@@ -445,6 +438,15 @@ __global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
     }
     __syncthreads();
   }
+}
+
+__global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
+  const PackDesc d = descs[blockIdx.y];
+  if (d.mode != SSR_PACK_FWD && d.mode != SSR_PACK_DGRAD && d.mode != SSR_PACK_DGRAD_S2) return;
+  __shared__ __nv_bfloat16 tile[16 * kPackNT * 64];   // [tap (kx * r + ky)][row][k]
+  if (d.r == 3) pack_tiles<3>(d, tile);               // (block-uniform branch: one descriptor per block row)
+  else if (d.r == 4) pack_tiles<4>(d, tile);
+  else pack_tiles<0>(d, tile);
 }
 
 // GEMM (1x1) forms for a conv computed through im2col: K' = (ky*R + kx)*cin + ci
