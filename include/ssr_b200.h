@@ -296,12 +296,16 @@ int ssr_col2im(const void* dcol, void* dx, int32_t dx_pix_stride, int32_t b, int
 /* y = a*x1 + b*x2 (x2 may be NULL), times the LeakyReLU(0.2) (mask_relu=0) or ReLU (1) derivative from `mask` (may be NULL) */
 int ssr_axpby(const void* x1, int32_t s1, float a, const void* x2, int32_t s2, float b, const void* mask, int32_t sm,
               int32_t mask_relu, void* y, int32_t sy, int64_t npix, int32_t c, void* stream);
-/* Tight-parity (split-bf16) forward, the epilogue as its own kernel: v = act(s1 + s2 + s3 + bias) * s0 + w1 * r1 + w2 * r2 over NHWC f32
- * [npix, c] (s2, s3, bias, r1, r2 may be NULL; act: 0 none, 1 LeakyReLU(0.2)), then out_f32[pix * c + ch] = v (may be NULL),
+/* Tight-parity (split-bf16) mode (tight.py), the conv epilogue as its own kernel: v = act(s1 + s2 + s3 + bias) * s0 + w1 * r1 + w2 * r2
+ * over NHWC f32 channel slices [npix, c] with their own pixel strides (s2, s3, bias, r1, r2 may be NULL; act: 0 none, 1 LeakyReLU(0.2));
+ * out_f32[pix * out32_stride + ch] = v (may be NULL); then v *= LeakyReLU'(mask) with mask the bf16 forward activation (may be NULL);
  * hi[pix * out_stride + ch] = bf16(v), lo[...] = bf16(v - hi) for ch < c and zeros for c <= ch < c_pad (hi / lo may be NULL). */
 int ssr_split_finish(const float* s1, const float* s2, const float* s3, int32_t sum_stride, int64_t npix, int32_t c, const float* bias,
-                     int32_t act, float s0, const float* r1, float w1, const float* r2, float w2, float* out_f32, void* hi, void* lo,
+                     int32_t act, float s0, const float* r1, int32_t r1_stride, float w1, const float* r2, int32_t r2_stride, float w2,
+                     const void* mask_bf16, int32_t mask_stride, float* out_f32, int32_t out32_stride, void* hi, void* lo,
                      int32_t out_stride, int32_t c_pad, void* stream);
+/* adjoint of the nearest x2 upsample in f32 (NHWC [b, 2h, 2w, c] -> [b, h, w, c], 2 x 2 sums): the split-bf16 backward */
+int ssr_sum_pool2x2_f32(const float* src, float* dst, int32_t b, int32_t h, int32_t w, int32_t c, void* stream);
 /* VGG19 feature extractor pieces of basicsr PerceptualLoss (ssr_esrgan_model.py:154): x holds 2b images (generated | gt) */
 int ssr_maxpool_relu(const void* x, void* y, int32_t b, int32_t h, int32_t w, int32_t c, void* stream);
 int ssr_feat_grad(const void* x, const void* dpool, void* dx, int32_t b, int32_t h, int32_t w, int32_t c, float l1_scale, void* stream);

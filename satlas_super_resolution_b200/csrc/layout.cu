@@ -478,12 +478,15 @@ __global__ void pack_gemm_kernel(const PackDesc* __restrict__ descs) {
   }
 }
 
-// ------------------------------------------------------------------ split-bf16 (tight parity) forward: the conv epilogue as a kernel
-// v = act(s1 + s2 + s3 + bias) * s0 + w1 * r1 + w2 * r2; f32 copy, and the bf16 pair (hi, lo) with hi + lo = v to ~2^-17
+// ------------------------------------------------------------------ split-bf16 (tight parity) mode: the conv epilogue as a kernel
+// v = act(s1 + s2 + s3 + bias) * s0 + w1 * r1 + w2 * r2 (every operand an NHWC f32 channel slice with its own pixel stride);
+// out_f32 = v; then v *= LeakyReLU'(mask) when a mask (bf16 forward activation) is given; the bf16 pair (hi, lo) with hi + lo = v
+// to ~2^-17 goes to hi / lo, channels [c, c_pad) zero-filled
 __global__ void split_finish_kernel(const float* __restrict__ s1, const float* __restrict__ s2, const float* __restrict__ s3, int sum_stride,
-                                    long npix, int c, const float* __restrict__ bias, int act, float s0, const float* __restrict__ r1, float w1,
-                                    const float* __restrict__ r2, float w2, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ hi,
-                                    __nv_bfloat16* __restrict__ lo, int out_stride, int c_pad) {
+                                    long npix, int c, const float* __restrict__ bias, int act, float s0, const float* __restrict__ r1,
+                                    int r1_stride, float w1, const float* __restrict__ r2, int r2_stride, float w2,
+                                    const __nv_bfloat16* __restrict__ mask, int mask_stride, float* __restrict__ out_f32, int out32_stride,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int out_stride, int c_pad) {
   const long total = npix * c_pad;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long pix = i / c_pad;
@@ -496,9 +499,10 @@ __global__ void split_finish_kernel(const float* __restrict__ s1, const float* _
       if (bias) v += bias[ch];
       if (act) v = v > 0.f ? v : 0.2f * v;
       v *= s0;
-      if (r1) v = fmaf(w1, r1[pix * c + ch], v);
-      if (r2) v = fmaf(w2, r2[pix * c + ch], v);
-      if (out_f32) out_f32[pix * c + ch] = v;
+      if (r1) v = fmaf(w1, r1[pix * r1_stride + ch], v);
+      if (r2) v = fmaf(w2, r2[pix * r2_stride + ch], v);
+      if (out_f32) out_f32[pix * out32_stride + ch] = v;
+      if (mask) v *= __bfloat162float(mask[pix * mask_stride + ch]) > 0.f ? 1.f : 0.2f;
     }
     const __nv_bfloat16 h = __float2bfloat16(v);
     if (hi) hi[pix * out_stride + ch] = h;
@@ -506,6 +510,21 @@ __global__ void split_finish_kernel(const float* __restrict__ s1, const float* _
   }
 }
 
+// the adjoint of F.interpolate(scale_factor=2, mode='nearest') in f32 (rrdbnet_arch.py:127-134 backwards): dst[n, y, x, :] = sum of
+// the 2 x 2 block of src[n, 2y .. 2y+1, 2x .. 2x+1, :]; NHWC f32, c channels
+__global__ void sum_pool2x2_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int h, int w, int c) {
+  const long total = (long)B * h * w * c;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    long p = i / c;
+    const int x = (int)(p % w);
+    p /= w;
+    const int y = (int)(p % h);
+    const long n = p / h;
+    const float* s = src + ((n * (2 * h) + 2 * y) * (long)(2 * w) + 2 * x) * c + ch;
+    dst[i] = (s[0] + s[c]) + (s[(long)2 * w * c] + s[(long)2 * w * c + c]);
+  }
+}
 }  // namespace ssr
 
 using namespace ssr;
@@ -640,15 +659,29 @@ extern "C" int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, 
 }
 
 extern "C" int ssr_split_finish(const float* s1, const float* s2, const float* s3, int32_t sum_stride, int64_t npix, int32_t c,
-                                const float* bias, int32_t act, float s0, const float* r1, float w1, const float* r2, float w2,
-                                float* out_f32, void* hi, void* lo, int32_t out_stride, int32_t c_pad, void* stream) {
+                                const float* bias, int32_t act, float s0, const float* r1, int32_t r1_stride, float w1, const float* r2,
+                                int32_t r2_stride, float w2, const void* mask_bf16, int32_t mask_stride, float* out_f32,
+                                int32_t out32_stride, void* hi, void* lo, int32_t out_stride, int32_t c_pad, void* stream) {
   SSR_REQUIRE(s1 && npix > 0 && c > 0 && c_pad >= c && sum_stride >= c, "ssr_split_finish: bad args");
   SSR_REQUIRE((hi == nullptr && lo == nullptr) || out_stride >= c_pad, "ssr_split_finish: out_stride %d < c_pad %d", out_stride, c_pad);
+  SSR_REQUIRE((!r1 || r1_stride >= c) && (!r2 || r2_stride >= c) && (!out_f32 || out32_stride >= c) && (!mask_bf16 || mask_stride >= c),
+              "ssr_split_finish: an operand's pixel stride is smaller than the channel count %d", c);
   const long total = (long)npix * c_pad;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 16 * 148) blocks = 16 * 148;
-  split_finish_kernel<<<blocks, 256, 0, STREAM(stream)>>>(s1, s2, s3, sum_stride, npix, c, bias, act, s0, r1, w1, r2, w2, out_f32,
+  split_finish_kernel<<<blocks, 256, 0, STREAM(stream)>>>(s1, s2, s3, sum_stride, npix, c, bias, act, s0, r1, r1_stride, w1, r2, r2_stride, w2,
+                                                        reinterpret_cast<const __nv_bfloat16*>(mask_bf16), mask_stride, out_f32, out32_stride,
                                                         reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), out_stride, c_pad);
   count_launch();
   return check_last("split_finish") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int ssr_sum_pool2x2_f32(const float* src, float* dst, int32_t b, int32_t h, int32_t w, int32_t c, void* stream) {
+  SSR_REQUIRE(src && dst && b > 0 && h > 0 && w > 0 && c > 0, "ssr_sum_pool2x2_f32: bad args");
+  const long total = (long)b * h * w * c;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 16 * 148) blocks = 16 * 148;
+  sum_pool2x2_f32_kernel<<<blocks, 256, 0, STREAM(stream)>>>(src, dst, b, h, w, c);
+  count_launch();
+  return check_last("sum_pool2x2_f32") ? SSR_OK : SSR_E_CUDA;
 }

@@ -210,20 +210,29 @@ struct UnpackDesc {
   float scale;
   int pad_;
 };
-__global__ void wgrad_unpack_batched_kernel(const UnpackDesc* __restrict__ descs) {
-  const UnpackDesc d = descs[blockIdx.y];
-  const long total = (long)d.cout * d.cin * d.r * d.r;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long t = i;
-    const int kxx = t % d.r;
-    t /= d.r;
-    const int kyy = t % d.r;
-    t /= d.r;
+// RT > 0: the filter size as a compile-time constant (the index arithmetic divides by r twice per element; with run-time 64-bit
+// divisions the kernel was instruction-bound: 0.19 ms per step at 16 % of the HBM roofline)
+template <int RT>
+__device__ __forceinline__ void wgrad_unpack_body(const UnpackDesc& d) {
+  const int r = RT > 0 ? RT : d.r;
+  const int T = r * r;
+  const int total = d.cout * d.cin * T;              // < 2^31: the largest conv of the path has 2.4 M weights
+  const int plane = T * d.cx_rows;                   // accumulator floats / 4 per output-channel quad
+  for (int i = blockIdx.x * (int)blockDim.x + threadIdx.x; i < total; i += (int)gridDim.x * (int)blockDim.x) {
+    const int tap = i % T;                           // OIHW order: (co, ci, ky, kx)
+    const int t = i / T;
     const int ci = t % d.cin;
     const int co = t / d.cin;
-    const float v = d.scale * d.acc[((long)(co >> 2) * (d.r * d.r * d.cx_rows) + (long)(kyy * d.r + kxx) * d.cx_rows + ci) * 4 + (co & 3)];
+    const float v = d.scale * d.acc[((long)(co >> 2) * plane + (long)tap * d.cx_rows + ci) * 4 + (co & 3)];
     if (d.accumulate) d.grad[i] += v; else d.grad[i] = v;
   }
+}
+
+__global__ void wgrad_unpack_batched_kernel(const UnpackDesc* __restrict__ descs) {
+  const UnpackDesc d = descs[blockIdx.y];
+  if (d.r == 3) wgrad_unpack_body<3>(d);             // (block-uniform branch: one descriptor per block row)
+  else if (d.r == 4) wgrad_unpack_body<4>(d);
+  else wgrad_unpack_body<0>(d);
 }
 
 // bias gradient: out[c] += scale * sum_p dy[p*stride + c]
@@ -241,6 +250,35 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, int strid
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
     atomicAdd(out + c, scale * s);
+  }
+}
+
+// the same with 16-byte loads (C and the pixel stride multiples of 8, C <= 256): a thread owns 8 channels of every (blockDim / groups)-th
+// pixel; the scalar form above reads 2 bytes per thread and ran at 7 % of the HBM roofline (profiles/r02b_hbm_table.md)
+__global__ void bias_grad_vec_kernel(const __nv_bfloat16* __restrict__ dy, int stride, long npix, int C, float* __restrict__ out, float scale) {
+  __shared__ float red[256 * 8];
+  const int groups = C >> 3;
+  const int ppb = (int)blockDim.x / groups;             // pixels one block pass covers
+  const int g = (int)threadIdx.x % groups, pl = (int)threadIdx.x / groups;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (pl < ppb)
+    for (long p = blockIdx.x * (long)ppb + pl; p < npix; p += (long)gridDim.x * ppb) {
+      const uint4 v = *reinterpret_cast<const uint4*>(dy + p * stride + g * 8);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += __uint_as_float(u[j] << 16);
+        acc[2 * j + 1] += __uint_as_float(u[j] & 0xFFFF0000u);
+      }
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[j];   // thread t = (pl, g): channels g * 8 + j
+  __syncthreads();
+  if ((int)threadIdx.x < C) {
+    const int c = (int)threadIdx.x;
+    float sum = 0.f;
+    for (int q = 0; q < ppb; ++q) sum += red[(q * groups + (c >> 3)) * 8 + (c & 7)];
+    atomicAdd(out + c, scale * sum);
   }
 }
 
@@ -412,6 +450,16 @@ extern "C" int ssr_wgrad_unpack_batched(const ssr_unpack_desc* descs_device, int
 extern "C" int ssr_bias_grad(const void* dy_bf16, int32_t dy_pix_stride, int64_t npix, int32_t c, float* out, float scale,
                              void* stream) {
   SSR_REQUIRE(dy_bf16 && out && c > 0, "ssr_bias_grad: bad args");
+  if (c % 8 == 0 && c <= 256 && dy_pix_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(dy_bf16) & 15) == 0) {
+    const int ppb = 256 / (c / 8);
+    long blocks = (npix + ppb * 8L - 1) / (ppb * 8L);   // >= 8 pixels per thread
+    if (blocks > 2 * 148) blocks = 2 * 148;
+    if (blocks < 1) blocks = 1;
+    bias_grad_vec_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16),
+                                                                                            dy_pix_stride, npix, c, out, scale);
+    count_launch();
+    return check_last("bias_grad launch") ? SSR_OK : SSR_E_CUDA;
+  }
   dim3 block(32, 8);
   long slabs = (npix + 8 * 64 - 1) / (8 * 64);
   if (slabs > 296) slabs = 296;

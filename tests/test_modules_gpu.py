@@ -301,7 +301,11 @@ def test_cuda_graph_replay_equals_eager():
         spread = rel_l2(outs[2][4][k], outs[0][4][k])
         dev = rel_l2(outs[1][4][k], outs[0][4][k])
         print(f"  step-2 grad {k}: eager-vs-eager {spread:.3e}  graph-vs-eager {dev:.3e}")
-        assert dev < 3 * spread + 2e-3, k
+        # the run-to-run spread is itself one draw of a heavy-tailed quantity: over six repetitions on the B200 the eager-vs-eager
+        # difference of the 3-element conv_last.bias ranged 2.7e-3 .. 3.0e-2 while graph-vs-eager stayed at 6e-3 .. 1.2e-2
+        # (profiles/r02b_logs/t_graph_repeats.log): a floor of 5e-2 keeps a low draw of `spread` from failing a correct replay;
+        # a replay that skipped or duplicated work shows up as O(1)
+        assert dev < 3 * spread + 5e-2, k
     for k in ("conv_first.weight", "body.0.rdb3.conv5.weight"):
         spread = rel_l2(outs[2][0][k], outs[0][0][k])
         assert rel_l2(outs[1][0][k], outs[0][0][k]) < 3 * spread + 1e-4, k
