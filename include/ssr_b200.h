@@ -236,6 +236,10 @@ typedef struct ssr_pack_desc {
   int32_t cout, cin, r, mode, k_pad, n_pad;
 } ssr_pack_desc;
 int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, int32_t n_layers, int32_t has_gemm_forms, void* stream);
+/* The same work as a flat list, one 8-row x 64-K tile of one operand per thread block: work_device = n_work pairs {descriptor index,
+ * tile index < ssr_pack_tile_count(k_pad, n_pad)} (SSR_PACK_FWD / DGRAD / DGRAD_S2 descriptors only). */
+int32_t ssr_pack_tile_count(int32_t k_pad, int32_t n_pad);
+int ssr_pack_conv_weights_tiled(const ssr_pack_desc* descs_device, const int32_t* work_device, int32_t n_work, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Weight gradient on tensor cores (MN-major operands straight from the NHWC buffers).

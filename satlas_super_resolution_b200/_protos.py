@@ -40,6 +40,8 @@ PROTOS = {
     "ssr_feat_grad": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, f32, vp]),
     "ssr_feat_l1": (C.c_int, [vp, i64, f32, vp, vp]),
     "ssr_l1_loss": (C.c_int, [vp, vp, i64, f32, vp, vp, i32, vp]),
+    "ssr_pack_tile_count": (C.c_int32, [i32, i32]),
+    "ssr_pack_conv_weights_tiled": (C.c_int, [vp, vp, i32, vp]),
     "ssr_split_finish": (C.c_int, [vp, vp, vp, i32, i64, i32, vp, i32, f32, vp, i32, f32, vp, i32, f32, vp, i32, vp, i32, vp, vp, i32, i32, vp]),
     "ssr_sum_pool2x2_f32": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "ssr_ssim_loss": (C.c_int, [vp, vp, i32, i32, i32, f32, vp, vp, i32, vp, vp]),

@@ -368,7 +368,7 @@ static constexpr int kPackNT = 8;
 // (profiles/r02b_pack_ncu.md: 246 us for the generator's 702 operands at 5 % of the DRAM roofline, the stalls "math / not selected")
 // showed the run-time divisions, not memory, bounding the kernel
 template <int RT>
-__device__ __forceinline__ void pack_tiles(const PackDesc& d, __nv_bfloat16* tile) {
+__device__ __forceinline__ void pack_tiles(const PackDesc& d, __nv_bfloat16* tile, int tl0, int tl_step) {
   const int r = RT > 0 ? RT : d.r;
   const bool s2 = d.mode == SSR_PACK_DGRAD_S2;        // r == 4: sixteen taps -> four parity classes of a 2 x 2 kernel
   const int chunks = d.k_pad / 64;
@@ -378,7 +378,7 @@ __device__ __forceinline__ void pack_tiles(const PackDesc& d, __nv_bfloat16* til
   const bool fwd = d.mode == SSR_PACK_FWD;
   const int n_valid = fwd ? d.cout : d.cin;     // rows (n) that exist
   const int k_valid = fwd ? d.cin : d.cout;     // K entries that exist
-  for (int tl = blockIdx.x; tl < chunks * n_tiles; tl += gridDim.x) {
+  for (int tl = tl0; tl < chunks * n_tiles; tl += tl_step) {
     const int c = tl / n_tiles, n0 = (tl - c * n_tiles) * kPackNT;
     const int total = kPackNT * 64 * T;
     // six source elements per thread in flight (one dependent load -> shared-memory store per iteration made this kernel
@@ -444,9 +444,21 @@ __global__ void pack_batched_kernel(const PackDesc* __restrict__ descs) {
   const PackDesc d = descs[blockIdx.y];
   if (d.mode != SSR_PACK_FWD && d.mode != SSR_PACK_DGRAD && d.mode != SSR_PACK_DGRAD_S2) return;
   __shared__ __nv_bfloat16 tile[16 * kPackNT * 64];   // [tap (kx * r + ky)][row][k]
-  if (d.r == 3) pack_tiles<3>(d, tile);               // (block-uniform branch: one descriptor per block row)
-  else if (d.r == 4) pack_tiles<4>(d, tile);
-  else pack_tiles<0>(d, tile);
+  if (d.r == 3) pack_tiles<3>(d, tile, (int)blockIdx.x, (int)gridDim.x);               // (block-uniform branch: one descriptor per block row)
+  else if (d.r == 4) pack_tiles<4>(d, tile, (int)blockIdx.x, (int)gridDim.x);
+  else pack_tiles<0>(d, tile, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// the same with ONE tile per block from a host-built work list {descriptor, tile}: the generator's 702 operands have 4 .. 24 tiles each,
+// so a fixed number of blocks per operand either idles most blocks or serialises three latency-bound tiles in one (174 us for 134 MB)
+__global__ void pack_tiled_kernel(const PackDesc* __restrict__ descs, const int2* __restrict__ work) {
+  const int2 e = work[blockIdx.x];
+  const PackDesc d = descs[e.x];
+  if (d.mode != SSR_PACK_FWD && d.mode != SSR_PACK_DGRAD && d.mode != SSR_PACK_DGRAD_S2) return;
+  __shared__ __nv_bfloat16 tile[16 * kPackNT * 64];
+  if (d.r == 3) pack_tiles<3>(d, tile, e.y, 1 << 30);
+  else if (d.r == 4) pack_tiles<4>(d, tile, e.y, 1 << 30);
+  else pack_tiles<0>(d, tile, e.y, 1 << 30);
 }
 
 // GEMM (1x1) forms for a conv computed through im2col: K' = (ky*R + kx)*cin + ci
@@ -656,6 +668,16 @@ extern "C" int ssr_pack_conv_weights_batched(const ssr_pack_desc* descs_device, 
     count_launch();
   }
   return check_last("pack_batched launch") ? SSR_OK : SSR_E_CUDA;
+}
+
+extern "C" int32_t ssr_pack_tile_count(int32_t k_pad, int32_t n_pad) { return (k_pad / 64) * ((n_pad + kPackNT - 1) / kPackNT); }
+
+extern "C" int ssr_pack_conv_weights_tiled(const ssr_pack_desc* descs_device, const int32_t* work_device, int32_t n_work, void* stream) {
+  SSR_REQUIRE(descs_device && work_device && n_work > 0, "ssr_pack_conv_weights_tiled: bad args");
+  pack_tiled_kernel<<<(unsigned)n_work, 256, 0, STREAM(stream)>>>(reinterpret_cast<const PackDesc*>(descs_device),
+                                                                 reinterpret_cast<const int2*>(work_device));
+  count_launch();
+  return check_last("pack_tiled launch") ? SSR_OK : SSR_E_CUDA;
 }
 
 extern "C" int ssr_split_finish(const float* s1, const float* s2, const float* s3, int32_t sum_stride, int64_t npix, int32_t c,

@@ -487,9 +487,26 @@ __global__ void sn_phase2(const SnDesc* __restrict__ descs, float eps) {
   const float inv = 1.f / fmaxf(sqrtf(norms[0]), eps);
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  // 16-byte loads when the rows allow it (every spectral-norm layer of the discriminator: cols = cin * k * k, a multiple of 16; the
+  // flat parameter buffer aligns tensors to 256 bytes): four independent products per load instead of one dependent fma per 4 bytes
+  const bool v4 = (d.cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(d.w) | reinterpret_cast<uintptr_t>(t)) & 15) == 0;
   for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < d.rows; i += gridDim.x * warps_per_block) {
     float acc = 0.f;
-    for (int j = lane; j < d.cols; j += 32) acc = fmaf(d.w[(long)i * d.cols + j], t[j] * inv, acc);
+    if (v4) {
+      const float4* w4 = reinterpret_cast<const float4*>(d.w + (long)i * d.cols);
+      const float4* t4 = reinterpret_cast<const float4*>(t);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int j = lane; j < (d.cols >> 2); j += 32) {
+        const float4 a = w4[j], b = t4[j];
+        a0 = fmaf(a.x, b.x, a0);
+        a1 = fmaf(a.y, b.y, a1);
+        a2 = fmaf(a.z, b.z, a2);
+        a3 = fmaf(a.w, b.w, a3);
+      }
+      acc = ((a0 + a1) + (a2 + a3)) * inv;
+    } else {
+      for (int j = lane; j < d.cols; j += 32) acc = fmaf(d.w[(long)i * d.cols + j], t[j] * inv, acc);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
@@ -534,7 +551,21 @@ __global__ void sn_bwd_dot(const SnDesc* __restrict__ descs) {
   float* norms = d.scratch + d.cols + d.rows;
   const long n = (long)d.rows * d.cols;
   float acc = 0.f;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) acc = fmaf(d.geff[i], d.w[i], acc);
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(d.geff) | reinterpret_cast<uintptr_t>(d.w)) & 15) == 0) {
+    const float4* g4 = reinterpret_cast<const float4*>(d.geff);
+    const float4* w4 = reinterpret_cast<const float4*>(d.w);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int i = blockIdx.x * (int)blockDim.x + threadIdx.x; i < (int)(n >> 2); i += (int)(gridDim.x * blockDim.x)) {
+      const float4 a = g4[i], b = w4[i];
+      a0 = fmaf(a.x, b.x, a0);
+      a1 = fmaf(a.y, b.y, a1);
+      a2 = fmaf(a.z, b.z, a2);
+      a3 = fmaf(a.w, b.w, a3);
+    }
+    acc = (a0 + a1) + (a2 + a3);
+  } else {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) acc = fmaf(d.geff[i], d.w[i], acc);
+  }
   acc = block_reduce_sum(acc);
   if (threadIdx.x == 0) atomicAdd(&norms[2], acc);
 }
@@ -545,6 +576,25 @@ __global__ void sn_bwd_apply(const SnDesc* __restrict__ descs) {
   const float coef = norms[2] / (sigma * sigma);
   const float inv = 1.f / sigma;
   const long n = (long)d.rows * d.cols;
+  if ((d.cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(d.geff) | reinterpret_cast<uintptr_t>(d.grad) | reinterpret_cast<uintptr_t>(d.v)) & 15) == 0) {
+    // a float4 never straddles two rows (cols % 4 == 0); 32-bit index arithmetic (n < 2^31), one division per 4 elements
+    const int q = d.cols >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(d.geff);
+    const float4* v4 = reinterpret_cast<const float4*>(d.v);
+    float4* o4 = reinterpret_cast<float4*>(d.grad);
+    for (int i = blockIdx.x * (int)blockDim.x + threadIdx.x; i < (int)(n >> 2); i += (int)(gridDim.x * blockDim.x)) {
+      const int r = i / q, c = i - r * q;
+      const float cu = coef * d.u[r];
+      const float4 g = g4[i], v = v4[c];
+      float4 o = o4[i];
+      o.x += g.x * inv - cu * v.x;
+      o.y += g.y * inv - cu * v.y;
+      o.z += g.z * inv - cu * v.z;
+      o.w += g.w * inv - cu * v.w;
+      o4[i] = o;
+    }
+    return;
+  }
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const int r = (int)(i / d.cols), c = (int)(i % d.cols);
     d.grad[i] += d.geff[i] * inv - coef * d.u[r] * d.v[c];
@@ -568,10 +618,24 @@ __global__ void blur1d_kernel(const float* __restrict__ src, float* __restrict__
     const long pl = t / H;
     const float* base = src + pl * H * W;
     float acc = 0.f;
+    // interior pixels (61 % of a 128-wide row at radius 25, whole warps of them): no reflection, a running pointer -- the reflected
+    // index cost six instructions per tap and made the four blur passes instruction-bound (2 % of the HBM roofline)
     if (dir == 0) {
-      for (int k = 0; k < taps; ++k) acc = fmaf(c_gauss[k], base[(long)y * W + reflect_idx(x + k - r, W)], acc);
+      if (x >= r && x + r < W) {
+        const float* q = base + (long)y * W + (x - r);
+#pragma unroll 17
+        for (int k = 0; k < taps; ++k) acc = fmaf(c_gauss[k], q[k], acc);
+      } else {
+        for (int k = 0; k < taps; ++k) acc = fmaf(c_gauss[k], base[(long)y * W + reflect_idx(x + k - r, W)], acc);
+      }
     } else {
-      for (int k = 0; k < taps; ++k) acc = fmaf(c_gauss[k], base[(long)reflect_idx(y + k - r, H) * W + x], acc);
+      if (y >= r && y + r < H) {
+        const float* q = base + (long)(y - r) * W + x;
+#pragma unroll 17
+        for (int k = 0; k < taps; ++k) acc = fmaf(c_gauss[k], q[(long)k * W], acc);
+      } else {
+        for (int k = 0; k < taps; ++k) acc = fmaf(c_gauss[k], base[(long)reflect_idx(y + k - r, H) * W + x], acc);
+      }
     }
     dst[i] = acc;
   }
@@ -757,7 +821,7 @@ extern "C" int ssr_spectral_norm(const ssr_sn_desc* descs_device, int32_t n_laye
   if (power_iteration) {
     sn_phase1<<<dim3(144, n_layers), 256, 0, STREAM(stream)>>>(d);   // 144 x 32 columns covers the widest layer (4608) in one pass
     count_launch();
-    sn_phase2<<<dim3(32, n_layers), 256, 0, STREAM(stream)>>>(d, eps);
+    sn_phase2<<<dim3(64, n_layers), 256, 0, STREAM(stream)>>>(d, eps);   // 512 warps per layer: one row each for the widest (512 rows)
     count_launch();
     sn_phase3<<<n_layers, 256, 0, STREAM(stream)>>>(d, eps);
   } else {
@@ -769,9 +833,9 @@ extern "C" int ssr_spectral_norm(const ssr_sn_desc* descs_device, int32_t n_laye
 extern "C" int ssr_spectral_norm_bwd(const ssr_sn_desc* descs_device, int32_t n_layers, void* stream) {
   SSR_REQUIRE(descs_device && n_layers > 0, "ssr_spectral_norm_bwd: bad args");
   const SnDesc* d = reinterpret_cast<const SnDesc*>(descs_device);
-  sn_bwd_dot<<<dim3(64, n_layers), 256, 0, STREAM(stream)>>>(d);
+  sn_bwd_dot<<<dim3(128, n_layers), 256, 0, STREAM(stream)>>>(d);
   count_launch();
-  sn_bwd_apply<<<dim3(128, n_layers), 256, 0, STREAM(stream)>>>(d);
+  sn_bwd_apply<<<dim3(256, n_layers), 256, 0, STREAM(stream)>>>(d);
   count_launch();
   sn_bwd_reset<<<n_layers, 32, 0, STREAM(stream)>>>(d);
   return LAUNCH_OK("spectral_norm_bwd");

@@ -145,10 +145,21 @@ class Packer:
         self.n = len(descs)
         self.has_gemm = int(any(d.mode in (L.PACK_FWD_GEMM, L.PACK_DGRAD_GEMM) for d in descs))
         self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        # flat work list {descriptor, tile}: one thread block per 8-row x 64-K tile (ssr_pack_conv_weights_tiled)
+        self.work = None
+        if not self.has_gemm:
+            work = []
+            for i, d in enumerate(descs):
+                work.extend((i, t) for t in range(lib().ssr_pack_tile_count(d.k_pad, d.n_pad)))
+            self.n_work = len(work)
+            self.work = torch.tensor(work, dtype=torch.int32).reshape(-1, 2).contiguous().to(device)
 
     def run(self, stream=None):
-        L.check(lib().ssr_pack_conv_weights_batched(self.table.data_ptr(), self.n, self.has_gemm,
-                                                    stream if stream is not None else cur_stream()))
+        s = stream if stream is not None else cur_stream()
+        if self.work is not None:
+            L.check(lib().ssr_pack_conv_weights_tiled(self.table.data_ptr(), self.work.data_ptr(), self.n_work, s))
+        else:
+            L.check(lib().ssr_pack_conv_weights_batched(self.table.data_ptr(), self.n, self.has_gemm, s))
 
 
 def conv_args(x_ptr, B, H, W, x_stride, cin, w_ptr, r, cout, n_pad, bias=None, act=0, s0=1.0,
