@@ -373,7 +373,7 @@ def train_rooflines(m, bands, peak, peak_src):
     chain_flop = N_RDB * F_RDB * B
     traffic = ncu_traffic()
     t_chain = dict(traffic.get("rdb_resident_kernel") or traffic.get("conv_chain_kernel") or {})
-    main = roofline_entry("ssr::rdb_resident_kernel (ResidualDenseBlocks -- up to three, an RRDB, per launch: their five forward convs each, or their five "
+    main = roofline_entry("ssr::rdb_resident_kernel (ResidualDenseBlocks -- up to twelve, four RRDBs, per launch: their five forward convs each, or their five "
                           "input-gradient convs; tcgen05 implicit GEMM over a shared-memory-resident 192-channel tile, one 4-CTA cluster per image)", 2 * chain_flop, ms[2] + ms[3], cnt[2] + cnt[3], peak, peak_src,
                           dict(traffic=t_chain.get("dram_bytes_per_launch"), traffic_note=t_chain.get("note"),
                                forward=roofline_entry("rdb_resident_kernel<false>, forward", chain_flop, ms[2], cnt[2], peak, peak_src),
@@ -384,7 +384,7 @@ def train_rooflines(m, bands, peak, peak_src):
     if gu:
         per_block_flop = chain_flop / N_RDB
         for key, ent in gu.items():
-            # one launch takes ssr_rdb_resident_max_blocks consecutive blocks (an RRDB): report per launch AND per dense block
+            # one launch takes ssr_rdb_resident_max_blocks consecutive blocks (four RRDBs): report per launch AND per dense block
             us_block = ent["us_per_launch"] * ent["launches"] / N_RDB
             ent["us_per_block"] = us_block
             ach = per_block_flop / (us_block * 1e-6) / 1e12

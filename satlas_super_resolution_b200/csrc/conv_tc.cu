@@ -88,9 +88,10 @@ struct ConvChainK {
   int multicast;       // resident kernel: every CTA of the cluster loads 1 / n of the weight taps and multicasts them to all
 };
 
-// the resident dense-block kernel takes up to kMaxRdbBlocks consecutive blocks (one RRDB) per launch: the activation tile stays in
-// shared memory across block boundaries, and launch / prologue / drain (8 us of a 41 us block) are paid once per group
-static constexpr int kMaxRdbBlocks = 3, kMaxRdb = kMaxChain * kMaxRdbBlocks;
+// the resident dense-block kernel takes up to kMaxRdbBlocks consecutive blocks (four RRDBs) per launch: the activation tile stays in
+// shared memory across block boundaries, and launch / prologue / drain (8 us of a 41 us block) are paid once per group.  60 layers x
+// (312 B of parameters + a 128 B tensor map) = 26.5 KB of kernel parameters (the limit is 32 764 B)
+static constexpr int kMaxRdbBlocks = 12, kMaxRdb = kMaxChain * kMaxRdbBlocks;
 struct RdbChainK {
   CUtensorMap tmA;             // the first block's input (later blocks read the tile)
   CUtensorMap tmB[kMaxRdb];
@@ -99,6 +100,7 @@ struct RdbChainK {
   long long* timeline;         // SSR_CHAIN_TIMELINE=1 and n_layers <= kMaxChain, else NULL
   int multicast;
 };
+static_assert(sizeof(RdbChainK) <= 32764, "kernel parameter space");
 
 static constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 // halo tile (resident dense block, and the 3 x 3 convs with stationary weights): 8-pixel strips with one halo pixel each side

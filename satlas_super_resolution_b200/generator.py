@@ -171,7 +171,7 @@ class _Workspace:
         n_rdb = 3 * nb
         # Training batches (one cluster of 4 CTAs per image, <= one wave of the 148 SMs) run dense blocks as shared-memory-
         # resident launches: latency-bound, but launch + prologue + drain are paid once per launch -- and one launch takes up to
-        # `fuse` consecutive blocks (ssr_rdb_resident_max_blocks: an RRDB), the tile staying in shared memory across the block
+        # `fuse` consecutive blocks (ssr_rdb_resident_max_blocks: 12 = four RRDBs), the tile staying in shared memory across the block
         # boundaries.  Large inference batches are the opposite regime -- many waves of CTAs: there the persistent per-layer
         # kernel (tiles streamed back to back through double-buffered TMEM) keeps the tensor pipe busier than a chain that
         # serialises five layers per CTA.
@@ -259,14 +259,15 @@ class _Workspace:
         GO32 = torch.empty((B, h, w, nf), dtype=torch.float32, device=dev)
         # One resident launch takes the input-gradient chains of up to `fuse` consecutive blocks; their weight gradients follow the
         # launch, so everything those read must survive it: one dY buffer per block of a group, fuse + 1 rotating block-gradient
-        # buffers (block i reads gR[(i+1) % m], writes gR[i % m]), and the RRDB-level gradient ping-pongs between two buffers
-        # (RRDB b reads gO[(b+1) & 1], writes gO[b & 1]).
+        # buffers (block i reads gR[(i+1) % m], writes gR[i % m]), and the RRDB-level gradient rotates over ceil(fuse / 3) + 1 buffers
+        # (RRDB b reads gO[(b+1) % n], writes gO[b % n]).
         tmem_chain = bool(eng.dgrad_tmem and lib().ssr_conv_tc_chain_acc_supported(B, h, w, cw))
         fuse = lib().ssr_rdb_resident_max_blocks(B, h, w) if tmem_chain else 1
         Dgs = [Act(B, h, w, cw, dev) for _ in range(fuse)]
         m_r = fuse + 1
         gR = [Act(B, h, w, nf, dev) for _ in range(m_r)]
-        gO = [Act(B, h, w, nf, dev), Act(B, h, w, nf, dev)]
+        n_o = (fuse + 2) // 3 + 1      # a group spans up to ceil(fuse / 3) RRDB boundaries, and the deferred weight gradients read them all
+        gO = [Act(B, h, w, nf, dev) for _ in range(n_o)]
         d_first = Act(B, h, w, nf, dev)
         self._bwd_keep = [gA, gB, d_feat, G32, GO32, Dgs, gR, gO, d_first]
 
@@ -321,7 +322,7 @@ class _Workspace:
         # ---- conv_body
         c = eng.cv["conv_body"]
         plan.conv(conv_args(d_feat.ptr(), B, h, w, nf, nf, c.packed_dg.data_ptr(), 3, nf, c.n_pad_dg,
-                            out=gO[nb & 1].ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf,
+                            out=gO[nb % n_o].ptr(), out_stride=nf, out32=GO32.data_ptr(), out32_mode=L.OUT32_PLANAR4, out32_stride=nf,
                             bias_grad=bgrad_ptr(3 * nb - 1, 5), bias_grad_scale=0.04))
         wgrad("conv_body", self.body_out.ptr(), nf, nf, d_feat.ptr(), nf, nf, B, h, w)
         # ---- the trunk, last block first
@@ -334,7 +335,7 @@ class _Workspace:
             # the block reads its incoming gradient from gR_in (written by block i+1) and hands its result on in gR_out: rotating,
             # because the weight-gradient launches (deferred to the end of the block / group) still read gR_in
             gR_in, gR_out = gR[(i + 1) % m_r], gR[i % m_r]
-            gO_in, gO_b = gO[(blk + 1) & 1], gO[blk & 1]   # RRDB-level gradient: read by the third block, written by the first
+            gO_in, gO_b = gO[(blk + 1) % n_o], gO[blk % n_o]   # RRDB-level gradient: read by the third block, written by the first
             Dg = Dgs[len(pend_batches)]
             if j == 2:
                 xin, s0, r1, r1s, s1 = gO_in, 0.04, GO32.data_ptr(), nf, 0.2
