@@ -1,8 +1,8 @@
 #!/bin/bash
-# One GPU-box visit: the changed kernels' tests first (short timeout), the suite (without the 2.5-minute trajectory test) and the bench.
+# Final visit of the round: the whole GPU suite exactly as the driver runs it, smoke(), and the default bench line.
 mkdir -p gpurun_out
 O=gpurun_out
-(time timeout 300 python -m pytest tests/test_conv_tc_gpu.py -x -q -k "several") > $O/t_new.log 2>&1; echo "rc=$?" >> $O/t_new.log; tail -4 $O/t_new.log
-(time timeout 600 python -m pytest tests -m gpu -q --deselect tests/test_depth_parity_gpu.py::test_trajectory_20_steps) > $O/t_suite.log 2>&1; echo "rc=$?" >> $O/t_suite.log; tail -6 $O/t_suite.log
-(timeout 300 python bench.py --no-cpu-baseline --no-extras) > $O/bench_f.json 2> $O/bench_f.err; cut -c1-160 $O/bench_f.json
-(SSR_RDB_FUSE=6 timeout 300 python bench.py --no-cpu-baseline --no-extras) > $O/bench_f6.json 2> $O/bench_f6.err; cut -c1-160 $O/bench_f6.json
+(time timeout 900 python -m pytest tests/ -x -q -m gpu) > $O/gputest_final.log 2>&1; echo "rc=$?" >> $O/gputest_final.log; tail -5 $O/gputest_final.log
+(time timeout 200 python -c "import __graft_entry__ as g; g.smoke()") > $O/smoke_final.log 2>&1; tail -2 $O/smoke_final.log
+(time timeout 400 python bench.py) > $O/bench_default_final.json 2> $O/bench_default_final.err; cut -c1-200 $O/bench_default_final.json
+(time timeout 200 python bench.py --impl reference --steps 2 --warmup 1) > $O/bench_reference_final.json 2> $O/bench_reference_final.err; cut -c1-300 $O/bench_reference_final.json
