@@ -104,10 +104,12 @@ class UNetDiscEngine:
             self._ws[key] = ws
         return ws
 
-    def forward(self, ws, training=True, stream=None):
-        """ws.x_in must hold the NHWC bf16 input; returns the engine-owned f32 [B,1,H,W] logits."""
+    def forward(self, ws, training=True, stream=None, prepared=False):
+        """ws.x_in must hold the NHWC bf16 input; returns the engine-owned f32 [B,1,H,W] logits.
+        prepared: prepare_weights(training) has already been issued for this pass (and is ordered before `stream`)."""
         s = stream if stream is not None else cur_stream()
-        self.prepare_weights(training, s)
+        if not prepared:
+            self.prepare_weights(training, s)
         ws.fwd.run(s)
         return ws.logits
 

@@ -13,12 +13,13 @@ import os
 import torch
 
 from . import _lib as L
-from .ops import Act, PackedConv, Packer, Plan, WgradSet, conv_args, cur_stream, lib, plan_wgrad, plan_wgrad_batch, round_up
+from .ops import (Act, PackedConv, Packer, Plan, WgradSet, conv_args, cur_stream, lib, overlap_enabled, plan_wgrad, plan_wgrad_batch,
+                  round_up)
 
 
 class RRDBNetEngine:
     def __init__(self, params, num_in_ch, num_out_ch=3, scale=4, num_feat=64, num_block=23, num_grow_ch=32,
-                 want_grad=True, grads=None):
+                 want_grad=True, grads=None, overlap=None):
         if scale not in (1, 2, 4, 8, 16):
             raise ValueError(f"RRDBNetEngine: scale {scale} (the reference builds 1, 2, 4, 8, 16: rrdbnet_arch.py:92-109)")
         if num_feat % 16 or num_grow_ch % 16:
@@ -34,6 +35,7 @@ class RRDBNetEngine:
             raise ValueError(f"conv_first.weight has {params['conv_first.weight'].shape[1]} input channels, expected {self.cin_eff}")
         self.cin_pad = round_up(self.cin_eff, 16)
         self.want_grad = want_grad
+        self.overlap = overlap_enabled() if overlap is None else bool(overlap)   # weight gradients on the side stream (_build_backward)
         self.n_up = {1: 2, 2: 2, 4: 2, 8: 3, 16: 4}[scale]
         nf, g = self.nf, self.g
         cv = {}
@@ -263,10 +265,18 @@ class _Workspace:
         # (RRDB b reads gO[(b+1) % n], writes gO[b % n]).
         tmem_chain = bool(eng.dgrad_tmem and lib().ssr_conv_tc_chain_acc_supported(B, h, w, cw))
         fuse = lib().ssr_rdb_resident_max_blocks(B, h, w) if tmem_chain else 1
-        Dgs = [Act(B, h, w, cw, dev) for _ in range(fuse)]
-        m_r = fuse + 1
+        # SSR_OVERLAP: a group's weight-gradient launches run on the side stream beside the NEXT group's input-gradient launch
+        # (which occupies 128 of the 148 SMs), so what they read must survive that launch too: two sets of dY buffers
+        # (group parity), 2 * fuse + 1 block-gradient and 2 * ceil(fuse / 3) + 2 RRDB-gradient buffers.  The launch after the
+        # next waits for them (plan.join()).
+        overlap = bool(tmem_chain and fuse > 1 and 3 * nb > fuse and eng.overlap)
+        self.overlap_bwd = overlap
+        n_sets = 2 if overlap else 1
+        Dgs = [Act(B, h, w, cw, dev) for _ in range(n_sets * fuse)]
+        m_r = n_sets * fuse + 1
         gR = [Act(B, h, w, nf, dev) for _ in range(m_r)]
-        n_o = (fuse + 2) // 3 + 1      # a group spans up to ceil(fuse / 3) RRDB boundaries, and the deferred weight gradients read them all
+        # a group spans up to ceil(fuse / 3) RRDB boundaries, and the deferred weight gradients read them all
+        n_o = n_sets * ((fuse + 2) // 3) + n_sets + (1 if overlap else 0)
         gO = [Act(B, h, w, nf, dev) for _ in range(n_o)]
         d_first = Act(B, h, w, nf, dev)
         self._bwd_keep = [gA, gB, d_feat, G32, GO32, Dgs, gR, gO, d_first]
@@ -327,6 +337,7 @@ class _Workspace:
         wgrad("conv_body", self.body_out.ptr(), nf, nf, d_feat.ptr(), nf, nf, B, h, w)
         # ---- the trunk, last block first
         pend_chain, pend_batches = [], []
+        n_group = 0
         for i in range(3 * nb - 1, -1, -1):
             blk, j = divmod(i, 3)
             cur = self.bufs[i]
@@ -336,7 +347,7 @@ class _Workspace:
             # because the weight-gradient launches (deferred to the end of the block / group) still read gR_in
             gR_in, gR_out = gR[(i + 1) % m_r], gR[i % m_r]
             gO_in, gO_b = gO[(blk + 1) % n_o], gO[blk % n_o]   # RRDB-level gradient: read by the third block, written by the first
-            Dg = Dgs[len(pend_batches)]
+            Dg = Dgs[(n_group % n_sets) * fuse + len(pend_batches)]
             if j == 2:
                 xin, s0, r1, r1s, s1 = gO_in, 0.04, GO32.data_ptr(), nf, 0.2
             else:
@@ -372,9 +383,18 @@ class _Workspace:
                 pend_batches.append(batch)
                 if len(pend_batches) == fuse or i == 0:
                     plan.chain_acc(pend_chain)       # ONE launch: the input-gradient chains of the group's blocks
-                    for bt in pend_batches:          # then each block's five weight gradients in one launch
-                        plan_wgrad_batch(plan, bt)
+                    if overlap:
+                        if n_group:
+                            plan.join()              # the NEXT launch rewrites the dY set group n_group - 1's weight gradients read
+                        plan.fork()
+                        with plan.side():
+                            for bt in pend_batches:
+                                plan_wgrad_batch(plan, bt)
+                    else:
+                        for bt in pend_batches:      # then each block's five weight gradients in one launch
+                            plan_wgrad_batch(plan, bt)
                     pend_chain, pend_batches = [], []
+                    n_group += 1
                 continue
             if eng.dgrad_tmem:
                 s0 = 1.0   # the factor lives in the packed weights (see RRDBNetEngine.__init__); the wgrad scale below keeps it

@@ -40,45 +40,152 @@ class Act:
         return self.t.data_ptr() + 2 * ch
 
 
+_FORK, _JOIN, _SIDE = "fork", "join", "side"     # lane markers inside Plan.calls (never equal to a ctypes function)
+
+
+def overlap_enabled():
+    """SSR_OVERLAP=1: independent launches run on a second stream beside the dense-block launches, which occupy 128 of the
+    148 SMs (one 4-CTA cluster per image at B = 32) -- DESIGN.md section 4.  Read when a plan is BUILT."""
+    import os
+    return os.environ.get("SSR_OVERLAP", "0") == "1"
+
+
+class SideLane:
+    """A second stream + fork / join events (capturable: inside a CUDA-graph capture the events become graph edges; every
+    fork must be joined before the capture ends)."""
+
+    _per_device = {}
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.handle = C.c_void_p(self.stream.cuda_stream)
+        self.dirty = False
+
+    @classmethod
+    def get(cls, device=None):
+        idx = torch.cuda.current_device() if device is None else torch.device(device).index
+        if idx is None:
+            idx = torch.cuda.current_device()
+        lane = cls._per_device.get(idx)
+        if lane is None:
+            lane = cls._per_device[idx] = SideLane(torch.device("cuda", idx))
+        return lane
+
+    @staticmethod
+    def _main(s):
+        cur = torch.cuda.current_stream()
+        if s is None or (s.value or 0) == cur.cuda_stream:
+            return cur
+        return torch.cuda.ExternalStream(s.value)
+
+    def fork(self, s=None):
+        """the side stream waits for everything issued on the main stream `s` so far"""
+        ev = torch.cuda.Event()
+        ev.record(self._main(s))
+        self.stream.wait_event(ev)
+        self.dirty = True
+
+    def join(self, s=None):
+        """the main stream waits for everything issued on the side stream so far"""
+        if not self.dirty:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        self._main(s).wait_event(ev)
+
+
 class Plan:
-    """A recorded, allocation-free sequence of C-ABI calls (replayed every step, CUDA-graph capturable)."""
+    """A recorded, allocation-free sequence of C-ABI calls (replayed every step, CUDA-graph capturable).
+
+    Calls recorded inside `with plan.side():` go to the side stream (ops.SideLane); `fork()` makes the side stream wait for the
+    main-lane calls recorded so far, `join()` the main lane for the side calls recorded so far.  `run` joins at its end."""
 
     def __init__(self):
         self.calls = []
         self.keep = []
+        self._lane = 0
+        self.has_side = False
+
+    def _emit(self, fn, args):
+        if self._lane:
+            self.calls.append((_SIDE, fn, args))
+            self.has_side = True
+        else:
+            self.calls.append((fn, args))
 
     def add(self, fn, *args):
-        self.calls.append((fn, args))
+        self._emit(fn, args)
 
     def conv(self, args):
         self.keep.append(args)
-        self.calls.append((lib().ssr_conv_tc, (C.byref(args),)))
+        self._emit(lib().ssr_conv_tc, (C.byref(args),))
 
     def chain(self, args_list):
         """consecutive convs over one image geometry, each reading what the previous ones wrote: ONE launch (ssr_conv_tc_chain)"""
         arr = (L.ConvTcArgs * len(args_list))(*args_list)
         self.keep.append(arr)
-        self.calls.append((lib().ssr_conv_tc_chain, (arr, len(args_list))))
+        self._emit(lib().ssr_conv_tc_chain, (arr, len(args_list)))
 
     def chain_acc(self, args_list):
         """input-gradient chain whose running sum stays in tensor memory (ssr_conv_tc_chain_acc)"""
         arr = (L.ConvTcArgs * len(args_list))(*args_list)
         self.keep.append(arr)
-        self.calls.append((lib().ssr_conv_tc_chain_acc, (arr, len(args_list))))
+        self._emit(lib().ssr_conv_tc_chain_acc, (arr, len(args_list)))
+
+    def fork(self):
+        self.calls.append((_FORK,))
+
+    def join(self):
+        self.calls.append((_JOIN,))
+
+    def side(self):
+        plan = self
+
+        class _Side:
+            def __enter__(self_):
+                plan._lane = 1
+
+            def __exit__(self_, *exc):
+                plan._lane = 0
+        return _Side()
 
     def extend(self, other):
         self.calls.extend(other.calls)
         self.keep.extend(other.keep)
+        self.has_side = self.has_side or other.has_side
 
-    def run(self, stream=None):
+    def run(self, stream=None, lane=None):
         s = stream if stream is not None else cur_stream()
-        for fn, args in self.calls:
-            rc = fn(*args, s)
+        if not self.has_side:
+            for fn, args in self.calls:
+                rc = fn(*args, s)
+                if rc != 0:
+                    L.check(rc)
+            return
+        if lane is None:
+            lane = SideLane.get()
+        for call in self.calls:
+            tag = call[0]
+            if tag is _SIDE:
+                rc = call[1](*call[2], lane.handle)
+            elif tag is _FORK:
+                lane.fork(s)
+                continue
+            elif tag is _JOIN:
+                lane.join(s)
+                continue
+            else:
+                rc = tag(*call[1], s)
             if rc != 0:
                 L.check(rc)
+        lane.join(s)
+
+    def main_calls(self):
+        """(fn, args) of the main-lane launches only"""
+        return [c for c in self.calls if c[0] not in (_FORK, _JOIN, _SIDE)]
 
     def __len__(self):
-        return len(self.calls)
+        return sum(1 for c in self.calls if c[0] not in (_FORK, _JOIN))
 
 
 class PackedConv:
@@ -312,7 +419,7 @@ class WgradSet:
 
 def plan_wgrad(plan, args):
     plan.keep.append(args)
-    plan.calls.append((lib().ssr_wgrad_tc, (C.byref(args),)))
+    plan._emit(lib().ssr_wgrad_tc, (C.byref(args),))
 
 
 def allreduce_sum_(flat, process_group=None):
@@ -347,4 +454,4 @@ def plan_wgrad_batch(plan, args_list):
     from ._protos import WgradArgs
     arr = (WgradArgs * len(args_list))(*args_list)
     plan.keep.append(arr)
-    plan.calls.append((lib().ssr_wgrad_tc_batched, (arr, len(args_list))))
+    plan._emit(lib().ssr_wgrad_tc_batched, (arr, len(args_list)))

@@ -13,7 +13,7 @@ import torch
 from . import _lib as L
 from .discriminator import UNetDiscEngine
 from .generator import RRDBNetEngine
-from .ops import FlatBuffer, allreduce_sum_, cur_stream, lib
+from .ops import FlatBuffer, SideLane, allreduce_sum_, cur_stream, lib, overlap_enabled
 from .vgg import PerceptualEngine
 
 LOSS_KEYS = ["l_g_pix", "l_g_percep", "l_g_gan", "l_d_real", "out_d_real", "l_d_fake", "out_d_fake", "l_g_ssim"]   # slots of loss_dev
@@ -95,7 +95,7 @@ class ESRGANTrainer:
         self.G = RRDBNetEngine(self.gbuf.views(), self.num_in_ch, g_state["conv_last.weight"].shape[0], scale=self.scale,
                                num_feat=g_state["conv_first.weight"].shape[0], num_block=self.num_block,
                                num_grow_ch=g_state["body.0.rdb1.conv1.weight"].shape[0], want_grad=True,
-                               grads=self.ggrad.views())
+                               grads=self.ggrad.views(), overlap=cfg.get("overlap"))
         self.G_ema = None
         # ---- discriminator
         learn = OrderedDict((k, tuple(v.shape)) for k, v in d_state.items() if not k.endswith(self.D_BUFFERS))
@@ -142,6 +142,11 @@ class ESRGANTrainer:
         self._warm = set()
         self._last_mode = "eager"
         self.use_graph = bool(cfg.get("cuda_graph", False))
+        # SSR_OVERLAP=1: the ground-truth half of the VGG pass and the discriminator's weight preparation
+        # run on a side stream beside the generator's dense-block launches (128 of the 148 SMs), like the dense blocks'
+        # weight gradients beside the next input-gradient launch (generator._build_backward)
+        self.overlap = overlap_enabled() if cfg.get("overlap") is None else bool(cfg["overlap"])
+        self._cap_stream = None
         self.log_dict = OrderedDict()
 
     def replicated_tensors(self):
@@ -252,19 +257,29 @@ class ESRGANTrainer:
         if phase == 1:
             loss.zero_()
             self.G.repack(s)
+            lane = None
+            if self.overlap and do_g and not (self.P is not None and self.P.range_norm):
+                # nothing below depends on the generator: issue it beside the dense-block launches
+                lane = SideLane.get(self.device)
+                lane.fork(s)
+                self.D.prepare_weights(True, lane.handle)
+                if self.P is not None:
+                    self.P.forward_gt(percep_gt, lane)
             out = self.G.forward(lr, train=True, stream=s)
             self.output = out
             if do_g:
                 self.ggrad.flat.zero_()
                 L.check(lb.ssr_l1_loss(out.data_ptr(), l1_gt.data_ptr(), n_img, self.pixel_weight, lp(0), d_out.data_ptr(), 0, s))
                 if self.P is not None:
-                    self.P.loss_and_grad(out, percep_gt, loss[1:2], d_out, s)
+                    self.P.loss_and_grad(out, percep_gt, loss[1:2], d_out, s, gt_lane=lane)
                 if self.ssim_weight:
                     # l_g_ssim = ssim_loss(self.output, percep_gt) -- ssr_esrgan_model.py:163-166
                     L.check(lb.ssr_ssim_loss(out.data_ptr(), percep_gt.data_ptr(), B * 3, H, W, self.ssim_weight, lp(7),
                                              d_out.data_ptr(), 1, io["ssim_scratch"].data_ptr(), s))
                 disc_in(out)
-                logits = self.D.forward(dws, training=True, stream=s)
+                if lane is not None:
+                    lane.join(s)
+                logits = self.D.forward(dws, training=True, stream=s, prepared=lane is not None)
                 L.check(lb.ssr_bce_logits(logits.data_ptr(), n_logit, 1.0, self.gan_weight, lp(2), None, d_logits.data_ptr(), s))
                 self.D.backward(dws, d_logits, need_wgrad=False, need_dinput=True, stream=s)
                 L.check(lb.ssr_egress_nchw(dws.d_in.ptr(), dws.d_in.stride, d_out.data_ptr(), B, 3, H, W, 1.0, 1, None, s))
@@ -325,16 +340,23 @@ class ESRGANTrainer:
             # capture once: the whole step as ONE graph on a single GPU, one graph per phase around the NCCL calls otherwise
             torch.cuda.synchronize()
             graphs = []
+            # with a side lane the capture stream gets a higher priority than the lane's: where both have thread blocks pending,
+            # the main lane's (the dense-block clusters) are placed first and the side lane's fill what is left
+            cap = {}
+            if self.overlap:
+                if self._cap_stream is None:
+                    self._cap_stream = torch.cuda.Stream(device=self.device, priority=-1)
+                cap = dict(stream=self._cap_stream)
             if self.world == 1:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, **cap):
                     self._step_kernels(self.io, do_g, cur_stream(), graph_mode=True)
                 graphs.append(g)
             else:
                 pool = None
                 for phase in (1, 2, 3, 4):
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, pool=pool):
+                    with torch.cuda.graph(g, pool=pool, **cap):
                         self._step_phase(phase, self.io, do_g, cur_stream(), graph_mode=True)
                     pool = g.pool()
                     graphs.append(g)

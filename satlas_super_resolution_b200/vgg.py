@@ -64,26 +64,44 @@ class PerceptualEngine:
             self._ws[key] = _PWorkspace(self, B, H, W)
         return self._ws[key]
 
-    def loss_and_grad(self, x, gt, loss_out, d_x, stream=None):
+    def _norm(self, ws):
+        """(x + 1) / 2 of range_norm folded into the mean shift: v = x*0.5 + 0.5"""
+        if not self.range_norm:
+            return self.mean, self.inv_std
+        ws.mean_t.copy_((self.mean - 0.5) / 0.5)
+        ws.inv_std_t.copy_(self.inv_std * 0.5)
+        return ws.mean_t, ws.inv_std_t
+
+    def forward_gt(self, gt, lane):
+        """The ground-truth half of the feature pass on its own (SSR_OVERLAP: issued on the side stream `lane` -- ops.SideLane,
+        already forked -- while the generator's dense-block launches leave 20 SMs idle); loss_and_grad(..., gt_lane=lane) then runs
+        the generated half only and joins the lane before the feature-L1 kernels."""
+        B, _, H, W = gt.shape
+        ws = self.workspace(B, H, W)
+        assert not self.range_norm, "forward_gt: range_norm rewrites the normalisation constants on the main stream"
+        mean, inv_std = self._norm(ws)
+        L.check(lib().ssr_ingest_nchw(gt.data_ptr(), L.SSR_F32, ws.inp.ptr() + 2 * B * H * W * 16, 16, B, 3, H, W, 16, 1.0,
+                                      mean.data_ptr(), inv_std.data_ptr(), lane.handle))
+        ws.half_plans()[1].run(lane.handle)
+
+    def loss_and_grad(self, x, gt, loss_out, d_x, stream=None, gt_lane=None):
         """x, gt: f32 NCHW [B,3,H,W].  Adds the weighted perceptual loss to the device scalar `loss_out` and, when d_x is
-        not None, ACCUMULATES d loss / d x into d_x (f32 NCHW)."""
+        not None, ACCUMULATES d loss / d x into d_x (f32 NCHW).  gt_lane: forward_gt(gt, gt_lane) has been issued."""
         s = stream if stream is not None else cur_stream()
         B, _, H, W = x.shape
         ws = self.workspace(B, H, W)
         lb = lib()
-        scale = 0.5 if self.range_norm else 1.0   # (x + 1) / 2 folded: v = x*0.5 + 0.5 -> handled through mean shift
-        mean = self.mean if not self.range_norm else (self.mean - 0.5) / 0.5
-        inv_std = self.inv_std if not self.range_norm else self.inv_std * 0.5
-        if self.range_norm:
-            ws.mean_t.copy_(mean)
-            ws.inv_std_t.copy_(inv_std)
-            mean, inv_std = ws.mean_t, ws.inv_std_t
+        mean, inv_std = self._norm(ws)
         L.check(lb.ssr_ingest_nchw(x.data_ptr(), L.SSR_F32, ws.inp.ptr(), 16, B, 3, H, W, 16, 1.0, mean.data_ptr(),
                                    inv_std.data_ptr(), s))
-        L.check(lb.ssr_ingest_nchw(gt.data_ptr(), L.SSR_F32, ws.inp.ptr() + 2 * B * H * W * 16, 16, B, 3, H, W, 16, 1.0,
-                                   mean.data_ptr(), inv_std.data_ptr(), s))
         ws.loss_ptr[0] = loss_out.data_ptr()
-        ws.fwd.run(s)
+        if gt_lane is not None:
+            ws.half_plans()[0].run(s)
+            gt_lane.join(s)
+        else:
+            L.check(lb.ssr_ingest_nchw(gt.data_ptr(), L.SSR_F32, ws.inp.ptr() + 2 * B * H * W * 16, 16, B, 3, H, W, 16, 1.0,
+                                       mean.data_ptr(), inv_std.data_ptr(), s))
+            ws.fwd.run(s)
         for fn, args in ws.loss_calls:
             L.check(fn(*args, loss_out.data_ptr(), s))
         if d_x is not None:
@@ -131,6 +149,8 @@ class _PWorkspace:
             cur, cur_c = out, cout
         self.fwd = fwd
         self.order = order
+        self._eng = eng
+        self._halves = None
         # ---------------- backward over the generated half (first B images of every buffer)
         self.d_inp = Act(B, H, W, 16, dev)
         self._keep = []
@@ -172,3 +192,26 @@ class _PWorkspace:
                                    out=dx.ptr(), out_stride=cin_c))
             g = dx
         self.bwd = bwd
+
+    def half_plans(self):
+        """the forward plan once per half of the 2B batch -- [generated images, ground truth] -- over the same buffers"""
+        if self._halves is None:
+            lb = lib()
+            B = self.B
+            off = lambda a, half: a.ptr() + half * B * a.H * a.W * a.C * 2
+            plans = []
+            for half in (0, 1):
+                plan = Plan()
+                for item in self.order:
+                    if item[0] == "pool":
+                        _, _, src, dst, hh, ww = item
+                        plan.add(lb.ssr_maxpool_relu, off(src, half), off(dst, half), B, hh, ww, src.C)
+                        continue
+                    _, name, src, out, hh, ww, cin_c = item
+                    pc = self._eng.cv[name]
+                    plan.conv(conv_args(off(src, half), B, hh, ww, src.stride, cin_c, pc.packed.data_ptr(), 3, out.C, pc.n_pad,
+                                        bias=pc.bias.data_ptr(), act=0 if name in self._eng.layer_weights else 2,
+                                        out=off(out, half), out_stride=out.C))
+                plans.append(plan)
+            self._halves = plans
+        return self._halves

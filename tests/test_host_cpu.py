@@ -218,3 +218,53 @@ def test_load_tile_dir_matches_the_reference_frame_choice(tmp_path):
         assert torch.equal(stack[k].float() / 255, want[0])
         assert np.array_equal(s2[i * 32:(i + 1) * 32, j * 32:(j + 1) * 32], first)
     assert stack.shape == (grid * grid, n * 3, 32, 32) and stack.dtype == torch.uint8
+
+
+def test_plan_lanes_order_forks_and_joins():
+    """Plan (ops.py): calls recorded inside plan.side() go to the side lane; fork / join are replayed where they were recorded and run()
+    joins at its end (a CUDA-graph capture must not end with an unjoined stream)."""
+    from satlas_super_resolution_b200.ops import Plan
+    log = []
+
+    class Lane:
+        handle = "side"
+
+        def fork(self, s):
+            log.append(("fork", s))
+
+        def join(self, s):
+            log.append(("join", s))
+
+    def k(name):
+        def fn(*args):
+            log.append((name, args[-1]))
+            return 0
+        return fn
+
+    plan = Plan()
+    plan.add(k("chain0"), 1)
+    plan.fork()
+    with plan.side():
+        plan.add(k("wgrad0"), 2)
+    plan.add(k("chain1"), 3)
+    plan.join()
+    plan.fork()
+    with plan.side():
+        plan.add(k("wgrad1"), 4)
+    plan.add(k("tail"), 5)
+    assert plan.has_side and len(plan) == 5 and [c[0].__name__ for c in plan.main_calls()] == ["fn"] * 3
+    plan.run("main", lane=Lane())
+    assert log == [("chain0", "main"), ("fork", "main"), ("wgrad0", "side"), ("chain1", "main"), ("join", "main"), ("fork", "main"),
+                   ("wgrad1", "side"), ("tail", "main"), ("join", "main")]
+    # a plan without side calls never touches a lane
+    log.clear()
+    p2 = Plan()
+    p2.add(k("a"), 0)
+    p2.run("main", lane=None)
+    assert log == [("a", "main")] and not p2.has_side
+    # a failing call raises through L.check
+    p3 = Plan()
+    with p3.side():
+        p3.add(lambda *a: 1, 0)
+    with pytest.raises(Exception):
+        p3.run("main", lane=Lane())

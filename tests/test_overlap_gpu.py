@@ -1,0 +1,73 @@
+"""SSR_OVERLAP / cfg['overlap']: the step with the side lane (dense-block weight gradients beside the next input-gradient launch,
+ground-truth VGG features and the discriminator's weight preparation beside the generator forward -- DESIGN.md section 4) computes
+what the single-stream step computes.  Only the launch ORDER changes, so the two may differ by the f32-atomic run-to-run spread of
+the weight gradients and by nothing else; a missing dependency (a buffer rewritten while a side launch still reads it) shows up as
+an O(1) difference."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+NB = 9          # 27 dense blocks: three resident input-gradient launches (12 + 12 + 3) -> fork, join + fork, join + fork, final join
+
+
+def rel_l2(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-20)).item()
+
+
+def _batch(B=2, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randint(1, 256, (B, 24, 32, 32), generator=g, dtype=torch.uint8),
+            torch.randint(1, 256, (B, 3, 128, 128), generator=g, dtype=torch.uint8))
+
+
+def _run(overlap, graph, iters, B=2):
+    from oracle import losses, nets
+    from satlas_super_resolution_b200.trainer import ESRGANTrainer
+    gp, dp, vp = nets.rrdbnet_init(24, 3, num_block=NB, seed=1), nets.unet_disc_init(27, seed=2), losses.vgg19_init(seed=3)
+    tr = ESRGANTrainer(gp, dp, vp, dict(ema_decay=0.999, lr=1e-4, network_g=dict(num_in_ch=24, num_block=NB), cuda_graph=graph,
+                                        overlap=overlap))
+    lr, hr = _batch(B)
+    snaps = []
+    for it in range(1, iters + 1):
+        tr.feed_data(lr, hr)
+        tr.optimize_parameters(it)
+        torch.cuda.synchronize()
+        snaps.append(({k: v.clone() for k, v in tr.g_grads().items()}, {k: v.clone() for k, v in tr.d_grads().items()},
+                      dict(tr.get_current_log())))
+    ws = tr.G.workspace(B, 32, 32, True)
+    return tr, ws, snaps
+
+
+def test_side_lane_first_step_equals_single_stream():
+    _, ws0, base = _run(False, False, 1)
+    _, ws1, over = _run(True, False, 1)
+    _, _, base2 = _run(False, False, 1)
+    assert not ws0.overlap_bwd and not ws0.bwd.has_side
+    assert ws1.overlap_bwd and ws1.bwd.has_side, "the overlapped plan was not built: nothing was tested"
+    worst = 0.0
+    for which, floor in ((0, 1e-2), (1, 2e-2)):          # generator / discriminator gradients: several times the measured run-to-run floors
+        for k, v in base[0][which].items():
+            spread = rel_l2(base2[0][which][k], v)
+            dev = rel_l2(over[0][which][k], v)
+            worst = max(worst, dev)
+            assert dev < 3 * spread + floor, (k, dev, spread)
+    print(f"  worst overlapped-vs-single-stream gradient difference {worst:.3e}")
+    for k, v in base[0][2].items():
+        assert abs(over[0][2][k] - v) < 2e-3 * abs(v) + 2e-4, k     # same forward (up to the atomics of the spectral-norm sums)
+
+
+def test_side_lane_inside_the_cuda_graph():
+    """iteration 1 eager, 2 = capture + replay, 3 = replay: the captured step has the side lane as parallel graph branches"""
+    _, _, eager = _run(False, False, 3)
+    tr, ws, graph = _run(True, True, 3)
+    assert tr._last_mode == "graph" and ws.overlap_bwd and tr._cap_stream is not None
+    _, _, eager2 = _run(False, False, 3)
+    for k in ("conv_first.weight", "body.4.rdb2.conv3.weight", "body.0.rdb1.conv1.weight", "conv_last.bias"):
+        spread = rel_l2(eager2[1][0][k], eager[1][0][k])
+        dev = rel_l2(graph[1][0][k], eager[1][0][k])
+        print(f"  step-2 grad {k}: eager-vs-eager {spread:.3e}  overlapped-graph-vs-eager {dev:.3e}")
+        assert dev < 3 * spread + 5e-2, k        # same bound as test_cuda_graph_replay_equals_eager (heavy-tailed spread, O(1) if wrong)
+    for k, v in eager[2][2].items():
+        assert abs(graph[2][2][k] - v) < 5e-3 * abs(v) + 5e-4, k
