@@ -363,7 +363,7 @@ def measure_train(args, bands, rank, world, local, lib, L, harness, steps, warmu
     except Exception as exc:   # diagnostics only: the per-launch numbers above stand on their own
         log(f"back-to-back dense-block timing skipped: {exc!r}")
     return dict(B=B, ms_step=ms_total / steps, ms_e2e=ms_e2e / steps, launches=int(launches), ms_cls=list(ms_cls), cnt_cls=list(cnt_cls),
-                h2d=int(lr_h.numel() + hr_h.numel()), model=model, graph_us=graph_us)
+                h2d=int(lr_h.numel() + hr_h.numel()), model=model, graph_us=graph_us, side_lane=bool(getattr(tr, "overlap", False)))
 
 
 def train_rooflines(m, bands, peak, peak_src):
@@ -552,7 +552,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": dict(train_config(bands), batch_per_gpu=B, global_batch=B * world, parallelism=f"dp{world}",
-                       cuda_graph=not args.no_graph, api="build_model(opt) -> SSRESRGANModel.feed_data / optimize_parameters / get_current_log",
+                       cuda_graph=not args.no_graph, side_lane=m.get("side_lane", False), api="build_model(opt) -> SSRESRGANModel.feed_data / optimize_parameters / get_current_log",
                        l2="no explicit flush: one step streams >10 GB of activations/gradients, far above the 126 MB L2"),
         "e2e": {"value": B * world / (m["ms_e2e"] / 1e3), "unit": "img-pairs/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 32},
         "gpu_launches": m["launches"] * args.steps, "gpu_launches_per_step": m["launches"],

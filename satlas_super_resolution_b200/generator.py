@@ -35,7 +35,7 @@ class RRDBNetEngine:
             raise ValueError(f"conv_first.weight has {params['conv_first.weight'].shape[1]} input channels, expected {self.cin_eff}")
         self.cin_pad = round_up(self.cin_eff, 16)
         self.want_grad = want_grad
-        self.overlap = overlap_enabled() if overlap is None else bool(overlap)   # weight gradients on the side stream (_build_backward)
+        self.overlap = overlap_enabled("bwd", overlap)   # dense-block weight gradients on the side stream (_build_backward)
         self.n_up = {1: 2, 2: 2, 4: 2, 8: 3, 16: 4}[scale]
         nf, g = self.nf, self.g
         cv = {}

@@ -1,6 +1,7 @@
 """A/B of the side lane (SSR_OVERLAP) at the benchmarked configuration, in ONE process on one box:
-(1) first-step gradients of every tensor, overlapped vs single-stream vs a second single-stream run (the run-to-run floor);
-(2) the captured step timed with CUDA events, both ways, interleaved.   python scripts/overlap_check.py [B] [num_block] > out.json"""
+(1) first-step gradients of every tensor, all parts overlapped vs single-stream vs a second single-stream run (the run-to-run floor);
+(2) the captured step timed with CUDA events for every variant ("0", "1", "bwd", ... separated by "/"), interleaved, three rounds of
+20 replays.   python scripts/overlap_check.py [B] [num_block] [variants] > out.json"""
 import json
 import sys
 
@@ -30,13 +31,17 @@ hr = torch.randint(1, 256, (B, 3, 128, 128), generator=g, dtype=torch.uint8)
 first = []
 for overlap in (False, True, False):
     tr = make(overlap, False)
+    p0, d0 = tr.gbuf.flat.clone(), tr.dbuf.flat.clone()
     tr.feed_data(lr, hr)
     tr.optimize_parameters(1)
     torch.cuda.synchronize()
     first.append(({k: v.clone() for k, v in tr.g_grads().items()}, {k: v.clone() for k, v in tr.d_grads().items()},
-                  dict(tr.get_current_log())))
+                  dict(tr.get_current_log()), tr.gbuf.flat - p0, tr.dbuf.flat - d0, tr.gema.flat - p0))
     del tr
 out = {"B": B, "num_block": NB}
+for name, i in (("adam_g_update", 3), ("adam_d_update", 4), ("ema_update", 5)):
+    out[name + "_overlap_vs_single"] = rel_l2(first[1][i], first[0][i])
+    out[name + "_single_vs_single"] = rel_l2(first[2][i], first[0][i])
 for name, which in (("g", 0), ("d", 1)):
     dev = {k: rel_l2(first[1][which][k], v) for k, v in first[0][which].items()}
     flo = {k: rel_l2(first[2][which][k], v) for k, v in first[0][which].items()}
@@ -47,23 +52,23 @@ for name, which in (("g", 0), ("d", 1)):
 out["losses_single"] = first[0][2]
 out["losses_overlap"] = first[1][2]
 
-trs = {ov: make(ov, True) for ov in (False, True)}
-for ov, tr in trs.items():
+variants = sys.argv[3].split("/") if len(sys.argv) > 3 else ["0", "1", "bwd", "fwd", "opt", "bwd,opt"]
+trs = {v: make(v, True) for v in variants}
+for tr in trs.values():
     for it in range(1, 6):
         tr.feed_data(lr, hr)
         tr.optimize_parameters(it)
 torch.cuda.synchronize()
-times = {False: [], True: []}
+times = {v: [] for v in variants}
 for rep in range(3):
-    for ov, tr in trs.items():
+    for v, tr in trs.items():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for it in range(20):
             tr.optimize_parameters(6 + rep * 20 + it)
         e1.record()
         torch.cuda.synchronize()
-        times[ov].append(e0.elapsed_time(e1) / 20)
-out["ms_per_step_single"] = times[False]
-out["ms_per_step_overlap"] = times[True]
-out["modes"] = {str(ov): tr._last_mode for ov, tr in trs.items()}
+        times[v].append(e0.elapsed_time(e1) / 20)
+out["ms_per_step"] = times
+out["modes"] = {v: tr._last_mode for v, tr in trs.items()}
 print(json.dumps(out))
