@@ -44,12 +44,11 @@ _FORK, _JOIN, _SIDE = "fork", "join", "side"     # lane markers inside Plan.call
 
 
 def overlap_enabled(part=None, setting=None):
-    """The side lane: independent launches run on a second stream beside launches that leave the machine
-    partly idle -- the resident dense-block launches occupy 128 of the 148 SMs (one 4-CTA cluster per image at B = 32).  Parts:
-    'bwd' = a group's dense-block weight gradients beside the next input-gradient launch; 'fwd' = the ground-truth half of the VGG
-    pass and the discriminator's weight preparation beside the generator forward; 'opt' = Adam(G) + EMA (HBM-bound) beside the
-    discriminator passes (tensor-bound).  `setting` (an option value) or $SSR_OVERLAP: 1 / True = all parts (the default),
-    0 / False = one stream, or a comma-separated list of parts.  Read when a plan / trainer is BUILT."""
+    """The side lane: independent launches run on a second stream beside the resident dense-block launches,
+    which occupy 128 of the 148 SMs (one 4-CTA cluster per image at B = 32).  Parts: 'bwd' = a group's dense-block weight
+    gradients beside the next input-gradient launch; 'fwd' = the ground-truth half of the VGG pass and the discriminator's weight
+    preparation beside the generator forward.  `setting` (an option value) or $SSR_OVERLAP: 1 / True = both parts (the default),
+    0 / False = one stream, 'fwd' / 'bwd' = that part only.  Read when a plan / trainer is BUILT."""
     import os
     v = os.environ.get("SSR_OVERLAP", "1") if setting is None else setting
     if isinstance(v, bool):
@@ -57,7 +56,7 @@ def overlap_enabled(part=None, setting=None):
     v = str(v).lower()
     if v in ("1", "true", "on", "all"):
         return True
-    parts = {p.strip() for p in v.split(",")} & {"fwd", "bwd", "opt"}
+    parts = {p.strip() for p in v.split(",")} & {"fwd", "bwd"}
     return bool(parts) if part is None else part in parts
 
 

@@ -146,7 +146,8 @@ class ESRGANTrainer:
         # run on a side stream beside the generator's dense-block launches (128 of the 148 SMs), like the dense blocks'
         # weight gradients beside the next input-gradient launch (generator._build_backward)
         self.overlap = overlap_enabled("fwd", cfg.get("overlap"))
-        self.overlap_opt = overlap_enabled("opt", cfg.get("overlap"))
+        # one CUDA graph per phase also on one GPU (what world > 1 replays around its all-reduces): a test hook for that capture path
+        self.phase_graphs = bool(cfg.get("phase_graphs", False))
         self._cap_stream = None
         self.log_dict = OrderedDict()
 
@@ -324,17 +325,6 @@ class ESRGANTrainer:
         run_phase(4)
 
     def _step_kernels(self, io, do_g, s, graph_mode=False):
-        if self.world == 1 and self.overlap_opt:
-            # one GPU, no exchange to hide: phase 3 (Adam(G) + EMA: 0.6 GB of HBM traffic, no tensor work) runs on the side lane beside
-            # the discriminator passes, which read neither the generator's parameters nor its gradients (see _step_phase)
-            lane = SideLane.get(self.device)
-            self._step_phase(1, io, do_g, s, graph_mode)
-            lane.fork(s)
-            self._step_phase(3, io, do_g, lane.handle, graph_mode)
-            self._step_phase(2, io, do_g, s, graph_mode)
-            lane.join(s)
-            self._step_phase(4, io, do_g, s, graph_mode)
-            return
         self._run_step(lambda ph: self._step_phase(ph, io, do_g, s, graph_mode), do_g)
 
     def optimize_parameters(self, current_iter=1):
@@ -355,11 +345,11 @@ class ESRGANTrainer:
             # with a side lane the capture stream gets a higher priority than the lane's: where both have thread blocks pending,
             # the main lane's (the dense-block clusters) are placed first and the side lane's fill what is left
             cap = {}
-            if self.overlap or self.overlap_opt or self.G.overlap:
+            if self.overlap or self.G.overlap:
                 if self._cap_stream is None:
                     self._cap_stream = torch.cuda.Stream(device=self.device, priority=-1)
                 cap = dict(stream=self._cap_stream)
-            if self.world == 1:
+            if self.world == 1 and not self.phase_graphs:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, **cap):
                     self._step_kernels(self.io, do_g, cur_stream(), graph_mode=True)
@@ -382,7 +372,7 @@ class ESRGANTrainer:
         if do_g:
             self.opt_g.before_replay()
         self.opt_d.before_replay()
-        if self.world == 1:
+        if len(graphs) == 1:
             graphs[0].replay()
         else:
             self._run_step(lambda ph: graphs[ph - 1].replay(), do_g)

@@ -52,7 +52,7 @@ for name, which in (("g", 0), ("d", 1)):
 out["losses_single"] = first[0][2]
 out["losses_overlap"] = first[1][2]
 
-variants = sys.argv[3].split("/") if len(sys.argv) > 3 else ["0", "1", "bwd", "fwd", "opt", "bwd,opt"]
+variants = sys.argv[3].split("/") if len(sys.argv) > 3 else ["0", "1", "bwd", "fwd"]
 trs = {v: make(v, True) for v in variants}
 for tr in trs.values():
     for it in range(1, 6):

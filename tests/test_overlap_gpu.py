@@ -22,12 +22,12 @@ def _batch(B=2, seed=0):
             torch.randint(1, 256, (B, 3, 128, 128), generator=g, dtype=torch.uint8))
 
 
-def _run(overlap, graph, iters, B=2):
+def _run(overlap, graph, iters, B=2, phase_graphs=False):
     from oracle import losses, nets
     from satlas_super_resolution_b200.trainer import ESRGANTrainer
     gp, dp, vp = nets.rrdbnet_init(24, 3, num_block=NB, seed=1), nets.unet_disc_init(27, seed=2), losses.vgg19_init(seed=3)
     tr = ESRGANTrainer(gp, dp, vp, dict(ema_decay=0.999, lr=1e-4, network_g=dict(num_in_ch=24, num_block=NB), cuda_graph=graph,
-                                        overlap=overlap))
+                                        overlap=overlap, phase_graphs=phase_graphs))
     lr, hr = _batch(B)
     snaps = []
     for it in range(1, iters + 1):
@@ -69,5 +69,21 @@ def test_side_lane_inside_the_cuda_graph():
         dev = rel_l2(graph[1][0][k], eager[1][0][k])
         print(f"  step-2 grad {k}: eager-vs-eager {spread:.3e}  overlapped-graph-vs-eager {dev:.3e}")
         assert dev < 3 * spread + 5e-2, k        # same bound as test_cuda_graph_replay_equals_eager (heavy-tailed spread, O(1) if wrong)
+    for k, v in eager[2][2].items():
+        assert abs(graph[2][2][k] - v) < 5e-3 * abs(v) + 5e-4, k
+
+
+def test_side_lane_inside_per_phase_graphs():
+    """world > 1 replays one graph per phase around its asynchronous all-reduces (captured on the same high-priority stream, sharing
+    one memory pool); `phase_graphs` takes that capture path on one GPU: the side lane forks and joins inside the phase-1 graph."""
+    _, _, eager = _run(False, False, 3)
+    tr, ws, graph = _run(True, True, 3, phase_graphs=True)
+    assert tr._last_mode == "graph" and ws.overlap_bwd and len(next(iter(tr._graphs.values()))) == 4
+    _, _, eager2 = _run(False, False, 3)
+    for k in ("conv_first.weight", "body.4.rdb2.conv3.weight", "conv_last.bias"):
+        spread = rel_l2(eager2[1][0][k], eager[1][0][k])
+        dev = rel_l2(graph[1][0][k], eager[1][0][k])
+        print(f"  step-2 grad {k}: eager-vs-eager {spread:.3e}  per-phase-graphs-vs-eager {dev:.3e}")
+        assert dev < 3 * spread + 5e-2, k
     for k, v in eager[2][2].items():
         assert abs(graph[2][2][k] - v) < 5e-3 * abs(v) + 5e-4, k
