@@ -118,7 +118,7 @@ class ESRGANTrainer:
             self.P = PerceptualEngine(vp, cfg.get("layer_weights", {"conv1_2": 0.1, "conv2_2": 0.1, "conv3_4": 1.0,
                                                                      "conv4_4": 1.0, "conv5_4": 1.0}),
                                       cfg.get("perceptual_weight", 1.0), cfg.get("use_input_norm", True),
-                                      cfg.get("range_norm", False))
+                                      cfg.get("range_norm", False), split_upto=cfg.get("vgg_split"))
         self.feed_disc_lr = cfg.get("feed_disc_lr", True)
         self.old_hr_ch = 0   # set by feed_data when the batch carries an `old_hr` image (ssr_esrgan_model.py:112-114)
         self.l1_gt_usm = cfg.get("l1_gt_usm", True)

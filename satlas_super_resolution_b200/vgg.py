@@ -20,8 +20,13 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
 class PerceptualEngine:
-    def __init__(self, params, layer_weights, perceptual_weight=1.0, use_input_norm=True, range_norm=False):
-        """params: 'conv1_1.weight' / '.bias' ... cuda f32 tensors (torchvision vgg19.features order)."""
+    def __init__(self, params, layer_weights, perceptual_weight=1.0, use_input_norm=True, range_norm=False, split_upto=None):
+        """params: 'conv1_1.weight' / '.bias' ... cuda f32 tensors (torchvision vgg19.features order).
+        split_upto: with the side lane (forward_gt) the layers up to and including this pool run once per half of the 2B batch --
+        the ground-truth half beside the generator forward -- and the deeper ones as ONE 2B batch after the join: at 16 x 16 and
+        8 x 8 pixels a half batch fills 43 .. 86 % of the SMs.  'all' = every layer per half; default $SSR_VGG_SPLIT or pool3."""
+        import os
+        self.split_upto = split_upto or os.environ.get("SSR_VGG_SPLIT", "pool3")
         self.device = params["conv1_1.weight"].device
         dev = self.device
         self.layer_weights = dict(layer_weights)
@@ -82,7 +87,7 @@ class PerceptualEngine:
         mean, inv_std = self._norm(ws)
         L.check(lib().ssr_ingest_nchw(gt.data_ptr(), L.SSR_F32, ws.inp.ptr() + 2 * B * H * W * 16, 16, B, 3, H, W, 16, 1.0,
                                       mean.data_ptr(), inv_std.data_ptr(), lane.handle))
-        ws.half_plans()[1].run(lane.handle)
+        ws.half_plans(self.split_upto)[1].run(lane.handle)
 
     def loss_and_grad(self, x, gt, loss_out, d_x, stream=None, gt_lane=None):
         """x, gt: f32 NCHW [B,3,H,W].  Adds the weighted perceptual loss to the device scalar `loss_out` and, when d_x is
@@ -96,8 +101,10 @@ class PerceptualEngine:
                                    inv_std.data_ptr(), s))
         ws.loss_ptr[0] = loss_out.data_ptr()
         if gt_lane is not None:
-            ws.half_plans()[0].run(s)
+            halves = ws.half_plans(self.split_upto)
+            halves[0].run(s)
             gt_lane.join(s)
+            halves[2].run(s)            # the layers below the split as one 2B batch (empty when every layer is split)
         else:
             L.check(lb.ssr_ingest_nchw(gt.data_ptr(), L.SSR_F32, ws.inp.ptr() + 2 * B * H * W * 16, 16, B, 3, H, W, 16, 1.0,
                                        mean.data_ptr(), inv_std.data_ptr(), s))
@@ -193,25 +200,32 @@ class _PWorkspace:
             g = dx
         self.bwd = bwd
 
-    def half_plans(self):
-        """the forward plan once per half of the 2B batch -- [generated images, ground truth] -- over the same buffers"""
+    def half_plans(self, split_upto="all"):
+        """[plan over the generated half, plan over the ground-truth half, plan over the whole 2B batch]: the layers up to and
+        including pool `split_upto` once per half, the deeper ones as one batch -- same buffers, same launches as self.fwd otherwise"""
         if self._halves is None:
             lb = lib()
             B = self.B
+            names = [item[1] for item in self.order]
+            n_split = names.index(split_upto) + 1 if split_upto in names else len(self.order)
             off = lambda a, half: a.ptr() + half * B * a.H * a.W * a.C * 2
-            plans = []
+
+            def emit(plan, item, half, nb):
+                if item[0] == "pool":
+                    _, _, src, dst, hh, ww = item
+                    plan.add(lb.ssr_maxpool_relu, off(src, half), off(dst, half), nb, hh, ww, src.C)
+                    return
+                _, name, src, out, hh, ww, cin_c = item
+                pc = self._eng.cv[name]
+                plan.conv(conv_args(off(src, half), nb, hh, ww, src.stride, cin_c, pc.packed.data_ptr(), 3, out.C, pc.n_pad,
+                                    bias=pc.bias.data_ptr(), act=0 if name in self._eng.layer_weights else 2,
+                                    out=off(out, half), out_stride=out.C))
+
+            plans = [Plan(), Plan(), Plan()]
             for half in (0, 1):
-                plan = Plan()
-                for item in self.order:
-                    if item[0] == "pool":
-                        _, _, src, dst, hh, ww = item
-                        plan.add(lb.ssr_maxpool_relu, off(src, half), off(dst, half), B, hh, ww, src.C)
-                        continue
-                    _, name, src, out, hh, ww, cin_c = item
-                    pc = self._eng.cv[name]
-                    plan.conv(conv_args(off(src, half), B, hh, ww, src.stride, cin_c, pc.packed.data_ptr(), 3, out.C, pc.n_pad,
-                                        bias=pc.bias.data_ptr(), act=0 if name in self._eng.layer_weights else 2,
-                                        out=off(out, half), out_stride=out.C))
-                plans.append(plan)
+                for item in self.order[:n_split]:
+                    emit(plans[half], item, half, B)
+            for item in self.order[n_split:]:
+                emit(plans[2], item, 0, 2 * B)
             self._halves = plans
         return self._halves

@@ -20,8 +20,12 @@ def rel_l2(a, b):
 
 
 def make(overlap, graph):
+    """overlap: False / True / '0' / '1' / 'bwd' / 'fwd', optionally ':<vgg split>' ('1:all', '1:pool2', ...)"""
+    split = None
+    if isinstance(overlap, str) and ":" in overlap:
+        overlap, split = overlap.split(":")
     return ESRGANTrainer(weights.rrdbnet_state(24, 3, num_block=NB, seed=0), weights.unet_disc_state(27, seed=1), weights.vgg19_state(seed=2),
-                         dict(ema_decay=0.999, lr=1e-4, network_g=dict(num_in_ch=24, num_block=NB), cuda_graph=graph, overlap=overlap))
+                         dict(ema_decay=0.999, lr=1e-4, network_g=dict(num_in_ch=24, num_block=NB), cuda_graph=graph, overlap=overlap, vgg_split=split))
 
 
 g = torch.Generator().manual_seed(0)
@@ -29,7 +33,8 @@ lr = torch.randint(1, 256, (B, 24, 32, 32), generator=g, dtype=torch.uint8)
 hr = torch.randint(1, 256, (B, 3, 128, 128), generator=g, dtype=torch.uint8)
 
 first = []
-for overlap in (False, True, False):
+TIMING_ONLY = len(sys.argv) > 4 and sys.argv[4] == "timing"
+for overlap in (() if TIMING_ONLY else (False, True, False)):
     tr = make(overlap, False)
     p0, d0 = tr.gbuf.flat.clone(), tr.dbuf.flat.clone()
     tr.feed_data(lr, hr)
@@ -39,20 +44,21 @@ for overlap in (False, True, False):
                   dict(tr.get_current_log()), tr.gbuf.flat - p0, tr.dbuf.flat - d0, tr.gema.flat - p0))
     del tr
 out = {"B": B, "num_block": NB}
-for name, i in (("adam_g_update", 3), ("adam_d_update", 4), ("ema_update", 5)):
+for name, i in (() if TIMING_ONLY else (("adam_g_update", 3), ("adam_d_update", 4), ("ema_update", 5))):
     out[name + "_overlap_vs_single"] = rel_l2(first[1][i], first[0][i])
     out[name + "_single_vs_single"] = rel_l2(first[2][i], first[0][i])
-for name, which in (("g", 0), ("d", 1)):
+for name, which in (() if TIMING_ONLY else (("g", 0), ("d", 1))):
     dev = {k: rel_l2(first[1][which][k], v) for k, v in first[0][which].items()}
     flo = {k: rel_l2(first[2][which][k], v) for k, v in first[0][which].items()}
     kd, kf = max(dev, key=dev.get), max(flo, key=flo.get)
     out[f"{name}_grad_overlap_vs_single_worst"] = [kd, dev[kd]]
     out[f"{name}_grad_single_vs_single_worst"] = [kf, flo[kf]]
     out[f"{name}_grad_tensors"] = len(dev)
-out["losses_single"] = first[0][2]
-out["losses_overlap"] = first[1][2]
+if not TIMING_ONLY:
+    out["losses_single"] = first[0][2]
+    out["losses_overlap"] = first[1][2]
 
-variants = sys.argv[3].split("/") if len(sys.argv) > 3 else ["0", "1", "bwd", "fwd"]
+variants = sys.argv[3].split("/") if len(sys.argv) > 3 else ["0", "1", "1:all", "1:pool2", "1:pool4", "bwd"]
 trs = {v: make(v, True) for v in variants}
 for tr in trs.values():
     for it in range(1, 6):

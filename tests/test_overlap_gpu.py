@@ -87,3 +87,42 @@ def test_side_lane_inside_per_phase_graphs():
         assert dev < 3 * spread + 5e-2, k
     for k, v in eager[2][2].items():
         assert abs(graph[2][2][k] - v) < 5e-3 * abs(v) + 5e-4, k
+
+
+@pytest.mark.parametrize("split", ["pool3", "all", "pool1"])
+def test_perceptual_pass_split_over_the_side_lane_equals_the_2b_batch(split):
+    """forward_gt (ground-truth half of the layers up to `split` on the side lane) + loss_and_grad(gt_lane=...) (generated half, join,
+    deeper layers as one 2B batch) == the plain 2B pass: same launches over the same buffers, only batched differently"""
+    from oracle import losses
+    from satlas_super_resolution_b200.ops import SideLane, cur_stream
+    from satlas_super_resolution_b200.vgg import PerceptualEngine
+    B, H = 3, 128
+    vp = {k: v.cuda() for k, v in losses.vgg19_init(seed=3).items()}
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(B, 3, H, H, generator=g).cuda()
+    gt = torch.rand(B, 3, H, H, generator=g).cuda()
+    res = []
+    for lane_split in (None, split):
+        eng = PerceptualEngine(vp, losses.DEFAULT_LAYER_WEIGHTS, split_upto=lane_split)
+        loss = torch.zeros(1, device="cuda")
+        dx = torch.zeros(B, 3, H, H, device="cuda")
+        if lane_split is None:
+            eng.loss_and_grad(x, gt, loss, dx)
+        else:
+            lane = SideLane.get()
+            lane.fork(cur_stream())
+            eng.forward_gt(gt, lane)
+            eng.loss_and_grad(x, gt, loss, dx, gt_lane=lane)
+            plans = eng.workspace(B, H, H).half_plans(split)
+            n_deep = {"pool3": 9, "all": 0, "pool1": 17}[split]      # 16 convs + 4 pools: 11 / 20 / 3 of them per half
+            assert len(plans[2]) == n_deep and len(plans[0]) == len(plans[1]) == 20 - n_deep
+        torch.cuda.synchronize()
+        feats = [item[3].t.float().clone() for item in eng.workspace(B, H, H).order if item[0] == "conv"]
+        res.append((loss.item(), dx.clone(), feats))
+    # the same tiles through the same kernel: expected bit-identical; asserted to 1e-5 so that a batch-dependent tiling choice inside
+    # the conv launcher (another accumulation order) could not fail it, while a wrong half / offset is O(1)
+    worst = max(rel_l2(a, b) for a, b in zip(res[1][2], res[0][2]))
+    print(f"  split {split}: worst feature difference {worst:.2e}, loss {res[1][0]:.7f} vs {res[0][0]:.7f}")
+    assert worst < 1e-5
+    assert abs(res[1][0] - res[0][0]) <= 1e-5 * abs(res[0][0])
+    assert rel_l2(res[1][1], res[0][1]) < 1e-4
