@@ -102,19 +102,64 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: ONE nvidia-smi process looping every 200 ms
+    (B200_PROFILING.md's clocks line: `-lms 200`, started before, killed after).  Spawning a fresh nvidia-smi per sample initialises
+    NVML every time and holds driver locks for tens of ms -- a stall the end-to-end loop (host on the critical path every step)
+    sees directly."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self._stop_flag, self.proc = index, [], False, None
+
+    @property
+    def stop_flag(self):
+        return self._stop_flag
+
+    @stop_flag.setter
+    def stop_flag(self, v):
+        self._stop_flag = v
+        if v and self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
 
     def run(self):
+        import select
+        import shutil
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
+        base = ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"]
+        looping = False
+        try:
+            pre = ["stdbuf", "-oL"] if shutil.which("stdbuf") else []
+            self.proc = subprocess.Popen(pre + base + ["-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+            fd, buf, t0 = self.proc.stdout.fileno(), b"", time.time()
+            while not self._stop_flag:
+                ready, _, _ = select.select([fd], [], [], 0.25)
+                if ready:
+                    chunk = os.read(fd, 65536)
+                    if not chunk:
+                        break
+                    buf += chunk
+                    *lines, buf = buf.split(b"\n")
+                    for line in lines:
+                        if line.strip():
+                            self.rows.append([c.strip() for c in line.decode(errors="replace").split(",")])
+                            looping = True
+                elif not looping and time.time() - t0 > 2.0:
+                    break        # nothing arrives through the pipe (block-buffered output?): one process per sample instead
+        except Exception:
+            pass
+        finally:
+            if self.proc is not None:
+                try:
+                    self.proc.terminate()
+                except Exception:
+                    pass
+        while not self._stop_flag and not looping:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                out = subprocess.run(base, capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
