@@ -103,7 +103,7 @@ class SSRESRGANModel:
                    feed_disc_lr=bool(opt.get("feed_disc_lr")), l1_gt_usm=opt.get("l1_gt_usm", True) is not False,
                    percep_gt_usm=opt.get("percep_gt_usm", True) is not False, gan_gt_usm=opt.get("gan_gt_usm", True) is not False,
                    net_d_iters=train_opt.get("net_d_iters", 1), net_d_init_iters=train_opt.get("net_d_init_iters", 0),
-                   cuda_graph=bool(opt.get("cuda_graph", True)))
+                   cuda_graph=bool(opt.get("cuda_graph", True)), overlap=opt.get("overlap"))   # overlap: None = $SSR_OVERLAP (ops.overlap_enabled)
         if per and not cfg["layer_weights"]:
             raise ValueError("perceptual_opt needs layer_weights")
         pg = torch.distributed.group.WORLD if (opt.get("dist") and torch.distributed.is_initialized()) else None
