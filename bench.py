@@ -440,6 +440,9 @@ def train_rooflines(m, bands, peak, peak_src):
             us = 0.5 * (gu["forward"]["us_per_block"] + gu["input_gradient"]["us_per_block"])
             ach = per_block_flop / (us * 1e-6) / 1e12
             main["in_graph"] = {"us_per_block": us, "achieved": ach, "frac": ach / peak}
+    main["timing"] = ("per-launch CUDA events (on the launching stream) in one eager step" +
+                      (" WITH the side lane: the input-gradient launches share the machine with the previous group's weight-gradient launches, the "
+                       "forward launches with the ground-truth VGG pass (the kernel on its own: in_graph)" if m.get("side_lane") else ""))
     main["operand_ceiling"] = {"forward_frac_of_peak": (504 * 16 + 216 * 32) / (504 * 40 + 216 * 48),
                                "note": "shared-memory operand bandwidth of SS-form MMAs: the forward block issues 504 MMAs with N = 32 (16 cycles of math, 40 of operand reads) and 216 with N = 64 (32 / 48); profiles/r02_conv64_ncu.md"}
     others = {

@@ -82,6 +82,16 @@ def test_bench_helpers():
     assert c12["num_in_ch_g"] == 96 and c12["num_in_ch_d"] == 99 and lr12.shape == (2, 96, 32, 32)
     opt = bench.model_opt(12, True, False)
     assert opt["network_g"]["num_in_ch"] == 96 and opt["network_d"]["num_in_ch"] == 99 and opt["model_type"] == "SSRESRGANModel"
+    # the roofline block from a measured dict (numbers of profiles/r02c_logs/bench_default_final.json): dominant kernel = resident dense blocks
+    m = dict(B=32, ms_cls=[5.9, 1.7, 2.84, 2.58, 2.2], cnt_cls=[130, 26, 6, 6, 69], side_lane=True,
+             graph_us={"forward": {"launches": 6, "us_per_launch": 446.3}, "input_gradient": {"launches": 6, "us_per_launch": 403.0}})
+    main, others = bench.train_rooflines(m, 3, 1452.2, "measured")
+    assert main["bound"] == "tensor" and main["unit"] == "TFLOP/s" and abs(main["frac"] - main["achieved"] / 1452.2) < 1e-9
+    assert 0.26 < main["frac"] < 0.29 and main["launches_per_step"] == 12 and "side lane" in main["timing"]
+    assert abs(main["forward"]["in_graph"]["us_per_block"] - 446.3 * 6 / 69) < 1e-6 and 0.30 < main["input_gradient"]["in_graph"]["frac"] < 0.32
+    assert main["traffic"] and main["traffic"] > 1e8        # per 12-block launch, from profiles/ncu_traffic.json (ncu --set full)
+    assert set(others) == {"conv_tc_kernel", "wgrad9_tc_batched_kernel", "wgrad_tc_kernels", "all_conv_fwd_dgrad"}
+    assert "side lane" not in bench.train_rooflines(dict(m, side_lane=False, graph_us={}), 3, 1452.2, "measured")[0]["timing"]
 
 
 def test_infer_format_matches_reference_semantics():
