@@ -211,3 +211,21 @@ def test_shard_guards_and_batcher(tmp_path):
         assert torch.equal(b["lr"][i], s["lr"]) and torch.equal(b["hr"][i], s["hr"])
     w = ds.get_tile_weight_sampler({"10_20": 5.0})
     assert len(list(iter(w))) == len(ds)
+    # the `tile_weights` option (a JSON of {chip: weight}; read by nothing in the reference) wired to the sampler, and the sampler to the batcher
+    import json
+    from satlas_super_resolution_b200.data import build_train_sampler
+    assert build_train_sampler(ds, {"use_shuffle": True}) is None
+    chips = [rec["naip"].split("/")[-1][:-4] for rec in ds.datapoints]
+    wpath = os.path.join(root, "weights.json")
+    json.dump({chips[0]: 1e9}, open(wpath, "w"))
+    with pytest.raises(ValueError, match="use_shuffle"):
+        build_train_sampler(ds, {"tile_weights": wpath, "use_shuffle": True})
+    sampler = build_train_sampler(ds, {"tile_weights": wpath, "use_shuffle": False})
+    np.random.seed(0)
+    drawn = list(iter(sampler))
+    assert len(drawn) == len(ds) and drawn.count(0) >= len(ds) - 1          # weight 1e9 against 1: (almost) always datapoint 0
+    assert [float(x) for x in sampler.weights] == [1e9] + [1.0] * (len(ds) - 1)
+    np.random.seed(0)
+    random.seed(11)
+    got = list(pb.batches(sampler))
+    assert len(got) == len(ds) // 3 and all(b["lr"].shape[0] == 3 for b in got)
