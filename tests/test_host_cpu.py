@@ -155,6 +155,30 @@ t = torch.tensor([float(rank + 1), 2.0])
 dist.reduce(t, dst=0)
 if rank == 0:
     assert torch.allclose(t / world, torch.tensor([1.5, 2.0]))
+# the step's exchange schedule (ESRGANTrainer._run_step): G gradients are exchanged asynchronously after phase 1 and summed before
+# phase 3 (Adam(G)), D gradients after phase 2 and before phase 4 (Adam(D)); without a generator step only D is exchanged
+from satlas_super_resolution_b200.trainer import ESRGANTrainer
+class Stub:
+    pass
+st = Stub()
+st.world, st.pg = world, dist.group.WORLD
+st.ggrad, st.dgrad = FlatBuffer(shapes, "cpu"), FlatBuffer(OrderedDict(d=(6,)), "cpu")
+st._exchange_async = ESRGANTrainer._exchange_async.__get__(st)
+for do_g in (True, False):
+    log = []
+    def run_phase(ph):
+        log.append(ph)
+        if ph == 1:
+            st.ggrad.flat.fill_(float(rank + 1))
+        elif ph == 2:
+            st.dgrad.flat.fill_(10.0 * (rank + 1))
+        elif ph == 3:
+            want = 3.0 if do_g else float(rank + 1)          # 1 + 2 summed over the two ranks, or untouched
+            assert torch.all(st.ggrad.flat == want), (do_g, st.ggrad.flat)
+        elif ph == 4:
+            assert torch.all(st.dgrad.flat == 30.0), st.dgrad.flat
+    ESRGANTrainer._run_step(st, run_phase, do_g)
+    assert log == [1, 2, 3, 4]
 dist.barrier()
 dist.destroy_process_group()
 print("gloo-ok", rank)
