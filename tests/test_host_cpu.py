@@ -302,3 +302,16 @@ def test_plan_lanes_order_forks_and_joins():
         p3.add(lambda *a: 1, 0)
     with pytest.raises(Exception):
         p3.run("main", lane=Lane())
+
+
+def test_side_lane_switch_parsing(monkeypatch):
+    """ops.overlap_enabled: option value first, then $SSR_OVERLAP, default on; 'fwd' / 'bwd' select one part"""
+    from satlas_super_resolution_b200.ops import overlap_enabled as on
+    monkeypatch.delenv("SSR_OVERLAP", raising=False)
+    assert on() and on("fwd") and on("bwd")
+    assert not on("fwd", False) and on("bwd", True) and on("fwd", "fwd") and not on("bwd", "fwd") and on("bwd", "fwd,bwd")
+    assert not on(None, "0") and not on("bwd", "off") and on(None, "bwd")
+    monkeypatch.setenv("SSR_OVERLAP", "0")
+    assert not on() and not on("fwd") and on("fwd", True)          # an explicit option overrides the environment
+    monkeypatch.setenv("SSR_OVERLAP", "bwd")
+    assert on("bwd") and not on("fwd")
