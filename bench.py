@@ -14,7 +14,8 @@ build_model(opt) -> MODEL_REGISTRY['SSRESRGANModel'].
   e2e   : the plugin call sequence model.feed_data({'lr','hr'} HOST pinned uint8) / model.optimize_parameters(it) /
           model.get_current_log(): H2D copy inside the timed region, loss scalars read back (D2H) every step
   roofline          : the dominant kernel, rdb_resident_kernel (a ResidualDenseBlock's five convs / five input-gradient convs per
-                      launch), algorithmic FLOPs / summed device time (per-launch CUDA events in one extra eager step)
+                      launch), algorithmic FLOPs / summed device time (per-launch CUDA events in one extra eager step; with the side lane on,
+                      those launches share the machine with weight-gradient / VGG launches -- `in_graph` is the kernel on its own)
   roofline_kernels  : the same for the single-launch conv kernel and the two weight-gradient kernels
   cpu_baseline      : the CPU restatement of the reference step (oracle/step.py, torch fp32) on this box's host cores
   The default run also measures the other two things BASELINE.json's metric names and attaches them to the same line:
