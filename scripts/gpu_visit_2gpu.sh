@@ -1,5 +1,6 @@
 #!/bin/bash
-# 2-GPU check of the side lane: the DDP equivalence tests and the N = 2 bench line (one graph per phase around the asynchronous all-reduces)
+# 2-GPU check of the side lane: the DDP equivalence tests and the N = 2 bench line (one graph per phase around the asynchronous all-reduces).
+# NOT run in round 2c (the GPU budget went to the 1-GPU visits; the per-phase capture is covered on one GPU by tests/test_overlap_gpu.py).
 mkdir -p gpurun_out/r2c
 O=gpurun_out/r2c
 (time timeout 150 python -m pytest tests/test_ddp_gpu.py -x -q -s) > $O/ddp_tests_2gpu.log 2>&1; echo "rc=$?" >> $O/ddp_tests_2gpu.log; tail -6 $O/ddp_tests_2gpu.log
